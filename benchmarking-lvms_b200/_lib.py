@@ -1,0 +1,58 @@
+"""ctypes binding of libblvm_b200.so (include/blvm_b200.h).  No libtorch linkage: tensors cross the boundary as raw
+device pointers + sizes + the current CUDA stream handle.  There is NO fallback: if the library is missing the import
+fails, and every op raises if its tensors are not CUDA tensors."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libblvm_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: the CUDA library is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C benchmarking-lvms_b200/csrc`) first. blvm_b200 has no CPU/PyTorch fallback."
+    )
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int
+_f32 = ctypes.c_float
+_f64 = ctypes.c_double
+
+SIGNATURES = {
+    "blvm_version": (_i32, []),
+    "blvm_last_error_string": (ctypes.c_char_p, []),
+    "blvm_dmol_chunks": (_i64, [_i64]),
+    "blvm_kl_chunks": (_i64, [_i64]),
+    "blvm_dmol_fwd": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p]),
+    "blvm_dmol_fwd_grad": (_i32, [_p, _p, _p, _p, _f32, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p, _p]),
+    "blvm_dl_fwd_grad": (_i32, [_p, _p, _p, _p, _f32, _i64, _i64, _i32, _f32, _i32, _p, _p, _p, _p, _p]),
+    "blvm_kl_gaussian_fwd": (_i32, [_p, _p, _p, _p, _i64, _p, _p]),
+    "blvm_kl_gaussian_bwd": (_i32, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
+    "blvm_kl_elbo_fwd_grad": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "blvm_kl_reduce_fwd_grad": (_i32, [_p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _p]),
+    "blvm_elbo_finalize": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64, _f64, _p, _p, _p]),
+    "blvm_quantize": (_i32, [_p, _i64, _p, _i64, _p, _p]),
+    "blvm_scale_inplace": (_i32, [_p, _i64, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = header and library out of sync
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+BLVM_FLAG_MASK_OUTPUT = 1
+BLVM_FLAG_SKIP_PADDED = 2
+BLVM_MAX_KL_LEVELS = 8
+
+
+class BlvmError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib.blvm_last_error_string().decode("utf-8", "replace")
+        raise BlvmError(f"{what} failed with code {rc}: {msg}")

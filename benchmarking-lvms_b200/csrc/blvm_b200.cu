@@ -1,0 +1,265 @@
+// C ABI of the blvm_b200 kernels (include/blvm_b200.h).  Validation + launch only: no allocation, no synchronisation.
+#include "../../include/blvm_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "dmol_kernels.cuh"
+#include "kl_kernels.cuh"
+#include "misc_kernels.cuh"
+
+using namespace blvm;
+
+static_assert(BLVM_DMOL_TILE == 128, "tile constant mirrors the kernel template argument");
+static_assert(BLVM_KL_TILE == kKlChunk, "tile constant mirrors the KL kernel");
+static_assert(BLVM_MAX_KL_LEVELS == kMaxLevels, "level cap");
+static_assert(BLVM_FLAG_MASK_OUTPUT == kFlagMaskOutput && BLVM_FLAG_SKIP_PADDED == kFlagSkipPadded, "flags");
+
+namespace {
+
+constexpr int kTile = BLVM_DMOL_TILE;
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return BLVM_OK;
+}
+
+// fp32 constants rounded from double exactly like torch rounds a Python scalar that meets an fp32 tensor.
+DmolConsts make_consts(int num_bins, float log_epsilon) {
+  DmolConsts C;
+  C.h = static_cast<float>(1.0 / (num_bins - 1));
+  C.two_h = static_cast<float>(2.0 / (num_bins - 1));
+  C.lo_thresh = static_cast<float>(2.0 / num_bins - 1.0);
+  C.hi_thresh = static_cast<float>(1.0 - 2.0 / num_bins);
+  C.log_half_bins = static_cast<float>(log(num_bins / 2.0));
+  C.log_eps = log_epsilon;
+  return C;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+template <int K, bool GRAD>
+int launch_tile(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
+  constexpr size_t smem = dmol_tile_smem_bytes<K, kTile>();
+  auto kern = dmol_tile_kernel<K, kTile, GRAD>;
+  static bool configured = false;  // per instantiation; benign race (idempotent attribute)
+  if (!configured) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
+  return check_launch("dmol_tile_kernel");
+}
+
+template <bool GRAD>
+int dispatch_dmol(const DmolArgs& A, cudaStream_t st) {
+  const int64_t tiles = A.B * A.chunks;
+  if (tiles == 0) return BLVM_OK;
+  if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)tiles);
+  if (A.D == 1) {
+    switch (A.K) {
+#define BLVM_CASE(KK) \
+  case KK:            \
+    return launch_tile<KK, GRAD>(A, tiles, st);
+      BLVM_CASE(1)
+      BLVM_CASE(2)
+      BLVM_CASE(3)
+      BLVM_CASE(4)
+      BLVM_CASE(5)
+      BLVM_CASE(6)
+      BLVM_CASE(8)
+      BLVM_CASE(10)
+      BLVM_CASE(12)
+      BLVM_CASE(16)
+      BLVM_CASE(20)
+      BLVM_CASE(30)
+#undef BLVM_CASE
+      default:
+        break;
+    }
+  }
+  dmol_generic_kernel<kTile, GRAD><<<static_cast<unsigned>(tiles), kTile, 0, st>>>(A);
+  return check_launch("dmol_generic_kernel");
+}
+
+int validate_dmol(const float* y, const float* raw, int64_t B, int64_t T, int K, int D, int num_bins) {
+  if (B < 0 || T < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "negative size B=%lld T=%lld", (long long)B, (long long)T);
+  if (K < 1 || D < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "K=%d D=%d must be >= 1", K, D);
+  if (num_bins < 2) return fail(BLVM_ERR_INVALID_ARGUMENT, "num_bins=%d must be >= 2", num_bins);
+  if (B * T > 0 && (!y || !raw)) return fail(BLVM_ERR_INVALID_ARGUMENT, "null y/raw");
+  if (!aligned(y, 4) || !aligned(raw, 4)) return fail(BLVM_ERR_INVALID_ARGUMENT, "y/raw must be 4-byte aligned");
+  return BLVM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int blvm_version(void) { return BLVM_B200_VERSION; }
+const char* blvm_last_error_string(void) { return g_err; }
+int64_t blvm_dmol_chunks(int64_t T) { return (T + kTile - 1) / kTile; }
+int64_t blvm_kl_chunks(int64_t row_elems) { return (row_elems + kKlChunk - 1) / kKlChunk; }
+
+int blvm_dmol_fwd(const float* y, const float* raw, const int64_t* x_sl, int64_t B, int64_t T, int K, int D, int num_bins,
+                  float log_epsilon, int flags, float* lp, double* partials, int* err_flag, blvm_stream_t stream) {
+  if (int rc = validate_dmol(y, raw, B, T, K, D, num_bins)) return rc;
+  DmolArgs A{};
+  A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = nullptr; A.gscale = 0.f; A.lp = lp; A.graw = nullptr;
+  A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T); A.K = K; A.D = D;
+  A.flags = flags; A.C = make_consts(num_bins, log_epsilon);
+  return dispatch_dmol<false>(A, static_cast<cudaStream_t>(stream));
+}
+
+int blvm_dmol_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale, int64_t B,
+                       int64_t T, int K, int D, int num_bins, float log_epsilon, int flags, float* lp, float* graw,
+                       double* partials, int* err_flag, blvm_stream_t stream) {
+  if (int rc = validate_dmol(y, raw, B, T, K, D, num_bins)) return rc;
+  if (B * T > 0 && !graw) return fail(BLVM_ERR_INVALID_ARGUMENT, "null graw");
+  if (!aligned(graw, 4)) return fail(BLVM_ERR_INVALID_ARGUMENT, "graw must be 4-byte aligned");
+  DmolArgs A{};
+  A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = gout; A.gscale = gscale; A.lp = lp; A.graw = graw;
+  A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T); A.K = K; A.D = D;
+  A.flags = flags; A.C = make_consts(num_bins, log_epsilon);
+  return dispatch_dmol<true>(A, static_cast<cudaStream_t>(stream));
+}
+
+int blvm_dl_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale, int64_t B,
+                     int64_t T, int num_bins, float log_epsilon, int flags, float* lp, float* graw, double* partials,
+                     int* err_flag, blvm_stream_t stream) {
+  if (int rc = validate_dmol(y, raw, B, T, 1, 1, num_bins)) return rc;
+  if (!aligned(raw, 8) || !aligned(graw, 8)) return fail(BLVM_ERR_INVALID_ARGUMENT, "raw/graw must be 8-byte aligned");
+  DmolArgs A{};
+  A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = gout; A.gscale = gscale; A.lp = lp; A.graw = graw;
+  A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T); A.K = 1; A.D = 1;
+  A.flags = flags; A.C = make_consts(num_bins, log_epsilon);
+  const int64_t tiles = A.B * A.chunks;
+  if (tiles == 0) return BLVM_OK;
+  if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (graw)
+    dl_kernel<kTile, true><<<static_cast<unsigned>(tiles), kTile, 0, st>>>(A);
+  else
+    dl_kernel<kTile, false><<<static_cast<unsigned>(tiles), kTile, 0, st>>>(A);
+  return check_launch("dl_kernel");
+}
+
+static int launch_kl(KlArgs& A, bool grad, cudaStream_t st) {
+  A.chunks = blvm_kl_chunks(A.row_elems);
+  const int64_t tiles = A.B * A.chunks;
+  if (tiles == 0) return BLVM_OK;
+  if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
+  bool vec = (A.row_elems % 4 == 0) && aligned(A.mu_q, 16) && aligned(A.sd_q, 16) && aligned(A.mu_p, 16) &&
+             aligned(A.sd_p, 16) && aligned(A.kl, 16);
+  if (grad) vec = vec && aligned(A.g_mu_q, 16) && aligned(A.g_sd_q, 16) && aligned(A.g_mu_p, 16) && aligned(A.g_sd_p, 16);
+  const unsigned g = static_cast<unsigned>(tiles);
+  if (vec && grad) kl_kernel<true, true><<<g, kKlTPB, 0, st>>>(A);
+  else if (vec) kl_kernel<true, false><<<g, kKlTPB, 0, st>>>(A);
+  else if (grad) kl_kernel<false, true><<<g, kKlTPB, 0, st>>>(A);
+  else kl_kernel<false, false><<<g, kKlTPB, 0, st>>>(A);
+  return check_launch("kl_kernel");
+}
+
+int blvm_kl_gaussian_fwd(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p, int64_t n, float* kl,
+                         blvm_stream_t stream) {
+  if (n < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "negative n");
+  if (n > 0 && (!mu_q || !sd_q || !mu_p || !sd_p || !kl)) return fail(BLVM_ERR_INVALID_ARGUMENT, "null pointer");
+  KlArgs A{};
+  A.mu_q = mu_q; A.sd_q = sd_q; A.mu_p = mu_p; A.sd_p = sd_p; A.kl = kl; A.B = 1; A.row_elems = n; A.Z = 1;
+  return launch_kl(A, false, static_cast<cudaStream_t>(stream));
+}
+
+int blvm_kl_gaussian_bwd(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p, const float* gout,
+                         int64_t n, float* g_mu_q, float* g_sd_q, float* g_mu_p, float* g_sd_p, blvm_stream_t stream) {
+  if (n < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "negative n");
+  if (n > 0 && (!mu_q || !sd_q || !mu_p || !sd_p || !gout || !g_mu_q || !g_sd_q || !g_mu_p || !g_sd_p))
+    return fail(BLVM_ERR_INVALID_ARGUMENT, "null pointer");
+  KlArgs A{};
+  A.mu_q = mu_q; A.sd_q = sd_q; A.mu_p = mu_p; A.sd_p = sd_p; A.gout = gout; A.gscale = 1.f;
+  A.g_mu_q = g_mu_q; A.g_sd_q = g_sd_q; A.g_mu_p = g_mu_p; A.g_sd_p = g_sd_p; A.B = 1; A.row_elems = n; A.Z = 1;
+  return launch_kl(A, true, static_cast<cudaStream_t>(stream));
+}
+
+int blvm_kl_elbo_fwd_grad(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p, const int64_t* lens,
+                          int64_t B, int64_t Tz, int64_t Z, double free_nats, float gscale, float* kl, float* g_mu_q,
+                          float* g_sd_q, float* g_mu_p, float* g_sd_p, double* part_kl, double* part_klfn,
+                          blvm_stream_t stream) {
+  if (B < 0 || Tz < 0 || Z < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad shape B=%lld Tz=%lld Z=%lld", (long long)B, (long long)Tz, (long long)Z);
+  if (B * Tz > 0 && (!mu_q || !sd_q || !mu_p || !sd_p)) return fail(BLVM_ERR_INVALID_ARGUMENT, "null input");
+  if (!part_kl || !part_klfn) return fail(BLVM_ERR_INVALID_ARGUMENT, "null partials");
+  const bool grad = g_mu_q != nullptr;
+  if (grad && (!g_sd_q || !g_mu_p || !g_sd_p)) return fail(BLVM_ERR_INVALID_ARGUMENT, "gradient outputs must be given together");
+  KlArgs A{};
+  A.mu_q = mu_q; A.sd_q = sd_q; A.mu_p = mu_p; A.sd_p = sd_p; A.lens = lens; A.gscale = gscale;
+  A.fn_enabled = (free_nats != 0.0) ? 1 : 0;
+  A.min_kl = static_cast<float>(free_nats / static_cast<double>(Z));  // python float / int, then torch.tensor(..., fp32)
+  A.kl = kl; A.g_mu_q = g_mu_q; A.g_sd_q = g_sd_q; A.g_mu_p = g_mu_p; A.g_sd_p = g_sd_p;
+  A.part_kl = part_kl; A.part_klfn = part_klfn; A.B = B; A.row_elems = Tz * Z; A.Z = Z;
+  return launch_kl(A, grad, static_cast<cudaStream_t>(stream));
+}
+
+int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int64_t Tz, int64_t Z, double free_nats,
+                            float gscale, float* gkl, double* part_kl, double* part_klfn, blvm_stream_t stream) {
+  if (B < 0 || Tz < 0 || Z < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad shape");
+  if (B * Tz > 0 && !kl) return fail(BLVM_ERR_INVALID_ARGUMENT, "null kl");
+  if (!part_kl || !part_klfn) return fail(BLVM_ERR_INVALID_ARGUMENT, "null partials");
+  KlReduceArgs A{};
+  A.kl = kl; A.lens = lens; A.gscale = gscale; A.fn_enabled = (free_nats != 0.0) ? 1 : 0;
+  A.min_kl = static_cast<float>(free_nats / static_cast<double>(Z));
+  A.gkl = gkl; A.part_kl = part_kl; A.part_klfn = part_klfn; A.B = B; A.row_elems = Tz * Z; A.Z = Z;
+  A.chunks = blvm_kl_chunks(A.row_elems);
+  const int64_t tiles = B * A.chunks;
+  if (tiles == 0) return BLVM_OK;
+  if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
+  kl_reduce_kernel<<<static_cast<unsigned>(tiles), kKlTPB, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  return check_launch("kl_reduce_kernel");
+}
+
+int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
+                       const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
+                       const int64_t* x_sl, int64_t B, double beta, double* rows, double* scalars, blvm_stream_t stream) {
+  if (n_levels < 0 || n_levels > kMaxLevels) return fail(BLVM_ERR_INVALID_ARGUMENT, "n_levels=%d out of [0, %d]", n_levels, kMaxLevels);
+  if (B < 0 || !x_sl || !rows || !scalars) return fail(BLVM_ERR_INVALID_ARGUMENT, "null x_sl/rows/scalars");
+  FinalizeArgs A{};
+  A.logp_part = logp_part; A.logp_chunks = logp_chunks; A.n_levels = n_levels; A.x_sl = x_sl; A.B = B; A.beta = beta;
+  A.rows = rows; A.scalars = scalars;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!kl_part_host[l] || !klfn_part_host[l]) return fail(BLVM_ERR_INVALID_ARGUMENT, "null KL partials at level %d", l);
+    A.kl_part[l] = kl_part_host[l]; A.klfn_part[l] = klfn_part_host[l]; A.kl_chunks[l] = kl_chunks_host[l];
+  }
+  elbo_finalize_kernel<<<1, kFinTPB, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  return check_launch("elbo_finalize_kernel");
+}
+
+int blvm_quantize(const float* x, int64_t n, const float* boundaries, int64_t n_bins, int64_t* out, blvm_stream_t stream) {
+  if (n < 0 || n_bins < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad sizes");
+  if (n > 0 && (!x || !boundaries || !out)) return fail(BLVM_ERR_INVALID_ARGUMENT, "null pointer");
+  if (n == 0) return BLVM_OK;
+  const int64_t blocks = (n + 255) / 256;
+  if (blocks > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many elements");
+  quantize_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, boundaries, n_bins, out);
+  return check_launch("quantize_kernel");
+}
+
+int blvm_scale_inplace(float* buf, int64_t n, const double* scale, blvm_stream_t stream) {
+  if (n < 0 || (n > 0 && (!buf || !scale))) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (n == 0) return BLVM_OK;
+  const int64_t want = (n + 1023) / 1024;
+  const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
+  scale_inplace_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(buf, n, scale);
+  return check_launch("scale_inplace_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// Per-element math of the blvm DMoL / Gaussian-KL path, written once for device (sm_100a, MUFU approximations) and
+// host (g++, libm) so that the closed forms can be checked on the CPU against the fp64 oracle before a GPU run
+// (tests/hostsim/).  The host build is test infrastructure; the product only ever runs the device instantiation.
+//
+// Reference semantics restated here (paths under /root/reference):
+//   blvm/modules/distributions.py:383-387   split of the Linear output, log_scale.clamp(min=log_epsilon)
+//   blvm/utils/log_likelihoods.py:198-231   the four-branch discretized logistic, log_softmax, logsumexp
+//   blvm/utils/variational.py:67-70,86-122  Gaussian KL (std-dev parametrisation), free nats
+//
+// Numerical design: the reference evaluates cdf_delta = sigmoid(a) - sigmoid(b) in fp32, which loses
+// up to 3 digits to cancellation when the bin is narrow (16-bit audio: half width 1.5e-5).  We evaluate the same
+// quantity without cancellation,
+//     sigmoid(a) - sigmoid(b) = sigmoid(a) * sigmoid(-b) * (1 - exp(-(a - b))),   a - b = 2 h / s,
+// and its derivatives as  d/dm = sigmoid(-a) - sigmoid(b),  d/du = (s'(a) + s'(b)) / delta  (a = m + u, b = m - u),
+// so results track the reference run in fp64 to ~1e-6 relative, inside the fp32 reference's own error band.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BLVM_HD __host__ __device__ __forceinline__
+#else
+#define BLVM_HD inline
+#endif
+
+namespace blvm {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kDeltaThresh = 1e-5f;   // log_likelihoods.py:222  `cdf_delta > 1e-5`   (fp32-rounded Python double)
+constexpr float kDeltaFloor = 1e-10f;   // log_likelihoods.py:222  `clamp(cdf_delta, min=1e-10)`
+
+// Constants derived on the host in double and rounded to fp32 exactly like torch rounds Python scalars that meet an
+// fp32 tensor (blvm_b200.cu: make_consts).
+struct DmolConsts {
+  float h;              // 1/(num_bins-1)            log_likelihoods.py:206,208
+  float two_h;          // 2/(num_bins-1)
+  float lo_thresh;      // 2/num_bins - 1            log_likelihoods.py:226   y <  lo  -> lower edge bin
+  float hi_thresh;      // 1 - 2/num_bins            log_likelihoods.py:227   y >  hi  -> upper edge bin
+  float log_half_bins;  // log(num_bins/2)           log_likelihoods.py:222
+  float log_eps;        // log_epsilon (-7)          distributions.py:386
+};
+
+BLVM_HD float fast_ex2(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return exp2f(x);
+#endif
+}
+BLVM_HD float fast_lg2(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return log2f(x);
+#endif
+}
+BLVM_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+BLVM_HD float fast_exp(float x) { return fast_ex2(x * kLog2e); }
+BLVM_HD float fast_log(float x) { return fast_lg2(x) * kLn2; }
+
+// 1 - exp(-x) for x >= 0 without cancellation.
+BLVM_HD float one_minus_exp_neg(float x) {
+  if (x < 0.25f) {
+    // x (1 - x/2 + x^2/6 - x^3/24 + x^4/120 - x^5/720 + x^6/5040); next term x^7/40320 < 1.6e-9 relative at 0.25
+    float p = 1.0f / 5040.0f;
+    p = fmaf(p, x, -1.0f / 720.0f);
+    p = fmaf(p, x, 1.0f / 120.0f);
+    p = fmaf(p, x, -1.0f / 24.0f);
+    p = fmaf(p, x, 1.0f / 6.0f);
+    p = fmaf(p, x, -0.5f);
+    p = fmaf(p, x, 1.0f);
+    return x * p;
+  }
+  return 1.0f - fast_exp(-x);
+}
+
+enum : int { kEdgeNone = 0, kEdgeLower = 1, kEdgeUpper = 2 };
+
+// Which of the two y-predicates fires (bit-exact fp32 compares against fp32-rounded constants; upper wins because it
+// is the last torch.where of log_likelihoods.py:226-227).
+BLVM_HD int dmol_edge(float y, const DmolConsts& C) {
+  return (y > C.hi_thresh) ? kEdgeUpper : ((y < C.lo_thresh) ? kEdgeLower : kEdgeNone);
+}
+
+// One (sample, component): log-prob of the discretized logistic and, if GRAD, d lp/d loc and d lp/d raw_log_scale
+// (the clamp's pass-at-equality gate included).
+template <bool GRAD>
+BLVM_HD void dl_component(float y, int edge, float mu, float raw_ls, const DmolConsts& C, float& lp, float& dmu,
+                          float& dls) {
+  const float ls = (raw_ls < C.log_eps) ? C.log_eps : raw_ls;  // clamp(min): NaN propagates like torch
+  const float inv = fast_ex2(-ls * kLog2e);                    // exp(-log_scale)            :203
+  const float c = y - mu;                                      // centered_y                 :202
+  float dm_ = 0.f, du_ = 0.f, dls_direct = 0.f, m_ = 0.f, u_ = 0.f;
+
+  if (edge == kEdgeLower) {
+    // lp = plus_in - softplus(plus_in) = log sigmoid(a)                                    :213
+    const float a = inv * (c + C.h);
+    const float e = fast_exp(-fabsf(a));
+    lp = fminf(a, 0.f) - fast_log(1.f + e);
+    if (GRAD) {
+      const float r = fast_rcp(1.f + e);
+      const float da = ((a >= 0.f) ? e : 1.f) * r;  // 1 - sigmoid(a)
+      dmu = -inv * da;
+      dls = -a * da;
+    }
+  } else if (edge == kEdgeUpper) {
+    // lp = -softplus(minus_in) = log(1 - sigmoid(b))                                       :216
+    const float b = inv * (c - C.h);
+    const float e = fast_exp(-fabsf(b));
+    lp = -fmaxf(b, 0.f) - fast_log(1.f + e);
+    if (GRAD) {
+      const float r = fast_rcp(1.f + e);
+      const float db = -((b >= 0.f) ? 1.f : e) * r;  // -sigmoid(b)
+      dmu = -inv * db;
+      dls = -b * db;
+    }
+  } else {
+    const float a = inv * (c + C.h);   // plus_in   :206
+    const float b = inv * (c - C.h);   // minus_in  :208
+    const float m = inv * c;           // mid_in    :219
+    const float ea = fast_exp(-fabsf(a));
+    const float eb = fast_exp(-fabsf(b));
+    const float pa = 1.f + ea, pb = 1.f + eb;
+    const float rab = fast_rcp(pa * pb);
+    const float t = one_minus_exp_neg(C.two_h * inv);          // 1 - exp(-(a - b))
+    const float num_sa = (a >= 0.f) ? 1.f : ea;                // numerator of sigmoid(a)
+    const float num_snb = (b >= 0.f) ? eb : 1.f;               // numerator of sigmoid(-b)
+    const float delta = t * num_sa * num_snb * rab;            // cdf_delta  :210, cancellation-free
+    if (delta > kDeltaThresh) {
+      lp = fast_log(fmaxf(delta, kDeltaFloor));                // :222 first arm
+      if (GRAD) {
+        const float ra = pb * rab, rb = pa * rab;              // 1/(1+ea), 1/(1+eb)
+        const float num_sna = (a >= 0.f) ? ea : 1.f;           // numerator of sigmoid(-a)
+        const float num_sb = (b >= 0.f) ? 1.f : eb;            // numerator of sigmoid(b)
+        dm_ = num_sna * ra - num_sb * rb;                      // sigmoid(-a) - sigmoid(b)
+        du_ = (ea * ra * ra + eb * rb * rb) * fast_rcp(delta); // (s'(a) + s'(b)) / delta
+        m_ = m;
+        u_ = C.h * inv;
+      }
+    } else {
+      // log_pdf_mid - log(num_bins/2) = m - ls - 2 softplus(m) - log(nb/2)                 :220-222 second arm
+      const float e = fast_exp(-fabsf(m));
+      lp = -fabsf(m) - ls - 2.f * fast_log(1.f + e) - C.log_half_bins;
+      if (GRAD) {
+        const float th = (1.f - e) * fast_rcp(1.f + e);        // tanh(|m|/2)
+        dm_ = (m >= 0.f) ? -th : th;                           // 1 - 2 sigmoid(m)
+        m_ = m;
+        dls_direct = -1.f;
+      }
+    }
+    if (GRAD) {
+      dmu = -inv * dm_;
+      dls = -(m_ * dm_ + u_ * du_) + dls_direct;
+    }
+  }
+  if (GRAD) {
+    if (raw_ls < C.log_eps) dls = 0.f;  // clamp(min=eps) blocks the gradient strictly below eps, passes at equality
+  }
+}
+
+// ---- Gaussian KL, std-dev parametrisation (variational.py:67-70), cancellation-free around q == p ----------------
+//   kl = log sd_p - log sd_q + (sd_q^2 + (mu_q-mu_p)^2) / (2 sd_p^2) - 1/2
+//      = -log1p(rho-1) + ((rho-1)(rho+1) + z^2)/2,   rho = sd_q/sd_p,  z = (mu_q-mu_p)/sd_p
+struct KlTerms {
+  float kl, z, rho_m1, rho_p1, inv_sp, q;  // q = (rho-1)(rho+1) + z^2
+};
+BLVM_HD KlTerms kl_gaussian_terms(float mu_q, float sd_q, float mu_p, float sd_p) {
+  KlTerms t;
+  t.inv_sp = 1.0f / sd_p;
+  t.z = (mu_q - mu_p) * t.inv_sp;
+  t.rho_m1 = (sd_q - sd_p) * t.inv_sp;
+  t.rho_p1 = (sd_q + sd_p) * t.inv_sp;
+  t.q = fmaf(t.rho_m1, t.rho_p1, t.z * t.z);
+  t.kl = 0.5f * t.q - log1pf(t.rho_m1);
+  return t;
+}
+// d kl / d (mu_q, sd_q, mu_p, sd_p), each multiplied by g.
+BLVM_HD void kl_gaussian_grads(const KlTerms& t, float sd_q, float g, float& g_mu_q, float& g_sd_q, float& g_mu_p,
+                               float& g_sd_p) {
+  g_mu_q = g * t.z * t.inv_sp;                       // (mu_q-mu_p)/sd_p^2
+  g_mu_p = -g_mu_q;
+  g_sd_q = g * (t.rho_m1 * t.rho_p1) / sd_q;          // -1/sd_q + sd_q/sd_p^2
+  g_sd_p = -g * t.q * t.inv_sp;                       // 1/sd_p - (sd_q^2 + d^2)/sd_p^3
+}
+// torch.maximum(kl, c) gradient routing: 1 above, 1/2 at the exact tie, 0 below.
+BLVM_HD float free_nats_gate(float kl, float c, bool enabled) {
+  if (!enabled) return 1.f;
+  return (kl > c) ? 1.f : ((kl == c) ? 0.5f : 0.f);
+}
+
+}  // namespace blvm
+
+namespace blvm {
+
+// One waveform sample of the K-component mixture (D = 1), everything in registers.
+//   in : r[0:K) logits, r[K:2K) locs, r[2K:3K) raw log-scales            (distributions.py:383-385 layout)
+//   out: returns log p(y) = logsumexp_k(lp_k + log_softmax(logits)_k)    (log_likelihoods.py:229-231)
+//        if GRAD, r[] is overwritten with g * d log p / d r[]
+// d/d logit_k = resp_k - softmax_k,  d/d loc_k = resp_k * dlp_k/dloc,  d/d ls_k = resp_k * dlp_k/dls.
+template <int K, bool GRAD>
+BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts& C) {
+  const int edge = dmol_edge(y, C);
+  float v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float lp, dmu = 0.f, dls = 0.f;
+    dl_component<GRAD>(y, edge, r[K + k], r[2 * K + k], C, lp, dmu, dls);
+    v[k] = lp + r[k];
+    if (GRAD) {
+      r[K + k] = dmu;
+      r[2 * K + k] = dls;
+    }
+  }
+  float m1 = v[0], m2 = r[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) {
+    m1 = fmaxf(m1, v[k]);
+    m2 = fmaxf(m2, r[k]);
+  }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    v[k] = fast_ex2((v[k] - m1) * kLog2e);
+    r[k] = fast_ex2((r[k] - m2) * kLog2e);
+    s1 += v[k];
+    s2 += r[k];
+  }
+  const float L = (m1 - m2) + kLn2 * (fast_lg2(s1) - fast_lg2(s2));
+  if (GRAD) {
+    const float g1 = g * fast_rcp(s1), g2 = g * fast_rcp(s2);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float gr = g1 * v[k];            // g * responsibility_k
+      r[k] = gr - g2 * r[k];                 // g * (resp_k - softmax_k)
+      r[K + k] *= gr;
+      r[2 * K + k] *= gr;
+    }
+  }
+  return L;
+}
+
+// Generic (runtime K, D >= 1) sample, two passes with recomputation; `p` is the sample's K(2D+1) parameters laid
+// out [logits K | d=0: locs K, log_scales K | d=1: ...] (distributions.py:383-385), `yv` its D targets, `o` the
+// gradient row (may alias nothing; written only if GRAD).  Used for shapes the register kernel is not instantiated for.
+template <bool GRAD>
+BLVM_HD float dmol_sample_generic(const float* yv, const float* p, int K, int D, float g, const DmolConsts& C, float* o) {
+  float m1 = -INFINITY, m2 = -INFINITY;
+  for (int k = 0; k < K; ++k) {
+    float lpk = 0.f;
+    for (int d = 0; d < D; ++d) {
+      float lp, a, b;
+      dl_component<false>(yv[d], dmol_edge(yv[d], C), p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, a, b);
+      lpk += lp;
+    }
+    const float vk = lpk + p[k];
+    m1 = fmaxf(m1, vk);
+    m2 = fmaxf(m2, p[k]);
+    if (vk != vk) m1 = vk;  // NaN propagates
+  }
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float lpk = 0.f;
+    for (int d = 0; d < D; ++d) {
+      float lp, a, b;
+      dl_component<false>(yv[d], dmol_edge(yv[d], C), p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, a, b);
+      lpk += lp;
+    }
+    s1 += fast_ex2((lpk + p[k] - m1) * kLog2e);
+    s2 += fast_ex2((p[k] - m2) * kLog2e);
+  }
+  const float L = (m1 - m2) + kLn2 * (fast_lg2(s1) - fast_lg2(s2));
+  if (GRAD) {
+    const float g1 = g * fast_rcp(s1), g2 = g * fast_rcp(s2);
+    for (int k = 0; k < K; ++k) {
+      float lpk = 0.f;
+      for (int d = 0; d < D; ++d) {
+        float lp, dmu, dls;
+        dl_component<true>(yv[d], dmol_edge(yv[d], C), p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, dmu, dls);
+        lpk += lp;
+        o[K + d * 2 * K + k] = dmu;
+        o[K + d * 2 * K + K + k] = dls;
+      }
+      const float gr = g1 * fast_ex2((lpk + p[k] - m1) * kLog2e);
+      o[k] = gr - g2 * fast_ex2((p[k] - m2) * kLog2e);
+      for (int d = 0; d < D; ++d) {
+        o[K + d * 2 * K + k] *= gr;
+        o[K + d * 2 * K + K + k] *= gr;
+      }
+    }
+  }
+  return L;
+}
+
+}  // namespace blvm

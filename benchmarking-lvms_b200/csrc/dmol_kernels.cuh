@@ -1,0 +1,274 @@
+// DMoL kernels for sm_100a.
+//
+// dmol_tile_kernel<K, TPB, GRAD>: the hot kernel.  One CTA = one tile of up to TPB consecutive waveform samples of ONE
+// utterance (row b), one thread per sample.  The tile's K-mixture parameters are the contiguous slab
+// raw[b, t0:t0+n, 0:3K] (3K*n floats): it is pulled into shared memory with one 1-D TMA bulk copy
+// (cp.async.bulk -> SASS UBLKCP) signalled on an mbarrier, each thread lifts its own 3K-float row into registers with
+// 64/128-bit LDS (row stride 3K floats; conflict-free for 3K/vec odd), evaluates value + gradient
+// in registers (blvm_math.cuh), writes the gradient row back over its own slab row and the slab leaves with one bulk
+// store.  y and the per-sample log-prob are plain coalesced 32-bit accesses.  The masked per-row sum is reduced in
+// fp64 (warp shuffles, then shared memory) into partials[b, chunk] — no atomics, deterministic.
+//
+// Algorithmic traffic per sample: read 4 (y) + 12K (params), write 4 (log-prob) + 12K (grads) = 4(2+6K) bytes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "blvm_math.cuh"
+#include "ptx_sm100.cuh"
+
+namespace blvm {
+
+enum : int {
+  kFlagMaskOutput = 1,   // per-sample log-prob output is multiplied by the sequence mask (compute_elbo semantics)
+  kFlagSkipPadded = 2,   // tiles that lie entirely in the padding are not read: outputs are exact zeros
+};
+
+struct DmolArgs {
+  const float* y;          // (B*T*D)
+  const float* raw;        // (B*T, P)  P = K(2D+1)
+  const int64_t* x_sl;     // (B) valid samples per row, device; nullptr = all valid
+  const float* gout;       // (B*T) upstream gradient per sample, nullptr = 1
+  float gscale;            // scalar multiplier of every gradient (e.g. -1/sum(x_sl))
+  float* lp;               // (B*T) per-sample log-prob out, nullptr = not wanted
+  float* graw;             // (B*T, P) gradient out (GRAD kernels)
+  double* partials;        // (B, chunks) masked per-tile sums of log-prob, nullptr = not wanted
+  int* err_flag;           // set to 1 if any y is outside [-1, 1] (the reference's assert, log_likelihoods.py:195)
+  int64_t B, T, chunks;
+  int K, D;
+  int flags;
+  DmolConsts C;
+};
+
+template <int NWARPS>
+__device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NWARPS; ++i) s += scratch[i];
+  }
+  return s;  // valid in thread 0
+}
+
+// Lift / drop one P-float row between shared memory and registers with the widest aligned vector the row stride allows.
+template <int P>
+__device__ __forceinline__ void row_load(const float* p, float (&r)[P]) {
+  if constexpr (P % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < P / 4; ++i) {
+      const float4 v = reinterpret_cast<const float4*>(p)[i];
+      r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+    }
+  } else if constexpr (P % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < P / 2; ++i) {
+      const float2 v = reinterpret_cast<const float2*>(p)[i];
+      r[2 * i] = v.x; r[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < P; ++i) r[i] = p[i];
+  }
+}
+template <int P>
+__device__ __forceinline__ void row_store(float* p, const float (&r)[P]) {
+  if constexpr (P % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < P / 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+  } else if constexpr (P % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < P / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(r[2 * i], r[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = r[i];
+  }
+}
+
+template <int K, int TPB>
+constexpr size_t dmol_tile_smem_bytes() {
+  return size_t(TPB) * 3 * K * sizeof(float) + 16 /*mbarrier*/ + (TPB / 32) * sizeof(double);
+}
+
+template <int K, int TPB, bool GRAD>
+__global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
+  constexpr int P = 3 * K;
+  constexpr int NW = TPB / 32;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* tile = reinterpret_cast<float*>(smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + size_t(TPB) * P * sizeof(float));
+  double* scratch = reinterpret_cast<double*>(smem + size_t(TPB) * P * sizeof(float) + 16);
+
+  const int tid = threadIdx.x;
+  const int64_t tile_id = blockIdx.x;
+  const int64_t b = tile_id / A.chunks;
+  const int64_t c = tile_id - b * A.chunks;
+  const int64_t t0 = c * TPB;
+  const int n = static_cast<int>(min(static_cast<int64_t>(TPB), A.T - t0));  // samples of this tile
+  const int64_t s0 = b * A.T + t0;                                           // first flat sample
+  int64_t len = A.x_sl ? A.x_sl[b] : A.T;
+  len = len < 0 ? 0 : (len > A.T ? A.T : len);
+  const int nvalid = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(n), len - t0)));
+
+  const float* gsrc = A.raw + s0 * P;
+  float* gdst = GRAD ? A.graw + s0 * P : nullptr;
+  const uint32_t bytes = static_cast<uint32_t>(n) * P * sizeof(float);
+  const bool skip = (A.flags & kFlagSkipPadded) && nvalid == 0;
+  const bool bulk_in = ((reinterpret_cast<uintptr_t>(gsrc) | bytes) & 15u) == 0;
+  const bool bulk_out = GRAD && ((reinterpret_cast<uintptr_t>(gdst) | bytes) & 15u) == 0;
+  const uint64_t pol = ptx::policy_evict_first();
+
+  if (!skip) {
+    if (bulk_in) {
+      if (tid == 0) {
+        ptx::mbar_init(bar, 1);
+        ptx::fence_mbar_init();
+        ptx::mbar_arrive_expect_tx(bar, bytes);
+        ptx::bulk_g2s(tile, gsrc, bytes, bar, pol);
+      }
+    } else {  // unaligned slab (odd T with even K, or an offset view): coalesced 32-bit loads
+      for (int i = tid; i < n * P; i += TPB) tile[i] = ptx::ldg_stream(gsrc + i);
+    }
+  }
+
+  const bool in_tile = tid < n;
+  const bool valid = tid < nvalid;
+  float yv = 0.f, g = 0.f;
+  if (in_tile) {
+    yv = ptx::ldg_stream(A.y + s0 + tid);
+    if (!(yv <= 1.0f && yv >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
+    if (GRAD) {
+      g = valid ? A.gscale : 0.f;
+      if (A.gout) g *= ptx::ldg_stream(A.gout + s0 + tid);
+    }
+  }
+  __syncthreads();  // mbarrier init / plain loads visible to everyone
+  if (!skip && bulk_in) ptx::mbar_wait(bar, 0);
+
+  float L = 0.f;
+  if (in_tile) {
+    float r[P];
+    float* row = tile + tid * P;
+    if (!skip) {
+      row_load<P>(row, r);
+      L = dmol_sample<K, GRAD>(yv, r, g, A.C);
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) r[i] = 0.f;
+    }
+    if (GRAD) row_store<P>(row, r);
+  }
+  // reference semantics: log_prob * mask (NaN/inf in the padding propagate like `* 0`), vrnn.py:268
+  const float Lm = valid ? L : L * 0.0f;
+  if (A.lp && in_tile) A.lp[s0 + tid] = (A.flags & kFlagMaskOutput) ? Lm : L;
+
+  if (GRAD) {
+    if (bulk_out) {
+      ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA unit
+      __syncthreads();
+      if (tid == 0) {
+        ptx::bulk_s2g(gdst, tile, bytes, pol);
+        ptx::bulk_commit();
+      }
+    } else {
+      __syncthreads();
+      for (int i = tid; i < n * P; i += TPB) ptx::stg_stream(gdst + i, tile[i]);
+    }
+  }
+  if (A.partials) {
+    const double s = block_sum_f64<NW>(static_cast<double>(Lm), scratch);
+    if (tid == 0) A.partials[tile_id] = s;
+  }
+  if (GRAD && bulk_out && tid == 0) ptx::bulk_wait_read0();  // smem must outlive the bulk store's read
+}
+
+// Generic shapes (any K, D >= 1): one thread per sample straight from global memory, two-pass recompute.
+// Correctness path for configurations the register kernel is not instantiated for; not tuned.
+template <int TPB, bool GRAD>
+__global__ void __launch_bounds__(TPB) dmol_generic_kernel(const DmolArgs A) {
+  __shared__ double scratch[TPB / 32];
+  const int tid = threadIdx.x;
+  const int64_t tile_id = blockIdx.x;
+  const int64_t b = tile_id / A.chunks;
+  const int64_t c = tile_id - b * A.chunks;
+  const int64_t t0 = c * TPB;
+  const int n = static_cast<int>(min(static_cast<int64_t>(TPB), A.T - t0));
+  const int64_t s0 = b * A.T + t0;
+  int64_t len = A.x_sl ? A.x_sl[b] : A.T;
+  len = len < 0 ? 0 : (len > A.T ? A.T : len);
+  const int nvalid = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(n), len - t0)));
+  const int P = A.K * (2 * A.D + 1);
+  const bool in_tile = tid < n, valid = tid < nvalid;
+  const bool skip = (A.flags & kFlagSkipPadded) && nvalid == 0;
+  float L = 0.f;
+  if (in_tile) {
+    const int64_t s = s0 + tid;
+    const float* yv = A.y + s * A.D;
+    for (int d = 0; d < A.D; ++d)
+      if (!(yv[d] <= 1.0f && yv[d] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
+    float g = 0.f;
+    if (GRAD) {
+      g = valid ? A.gscale : 0.f;
+      if (A.gout) g *= A.gout[s];
+    }
+    if (!skip) {
+      L = dmol_sample_generic<GRAD>(yv, A.raw + s * P, A.K, A.D, g, A.C, GRAD ? A.graw + s * P : nullptr);
+    } else if (GRAD) {
+      for (int i = 0; i < P; ++i) A.graw[s * P + i] = 0.f;
+    }
+  }
+  const float Lm = valid ? L : L * 0.0f;
+  if (A.lp && in_tile) A.lp[s0 + tid] = (A.flags & kFlagMaskOutput) ? Lm : L;
+  if (A.partials) {
+    const double s = block_sum_f64<TPB / 32>(static_cast<double>(Lm), scratch);
+    if (tid == 0) A.partials[tile_id] = s;
+  }
+}
+
+// Single discretized logistic (DiscretizedLogisticDense, distributions.py:268-307): raw (B*T, 2) = [mu | log_scale],
+// one thread per sample with a 64-bit load/store; same tiling, mask and partial-sum contract as the mixture kernel.
+template <int TPB, bool GRAD>
+__global__ void __launch_bounds__(TPB) dl_kernel(const DmolArgs A) {
+  __shared__ double scratch[TPB / 32];
+  const int tid = threadIdx.x;
+  const int64_t tile_id = blockIdx.x;
+  const int64_t b = tile_id / A.chunks;
+  const int64_t c = tile_id - b * A.chunks;
+  const int64_t t0 = c * TPB;
+  const int n = static_cast<int>(min(static_cast<int64_t>(TPB), A.T - t0));
+  const int64_t s0 = b * A.T + t0;
+  int64_t len = A.x_sl ? A.x_sl[b] : A.T;
+  len = len < 0 ? 0 : (len > A.T ? A.T : len);
+  const int nvalid = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(n), len - t0)));
+  const bool in_tile = tid < n, valid = tid < nvalid;
+  const bool skip = (A.flags & kFlagSkipPadded) && nvalid == 0;
+  float L = 0.f;
+  if (in_tile) {
+    const int64_t s = s0 + tid;
+    const float yv = A.y[s];
+    if (!(yv <= 1.0f && yv >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
+    float g = 0.f;
+    if (GRAD) {
+      g = valid ? A.gscale : 0.f;
+      if (A.gout) g *= A.gout[s];
+    }
+    float dmu = 0.f, dls = 0.f;
+    if (!skip) {
+      const float2 p = reinterpret_cast<const float2*>(A.raw)[s];
+      dl_component<GRAD>(yv, dmol_edge(yv, A.C), p.x, p.y, A.C, L, dmu, dls);
+    }
+    if (GRAD) reinterpret_cast<float2*>(A.graw)[s] = make_float2(g * dmu, g * dls);
+  }
+  const float Lm = valid ? L : L * 0.0f;
+  if (A.lp && in_tile) A.lp[s0 + tid] = (A.flags & kFlagMaskOutput) ? Lm : L;
+  if (A.partials) {
+    const double s = block_sum_f64<TPB / 32>(static_cast<double>(Lm), scratch);
+    if (tid == 0) A.partials[tile_id] = s;
+  }
+}
+
+}  // namespace blvm

@@ -1,0 +1,227 @@
+// Gaussian-KL + free-nats + sequence-mask kernels and the ELBO finalize kernel (sm_100a).
+//
+// kl_kernel<VEC, GRAD>: elementwise over the (B, Tz, Z) latent grid, 4 inputs in / up to 4 gradients out, 128-bit
+// vectorised when the row length allows; one CTA = one chunk of one utterance so that the masked fp64 partial sums
+// (raw KL and free-nats-discounted KL) land in partials[b, chunk] without atomics.
+// Algorithmic traffic: 16 B read + 16 B written per latent element (fwd+bwd fused) = 32 B.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "blvm_math.cuh"
+#include "dmol_kernels.cuh"  // block_sum_f64
+#include "ptx_sm100.cuh"
+
+namespace blvm {
+
+struct KlArgs {
+  const float *mu_q, *sd_q, *mu_p, *sd_p;
+  const int64_t* lens;   // (B) valid latent steps per row, nullptr = all
+  const float* gout;     // per-element upstream gradient, nullptr = 1
+  float gscale;          // scalar multiplier of every gradient (e.g. beta / sum(x_sl))
+  float min_kl;          // free_nats / Z
+  int fn_enabled;        // 0 = discount_free_nats is the identity (free_nats None/0, variational.py:107-108)
+  float* kl;             // per-element raw KL out (nullable)
+  float *g_mu_q, *g_sd_q, *g_mu_p, *g_sd_p;  // gradients out (GRAD)
+  double* part_kl;       // (B, chunks) masked sums of kl (nullable)
+  double* part_klfn;     // (B, chunks) masked sums of max(kl, min_kl) (nullable)
+  int64_t B, row_elems, Z, chunks;
+};
+
+constexpr int kKlTPB = 256;
+constexpr int kKlVec = 4;
+constexpr int kKlChunk = kKlTPB * kKlVec;  // elements per CTA
+
+template <bool GRAD>
+__device__ __forceinline__ void kl_element(const KlArgs& A, int64_t idx, bool valid, float mq, float sq, float mp, float sp,
+                                           float& kl, float& gmq, float& gsq, float& gmp, float& gsp, double& s_kl,
+                                           double& s_fn) {
+  const KlTerms t = kl_gaussian_terms(mq, sq, mp, sp);
+  kl = t.kl;
+  const float klfn = (A.fn_enabled && kl < A.min_kl) ? A.min_kl : kl;  // torch.maximum; NaN propagates
+  s_kl += static_cast<double>(valid ? kl : kl * 0.0f);                 // `kld * mask` semantics (vrnn.py:272)
+  s_fn += static_cast<double>(valid ? klfn : klfn * 0.0f);
+  if (GRAD) {
+    float g = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
+    if (A.gout) g *= A.gout[idx];
+    kl_gaussian_grads(t, sq, g, gmq, gsq, gmp, gsp);
+  }
+}
+
+template <bool VEC, bool GRAD>
+__global__ void __launch_bounds__(kKlTPB) kl_kernel(const KlArgs A) {
+  __shared__ double scratch[2][kKlTPB / 32];
+  const int tid = threadIdx.x;
+  const int64_t tile_id = blockIdx.x;
+  const int64_t b = tile_id / A.chunks;
+  const int64_t c = tile_id - b * A.chunks;
+  const int64_t e0 = c * kKlChunk;                       // first element of this chunk within the row
+  int64_t len = A.lens ? A.lens[b] : (A.row_elems / A.Z);
+  const int64_t max_steps = A.row_elems / A.Z;
+  len = len < 0 ? 0 : (len > max_steps ? max_steps : len);
+  const int64_t nvalid_row = len * A.Z;
+  const int64_t base = b * A.row_elems;
+  double s_kl = 0.0, s_fn = 0.0;
+
+  if (VEC) {
+    const int64_t e = e0 + static_cast<int64_t>(tid) * kKlVec;
+    if (e < A.row_elems) {  // row_elems % 4 == 0 on this path, so the whole vector is inside the row
+      const int64_t i = base + e;
+      const float4 mq = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.mu_q + i));
+      const float4 sq = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.sd_q + i));
+      const float4 mp = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.mu_p + i));
+      const float4 sp = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.sd_p + i));
+      float4 kl, gmq, gsq, gmp, gsp;
+      kl_element<GRAD>(A, i + 0, e + 0 < nvalid_row, mq.x, sq.x, mp.x, sp.x, kl.x, gmq.x, gsq.x, gmp.x, gsp.x, s_kl, s_fn);
+      kl_element<GRAD>(A, i + 1, e + 1 < nvalid_row, mq.y, sq.y, mp.y, sp.y, kl.y, gmq.y, gsq.y, gmp.y, gsp.y, s_kl, s_fn);
+      kl_element<GRAD>(A, i + 2, e + 2 < nvalid_row, mq.z, sq.z, mp.z, sp.z, kl.z, gmq.z, gsq.z, gmp.z, gsp.z, s_kl, s_fn);
+      kl_element<GRAD>(A, i + 3, e + 3 < nvalid_row, mq.w, sq.w, mp.w, sp.w, kl.w, gmq.w, gsq.w, gmp.w, gsp.w, s_kl, s_fn);
+      if (A.kl) ptx::stg_stream4(reinterpret_cast<float4*>(A.kl + i), kl);
+      if (GRAD) {
+        ptx::stg_stream4(reinterpret_cast<float4*>(A.g_mu_q + i), gmq);
+        ptx::stg_stream4(reinterpret_cast<float4*>(A.g_sd_q + i), gsq);
+        ptx::stg_stream4(reinterpret_cast<float4*>(A.g_mu_p + i), gmp);
+        ptx::stg_stream4(reinterpret_cast<float4*>(A.g_sd_p + i), gsp);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kKlVec; ++j) {
+      const int64_t e = e0 + static_cast<int64_t>(j) * kKlTPB + tid;
+      if (e < A.row_elems) {
+        const int64_t i = base + e;
+        float kl, gmq, gsq, gmp, gsp;
+        kl_element<GRAD>(A, i, e < nvalid_row, A.mu_q[i], A.sd_q[i], A.mu_p[i], A.sd_p[i], kl, gmq, gsq, gmp, gsp, s_kl, s_fn);
+        if (A.kl) A.kl[i] = kl;
+        if (GRAD) {
+          A.g_mu_q[i] = gmq;
+          A.g_sd_q[i] = gsq;
+          A.g_mu_p[i] = gmp;
+          A.g_sd_p[i] = gsp;
+        }
+      }
+    }
+  }
+  if (A.part_kl) {
+    const double a = block_sum_f64<kKlTPB / 32>(s_kl, scratch[0]);
+    const double f = block_sum_f64<kKlTPB / 32>(s_fn, scratch[1]);
+    if (tid == 0) {
+      A.part_kl[tile_id] = a;
+      A.part_klfn[tile_id] = f;
+    }
+  }
+}
+
+// KL already materialised by the caller (the reference's compute_elbo receives `kld_twise`): masked sums of kl and
+// max(kl, min_kl) plus d/d kl = gscale * gate * mask.  8 B per latent element.
+struct KlReduceArgs {
+  const float* kl;
+  const int64_t* lens;
+  float gscale, min_kl;
+  int fn_enabled;
+  float* gkl;  // nullable
+  double *part_kl, *part_klfn;
+  int64_t B, row_elems, Z, chunks;
+};
+
+__global__ void __launch_bounds__(kKlTPB) kl_reduce_kernel(const KlReduceArgs A) {
+  __shared__ double scratch[2][kKlTPB / 32];
+  const int tid = threadIdx.x;
+  const int64_t tile_id = blockIdx.x;
+  const int64_t b = tile_id / A.chunks;
+  const int64_t c = tile_id - b * A.chunks;
+  const int64_t e0 = c * kKlChunk;
+  const int64_t max_steps = A.row_elems / A.Z;
+  int64_t len = A.lens ? A.lens[b] : max_steps;
+  len = len < 0 ? 0 : (len > max_steps ? max_steps : len);
+  const int64_t nvalid_row = len * A.Z;
+  const int64_t base = b * A.row_elems;
+  double s_kl = 0.0, s_fn = 0.0;
+#pragma unroll
+  for (int j = 0; j < kKlVec; ++j) {
+    const int64_t e = e0 + static_cast<int64_t>(j) * kKlTPB + tid;
+    if (e < A.row_elems) {
+      const int64_t i = base + e;
+      const bool valid = e < nvalid_row;
+      const float kl = A.kl[i];
+      const float klfn = (A.fn_enabled && kl < A.min_kl) ? A.min_kl : kl;
+      s_kl += static_cast<double>(valid ? kl : kl * 0.0f);
+      s_fn += static_cast<double>(valid ? klfn : klfn * 0.0f);
+      if (A.gkl) A.gkl[i] = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
+    }
+  }
+  const double a = block_sum_f64<kKlTPB / 32>(s_kl, scratch[0]);
+  const double f = block_sum_f64<kKlTPB / 32>(s_fn, scratch[1]);
+  if (tid == 0) {
+    A.part_kl[tile_id] = a;
+    A.part_klfn[tile_id] = f;
+  }
+}
+
+// ---- finalize: per-tile partials -> per-utterance sums -> loss / ELBO / bits-per-dim --------------------------------
+constexpr int kMaxLevels = 8;
+struct FinalizeArgs {
+  const double* logp_part;          // (B, logp_chunks), nullable (=> log p = 0)
+  int64_t logp_chunks;
+  const double* kl_part[kMaxLevels];    // per level (B, kl_chunks[l])
+  const double* klfn_part[kMaxLevels];
+  int64_t kl_chunks[kMaxLevels];
+  int n_levels;
+  const int64_t* x_sl;              // (B) device
+  int64_t B;
+  double beta;
+  double* rows;                     // (4 + n_levels, B): logp, kl, kl_fn, elbo, kl_level_l...
+  double* scalars;                  // (8): loss, sum logp, sum kl, sum kl_fn, sum elbo, sum x_sl, bpd, nan-safe loss
+};
+
+constexpr int kFinTPB = 256;
+
+__global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeArgs A) {
+  __shared__ double scratch[6][kFinTPB / 32];
+  const int tid = threadIdx.x;
+  double t_logp = 0, t_kl = 0, t_fn = 0, t_len = 0, t_nan_logp = 0, t_obj = 0;
+  for (int64_t b = tid; b < A.B; b += kFinTPB) {
+    double logp = 0.0;
+    if (A.logp_part)
+      for (int64_t c = 0; c < A.logp_chunks; ++c) logp += A.logp_part[b * A.logp_chunks + c];
+    double kl = 0.0, fn = 0.0;
+    for (int l = 0; l < A.n_levels; ++l) {
+      double kl_l = 0.0, fn_l = 0.0;
+      for (int64_t c = 0; c < A.kl_chunks[l]; ++c) {
+        kl_l += A.kl_part[l][b * A.kl_chunks[l] + c];
+        fn_l += A.klfn_part[l][b * A.kl_chunks[l] + c];
+      }
+      A.rows[(4 + l) * A.B + b] = kl_l;
+      kl += kl_l;   // sum over levels (clockwork_vae.py:155, stcn.py:290)
+      fn += fn_l;
+    }
+    A.rows[0 * A.B + b] = logp;
+    A.rows[1 * A.B + b] = kl;
+    A.rows[2 * A.B + b] = fn;
+    A.rows[3 * A.B + b] = logp - kl;                     // elbo (vrnn.py:273)
+    t_logp += logp;
+    t_kl += kl;
+    t_fn += fn;
+    t_obj += logp - A.beta * fn;                         // vrnn.py:277 numerator
+    t_nan_logp += (logp == logp) ? logp : 0.0;           // nansum (wavenet.py:145)
+    t_len += static_cast<double>(A.x_sl[b]);
+  }
+  const double s_logp = block_sum_f64<kFinTPB / 32>(t_logp, scratch[0]);
+  const double s_kl = block_sum_f64<kFinTPB / 32>(t_kl, scratch[1]);
+  const double s_fn = block_sum_f64<kFinTPB / 32>(t_fn, scratch[2]);
+  const double s_obj = block_sum_f64<kFinTPB / 32>(t_obj, scratch[3]);
+  const double s_nan = block_sum_f64<kFinTPB / 32>(t_nan_logp, scratch[4]);
+  const double s_len = block_sum_f64<kFinTPB / 32>(t_len, scratch[5]);
+  if (tid == 0) {
+    A.scalars[0] = -s_obj / s_len;                       // loss
+    A.scalars[1] = s_logp;
+    A.scalars[2] = s_kl;
+    A.scalars[3] = s_fn;
+    A.scalars[4] = s_logp - s_kl;                        // sum elbo
+    A.scalars[5] = s_len;
+    A.scalars[6] = -(s_logp - s_kl) / 0.6931471805599453 / s_len;  // bits per dim (metrics.py:456)
+    A.scalars[7] = -s_nan / s_len;                       // WaveNet's nansum loss
+  }
+}
+
+}  // namespace blvm

@@ -1,0 +1,33 @@
+// Small helpers around the hot path: the integer Quantize transform and an early-exit in-place scale.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace blvm {
+
+// torch.bucketize(x, boundaries, right=False) (blvm/data/transforms.py:257): lower bound, i.e. the first index i with
+// boundaries[i] >= x; the predicate is written `!(b >= x)` like ATen's so that NaN maps to n_bins.
+__global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ x, int64_t n,
+                                                       const float* __restrict__ boundaries, int64_t n_bins,
+                                                       int64_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  int64_t lo = 0, hi = n_bins;
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (!(__ldg(boundaries + mid) >= v)) lo = mid + 1;
+    else hi = mid;
+  }
+  out[i] = lo;
+}
+
+// buf *= *scale, skipped entirely (no memory traffic beyond the scalar) when *scale == 1.
+__global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ buf, int64_t n, const double* __restrict__ scale) {
+  const float s = static_cast<float>(*scale);
+  if (s == 1.0f) return;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) buf[i] *= s;
+}
+
+}  // namespace blvm

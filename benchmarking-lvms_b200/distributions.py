@@ -1,0 +1,210 @@
+"""Likelihood modules with the reference's class names, constructor arguments, attributes, state-dict keys and method
+contracts (blvm/modules/distributions.py:268-387) — the drop-in boundary of SURVEY.md §8b.
+
+`forward` keeps the Linear (a cuBLAS GEMM, not on the hot path) and returns a parameter container that indexes like the
+reference's `(logit_probs, locs, log_scales)` tuple but also carries the packed Linear output, so `log_prob` and the
+fused ELBO read it once and clamp inside the kernel instead of materialising the clamped copy (distributions.py:386).
+"""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .log_likelihoods import discretized_logistic_ll, discretized_logistic_mixture_ll
+
+__all__ = ["ConditionalDistribution", "DiscretizedLogisticMixtureDense", "DiscretizedLogisticDense", "DMoLParams",
+           "DLParams"]
+
+
+class ConditionalDistribution(nn.Module):
+    """Same abstract surface as blvm/modules/distributions.py:28-52."""
+
+    def reset_parameters(self):
+        pass
+
+    @staticmethod
+    def get_distribution(*args, **kwargs):
+        raise NotImplementedError()
+
+    @staticmethod
+    def sample(params):
+        raise NotImplementedError()
+
+    @staticmethod
+    def rsample(params):
+        raise NotImplementedError()
+
+    @staticmethod
+    def mode(params):
+        raise NotImplementedError()
+
+    def log_prob(self, x):
+        raise NotImplementedError()
+
+
+class DMoLParams:
+    """What DiscretizedLogisticMixtureDense.forward returns: behaves like the reference's 3-tuple
+    `(logit_probs (*, K), locs (*, D, K), log_scales (*, D, K) clamped at log_epsilon)` under indexing, iteration and
+    len(), and keeps `raw (*, K(2D+1))`, the packed Linear output the kernels consume.  The clamped log-scales are only
+    materialised if somebody asks for them (`params[2]`, e.g. `sample`)."""
+
+    __slots__ = ("raw", "K", "D", "log_epsilon", "_cache")
+
+    def __init__(self, raw: torch.Tensor, K: int, D: int, log_epsilon: float):
+        self.raw, self.K, self.D, self.log_epsilon = raw, K, D, log_epsilon
+        self._cache = {}
+
+    def _tag(self, t):
+        t._blvm_packed = (self.raw, self.K, self.D, self.log_epsilon)
+        return t
+
+    def __len__(self):
+        return 3
+
+    def __iter__(self):
+        return iter((self[0], self[1], self[2]))
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return tuple(self)[i]
+        if i < 0:
+            i += 3
+        if i not in self._cache:
+            raw, K, D = self.raw, self.K, self.D
+            if i == 0:
+                t = raw[..., :K]                                                    # distributions.py:383
+            elif i in (1, 2):
+                lls = raw[..., K:].view(*raw.shape[:-1], D, 2 * K)                  # :384
+                t = lls[..., :K] if i == 1 else lls[..., K:].clamp(min=self.log_epsilon)  # :385-386
+            else:
+                raise IndexError(i)
+            self._cache[i] = self._tag(t)
+        return self._cache[i]
+
+    def detach(self):
+        return DMoLParams(self.raw.detach(), self.K, self.D, self.log_epsilon)
+
+
+class DLParams:
+    """Same idea for DiscretizedLogisticDense: indexes like `(mu (*, D), log_scale (*, D) clamped)`, carries raw (*, 2D)."""
+
+    __slots__ = ("raw", "D", "log_epsilon", "_cache")
+
+    def __init__(self, raw, D, log_epsilon):
+        self.raw, self.D, self.log_epsilon = raw, D, log_epsilon
+        self._cache = {}
+
+    def __len__(self):
+        return 2
+
+    def __iter__(self):
+        return iter((self[0], self[1]))
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += 2
+        if i not in self._cache:
+            mu, ls = self.raw.chunk(2, dim=-1)                                      # distributions.py:305
+            t = mu if i == 0 else ls.clamp(min=self.log_epsilon)                    # :306
+            if i not in (0, 1):
+                raise IndexError(i)
+            t._blvm_packed_dl = (self.raw, self.log_epsilon)
+            self._cache[i] = t
+        return self._cache[i]
+
+
+def _rsample_logistic(mu, log_scale, eps: float = 1e-8):
+    """mu + exp(log_scale) * logit(u), u ~ U(eps, 1-eps)  (blvm/utils/variational.py:282-294), then clamp to [-1, 1]
+    (:296-306).  Sampling is not on the hot path: plain torch."""
+    u = torch.empty_like(mu).uniform_(eps, 1 - eps)
+    return (mu + torch.exp(log_scale) * (torch.log(u) - torch.log(1 - u))).clamp(-1, 1)
+
+
+class DiscretizedLogisticDense(ConditionalDistribution):
+    """Drop-in for blvm/modules/distributions.py:268-307 (state-dict keys `params.weight`, `params.bias`)."""
+
+    def __init__(self, x_dim: int, y_dim: int, num_bins: int = 256, log_epsilon: float = -7.0):
+        super().__init__()
+        self.x_dim = x_dim
+        self.y_dim = y_dim
+        self.num_bins = num_bins
+        self.log_epsilon = log_epsilon
+        self.out_features = y_dim * 2
+        self.params = nn.Linear(x_dim, self.out_features)
+        self.reset_parameters()
+
+    @staticmethod
+    def rsample(params):
+        return _rsample_logistic(params[0], params[1])
+
+    @staticmethod
+    @torch.no_grad()
+    def sample(params):
+        return _rsample_logistic(params[0], params[1])
+
+    def mode(self, params):
+        return params[0]
+
+    def log_prob(self, y, params, reduce_dim: Optional[int] = None):
+        """Inputs are assumed to be in [-1, 1]."""
+        if isinstance(params, DLParams) and self.y_dim == 1 and y.shape == params.raw.shape[:-1] + (1,):
+            log_prob = ops.dl_log_prob(y, params.raw, self.num_bins, self.log_epsilon).unsqueeze(-1)
+            if reduce_dim:
+                return log_prob.squeeze(reduce_dim) if log_prob.size(reduce_dim) == 1 else log_prob.sum(reduce_dim)
+            return log_prob
+        return discretized_logistic_ll(y, params[0], params[1], num_bins=self.num_bins, reduce_dim=reduce_dim)
+
+    def forward(self, x):
+        return DLParams(self.params(x), self.y_dim, self.log_epsilon)
+
+
+class DiscretizedLogisticMixtureDense(ConditionalDistribution):
+    """Drop-in for blvm/modules/distributions.py:310-387: `3 * num_mix` parameters per output channel
+    (mixture logit, mean, log-scale); data assumed rescaled to `num_bins` discrete values in [-1, 1]."""
+
+    def __init__(self, x_dim: int, y_dim: int, num_mix: int = 10, num_bins: int = 256, log_epsilon: float = -7.0):
+        super().__init__()
+        self.x_dim = x_dim
+        self.y_dim = y_dim
+        self.num_mix = num_mix
+        self.num_bins = num_bins
+        self.log_epsilon = log_epsilon
+        self.out_features = num_mix * (2 * y_dim + 1)
+        self.params = nn.Linear(x_dim, self.out_features)
+        self.reset_parameters()
+
+    @staticmethod
+    def get_distribution(params):
+        raise NotImplementedError("Discretized mixture of logistics does not have a Distribution object (yet)")
+
+    def rsample(self, params):
+        """Gumbel-max over the mixture logits, gather the chosen component, sample its logistic
+        (blvm/utils/variational.py:309-349 with the defaults eps=1e-5, hard argmax)."""
+        logit_probs, locs, log_scales = params[0], params[1], params[2]
+        u = torch.empty_like(logit_probs).uniform_(1e-5, 1.0 - 1e-5)
+        choice = torch.argmax(logit_probs - torch.log(-torch.log(u)), dim=-1, keepdim=True)   # (*, 1)
+        index = choice.expand(*choice.shape[:-1], locs.size(-2)).unsqueeze(-1)                 # (*, D, 1)
+        loc = torch.gather(locs, index=index, dim=-1).squeeze(-1)
+        log_scale = torch.gather(log_scales, index=index, dim=-1).squeeze(-1)
+        return _rsample_logistic(loc, log_scale)
+
+    @torch.no_grad()
+    def sample(self, params):
+        return self.rsample(params)
+
+    def mode(self, params):
+        """Mean of the most probable component (distributions.py:363-368)."""
+        component = params[0].argmax(-1, keepdim=True).unsqueeze(-2)
+        component = component.expand(*component.shape[:-2], params[1].size(-2), 1)
+        return torch.gather(params[1], index=component, dim=-1).squeeze(-1).contiguous()
+
+    def log_prob(self, y, params, reduce_dim: int = -1):
+        """Per-sample log-likelihood (*); inputs are assumed to be in [-1, 1] (distributions.py:370-379)."""
+        if isinstance(params, DMoLParams) and y.shape == params.raw.shape[:-1] + (self.y_dim,) and reduce_dim in (-1, y.ndim - 1):
+            return ops.dmol_log_prob(y, params.raw, self.num_mix, self.y_dim, self.num_bins, self.log_epsilon)
+        return discretized_logistic_mixture_ll(y, params[0], params[1], params[2], num_bins=self.num_bins,
+                                               reduce_dim=reduce_dim)
+
+    def forward(self, x):
+        return DMoLParams(self.params(x), self.num_mix, self.y_dim, self.log_epsilon)

@@ -1,0 +1,206 @@
+"""The masked ELBO reduction, fused: `fused_elbo` plus drop-in replacements for each reference model's
+`compute_elbo` / `compute_loss` with identical signatures, return tuples, dtypes and quirks.
+
+One step of the path = 1 DMoL kernel (value + gradient + masked row partials) + 1 KL kernel per latent level
+(value + free nats + mask + gradient + row partials) + 1 finalize kernel.  `d loss / d log_prob[b, t] = -mask / sum(x_sl)`
+is known before the kernels run (x_sl lives on the host), so parameter gradients are produced in the same pass and
+`loss.backward()` only rescales them by the incoming grad_output (a no-op kernel when it is 1).
+"""
+import math
+from types import SimpleNamespace
+from typing import List, Optional, Sequence, Union
+
+import torch
+
+from . import ops
+from .distributions import DLParams, DMoLParams
+from .operations import level_lengths, sequence_mask
+
+__all__ = ["KLLevel", "fused_elbo", "vrnn_compute_elbo", "srnn_compute_elbo", "cwvae_compute_elbo", "stcn_compute_loss",
+           "wavenet_compute_loss", "pack_dmol_params"]
+
+
+class KLLevel:
+    """One latent layer's contribution to the ELBO.
+
+    Either the four Gaussian parameter tensors `(mu_q, sd_q, mu_p, sd_p)`, each (B, Tz, Z) — KL, free nats, mask, sums
+    and gradients then run in one kernel — or an already materialised elementwise `kld` (B, Tz, Z) as the reference's
+    compute_elbo receives it.  `stride` = temporal stride of the layer relative to the waveform (valid steps =
+    ceil(x_sl / stride)); alternatively explicit `lens` (B).  `free_nats` overrides the op-level budget for this level
+    (Clockwork-VAE scales it per level, clockwork_vae.py:151).
+    """
+
+    def __init__(self, mu_q=None, sd_q=None, mu_p=None, sd_p=None, *, kld=None, stride: Optional[int] = None,
+                 lens: Optional[torch.Tensor] = None, free_nats: Optional[float] = None):
+        if kld is None and any(t is None for t in (mu_q, sd_q, mu_p, sd_p)):
+            raise ValueError("KLLevel needs either (mu_q, sd_q, mu_p, sd_p) or kld=")
+        if stride is None and lens is None:
+            raise ValueError("KLLevel needs stride= or lens=")
+        self.tensors = [kld] if kld is not None else [mu_q, sd_q, mu_p, sd_p]
+        self.kind = "kld" if kld is not None else "inputs"
+        self.stride, self.lens, self.free_nats = stride, lens, free_nats
+
+
+def pack_dmol_params(parameters) -> "DMoLParams":
+    """Accept what `likelihood(x)` returned: our DMoLParams (zero-copy) or a reference-style
+    (logit_probs, locs, log_scales) tuple, which is packed into the (.., K(2D+1)) layout with one cat (the log-scales
+    are then already clamped, so the kernel clamp is disabled)."""
+    if isinstance(parameters, DMoLParams):
+        return parameters
+    logit_probs, locs, log_scales = parameters[0], parameters[1], parameters[2]
+    src = getattr(log_scales, "_blvm_packed", None)
+    if src is not None and getattr(logit_probs, "_blvm_packed", (None,))[0] is src[0]:
+        return DMoLParams(*src)
+    K, D = logit_probs.size(-1), locs.size(-2)
+    raw = torch.cat([logit_probs, torch.cat([locs, log_scales], dim=-1).flatten(-2)], dim=-1)
+    return DMoLParams(raw, K, D, -math.inf)
+
+
+def _host_lengths(x_sl) -> torch.Tensor:
+    if not isinstance(x_sl, torch.Tensor):
+        x_sl = torch.as_tensor(x_sl)
+    return x_sl.to(torch.int64)
+
+
+def fused_elbo(
+    y: torch.Tensor,
+    parameters,
+    x_sl: Union[torch.Tensor, Sequence[int]],
+    kl_levels: Sequence[KLLevel] = (),
+    beta: float = 1.0,
+    free_nats: float = 0.0,
+    *,
+    num_bins: int,
+    denom: Optional[float] = None,
+    want_twise: bool = False,
+    skip_padded: bool = False,
+):
+    """ELBO of a batch in one pass.
+
+    Args:
+        y: targets (B, T) or (B, T, D) in [-1, 1].
+        parameters: `likelihood(x)` output (DMoLParams / DLParams / reference-style tuple) over (B, T), or None for a
+            KL-only call.
+        x_sl: valid samples per utterance (B), CPU int64 like in the reference (a CUDA tensor costs one sync).
+        kl_levels: the latent layers (see KLLevel).
+        beta, free_nats: as in `Model.forward(x, x_sl, beta=, free_nats=)`.
+        num_bins: likelihood.num_bins.
+        denom: normaliser of the loss; default sum(x_sl).  Data-parallel callers pass global_sum / world_size so that
+            the mean of the per-rank losses (what DDP's gradient averaging implements) is the global loss.
+        want_twise: also return the masked per-sample log-prob (B, T) (WaveNet returns it).
+        skip_padded: do not read tiles that lie entirely in the padding (their outputs become exact zeros instead of
+            `value * 0`; only differs from the reference if padded parameters are non-finite).
+
+    Returns a namespace with fp64 tensors: loss (), elbo, log_prob, kl, kl_fn (B,), kl_levels [(B,)],
+    sums (8,) = [loss, sum log_prob, sum kl, sum kl_fn, sum elbo, sum x_sl, bits-per-dim, nansum-loss] and
+    log_prob_twise (B, T) fp32 or None.  Only `loss` is differentiable (w.r.t. the likelihood parameters and the
+    tensors of every KLLevel); the others are detached.
+    """
+    x_sl_host = _host_lengths(x_sl)
+    dev = (parameters.raw if parameters is not None and hasattr(parameters, "raw") else
+           (parameters[0] if parameters is not None else kl_levels[0].tensors[0])).device
+    if x_sl_host.is_cuda:
+        x_sl_dev = x_sl_host
+        total = float(x_sl_host.sum().item()) if denom is None else float(denom)
+    else:
+        total = float(x_sl_host.sum()) if denom is None else float(denom)
+        x_sl_dev = x_sl_host.to(dev, non_blocking=True)
+    B = x_sl_dev.shape[0]
+
+    likelihood, raw, K, D, log_eps = "none", None, 1, 1, -7.0
+    if parameters is not None:
+        if isinstance(parameters, DLParams):
+            likelihood, raw, log_eps = "dl", parameters.raw, parameters.log_epsilon
+            if parameters.D != 1:
+                raise NotImplementedError("fused_elbo supports DiscretizedLogisticDense with y_dim == 1")
+        else:
+            p = pack_dmol_params(parameters)
+            likelihood, raw, K, D, log_eps = "dmol", p.raw, p.K, p.D, p.log_epsilon
+        if raw.dim() != 3 or raw.shape[0] != B:
+            raise ValueError(f"likelihood parameters must be (B, T, P) with B = len(x_sl) = {B}; got {tuple(raw.shape)}")
+        if raw.dtype != torch.float32:
+            raw = raw.float()  # AMP hands over fp16/bf16 Linear outputs; the kernels compute in fp32
+        raw = raw.contiguous()
+        T = raw.shape[1]
+        y = y.reshape(B, T, D) if y.numel() == B * T * D else y
+        if y.shape[:2] != (B, T):
+            raise ValueError(f"y {tuple(y.shape)} does not match parameters (B, T) = ({B}, {T})")
+        y = y.to(torch.float32).contiguous()
+
+    specs, flat = [], []
+    for lv in kl_levels:
+        ts = [t.to(torch.float32).contiguous() for t in torch.broadcast_tensors(*lv.tensors)]
+        if ts[0].dim() != 3 or ts[0].shape[0] != B:
+            raise ValueError(f"KL tensors must be (B, Tz, Z) with B = {B}; got {tuple(ts[0].shape)}")
+        lens = lv.lens if lv.lens is not None else level_lengths(x_sl_dev, int(lv.stride))
+        lens = lens.to(device=dev, dtype=torch.int64)
+        fn = free_nats if lv.free_nats is None else lv.free_nats
+        specs.append(ops.KLLevelSpec(lv.kind, float(fn or 0.0), lens, len(ts)))
+        flat += ts
+
+    need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in ([raw] if raw is not None else []) + flat)
+    spec = ops.ELBOSpec(K=K, D=D, num_bins=int(num_bins), log_epsilon=float(log_eps), beta=float(beta), denom=total,
+                        levels=specs, want_twise=want_twise, skip_padded=skip_padded, need_grad=need_grad,
+                        likelihood=likelihood)
+    loss, sums, rows, twise = ops.fused_elbo_apply(spec, y, x_sl_dev, raw, flat)
+    return SimpleNamespace(loss=loss, log_prob=rows[0], kl=rows[1], kl_fn=rows[2], elbo=rows[3],
+                           kl_levels=[rows[4 + l] for l in range(len(specs))], sums=sums,
+                           log_prob_twise=twise if want_twise else None, x_sl=x_sl_dev)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# drop-in reducers (bound as methods by patch_blvm; `self` only needs the attributes the reference methods read)
+# ----------------------------------------------------------------------------------------------------------------------
+def _vrnn_like(self, y, parameters, kld_twise, x_sl, stride, beta, free_nats, return_fn_kl):
+    r = fused_elbo(y, parameters, x_sl, [KLLevel(kld=kld_twise, stride=stride)], beta, free_nats,
+                   num_bins=self.likelihood.num_bins)
+    seq_mask = sequence_mask(x_sl, dtype=torch.float64, device=y.device)   # vrnn.py:266: dtype=float => float64
+    kld = r.kl_fn if return_fn_kl else r.kl
+    return r.loss, r.elbo, r.log_prob, kld, seq_mask                      # all float64 like the reference
+
+
+def vrnn_compute_elbo(self, y, parameters, kld_twise, x_sl, stride: int, beta: float = 1, free_nats: float = 0):
+    """Drop-in for VRNN.compute_elbo (blvm/models/vrnn.py:255-279): returns (loss, elbo, log_prob, kld, seq_mask), all
+    float64.  Quirk kept: the returned `kld` is the free-nats-discounted KL (:276-279 overwrites it)."""
+    return _vrnn_like(self, y, parameters, kld_twise, x_sl, stride, beta, free_nats, True)
+
+
+def srnn_compute_elbo(self, y, parameters, kld_twise, x_sl, stride: int, beta: float = 1, free_nats: float = 0):
+    """Drop-in for SRNN.compute_elbo (blvm/models/srnn.py:137-160): same, but returns the raw KL (:153,160)."""
+    return _vrnn_like(self, y, parameters, kld_twise, x_sl, stride, beta, free_nats, False)
+
+
+def cwvae_compute_elbo(self, y, seq_mask, level_masks, x_sl, parameters, kld_layerwise: List[torch.Tensor],
+                       beta: float = 1, free_nats: float = 0):
+    """Drop-in for CWVAE.compute_elbo (blvm/models/clockwork_vae/clockwork_vae.py:132-161): float32 outputs,
+    per-level free nats scaled by overall_strides[l] / overall_strides[0] (:151), KL summed over levels (:155).
+    The (prefix) masks the caller built (:231-240) are turned back into lengths."""
+    levels = []
+    for l in range(self.num_levels):
+        fn = free_nats * self.overall_strides[l] / self.overall_strides[0]
+        levels.append(KLLevel(kld=kld_layerwise[l], lens=level_masks[l].sum(1), free_nats=fn))
+    r = fused_elbo(y, parameters, x_sl, levels, beta, free_nats, num_bins=self.likelihood.num_bins)
+    f = torch.float32
+    return r.loss.to(f), r.elbo.to(f), r.log_prob.to(f), r.kl.to(f), [k.to(f) for k in r.kl_levels]
+
+
+def stcn_compute_loss(self, y, x_sl, parameters, mu_p, sd_p, mu_q, sd_q, z, free_nats: float, beta: float):
+    """Drop-in for STCN.compute_loss (blvm/models/stcn/stcn.py:256-297), top-down (analytic KL) variant: every latent
+    level goes through the fully fused KL kernel.  mask -> free nats -> mask (:286-289) equals max(kl, fn/Z) on valid
+    steps and 0 on padded ones, which is what the kernel computes."""
+    if not self.top_down:
+        raise NotImplementedError("bottom-up STCN uses the Monte-Carlo KL (variational.py:73-83), outside this path")
+    levels = [KLLevel(mu_q[l], sd_q[l], mu_p[l], sd_p[l], stride=self.n_stack_frames) for l in range(self.n_latents)]
+    r = fused_elbo(y, parameters, x_sl, levels, beta, free_nats, num_bins=self.likelihood_module.num_bins)
+    f = torch.float32
+    return r.loss.to(f), r.elbo.to(f), r.log_prob.to(f), r.kl.to(f), [k.to(f) for k in r.kl_levels]
+
+
+def wavenet_compute_loss(self, y, x_sl, parameters):
+    """Drop-in for WaveNet.compute_loss (blvm/models/wavenet/wavenet.py:128-146): (loss, log_prob (B,),
+    log_prob_twise (B, T)); the loss uses nansum over utterances (:145)."""
+    r = fused_elbo(y, parameters, x_sl, (), 1.0, 0.0, num_bins=self.likelihood.num_bins, want_twise=True)
+    f = torch.float32
+    # loss == nansum-loss whenever every utterance log-prob is finite; select without a sync
+    loss = torch.where(torch.isnan(r.loss.detach()), r.sums[7], r.loss)
+    return loss.to(f), r.log_prob.to(f), r.log_prob_twise

@@ -1,0 +1,365 @@
+"""Tensor-level wrappers and autograd Functions over the C ABI (include/blvm_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; all arithmetic of the path runs in the CUDA
+kernels of libblvm_b200.so.  There is no CPU path: CPU tensors raise.
+"""
+import ctypes
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _lib
+from ._lib import BLVM_FLAG_MASK_OUTPUT, BLVM_FLAG_SKIP_PADDED, check, lib
+
+__all__ = [
+    "dmol_log_prob", "dl_log_prob", "kl_gaussian", "KLLevelSpec", "ELBOSpec", "fused_elbo_apply", "quantize_indices",
+    "check_input_range", "launch_count", "reset_launch_count",
+]
+
+_STRICT = os.environ.get("BLVM_B200_STRICT", "0") == "1"
+_err_flags = {}
+_launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                f"blvm_b200 kernels need CUDA tensors (got a tensor on {t.device}); there is no CPU fallback — "
+                "use the reference implementation for CPU work.")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _err_flag(device: torch.device) -> torch.Tensor:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    flag = _err_flags.get(key)
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        _err_flags[key] = flag
+    return flag
+
+
+def check_input_range(device=None):
+    """Raise AssertionError if any target passed to the DMoL/DL kernels since the last check was outside [-1, 1].
+
+    The reference asserts this synchronously on every call (`assert torch.max(y) <= 1.0 and torch.min(y) >= -1.0`,
+    blvm/utils/log_likelihoods.py:131,195), which costs two reductions and a device->host sync per step; the kernels
+    record the violation in a device flag instead and this function reads it (one sync).  Set BLVM_B200_STRICT=1 to
+    check after every call.
+    """
+    for key, flag in list(_err_flags.items()):
+        if device is not None and torch.device(device).index not in (None, key):
+            continue
+        if int(flag.item()) != 0:
+            flag.zero_()
+            raise AssertionError("blvm_b200: targets outside [-1, 1] were passed to a discretized-logistic likelihood")
+
+
+def _maybe_strict(device):
+    if _STRICT:
+        check_input_range(device)
+
+
+def _as_f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# raw kernel calls
+# ----------------------------------------------------------------------------------------------------------------------
+def _dmol_call(y, raw, x_sl_dev, gout, gscale, B, T, K, D, num_bins, log_eps, flags, lp, graw, partials):
+    _require_cuda(y, raw, x_sl_dev, gout, lp, graw, partials)
+    with torch.cuda.device(raw.device):
+        err = _err_flag(raw.device)
+        if graw is None:
+            rc = lib.blvm_dmol_fwd(_ptr(y), _ptr(raw), _ptr(x_sl_dev), B, T, K, D, num_bins, log_eps, flags, _ptr(lp),
+                                   _ptr(partials), _ptr(err), _stream())
+            check(rc, "blvm_dmol_fwd")
+        else:
+            rc = lib.blvm_dmol_fwd_grad(_ptr(y), _ptr(raw), _ptr(x_sl_dev), _ptr(gout), gscale, B, T, K, D, num_bins,
+                                        log_eps, flags, _ptr(lp), _ptr(graw), _ptr(partials), _ptr(err), _stream())
+            check(rc, "blvm_dmol_fwd_grad")
+    _count()
+
+
+def _dl_call(y, raw, x_sl_dev, gout, gscale, B, T, num_bins, log_eps, flags, lp, graw, partials):
+    _require_cuda(y, raw, x_sl_dev, gout, lp, graw, partials)
+    with torch.cuda.device(raw.device):
+        err = _err_flag(raw.device)
+        rc = lib.blvm_dl_fwd_grad(_ptr(y), _ptr(raw), _ptr(x_sl_dev), _ptr(gout), gscale, B, T, num_bins, log_eps, flags,
+                                  _ptr(lp), _ptr(graw), _ptr(partials), _ptr(err), _stream())
+        check(rc, "blvm_dl_fwd_grad")
+    _count()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# per-sample log-prob with a generic autograd backward (recompute): the drop-in for `likelihood.log_prob(y, params)`
+# ----------------------------------------------------------------------------------------------------------------------
+class _DMoLLogProb(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, y, raw, K, D, num_bins, log_eps):
+        y = y.contiguous()
+        raw = raw.contiguous()
+        P = K * (2 * D + 1)
+        assert raw.shape[-1] == P, f"raw last dim {raw.shape[-1]} != K(2D+1) = {P}"
+        N = raw.numel() // P
+        assert y.numel() == N * D, f"y has {y.numel()} elements, expected {N * D}"
+        lp = torch.empty(raw.shape[:-1], dtype=torch.float32, device=raw.device)
+        _dmol_call(y, raw, None, None, 0.0, 1, N, K, D, num_bins, log_eps, 0, lp, None, None)
+        ctx.save_for_backward(y, raw)
+        ctx.cfg = (K, D, num_bins, log_eps, N)
+        _maybe_strict(raw.device)
+        return lp
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        y, raw = ctx.saved_tensors
+        K, D, num_bins, log_eps, N = ctx.cfg
+        graw = torch.empty_like(raw)
+        _dmol_call(y, raw, None, _as_f32c(g), 1.0, 1, N, K, D, num_bins, log_eps, 0, None, graw, None)
+        return None, graw, None, None, None, None
+
+
+def dmol_log_prob(y: torch.Tensor, raw: torch.Tensor, K: int, D: int, num_bins: int, log_epsilon: float) -> torch.Tensor:
+    """log p(y) per element of the batch shape `raw.shape[:-1]` from the packed Linear output `raw (*, K(2D+1))`."""
+    return _DMoLLogProb.apply(y, raw, K, D, num_bins, float(log_epsilon))
+
+
+class _DLLogProb(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, y, raw, num_bins, log_eps):
+        y = y.contiguous()
+        raw = raw.contiguous()
+        N = raw.numel() // 2
+        assert y.numel() == N
+        lp = torch.empty(raw.shape[:-1], dtype=torch.float32, device=raw.device)
+        _dl_call(y, raw, None, None, 0.0, 1, N, num_bins, log_eps, 0, lp, None, None)
+        ctx.save_for_backward(y, raw)
+        ctx.cfg = (num_bins, log_eps, N)
+        _maybe_strict(raw.device)
+        return lp
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        y, raw = ctx.saved_tensors
+        num_bins, log_eps, N = ctx.cfg
+        graw = torch.empty_like(raw)
+        _dl_call(y, raw, None, _as_f32c(g), 1.0, 1, N, num_bins, log_eps, 0, None, graw, None)
+        return None, graw, None, None
+
+
+def dl_log_prob(y: torch.Tensor, raw: torch.Tensor, num_bins: int, log_epsilon: float) -> torch.Tensor:
+    """Elementwise discretized-logistic log-prob from packed `raw (*, 2) = [mu | log_scale]`, y (*)."""
+    return _DLLogProb.apply(y, raw, num_bins, float(log_epsilon))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# elementwise Gaussian KL
+# ----------------------------------------------------------------------------------------------------------------------
+class _KLGaussian(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, mu_q, sd_q, mu_p, sd_p):
+        ins = [t.contiguous() for t in (mu_q, sd_q, mu_p, sd_p)]
+        _require_cuda(*ins)
+        kl = torch.empty_like(ins[0])
+        with torch.cuda.device(kl.device):
+            check(lib.blvm_kl_gaussian_fwd(*[_ptr(t) for t in ins], kl.numel(), _ptr(kl), _stream()), "blvm_kl_gaussian_fwd")
+        _count()
+        ctx.save_for_backward(*ins)
+        return kl
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        ins = ctx.saved_tensors
+        g = _as_f32c(g)
+        outs = [torch.empty_like(ins[0]) for _ in range(4)]
+        with torch.cuda.device(g.device):
+            check(lib.blvm_kl_gaussian_bwd(*[_ptr(t) for t in ins], _ptr(g), g.numel(), *[_ptr(t) for t in outs], _stream()),
+                  "blvm_kl_gaussian_bwd")
+        _count()
+        return tuple(outs)
+
+
+def kl_gaussian(mu_q, sd_q, mu_p, sd_p):
+    mu_q, sd_q, mu_p, sd_p = torch.broadcast_tensors(mu_q, sd_q, mu_p, sd_p)
+    return _KLGaussian.apply(mu_q, sd_q, mu_p, sd_p)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the fused ELBO op: DMoL value+grad, KL value+grad per level, finalize — gradients are produced in the forward pass
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class KLLevelSpec:
+    kind: str                      # "inputs" (mu_q, sd_q, mu_p, sd_p given: fully fused) or "kld" (elementwise KL given)
+    free_nats: float               # budget per latent step for this level (already scaled, clockwork_vae.py:151)
+    lens: Optional[torch.Tensor]   # (B) int64 on device: valid latent steps, None = all
+    n_tensors: int = 4
+
+
+@dataclass
+class ELBOSpec:
+    K: int
+    D: int
+    num_bins: int
+    log_epsilon: float
+    beta: float
+    denom: float                   # sum(x_sl) (global / world_size under data parallelism)
+    levels: List[KLLevelSpec] = field(default_factory=list)
+    want_twise: bool = False
+    skip_padded: bool = False
+    need_grad: bool = True
+    likelihood: str = "dmol"       # "dmol" | "dl" | "none"
+
+
+class _FusedELBO(torch.autograd.Function):
+    """inputs: spec, y (B,T[,D]), x_sl_dev (B) int64, raw (B,T,P), then the KL tensors of every level, flattened.
+    outputs: loss () fp64 [differentiable], scalars (8) fp64, rows (4+L, B) fp64, log_prob_twise (B,T) or empty."""
+
+    @staticmethod
+    def forward(ctx, spec: ELBOSpec, y, x_sl_dev, raw, *kl_tensors):
+        dev = raw.device if raw is not None else kl_tensors[0].device
+        B = int(x_sl_dev.shape[0])
+        L = len(spec.levels)
+        assert L <= _lib.BLVM_MAX_KL_LEVELS, f"at most {_lib.BLVM_MAX_KL_LEVELS} KL levels"
+        out = torch.empty(8 + (4 + L) * B, dtype=torch.float64, device=dev)
+        scalars = out[:8]
+        rows = out[8:].view(4 + L, B)
+        grads: List[Optional[torch.Tensor]] = []
+        keep = []  # partial-sum buffers must outlive the finalize launch (stream-ordered; the caching allocator is
+        #            stream-aware, but holding them until return keeps this independent of allocator behaviour)
+        twise = torch.empty(0, device=dev)
+        logp_part, logp_chunks = None, 0
+
+        if spec.likelihood != "none":
+            T = raw.shape[1]
+            flags = BLVM_FLAG_MASK_OUTPUT | (BLVM_FLAG_SKIP_PADDED if spec.skip_padded else 0)
+            logp_chunks = int(lib.blvm_dmol_chunks(T))
+            logp_part = torch.empty(B * logp_chunks, dtype=torch.float64, device=dev)
+            keep.append(logp_part)
+            if spec.want_twise:
+                twise = torch.empty(B, T, dtype=torch.float32, device=dev)
+            graw = torch.empty_like(raw) if spec.need_grad else None
+            gscale = -1.0 / spec.denom
+            lp_arg = twise if spec.want_twise else None
+            if spec.likelihood == "dmol":
+                _dmol_call(y, raw, x_sl_dev, None, gscale, B, T, spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags,
+                           lp_arg, graw, logp_part)
+            else:
+                _dl_call(y, raw, x_sl_dev, None, gscale, B, T, spec.num_bins, spec.log_epsilon, flags, lp_arg, graw,
+                         logp_part)
+            grads.append(graw)
+        else:
+            grads.append(None)
+
+        kl_parts, klfn_parts, kl_chunks = [], [], []
+        i = 0
+        with torch.cuda.device(dev):
+            for lv in spec.levels:
+                ts = kl_tensors[i:i + lv.n_tensors]
+                i += lv.n_tensors
+                _require_cuda(*ts)
+                Bz, Tz, Z = ts[0].shape
+                assert Bz == B, f"KL level batch {Bz} != {B}"
+                chunks = int(lib.blvm_kl_chunks(Tz * Z))
+                pk = torch.empty(B * chunks, dtype=torch.float64, device=dev)
+                pf = torch.empty(B * chunks, dtype=torch.float64, device=dev)
+                keep += [pk, pf]
+                gscale = spec.beta / spec.denom
+                if lv.kind == "inputs":
+                    g4 = [torch.empty_like(ts[0]) for _ in range(4)] if spec.need_grad else [None] * 4
+                    rc = lib.blvm_kl_elbo_fwd_grad(*[_ptr(t) for t in ts], _ptr(lv.lens), B, Tz, Z, float(lv.free_nats),
+                                                   gscale, None, *[_ptr(g) for g in g4], _ptr(pk), _ptr(pf), _stream())
+                    check(rc, "blvm_kl_elbo_fwd_grad")
+                    grads += g4
+                else:
+                    gk = torch.empty_like(ts[0]) if spec.need_grad else None
+                    rc = lib.blvm_kl_reduce_fwd_grad(_ptr(ts[0]), _ptr(lv.lens), B, Tz, Z, float(lv.free_nats), gscale,
+                                                     _ptr(gk), _ptr(pk), _ptr(pf), _stream())
+                    check(rc, "blvm_kl_reduce_fwd_grad")
+                    grads.append(gk)
+                _count()
+                kl_parts.append(pk)
+                klfn_parts.append(pf)
+                kl_chunks.append(chunks)
+
+            PtrArr = ctypes.c_void_p * max(L, 1)
+            I64Arr = ctypes.c_int64 * max(L, 1)
+            rc = lib.blvm_elbo_finalize(_ptr(logp_part), logp_chunks, PtrArr(*[t.data_ptr() for t in kl_parts]),
+                                        PtrArr(*[t.data_ptr() for t in klfn_parts]), I64Arr(*kl_chunks), L,
+                                        _ptr(x_sl_dev), B, float(spec.beta), _ptr(rows), _ptr(scalars), _stream())
+            check(rc, "blvm_elbo_finalize")
+            _count()
+
+        loss = scalars[:1].view(())
+        ctx.grads = grads
+        ctx.consumed = False
+        ctx.mark_non_differentiable(scalars, rows, twise)
+        _maybe_strict(dev)
+        return loss, scalars, rows, twise
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        if ctx.consumed:
+            raise RuntimeError("blvm_b200 fused ELBO: backward called twice (gradients are produced in the forward pass "
+                               "and scaled in place; call the op again instead of retain_graph=True)")
+        ctx.consumed = True
+        g = g_loss.to(torch.float64).contiguous()
+        out = [None, None, None]
+        with torch.cuda.device(g.device):
+            for buf in ctx.grads:
+                if buf is not None:
+                    check(lib.blvm_scale_inplace(_ptr(buf), buf.numel(), _ptr(g), _stream()), "blvm_scale_inplace")
+                    _count()
+                out.append(buf)
+        ctx.grads = None
+        return tuple(out)
+
+
+def fused_elbo_apply(spec: ELBOSpec, y, x_sl_dev, raw, kl_tensors: Sequence[torch.Tensor]):
+    return _FusedELBO.apply(spec, y, x_sl_dev, raw, *kl_tensors)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Quantize
+# ----------------------------------------------------------------------------------------------------------------------
+def quantize_indices(x: torch.Tensor, boundaries: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, boundaries)
+    x = _as_f32c(x)
+    boundaries = _as_f32c(boundaries)
+    out = torch.empty(x.shape, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.blvm_quantize(_ptr(x), x.numel(), _ptr(boundaries), boundaries.numel(), _ptr(out), _stream()), "blvm_quantize")
+    _count()
+    return out

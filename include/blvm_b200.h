@@ -1,0 +1,150 @@
+/*
+ * blvm_b200 — C ABI of the B200-native (sm_100a) DMoL + Gaussian-KL + masked-ELBO kernels.
+ *
+ * This is the drop-in boundary for the one hot path of JakobHavtorn/benchmarking-lvms that this repo replaces.
+ * The reference has no FFI layer (it is pure PyTorch); each entry point below names the reference Python function
+ * (path:line under the reference tree) whose eager-op chain it replaces.  The Python package
+ * `benchmarking-lvms_b200/` binds these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - all tensors are dense row-major fp32 unless stated; row sums / scalars are fp64;
+ *  - `stream` is a `cudaStream_t` (CUstream) passed as an opaque pointer; every call is asynchronous, stream-ordered,
+ *    never allocates and never synchronises;
+ *  - return value 0 = OK, otherwise a BLVM_ERR_* code; `blvm_last_error_string()` (thread-local) describes it;
+ *  - nullable arguments are marked `nullable`.
+ *  - the caller owns all buffers and must keep them alive until the stream has passed the call.
+ */
+#ifndef BLVM_B200_H_
+#define BLVM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLVM_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+  BLVM_OK = 0,
+  BLVM_ERR_INVALID_ARGUMENT = 1,
+  BLVM_ERR_UNSUPPORTED = 2,
+  BLVM_ERR_CUDA = 3,
+};
+
+/* flags for the DMoL / DL entry points */
+enum {
+  BLVM_FLAG_MASK_OUTPUT = 1, /* per-sample log-prob output is multiplied by the sequence mask (vrnn.py:268) */
+  BLVM_FLAG_SKIP_PADDED = 2, /* tiles entirely inside the padding are not read; their outputs are exact zeros */
+};
+
+#define BLVM_MAX_KL_LEVELS 8
+#define BLVM_DMOL_TILE 128   /* samples per partial sum of the DMoL / DL kernels  */
+#define BLVM_KL_TILE 1024    /* latent elements per partial sum of the KL kernels */
+
+typedef void* blvm_stream_t;
+
+int blvm_version(void);
+const char* blvm_last_error_string(void);
+
+/* Number of fp64 partial sums per utterance the kernels write: ceil(T / BLVM_DMOL_TILE), ceil(Tz*Z / BLVM_KL_TILE). */
+int64_t blvm_dmol_chunks(int64_t T);
+int64_t blvm_kl_chunks(int64_t row_elems);
+
+/*
+ * Discretized mixture of logistics, forward only.
+ * Replaces DiscretizedLogisticMixtureDense.forward's split+clamp (blvm/modules/distributions.py:383-387) and
+ * discretized_logistic_mixture_ll (blvm/utils/log_likelihoods.py:170-231), plus `* seq_mask` and the per-utterance
+ * sum of compute_elbo (blvm/models/vrnn.py:266-269).
+ *   y        (B, T, D)         targets in [-1, 1]
+ *   raw      (B, T, K(2D+1))   the Linear output: [logits K | per d: locs K, log_scales K]; log-scales are clamped
+ *                              at log_epsilon inside the kernel
+ *   x_sl     (B) int64, nullable: valid samples per utterance (None = all T)
+ *   lp       (B, T), nullable: per-sample log-prob out
+ *   partials (B, blvm_dmol_chunks(T)) fp64, nullable: masked per-tile sums of log-prob
+ *   err_flag int32, nullable: set to 1 if some y is outside [-1, 1] (the reference's assert, log_likelihoods.py:195)
+ */
+int blvm_dmol_fwd(const float* y, const float* raw, const int64_t* x_sl, int64_t B, int64_t T, int K, int D,
+                  int num_bins, float log_epsilon, int flags, float* lp, double* partials, int* err_flag,
+                  blvm_stream_t stream);
+
+/*
+ * Single pass forward + gradient: additionally writes
+ *   graw (B, T, K(2D+1)) = gscale * gout[b,t] * mask[b,t] * d log p(y[b,t]) / d raw[b,t,:]
+ * which is what autograd produces through log_likelihoods.py:198-231 and the clamp of distributions.py:386
+ * (gradient passes at raw == log_epsilon).  `gout` (B, T) nullable = 1.  With gscale = -1/sum(x_sl) this is
+ * d loss / d raw of vrnn.py:277.  Also serves as the backward of a generic log_prob call (lp = NULL).
+ */
+int blvm_dmol_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale,
+                       int64_t B, int64_t T, int K, int D, int num_bins, float log_epsilon, int flags, float* lp,
+                       float* graw, double* partials, int* err_flag, blvm_stream_t stream);
+
+/*
+ * Single discretized logistic (K = 1, no mixture weights), packed raw (B, T, 2) = [mu | log_scale].
+ * Replaces DiscretizedLogisticDense.forward/log_prob (distributions.py:298-307) and discretized_logistic_ll
+ * (log_likelihoods.py:98-166).  graw nullable (forward only).
+ */
+int blvm_dl_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale, int64_t B,
+                     int64_t T, int num_bins, float log_epsilon, int flags, float* lp, float* graw, double* partials,
+                     int* err_flag, blvm_stream_t stream);
+
+/*
+ * Diagonal-Gaussian KL(q||p), std-dev parametrisation, elementwise over n elements.
+ * Replaces kl_divergence_gaussian (blvm/utils/variational.py:67-70).
+ */
+int blvm_kl_gaussian_fwd(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p, int64_t n, float* kl,
+                         blvm_stream_t stream);
+/* its autograd backward: g_* = gout * d kl / d *. */
+int blvm_kl_gaussian_bwd(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p, const float* gout,
+                         int64_t n, float* g_mu_q, float* g_sd_q, float* g_mu_p, float* g_sd_p, blvm_stream_t stream);
+
+/*
+ * Fused KL + free nats + sequence mask + per-utterance sums + gradients, one latent level (B, Tz, Z).
+ * Replaces kl_divergence_gaussian + discount_free_nats(shared_dims=-1) (variational.py:86-122) + the masked sums of
+ * compute_elbo (vrnn.py:271-276, srnn.py:150-156, clockwork_vae.py:147-153, stcn.py:284-292).
+ *   lens        (B) int64, nullable: valid latent steps per utterance (= ceil(x_sl / stride))
+ *   free_nats   budget per latent step (shared over Z); 0 disables (variational.py:107)
+ *   gscale      multiplier of the gradients (beta / sum(x_sl) for vrnn.py:277)
+ *   kl          (B, Tz, Z) nullable: raw elementwise KL out
+ *   g_*         (B, Tz, Z) nullable together: d(gscale * sum_masked max(kl, free_nats/Z)) / d inputs,
+ *               torch.maximum's 1/2-1/2 rule at exact ties
+ *   part_kl, part_klfn (B, blvm_kl_chunks(Tz*Z)) fp64: masked per-tile sums of kl and of max(kl, free_nats/Z)
+ */
+int blvm_kl_elbo_fwd_grad(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p,
+                          const int64_t* lens, int64_t B, int64_t Tz, int64_t Z, double free_nats, float gscale,
+                          float* kl, float* g_mu_q, float* g_sd_q, float* g_mu_p, float* g_sd_p, double* part_kl,
+                          double* part_klfn, blvm_stream_t stream);
+
+/* Same reduction when the caller already holds the elementwise KL (compute_elbo's `kld_twise` argument). gkl nullable. */
+int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int64_t Tz, int64_t Z, double free_nats,
+                            float gscale, float* gkl, double* part_kl, double* part_klfn, blvm_stream_t stream);
+
+/*
+ * Partials -> per-utterance log p(x|z), KL, free-nats KL, ELBO -> loss and bits-per-dim.
+ * Replaces vrnn.py:269-277 / srnn.py:149-158 / clockwork_vae.py:155-159 / stcn.py:290-297 / wavenet.py:143-145 and
+ * the BitsPerDimMetric arithmetic (blvm/evaluation/metrics.py:443-468).
+ *   kl_part_host / klfn_part_host / kl_chunks_host: HOST arrays of n_levels device pointers / chunk counts
+ *   rows     (4 + n_levels, B) fp64: logp, kl (sum over levels), kl_fn, elbo, then kl of each level
+ *   scalars  (8) fp64: loss = -sum_b(logp - beta kl_fn)/sum(x_sl), sum logp, sum kl, sum kl_fn, sum elbo, sum x_sl,
+ *            bits-per-dim = -sum elbo / ln 2 / sum x_sl, nansum-loss = -nansum(logp)/sum x_sl (wavenet.py:145)
+ */
+int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
+                       const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
+                       const int64_t* x_sl, int64_t B, double beta, double* rows, double* scalars,
+                       blvm_stream_t stream);
+
+/*
+ * Quantize: torch.bucketize(x, boundaries, right=False) (blvm/data/transforms.py:257) -> int64 bin index,
+ * bit-exact: first i with boundaries[i] >= x.  boundaries (n_bins) fp32 ascending, device.
+ */
+int blvm_quantize(const float* x, int64_t n, const float* boundaries, int64_t n_bins, int64_t* out, blvm_stream_t stream);
+
+/* In-place `buf *= (float)*scale` (fp64 device scalar) that exits early when *scale == 1: the autograd backward of the
+ * fused ELBO op uses it to apply an upstream grad_output (e.g. an AMP loss scale) without a host sync. */
+int blvm_scale_inplace(float* buf, int64_t n, const double* scale, blvm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLVM_B200_H_ */

@@ -1,0 +1,74 @@
+// Host build of the per-element device math (benchmarking-lvms_b200/csrc/blvm_math.cuh) for CPU-side validation of
+// the closed forms against the fp64 golden vectors.  TEST INFRASTRUCTURE: compiled by tests/test_hostsim_math.py
+// with g++, loaded only by that test.  The MUFU approximations are replaced by libm (exp2f/log2f, 1/x), so this
+// checks the algebra and the branch logic, not the last ulps of the GPU result (tests -m gpu do that).
+#include <cmath>
+#include <cstdint>
+#include "blvm_math.cuh"
+
+using namespace blvm;
+
+static DmolConsts make_consts(int num_bins, float log_eps) {
+  DmolConsts C;
+  C.h = (float)(1.0 / (num_bins - 1));
+  C.two_h = (float)(2.0 / (num_bins - 1));
+  C.lo_thresh = (float)(2.0 / num_bins - 1.0);
+  C.hi_thresh = (float)(1.0 - 2.0 / num_bins);
+  C.log_half_bins = (float)std::log(num_bins / 2.0);
+  C.log_eps = log_eps;
+  return C;
+}
+
+template <int K>
+static void run_fixed(const float* y, const float* raw, const float* gout, int64_t N, const DmolConsts& C, float* lp,
+                      float* graw) {
+  for (int64_t n = 0; n < N; ++n) {
+    float r[3 * K];
+    for (int i = 0; i < 3 * K; ++i) r[i] = raw[n * 3 * K + i];
+    lp[n] = dmol_sample<K, true>(y[n], r, gout ? gout[n] : 1.f, C);
+    for (int i = 0; i < 3 * K; ++i) graw[n * 3 * K + i] = r[i];
+  }
+}
+
+extern "C" int hostsim_dmol(const float* y, const float* raw, const float* gout, int64_t N, int K, int D, int num_bins,
+                            float log_eps, int force_generic, float* lp, float* graw) {
+  const DmolConsts C = make_consts(num_bins, log_eps);
+  if (D == 1 && !force_generic) {
+    switch (K) {
+      case 1: run_fixed<1>(y, raw, gout, N, C, lp, graw); return 0;
+      case 2: run_fixed<2>(y, raw, gout, N, C, lp, graw); return 0;
+      case 5: run_fixed<5>(y, raw, gout, N, C, lp, graw); return 0;
+      case 10: run_fixed<10>(y, raw, gout, N, C, lp, graw); return 0;
+      case 30: run_fixed<30>(y, raw, gout, N, C, lp, graw); return 0;
+      default: break;
+    }
+  }
+  const int P = K * (2 * D + 1);
+  for (int64_t n = 0; n < N; ++n)
+    lp[n] = dmol_sample_generic<true>(y + n * D, raw + n * P, K, D, gout ? gout[n] : 1.f, C, graw + n * P);
+  return 1;
+}
+
+extern "C" void hostsim_dl(const float* y, const float* raw, const float* gout, int64_t N, int num_bins, float log_eps,
+                           float* lp, float* graw) {
+  const DmolConsts C = make_consts(num_bins, log_eps);
+  for (int64_t n = 0; n < N; ++n) {
+    float dmu, dls;
+    dl_component<true>(y[n], dmol_edge(y[n], C), raw[2 * n], raw[2 * n + 1], C, lp[n], dmu, dls);
+    const float g = gout ? gout[n] : 1.f;
+    graw[2 * n] = g * dmu;
+    graw[2 * n + 1] = g * dls;
+  }
+}
+
+extern "C" void hostsim_kl(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p, const float* gout,
+                           int64_t n, float min_kl, int fn_enabled, float* kl, float* kl_fn, float* g_mu_q,
+                           float* g_sd_q, float* g_mu_p, float* g_sd_p) {
+  for (int64_t i = 0; i < n; ++i) {
+    KlTerms t = kl_gaussian_terms(mu_q[i], sd_q[i], mu_p[i], sd_p[i]);
+    kl[i] = t.kl;
+    kl_fn[i] = (fn_enabled && t.kl < min_kl) ? min_kl : t.kl;
+    const float g = (gout ? gout[i] : 1.f) * free_nats_gate(t.kl, min_kl, fn_enabled != 0);
+    kl_gaussian_grads(t, sd_q[i], g, g_mu_q[i], g_sd_q[i], g_mu_p[i], g_sd_p[i]);
+  }
+}

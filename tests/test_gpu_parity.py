@@ -1,0 +1,482 @@
+"""GPU parity: the CUDA path (through the Python boundary -> ctypes -> C ABI -> sm_100a kernels) against the golden
+vectors generated from the reference and against the numpy oracle.  Run on the B200 box: pytest -m gpu."""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from parity import RTOL, assert_grads_close, assert_sums_close, assert_values_close
+
+pytestmark = pytest.mark.gpu
+
+DMOL_CASES = ["dmol_K1_nb256", "dmol_K1_nb65536", "dmol_K2_nb256", "dmol_K2_nb65536", "dmol_K10_nb256",
+              "dmol_K10_nb65536", "dmol_K30_nb256", "dmol_K30_nb65536", "dmol_K5_nb255"]
+
+
+@pytest.fixture(scope="module")
+def B():
+    import blvm_b200
+    assert torch.cuda.is_available()
+    return blvm_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import blvm_oracle
+    return blvm_oracle
+
+
+def cu(a, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a)).to(dtype).cuda()
+
+
+def _edge_rows(g, O):
+    """Rows where the y-edge predicate evaluated in fp64 (golden *64) differs from fp32 (the reference's native
+    arithmetic; only possible for non power-of-two num_bins): there the fp32 run is the truth."""
+    nb = int(g["num_bins"])
+    y32 = g["y"].astype(np.float32)
+    lo32, hi32 = np.float32(2 / nb - 1), np.float32(1 - 2 / nb)
+    e32 = np.where(y32 > hi32, 2, np.where(y32 < lo32, 1, 0))
+    y64 = g["y"].astype(np.float64)
+    e64 = np.where(y64 > 1 - 2 / nb, 2, np.where(y64 < 2 / nb - 1, 1, 0))
+    return (e32 != e64).any(-1)
+
+
+@pytest.mark.parametrize("case", DMOL_CASES)
+def test_dmol_module_golden(case, B, O):
+    g = load_golden(case)
+    K, D, nb = int(g["K"]), int(g["D"]), int(g["num_bins"])
+    lik = B.DiscretizedLogisticMixtureDense(3 * K, D, num_mix=K, num_bins=nb)
+    raw = cu(g["raw"]).requires_grad_(True)
+    params = B.DMoLParams(raw, K, D, lik.log_epsilon)
+    lp = lik.log_prob(cu(g["y"]), params)
+    assert lp.shape == (raw.shape[0],) and lp.dtype == torch.float32
+    (lp * cu(g["gout"])).sum().backward()
+    B.check_input_range()
+    flip = _edge_rows(g, O)
+    ok = ~flip
+    assert_values_close(lp.detach().cpu().numpy()[ok], g["lp64"][ok], "log-prob vs reference fp64")
+    assert_grads_close(raw.grad.cpu().numpy()[ok], g["graw64"][ok], K, np.abs(g["gout"])[ok], "d/d raw vs reference fp64")
+    if flip.any():  # fp32 predicates are the reference's: compare those rows with its fp32 run, loosely (see parity.py)
+        np.testing.assert_allclose(lp.detach().cpu().numpy()[flip], g["lp32"][flip], rtol=2e-3)
+    # where the reference's fp32 run is self-consistent with its fp64 run, we also match it directly
+    good = ok & (np.abs(g["lp32"] - g["lp64"]) <= 1e-6 * np.abs(g["lp64"]))
+    assert_values_close(lp.detach().cpu().numpy()[good], g["lp32"][good], "log-prob vs reference fp32", rtol=1.1e-5)
+    # and we are never further from the fp64 truth than the fp32 reference is (plus the tolerance)
+    ours_err = np.abs(lp.detach().cpu().numpy().astype(np.float64) - g["lp64"])[ok]
+    ref_err = np.abs(g["lp32"].astype(np.float64) - g["lp64"])[ok]
+    assert (ours_err <= ref_err + RTOL * np.abs(g["lp64"][ok]) + 1e-6).all()
+
+
+def test_dmol_branch_coverage(O):
+    """The golden batches exercise all four branches of log_likelihoods.py:221-227 in both bin widths."""
+    for case in ("dmol_K10_nb256", "dmol_K10_nb65536"):
+        g = load_golden(case)
+        br, _ = O.dmol_branches(g["y"].astype(np.float64), g["raw"].astype(np.float64), 10, 1, int(g["num_bins"]))
+        assert set(np.unique(br)) == {0, 1, 2, 3}
+
+
+def test_dmol_generic_kernel_D2(B):
+    g = load_golden("dmol_K10_nb65536_D2")
+    K, D, nb = 10, 2, 65536
+    lik = B.DiscretizedLogisticMixtureDense(3, D, num_mix=K, num_bins=nb)
+    raw = cu(g["raw"]).requires_grad_(True)
+    lp = lik.log_prob(cu(g["y"]), B.DMoLParams(raw, K, D, -7.0))
+    (lp * cu(g["gout"])).sum().backward()
+    assert_values_close(lp.detach().cpu().numpy(), g["lp64"], "D=2 log-prob")
+    assert_grads_close(raw.grad.cpu().numpy(), g["graw64"], K, np.abs(g["gout"]), "D=2 grads")
+
+
+@pytest.mark.parametrize("K", [7, 10])
+def test_dmol_functional_unpacked_and_broadcast(K, B, O):
+    """Functional API with separate (already clamped) tensors, a K without a register kernel (7 -> generic kernel), and
+    broadcast parameters as in experiments/experiment_distribution_audio.py:122-131."""
+    rng = np.random.default_rng(K)
+    N, nb = 300, 65536
+    y = (rng.integers(0, nb, (N, 1)) / (nb - 1) * 2 - 1).astype(np.float32)
+    logits = rng.normal(size=(N, K)).astype(np.float32)
+    locs = (y[:, None, :] + 0.05 * rng.normal(size=(N, 1, K))).astype(np.float32)
+    ls = np.maximum(rng.normal(size=(N, 1, K)) * 2 - 4, -7).astype(np.float32)
+    t = [cu(a).requires_grad_(True) for a in (logits, locs, ls)]
+    lp = B.discretized_logistic_mixture_ll(cu(y), *t, num_bins=nb)
+    lp.sum().backward()
+    ref = O.discretized_logistic_mixture_ll(y.astype(np.float64), logits.astype(np.float64), locs.astype(np.float64),
+                                            ls.astype(np.float64), nb)
+    assert_values_close(lp.detach().cpu().numpy(), ref, "functional log-prob")
+    raw = np.concatenate([logits, locs[:, 0], ls[:, 0]], -1).astype(np.float64)
+    _, gref = O.dmol_value_and_grad(y.astype(np.float64), raw, K, 1, nb, log_epsilon=-np.inf)
+    ours = np.concatenate([t[0].grad.cpu().numpy(), t[1].grad.cpu().numpy()[:, 0], t[2].grad.cpu().numpy()[:, 0]], -1)
+    assert_grads_close(ours, gref, K, np.ones(N), "functional grads")
+    # broadcast (K,) / (1, K) parameters against y (B, T, 1)
+    yb = cu(y[:64].reshape(4, 16, 1))
+    lpb = B.discretized_logistic_mixture_ll(yb, cu(logits[0]), cu(locs[0]), cu(ls[0]), num_bins=nb)
+    refb = O.discretized_logistic_mixture_ll(y[:64].reshape(4, 16, 1).astype(np.float64), logits[0].astype(np.float64),
+                                             locs[0].astype(np.float64), ls[0].astype(np.float64), nb)
+    assert lpb.shape == (4, 16)
+    assert_values_close(lpb.cpu().numpy(), refb, "broadcast log-prob")
+
+
+@pytest.mark.parametrize("nb", [256, 65536])
+def test_dl_golden(nb, B):
+    g = load_golden(f"dl_nb{nb}")
+    lik = B.DiscretizedLogisticDense(4, 1, num_bins=nb)
+    raw = cu(g["raw"]).requires_grad_(True)
+    lp = lik.log_prob(cu(g["y"]).unsqueeze(-1), B.DLParams(raw, 1, -7.0))
+    assert lp.shape == (raw.shape[0], 1)
+    (lp.squeeze(-1) * cu(g["gout"])).sum().backward()
+    assert_values_close(lp.detach().cpu().numpy()[:, 0], g["lp64"], "DL log-prob")
+    assert_grads_close(raw.grad.cpu().numpy(), g["graw64"], 1, np.abs(g["gout"]), "DL grads")
+    # functional form with separate tensors
+    mu, ls = cu(g["raw"][:, 0]), cu(np.maximum(g["raw"][:, 1], -7.0))
+    lp2 = B.discretized_logistic_ll(cu(g["y"]), mu, ls, num_bins=nb, reduce_dim=None)
+    assert_values_close(lp2.cpu().numpy(), g["lp64"], "DL functional")
+
+
+def test_kl_gaussian_golden(B):
+    g = load_golden("kl_free_nats")
+    ins = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+    kl = B.kl_divergence_gaussian(*ins)
+    (kl * cu(g["gout"])).sum().backward()
+    assert_values_close(kl.detach().cpu().numpy(), g["kl64"], "KL", atol=1e-6)
+    for t, n in zip(ins, ("mu_q", "sd_q", "mu_p", "sd_p")):
+        ref = g[f"g_{n}64_0"]
+        np.testing.assert_allclose(t.grad.cpu().numpy(), ref, rtol=RTOL, atol=RTOL * np.abs(ref).max() * 1e-2, err_msg=n)
+    # identical distributions: exactly zero
+    assert (kl.detach().cpu().numpy()[0, 0, :4] == 0).all()
+
+
+def test_kl_free_nats_fused_with_ties(B, O):
+    """Fused KL + free nats + mask: values, sums and gradients incl. torch.maximum's 1/2 rule at the exact tie."""
+    g = load_golden("kl_free_nats")
+    Bn, Tz, Z = g["mu_q"].shape
+    x_sl = torch.tensor([Tz, Tz - 4, 3])  # stride 1
+    for i, fn in enumerate(g["free_nats"]):
+        ins = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+        out = B.fused_elbo(None, None, x_sl, [B.KLLevel(*ins, stride=1)], beta=0.7, free_nats=float(fn), num_bins=2)
+        out.loss.backward()
+        ref = O.fused_elbo_value_and_grad(np.zeros((Bn, Tz)), np.zeros((Bn, Tz, 3)), x_sl.numpy(), [], 0.7, 1, 256)
+        lv = dict(mu_q=g["mu_q"], sd_q=g["sd_q"], mu_p=g["mu_p"], sd_p=g["sd_p"], stride=1, free_nats=float(fn))
+        m = O.sequence_mask(x_sl.numpy(), max_len=Tz)[..., None].astype(np.float64)
+        kl, kl_fn, grads = O.kl_value_and_grad(*[g[n].astype(np.float64) for n in ("mu_q", "sd_q", "mu_p", "sd_p")],
+                                               free_nats=float(fn), gout=m * (0.7 / float(x_sl.sum())))
+        assert_sums_close(out.kl.cpu().numpy(), (kl * m).sum((1, 2)), "kl rows")
+        assert_sums_close(out.kl_fn.cpu().numpy(), (kl_fn * m).sum((1, 2)), "kl_fn rows", rtol=2e-6)
+        assert_sums_close(out.loss.item(), 0.7 * (kl_fn * m).sum() / float(x_sl.sum()), "loss", rtol=2e-6)
+        for t, r in zip(ins, grads):
+            np.testing.assert_allclose(t.grad.cpu().numpy(), r, rtol=RTOL, atol=RTOL * 1e-2 * np.abs(r).max())
+    # the tie element: gradient is exactly half of the unconstrained one
+    i, j, k = g["tie_index"]
+    ins = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+    full = torch.tensor([Tz] * Bn)
+    B.fused_elbo(None, None, full, [B.KLLevel(*ins, stride=1)], 1.0, float(g["free_nats"][3]), num_bins=2).loss.backward()
+    ins0 = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+    B.fused_elbo(None, None, full, [B.KLLevel(*ins0, stride=1)], 1.0, 0.0, num_bins=2).loss.backward()
+    # the CUDA KL value must hit the fp32 tie bit-exactly for this to hold; it is formulated differently from the
+    # reference (log1p form), so only check the rule when it does
+    kl_dev = B.kl_divergence_gaussian(*[t.detach() for t in ins])[i, j, k].item()
+    if np.float32(kl_dev) == np.float32(g["free_nats"][3] / Z):
+        assert math.isclose(ins[0].grad[i, j, k].item(), 0.5 * ins0[0].grad[i, j, k].item(), rel_tol=1e-6)
+
+
+def _check_dmol_grads_fused(graw, g, K):
+    x_sl = g["x_sl"]
+    gabs = np.full(g["raw"].shape[:2], 1.0 / x_sl.sum()).reshape(-1)
+    assert_grads_close(graw.reshape(-1, 3 * K), g["graw64"].reshape(-1, 3 * K), K, gabs, "d loss / d raw")
+
+
+@pytest.mark.parametrize("name", ["elbo_vrnn_a", "elbo_vrnn_b", "elbo_srnn_a", "elbo_srnn_b"])
+def test_vrnn_srnn_compute_elbo(name, B):
+    g = load_golden(name)
+    K, nb = int(g["K"]), int(g["num_bins"])
+    fn = B.vrnn_compute_elbo if "vrnn" in name else B.srnn_compute_elbo
+    self = SimpleNamespace(likelihood=B.DiscretizedLogisticMixtureDense(3 * K, 1, K, nb))
+    raw = cu(g["raw"]).requires_grad_(True)
+    ins = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+    kld = B.kl_divergence_gaussian(*ins)
+    x_sl = torch.as_tensor(g["x_sl"])
+    loss, elbo, logp, kl, mask = fn(self, cu(g["y"]).unsqueeze(-1), B.DMoLParams(raw, K, 1, -7.0), kld, x_sl,
+                                    int(g["stride"]), float(g["beta"]), float(g["free_nats"]))
+    loss.backward()
+    for t in (loss, elbo, logp, kl, mask):
+        assert t.dtype == torch.float64  # the reference's float64 quirk (vrnn.py:266)
+    assert mask.shape == (len(x_sl), int(x_sl.max()))
+    assert_sums_close(loss.item(), g["loss64"], "loss")
+    assert_sums_close(elbo.detach().cpu().numpy(), g["elbo64"], "elbo")
+    assert_sums_close(logp.detach().cpu().numpy(), g["logp64"], "log_prob")
+    assert_sums_close(kl.detach().cpu().numpy(), g["kl64"], "kl", rtol=2e-6)
+    _check_dmol_grads_fused(raw.grad.cpu().numpy(), g, K)
+    for t, n in zip(ins, ("mu_q", "sd_q", "mu_p", "sd_p")):
+        ref = g[f"g_{n}64"]
+        np.testing.assert_allclose(t.grad.cpu().numpy(), ref, rtol=RTOL, atol=RTOL * 1e-2 * np.abs(ref).max(), err_msg=n)
+    assert math.isclose(B.bits_per_dim(elbo, x_sl), -g["elbo64"].sum() / math.log(2) / g["x_sl"].sum(), rel_tol=1e-6)
+
+
+def test_cwvae_compute_elbo(B):
+    g = load_golden("elbo_cwvae")
+    K, nb = int(g["K"]), int(g["num_bins"])
+    ostr = [int(s) for s in g["overall_strides"]]
+    self = SimpleNamespace(likelihood=B.DiscretizedLogisticMixtureDense(3 * K, 1, K, nb), num_levels=3, overall_strides=ostr)
+    raw = cu(g["raw"]).requires_grad_(True)
+    x_sl = torch.as_tensor(g["x_sl"])
+    T = g["y"].shape[1]
+    lv = [[cu(g[f"{n}_{l}"]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")] for l in range(3)]
+    klds = [B.kl_divergence_gaussian(*ins) for ins in lv]
+    seq_mask = B.sequence_mask(x_sl, max_len=T, device="cuda")
+    level_masks = [B.sequence_mask((x_sl / s).ceil().int(), max_len=T // s, device="cuda") for s in ostr]
+    loss, elbo, logp, kld, kld_l = B.cwvae_compute_elbo(self, cu(g["y"]).unsqueeze(-1), seq_mask, level_masks, x_sl,
+                                                        B.DMoLParams(raw, K, 1, -7.0), klds, float(g["beta"]),
+                                                        float(g["free_nats"]))
+    loss.backward()
+    assert elbo.dtype == torch.float32 and loss.dtype == torch.float32  # clockwork_vae uses bool masks
+    np.testing.assert_allclose(loss.item(), g["loss64"], rtol=1e-6)
+    np.testing.assert_allclose(elbo.detach().cpu().numpy(), g["elbo64"], rtol=1e-6)
+    np.testing.assert_allclose(kld.detach().cpu().numpy(), g["kl64"], rtol=2e-6)
+    for l in range(3):
+        np.testing.assert_allclose(kld_l[l].detach().cpu().numpy(), g[f"kl_l{l}_64"], rtol=2e-6)
+        for t, n in zip(lv[l], ("mu_q", "sd_q", "mu_p", "sd_p")):
+            ref = g[f"g_{n}_{l}_64"]
+            np.testing.assert_allclose(t.grad.cpu().numpy(), ref, rtol=RTOL, atol=RTOL * 1e-2 * np.abs(ref).max())
+    _check_dmol_grads_fused(raw.grad.cpu().numpy(), g, K)
+
+
+def test_stcn_compute_loss(B):
+    g = load_golden("elbo_stcn")
+    K, nb, n = int(g["K"]), int(g["num_bins"]), int(g["n_latents"])
+    self = SimpleNamespace(likelihood_module=B.DiscretizedLogisticMixtureDense(3 * K, 1, K, nb),
+                           n_stack_frames=int(g["n_stack_frames"]), top_down=True, n_latents=n)
+    raw = cu(g["raw"]).requires_grad_(True)
+    lv = [[cu(g[f"{nm}_{l}"]).requires_grad_(True) for nm in ("mu_q", "sd_q", "mu_p", "sd_p")] for l in range(n)]
+    mu_q, sd_q, mu_p, sd_p = ([ins[i] for ins in lv] for i in range(4))
+    loss, elbo, logp, kld, klds = B.stcn_compute_loss(self, cu(g["y"]).unsqueeze(-1), torch.as_tensor(g["x_sl"]),
+                                                      B.DMoLParams(raw, K, 1, -7.0), mu_p, sd_p, mu_q, sd_q, None,
+                                                      float(g["free_nats"]), float(g["beta"]))
+    loss.backward()
+    assert elbo.dtype == torch.float32
+    np.testing.assert_allclose(loss.item(), g["loss64"], rtol=1e-6)
+    np.testing.assert_allclose(elbo.detach().cpu().numpy(), g["elbo64"], rtol=1e-6)
+    for l in range(n):
+        np.testing.assert_allclose(klds[l].detach().cpu().numpy(), g[f"kl_l{l}_64"], rtol=2e-6)
+        for t, nm in zip(lv[l], ("mu_q", "sd_q", "mu_p", "sd_p")):
+            ref = g[f"g_{nm}_{l}_64"]
+            np.testing.assert_allclose(t.grad.cpu().numpy(), ref, rtol=RTOL, atol=RTOL * 1e-2 * np.abs(ref).max())
+    _check_dmol_grads_fused(raw.grad.cpu().numpy(), g, K)
+
+
+def test_wavenet_compute_loss(B):
+    g = load_golden("elbo_wavenet")
+    K, nb = int(g["K"]), int(g["num_bins"])
+    self = SimpleNamespace(likelihood=B.DiscretizedLogisticMixtureDense(3 * K, 1, K, nb))
+    raw = cu(g["raw"]).requires_grad_(True)
+    x_sl = torch.as_tensor(g["x_sl"])
+    loss, logp, twise = B.wavenet_compute_loss(self, cu(g["y"]).unsqueeze(-1), x_sl, B.DMoLParams(raw, K, 1, -7.0))
+    loss.backward()
+    assert logp.dtype == torch.float32 and twise.shape == g["logp_twise64"].shape
+    np.testing.assert_allclose(loss.item(), g["loss64"], rtol=1e-6)
+    np.testing.assert_allclose(logp.detach().cpu().numpy(), g["logp64"], rtol=1e-6)
+    assert_values_close(twise.cpu().numpy(), g["logp_twise64"], "log_prob_twise")
+    assert (twise.cpu().numpy()[3, 1:] == 0).all()  # x_sl = 1: everything after the first sample is masked
+    _check_dmol_grads_fused(raw.grad.cpu().numpy(), g, K)
+    np.testing.assert_allclose(B.bits_per_dim(logp, x_sl), float(g["bpd32"]), rtol=1e-6)
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+def test_quantize_bit_exact(bits, B):
+    g = load_golden("quantize")
+    q = B.Quantize(bits=bits).cuda()
+    assert np.array_equal(q.boundaries.cpu().numpy(), g[f"boundaries_{bits}"])
+    pcm = torch.arange(-32768, 32768, dtype=torch.float32) / 32768
+    assert np.array_equal(q(pcm.cuda()).cpu().numpy(), g[f"pcm_idx_{bits}"])
+    assert np.array_equal(q(cu(g["rnd"])).cpu().numpy(), g[f"rnd_idx_{bits}"])
+    assert np.array_equal(q(cu(g[f"boundaries_{bits}"])).cpu().numpy(), g[f"bnd_idx_{bits}"])
+    grid = torch.arange(0, 2 ** bits, dtype=torch.float32) / (2 ** bits - 1) * 2 - 1
+    out = q(grid.cuda())
+    assert out.dtype == torch.int64 and np.array_equal(out.cpu().numpy(), g[f"grid_idx_{bits}"])
+
+
+# ---- edge cases: ragged / empty / unaligned shapes ------------------------------------------------------------------
+@pytest.mark.parametrize("T,K", [(1, 10), (7, 10), (127, 10), (129, 10), (255, 3), (301, 1), (130, 2), (64, 30)])
+def test_ragged_and_unaligned_shapes(T, K, B, O):
+    """Odd T makes row slabs 8- or 4-byte aligned only (the non-TMA path), T < tile and T = tile+1 hit the tail tile;
+    lengths include 0 and T."""
+    rng = np.random.default_rng(T * 31 + K)
+    Bn, nb = 5, 65536
+    x_sl = np.array([T, max(T - 1, 0), T // 2, 1 if T > 1 else 0, 0])
+    if x_sl.sum() == 0:
+        x_sl[0] = T
+    y = (rng.integers(0, nb, (Bn, T)) / (nb - 1) * 2 - 1).astype(np.float32)
+    raw = rng.normal(size=(Bn, T, 3 * K)).astype(np.float32)
+    raw[..., K:2 * K] = y[..., None] + 0.05 * rng.normal(size=(Bn, T, K))
+    raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+    for skip in (False, True):
+        r = cu(raw).requires_grad_(True)
+        out = B.fused_elbo(cu(y), B.DMoLParams(r, K, 1, -7.0), torch.as_tensor(x_sl), (), 1.0, 0.0, num_bins=nb,
+                           want_twise=True, skip_padded=skip)
+        out.loss.backward()
+        ref = O.fused_elbo_value_and_grad(y, raw, x_sl, [], 1.0, K, nb)
+        assert_sums_close(out.loss.item(), ref["loss"], "loss")
+        assert_sums_close(out.log_prob.cpu().numpy(), ref["logp"], "rows")
+        assert_values_close(out.log_prob_twise.cpu().numpy(), ref["lp_twise"], "twise")
+        gabs = np.full(Bn * T, 1.0 / x_sl.sum())
+        assert_grads_close(r.grad.cpu().numpy().reshape(-1, 3 * K), ref["graw"].reshape(-1, 3 * K), K, gabs)
+        m = O.sequence_mask(x_sl, max_len=T)
+        assert (r.grad.cpu().numpy()[~m] == 0).all()  # padded positions get exact zeros
+
+
+def test_offset_view_inputs(B, O):
+    """Parameters that are a non-16-byte-aligned view of a larger buffer (odd float offset)."""
+    rng = np.random.default_rng(5)
+    Bn, T, K, nb = 2, 200, 10, 65536
+    big = torch.zeros(Bn * T * 3 * K + 3, device="cuda")
+    raw_np = rng.normal(size=(Bn, T, 3 * K)).astype(np.float32)
+    raw_np[..., 2 * K:] = raw_np[..., 2 * K:] * 2 - 4
+    view = big[3:].view(Bn, T, 3 * K)
+    view.copy_(cu(raw_np))
+    assert view.data_ptr() % 16 != 0
+    y = (rng.integers(0, nb, (Bn, T)) / (nb - 1) * 2 - 1).astype(np.float32)
+    lik = B.DiscretizedLogisticMixtureDense(3, 1, K, nb)
+    lp = lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(view, K, 1, -7.0))
+    ref, _ = O.dmol_value_and_grad(y.reshape(-1).astype(np.float64), raw_np.reshape(-1, 3 * K).astype(np.float64), K, 1, nb)
+    assert_values_close(lp.cpu().numpy().reshape(-1), ref, "offset view")
+
+
+def test_empty_batch(B):
+    lik = B.DiscretizedLogisticMixtureDense(3, 1, 10, 65536)
+    lp = lik.log_prob(torch.zeros(0, 5, 1, device="cuda"), B.DMoLParams(torch.zeros(0, 5, 30, device="cuda"), 10, 1, -7.0))
+    assert lp.shape == (0, 5)
+    kl = B.kl_divergence_gaussian(*[torch.ones(0, 3, 4, device="cuda")] * 4)
+    assert kl.shape == (0, 3, 4)
+
+
+def test_cpu_tensors_raise(B):
+    lik = B.DiscretizedLogisticMixtureDense(3, 1, 10, 65536)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lik.log_prob(torch.zeros(2, 5, 1), B.DMoLParams(torch.zeros(2, 5, 30), 10, 1, -7.0))
+
+
+def test_out_of_range_targets_are_flagged(B):
+    lik = B.DiscretizedLogisticMixtureDense(3, 1, 10, 65536)
+    y = torch.zeros(2, 5, 1, device="cuda")
+    y[1, 2, 0] = 1.5
+    lik.log_prob(y, B.DMoLParams(torch.zeros(2, 5, 30, device="cuda"), 10, 1, -7.0))
+    with pytest.raises(AssertionError):
+        B.check_input_range()
+    B.check_input_range()  # flag was reset
+
+
+def test_nan_propagates(B):
+    """NaN parameters poison that sample (and, through `* mask`, its utterance sum) like in the reference."""
+    raw = torch.zeros(2, 130, 30, device="cuda")
+    raw[0, 3, 12] = float("nan")
+    out = B.fused_elbo(torch.zeros(2, 130, device="cuda"), B.DMoLParams(raw, 10, 1, -7.0), torch.tensor([130, 130]), (),
+                       num_bins=65536, want_twise=True)
+    tw = out.log_prob_twise.cpu().numpy()
+    assert np.isnan(tw[0, 3]) and np.isfinite(np.delete(tw.reshape(-1), 3)).all()
+    assert np.isnan(out.log_prob[0].item()) and np.isfinite(out.log_prob[1].item())
+
+
+def test_upstream_grad_scale_and_double_backward(B):
+    """loss * c backpropagates c * grads through the early-exit scale kernel (AMP GradScaler path)."""
+    g = load_golden("elbo_srnn_a")
+    K, nb = 10, 65536
+
+    def run(scale):
+        raw = cu(g["raw"]).requires_grad_(True)
+        ins = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+        out = B.fused_elbo(cu(g["y"]), B.DMoLParams(raw, K, 1, -7.0), torch.as_tensor(g["x_sl"]),
+                           [B.KLLevel(*ins, stride=int(g["stride"]))], 0.5, 0.0625, num_bins=nb)
+        (out.loss * scale).backward()
+        return raw.grad, ins[1].grad, out
+
+    g1, k1, out = run(1.0)
+    g3, k3, _ = run(1024.0)
+    torch.testing.assert_close(g3, g1 * 1024.0, rtol=1e-6, atol=0)
+    torch.testing.assert_close(k3, k1 * 1024.0, rtol=1e-6, atol=0)
+    with pytest.raises(RuntimeError, match="backward called twice"):
+        out.loss.backward()
+
+
+def test_no_grad_eval_path(B):
+    g = load_golden("elbo_vrnn_b")
+    raw = cu(g["raw"]).requires_grad_(True)
+    with torch.no_grad():
+        out = B.fused_elbo(cu(g["y"]), B.DMoLParams(raw, 10, 1, -7.0), torch.as_tensor(g["x_sl"]), (), num_bins=65536)
+    assert not out.loss.requires_grad
+    assert_sums_close(out.log_prob.cpu().numpy(), g["logp64"], "eval rows")
+    m = B.elbo_metrics(out)
+    assert math.isclose(m.bpd, -g["logp64"].sum() / math.log(2) / g["x_sl"].sum(), rel_tol=1e-6)
+
+
+def test_autocast_inputs(B):
+    """Under AMP the Linear output arrives in bf16/fp16: it is upcast once, results equal the fp32 call on the rounded
+    parameters."""
+    g = load_golden("dmol_K10_nb65536")
+    raw16 = cu(g["raw"]).to(torch.bfloat16)
+    lik = B.DiscretizedLogisticMixtureDense(3, 1, 10, 65536)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        lp16 = lik.log_prob(cu(g["y"]), B.DMoLParams(raw16, 10, 1, -7.0))
+    lp32 = lik.log_prob(cu(g["y"]), B.DMoLParams(raw16.float(), 10, 1, -7.0))
+    assert lp16.dtype == torch.float32 and torch.equal(lp16, lp32)
+
+
+# ---- full benchmark size: size-independent properties ---------------------------------------------------------------
+def test_full_size_properties(B, O):
+    """BASELINE config 5 (B=256, T=16000, K=10): determinism, twise/row-sum consistency, component-permutation
+    invariance, gradient identities, and a row subset against the oracle."""
+    torch.manual_seed(1234)
+    Bn, T, K, nb, S, Z = 256, 16000, 10, 65536, 64, 64
+    dev = "cuda"
+    y = (torch.randint(0, nb, (Bn, T), device=dev).float() / (nb - 1) * 2 - 1)
+    raw = torch.randn(Bn, T, 3 * K, device=dev)
+    raw[..., K:2 * K] = y.unsqueeze(-1) + 0.1 * torch.randn(Bn, T, K, device=dev)
+    raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+    x_sl = (T * (0.5 + 0.5 * torch.rand(Bn))).long()
+    x_sl[0] = T
+    Tz = T // S
+    kl = [torch.randn(Bn, Tz, Z, device=dev), torch.nn.functional.softplus(torch.randn(Bn, Tz, Z, device=dev)) + 1e-3,
+          torch.randn(Bn, Tz, Z, device=dev), torch.nn.functional.softplus(torch.randn(Bn, Tz, Z, device=dev)) + 1e-3]
+
+    def run(raw_in, kl_in):
+        r = raw_in.clone().requires_grad_(True)
+        k = [t.clone().requires_grad_(True) for t in kl_in]
+        out = B.fused_elbo(y, B.DMoLParams(r, K, 1, -7.0), x_sl, [B.KLLevel(*k, stride=S)], 0.5, 0.0625, num_bins=nb,
+                           want_twise=True)
+        out.loss.backward()
+        return out, r.grad, [t.grad for t in k]
+
+    out1, g1, kg1 = run(raw, kl)
+    out2, g2, kg2 = run(raw, kl)
+    # (1) deterministic: bit-identical run to run (no atomics)
+    assert torch.equal(out1.elbo, out2.elbo) and torch.equal(g1, g2) and torch.equal(out1.loss, out2.loss)
+    # (2) per-sample values are consistent with the per-utterance sums, and masked positions are zero
+    tw = out1.log_prob_twise.double()
+    torch.testing.assert_close(tw.sum(1), out1.log_prob, rtol=1e-9, atol=0)
+    mask = torch.arange(T, device=dev)[None] < x_sl.to(dev)[:, None]
+    assert (tw[~mask] == 0).all() and (g1[~mask] == 0).all()
+    # (3) loss identity and bpd
+    loss = -(out1.log_prob - 0.5 * out1.kl_fn).sum() / x_sl.sum()
+    torch.testing.assert_close(out1.loss, loss.to(out1.loss.device), rtol=1e-12, atol=0)
+    assert (out1.kl_fn >= out1.kl - 1e-9).all()
+    # (4) softmax identity: d/d logits sums to zero per sample
+    assert g1[..., :K].sum(-1).abs().max().item() < 1e-6 / x_sl.sum().item() * 50
+    # (5) permuting the mixture components permutes the gradients and leaves every value unchanged (to rounding)
+    perm = torch.randperm(K, device=dev)
+    idx = torch.cat([perm, K + perm, 2 * K + perm])
+    out3, g3, _ = run(raw[..., idx].contiguous(), kl)
+    torch.testing.assert_close(out3.log_prob_twise, out1.log_prob_twise, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out3.log_prob, out1.log_prob, rtol=1e-7, atol=0)
+    torch.testing.assert_close(g3, g1[..., idx], rtol=1e-4, atol=1e-6 / x_sl.sum().item())
+    # (6) a row subset against the oracle (fp64), full length
+    rows = [0, 17, 255]
+    ref = O.fused_elbo_value_and_grad(y[rows].cpu().numpy(), raw[rows].cpu().numpy(), x_sl[rows].numpy(),
+                                      [dict(mu_q=kl[0][rows].cpu().numpy(), sd_q=kl[1][rows].cpu().numpy(),
+                                            mu_p=kl[2][rows].cpu().numpy(), sd_p=kl[3][rows].cpu().numpy(), stride=S,
+                                            free_nats=0.0625)], 0.5, K, nb)
+    assert_sums_close(out1.log_prob[rows].cpu().numpy(), ref["logp"], "rows vs oracle")
+    assert_sums_close(out1.kl[rows].cpu().numpy(), ref["kl"], "kl vs oracle", rtol=2e-6)
+    assert_values_close(out1.log_prob_twise[rows].cpu().numpy(), ref["lp_twise"], "twise vs oracle")
+    scale = float(x_sl[rows].sum()) / float(x_sl.sum())  # oracle normalised by the subset's length
+    gabs = np.full(len(rows) * T, 1.0 / float(x_sl.sum()))
+    assert_grads_close(g1[rows].cpu().numpy().reshape(-1, 3 * K), ref["graw"].reshape(-1, 3 * K) * scale, K, gabs)

@@ -1,0 +1,84 @@
+"""Device-only timing of the individual kernels (development aid; bench.py is the contract benchmark)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import blvm_b200  # noqa: E402
+from blvm_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=256)
+    ap.add_argument("--T", type=int, default=16000)
+    ap.add_argument("--Ks", type=int, nargs="+", default=[10])
+    ap.add_argument("--ragged", action="store_true")
+    args = ap.parse_args()
+    dev = "cuda"
+    B, T = args.B, args.T
+    nb = 65536
+    a = torch.empty(1 << 28, device=dev)  # 1 GiB
+    b = torch.empty_like(a)
+    med, best = timeit(lambda: b.copy_(a))
+    print(f"copy 1GiB fp32: {2 * a.numel() * 4 / best / 1e6:.0f} GB/s best, {2 * a.numel() * 4 / med / 1e6:.0f} median")
+    del a, b
+    for K in args.Ks:
+        y = torch.randint(0, nb, (B, T), device=dev).float() / (nb - 1) * 2 - 1
+        raw = torch.randn(B, T, 3 * K, device=dev)
+        raw[..., K:2 * K] = y.unsqueeze(-1) + 0.1 * torch.randn(B, T, K, device=dev)
+        raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+        x_sl = torch.full((B,), T, dtype=torch.int64)
+        if args.ragged:
+            x_sl = (T * (0.5 + 0.5 * torch.rand(B))).long()
+        x_dev = x_sl.to(dev)
+        lp = torch.empty(B, T, device=dev)
+        graw = torch.empty_like(raw)
+        part = torch.empty(B * ((T + 127) // 128), dtype=torch.float64, device=dev)
+        N = B * T
+        g = -1.0 / float(x_sl.sum())
+        med, best = timeit(lambda: ops._dmol_call(y, raw, x_dev, None, g, B, T, K, 1, nb, -7.0, 1, lp, graw, part))
+        byt = N * 4 * (2 + 6 * K)
+        print(f"K={K:2d} dmol fwd+grad: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
+              f"{byt / med / 1e6:7.0f} GB/s algorithmic")
+        med, best = timeit(lambda: ops._dmol_call(y, raw, x_dev, None, 0.0, B, T, K, 1, nb, -7.0, 1, lp, None, part))
+        byt = N * 4 * (2 + 3 * K)
+        print(f"K={K:2d} dmol fwd only: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
+              f"{byt / med / 1e6:7.0f} GB/s algorithmic")
+        del raw, graw
+    # KL fused
+    S, Z = 64, 64
+    Tz = T // S
+    ins = [torch.randn(B, Tz, Z, device=dev), torch.rand(B, Tz, Z, device=dev) + 0.1, torch.randn(B, Tz, Z, device=dev),
+           torch.rand(B, Tz, Z, device=dev) + 0.1]
+    for t in ins:
+        t.requires_grad_(True)
+    y = torch.zeros(B, T, device=dev)
+
+    def kl_step():
+        out = blvm_b200.fused_elbo(None, None, torch.full((B,), T), [blvm_b200.KLLevel(*ins, stride=S)], 0.5, 0.0625, num_bins=2)
+        return out
+
+    med, best = timeit(kl_step)
+    L = B * Tz * Z
+    print(f"KL fused (+finalize, python): {med * 1e3:.1f} us median; {32 * L / med / 1e6:.0f} GB/s algorithmic (L={L})")
+
+
+if __name__ == "__main__":
+    main()
