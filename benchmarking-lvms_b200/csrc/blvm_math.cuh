@@ -69,22 +69,37 @@ BLVM_HD float fast_rcp(float x) {
 #endif
 }
 BLVM_HD float fast_exp(float x) { return fast_ex2(x * kLog2e); }
+// exp(x) with the rounding of the scaled argument compensated: x*log2(e) = p_hi + p_lo exactly (to ~2^-48),
+// exp(x) = 2^p_hi * (1 + ln2 * p_lo).  Leaves only the MUFU.EX2 error (~2^-22.5); 3 extra FMA-pipe ops.
+BLVM_HD float accurate_exp(float x) {
+  constexpr float kLog2eLo = 1.925963033500011e-08f;  // log2(e) - float(log2(e))
+  const float p_hi = x * kLog2e;
+  const float p_lo = fmaf(x, kLog2eLo, fmaf(x, kLog2e, -p_hi));
+  const float e = fast_ex2(p_hi);
+  return fmaf(e, p_lo * kLn2, e);
+}
 BLVM_HD float fast_log(float x) { return fast_lg2(x) * kLn2; }
 
+// (1 - exp(-x)) / x for 0 <= x < 0.25:  1 - x/2 + x^2/6 - x^3/24 + x^4/120 - x^5/720 + x^6/5040
+// (next term x^7/40320 < 1.6e-9 relative at 0.25).  FMA pipe only.
+BLVM_HD float expm1_neg_ratio_small(float x) {
+  float p = 1.0f / 5040.0f;
+  p = fmaf(p, x, -1.0f / 720.0f);
+  p = fmaf(p, x, 1.0f / 120.0f);
+  p = fmaf(p, x, -1.0f / 24.0f);
+  p = fmaf(p, x, 1.0f / 6.0f);
+  p = fmaf(p, x, -0.5f);
+  p = fmaf(p, x, 1.0f);
+  return p;
+}
 // 1 - exp(-x) for x >= 0 without cancellation.
 BLVM_HD float one_minus_exp_neg(float x) {
-  if (x < 0.25f) {
-    // x (1 - x/2 + x^2/6 - x^3/24 + x^4/120 - x^5/720 + x^6/5040); next term x^7/40320 < 1.6e-9 relative at 0.25
-    float p = 1.0f / 5040.0f;
-    p = fmaf(p, x, -1.0f / 720.0f);
-    p = fmaf(p, x, 1.0f / 120.0f);
-    p = fmaf(p, x, -1.0f / 24.0f);
-    p = fmaf(p, x, 1.0f / 6.0f);
-    p = fmaf(p, x, -0.5f);
-    p = fmaf(p, x, 1.0f);
-    return x * p;
-  }
+  if (x < 0.25f) return x * expm1_neg_ratio_small(x);
   return 1.0f - fast_exp(-x);
+}
+// same, when e = exp(-x) is already at hand
+BLVM_HD float one_minus_exp_neg_given(float x, float e) {
+  return (x < 0.25f) ? x * expm1_neg_ratio_small(x) : 1.0f - e;
 }
 
 enum : int { kEdgeNone = 0, kEdgeLower = 1, kEdgeUpper = 2 };
@@ -101,7 +116,7 @@ template <bool GRAD>
 BLVM_HD void dl_component(float y, int edge, float mu, float raw_ls, const DmolConsts& C, float& lp, float& dmu,
                           float& dls) {
   const float ls = (raw_ls < C.log_eps) ? C.log_eps : raw_ls;  // clamp(min): NaN propagates like torch
-  const float inv = fast_ex2(-ls * kLog2e);                    // exp(-log_scale)            :203
+  const float inv = accurate_exp(-ls);                         // exp(-log_scale)            :203
   const float c = y - mu;                                      // centered_y                 :202
   float dm_ = 0.f, du_ = 0.f, dls_direct = 0.f, m_ = 0.f, u_ = 0.f;
 
@@ -145,7 +160,16 @@ BLVM_HD void dl_component(float y, int edge, float mu, float raw_ls, const DmolC
         const float ra = pb * rab, rb = pa * rab;              // 1/(1+ea), 1/(1+eb)
         const float num_sna = (a >= 0.f) ? ea : 1.f;           // numerator of sigmoid(-a)
         const float num_sb = (b >= 0.f) ? 1.f : eb;            // numerator of sigmoid(b)
-        dm_ = num_sna * ra - num_sb * rb;                      // sigmoid(-a) - sigmoid(b)
+        // sigmoid(-a) - sigmoid(b); near the bin centre (m -> 0) the two terms cancel, so use the product form
+        //   sigmoid(-a) - sigmoid(b) = -sgn(m) sigmoid(sgn(m) a) sigmoid(sgn(m) b) (1 - exp(-2|m|))
+        const float am = fabsf(m);
+        if (am < 0.125f) {
+          const float ss = (m >= 0.f) ? (num_sa * num_sb) : (num_sna * num_snb);
+          const float w = ss * ra * rb * (2.f * am) * expm1_neg_ratio_small(2.f * am);
+          dm_ = (m >= 0.f) ? -w : w;
+        } else {
+          dm_ = num_sna * ra - num_sb * rb;
+        }
         du_ = (ea * ra * ra + eb * rb * rb) * fast_rcp(delta); // (s'(a) + s'(b)) / delta
         m_ = m;
         u_ = C.h * inv;
@@ -155,7 +179,7 @@ BLVM_HD void dl_component(float y, int edge, float mu, float raw_ls, const DmolC
       const float e = fast_exp(-fabsf(m));
       lp = -fabsf(m) - ls - 2.f * fast_log(1.f + e) - C.log_half_bins;
       if (GRAD) {
-        const float th = (1.f - e) * fast_rcp(1.f + e);        // tanh(|m|/2)
+        const float th = one_minus_exp_neg_given(fabsf(m), e) * fast_rcp(1.f + e);  // tanh(|m|/2), no cancellation at m -> 0
         dm_ = (m >= 0.f) ? -th : th;                           // 1 - 2 sigmoid(m)
         m_ = m;
         dls_direct = -1.f;
@@ -184,7 +208,10 @@ BLVM_HD KlTerms kl_gaussian_terms(float mu_q, float sd_q, float mu_p, float sd_p
   t.rho_m1 = (sd_q - sd_p) * t.inv_sp;
   t.rho_p1 = (sd_q + sd_p) * t.inv_sp;
   t.q = fmaf(t.rho_m1, t.rho_p1, t.z * t.z);
-  t.kl = 0.5f * t.q - log1pf(t.rho_m1);
+  // log(rho): log1p(rho-1) is exact near rho = 1 (where kl cancels) but ill-conditioned for rho -> 0, where rho-1
+  // rounds at 6e-8 absolute; there the plain quotient is the accurate argument.
+  const float log_rho = (fabsf(t.rho_m1) < 0.5f) ? log1pf(t.rho_m1) : logf(sd_q * t.inv_sp);
+  t.kl = 0.5f * t.q - log_rho;
   return t;
 }
 // d kl / d (mu_q, sd_q, mu_p, sd_p), each multiplied by g.

@@ -57,7 +57,15 @@ def test_dmol_module_golden(case, B, O):
     (lp * cu(g["gout"])).sum().backward()
     B.check_input_range()
     flip = _edge_rows(g, O)
-    ok = ~flip
+    # knife-edge rows: a component whose cdf_delta sits within 1e-5 relative of the 1e-5 threshold (log_likelihoods.py:222).
+    # The reference's two arms differ there by log(nb/(nb-1)) (bin width 2/nb vs 2/(nb-1)), so which side an
+    # implementation lands on is decided by its last ulps; checked separately below.
+    _, delta64 = O.dmol_branches(g["y"].astype(np.float64), g["raw"].astype(np.float64), K, D, nb)
+    knife = (np.abs(delta64 / 1e-5 - 1) < 1e-5).reshape(len(flip), -1).any(-1)
+    ok = ~flip & ~knife
+    if knife.any():
+        d = np.abs(lp.detach().cpu().numpy()[knife] - g["lp64"][knife])
+        assert (d <= math.log(nb / (nb - 1)) + 1e-4).all()
     assert_values_close(lp.detach().cpu().numpy()[ok], g["lp64"][ok], "log-prob vs reference fp64")
     assert_grads_close(raw.grad.cpu().numpy()[ok], g["graw64"][ok], K, np.abs(g["gout"])[ok], "d/d raw vs reference fp64")
     if flip.any():  # fp32 predicates are the reference's: compare those rows with its fp32 run, loosely (see parity.py)
@@ -165,8 +173,11 @@ def test_kl_free_nats_fused_with_ties(B, O):
         assert_sums_close(out.kl.cpu().numpy(), (kl * m).sum((1, 2)), "kl rows")
         assert_sums_close(out.kl_fn.cpu().numpy(), (kl_fn * m).sum((1, 2)), "kl_fn rows", rtol=2e-6)
         assert_sums_close(out.loss.item(), 0.7 * (kl_fn * m).sum() / float(x_sl.sum()), "loss", rtol=2e-6)
+        tie = np.zeros(g["mu_q"].shape, bool)
+        if i == 3:  # an exact tie of the reference's fp32 formula; in fp64 (the oracle here) it is not a tie
+            tie[tuple(g["tie_index"])] = True
         for t, r in zip(ins, grads):
-            np.testing.assert_allclose(t.grad.cpu().numpy(), r, rtol=RTOL, atol=RTOL * 1e-2 * np.abs(r).max())
+            np.testing.assert_allclose(t.grad.cpu().numpy()[~tie], r[~tie], rtol=RTOL, atol=RTOL * 1e-2 * np.abs(r).max())
     # the tie element: gradient is exactly half of the unconstrained one
     i, j, k = g["tie_index"]
     ins = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]

@@ -1,0 +1,126 @@
+"""CPU check of the closed forms the CUDA kernels evaluate: csrc/blvm_math.cuh is compiled for the host (g++, libm in
+place of the MUFU approximations) and compared with the reference's fp64 golden vectors under the same tolerances as
+the GPU parity suite.  Catches algebra / branch / sign errors without a GPU; the last ulps are checked by -m gpu."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from parity import assert_grads_close, assert_values_close
+
+SRC = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+OUT_DIR = os.path.join(ROOT, "tests", "hostsim", "_build")
+LIB = os.path.join(OUT_DIR, "libhostsim.so")
+FP = ctypes.POINTER(ctypes.c_float)
+
+
+@pytest.fixture(scope="module")
+def sim():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I",
+                    os.path.join(ROOT, "benchmarking-lvms_b200", "csrc"), "-o", LIB, SRC], check=True)
+    return ctypes.CDLL(LIB)
+
+
+def P(a):
+    return a.ctypes.data_as(FP)
+
+
+def run_dmol(sim, g, force_generic=0):
+    K, D, nb = int(g["K"]), int(g["D"]), int(g["num_bins"])
+    y = np.ascontiguousarray(g["y"], np.float32)
+    raw = np.ascontiguousarray(g["raw"], np.float32)
+    gout = np.ascontiguousarray(g["gout"], np.float32)
+    N = raw.shape[0]
+    lp = np.empty(N, np.float32)
+    gr = np.empty_like(raw)
+    sim.hostsim_dmol(P(y), P(raw), P(gout), ctypes.c_int64(N), K, D, nb, ctypes.c_float(-7.0), force_generic, P(lp), P(gr))
+    return lp, gr
+
+
+@pytest.mark.parametrize("case", ["dmol_K1_nb256", "dmol_K1_nb65536", "dmol_K2_nb256", "dmol_K2_nb65536", "dmol_K10_nb256",
+                                  "dmol_K10_nb65536", "dmol_K30_nb256", "dmol_K30_nb65536", "dmol_K10_nb65536_D2"])
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_dmol_closed_forms(sim, case, force_generic):
+    g = load_golden(case)
+    lp, gr = run_dmol(sim, g, force_generic)
+    assert_values_close(lp, g["lp64"], "log-prob")
+    assert_grads_close(gr, g["graw64"], int(g["K"]), np.abs(g["gout"]), "grads")
+
+
+def test_dmol_non_power_of_two_bins(sim):
+    """num_bins = 255: the y-edge thresholds are not exact in fp32, so the predicates follow the reference's fp32
+    compare (rows where the fp64 run decides differently are compared with its fp32 run), and one forced row sits on
+    the cdf_delta threshold where the reference's two arms differ by log(nb/(nb-1))."""
+    from oracle import blvm_oracle as O
+    g = load_golden("dmol_K5_nb255")
+    K, nb = 5, 255
+    lp, gr = run_dmol(sim, g)
+    y32 = g["y"].astype(np.float32)
+    e32 = np.where(y32 > np.float32(1 - 2 / nb), 2, np.where(y32 < np.float32(2 / nb - 1), 1, 0))
+    y64 = y32.astype(np.float64)
+    e64 = np.where(y64 > 1 - 2 / nb, 2, np.where(y64 < 2 / nb - 1, 1, 0))
+    flip = (e32 != e64).any(-1)
+    assert flip.sum() >= 4
+    _, delta64 = O.dmol_branches(y64, g["raw"].astype(np.float64), K, 1, nb)
+    knife = (np.abs(delta64 / 1e-5 - 1) < 1e-5).reshape(len(flip), -1).any(-1)
+    ok = ~flip & ~knife
+    assert_values_close(lp[ok], g["lp64"][ok], "log-prob")
+    assert_grads_close(gr[ok], g["graw64"][ok], K, np.abs(g["gout"])[ok], "grads")
+    np.testing.assert_allclose(lp[flip], g["lp32"][flip], rtol=2e-3)   # bit-exact predicate, fp32-noisy reference value
+    assert (np.abs(lp[knife] - g["lp64"][knife]) <= np.log(nb / (nb - 1)) + 1e-4).all()
+
+
+def test_dmol_small_m_gradients_do_not_cancel(sim):
+    """y within 1e-4 scale units of a component mean: d/d loc ~ -inv * m / 2 must keep relative accuracy."""
+    rng = np.random.default_rng(0)
+    N, K = 4096, 1
+    for nb in (256, 65536):
+        y = (rng.integers(0, nb, N) / (nb - 1) * 2 - 1).astype(np.float32).clip(-0.99, 0.99)
+        ls = rng.uniform(-6.5, -1.0, N).astype(np.float32)
+        mu = (y + np.exp(ls) * rng.uniform(-3e-3, 3e-3, N)).astype(np.float32)
+        raw = np.stack([np.zeros(N, np.float32), mu, ls], -1)
+        g = dict(K=1, D=1, num_bins=nb, y=y[:, None], raw=raw, gout=np.ones(N, np.float32))
+        _, gr = run_dmol(sim, g)
+        from oracle import blvm_oracle as O
+        _, ref = O.dmol_value_and_grad(y.astype(np.float64), raw.astype(np.float64), 1, 1, nb)
+        m = (y.astype(np.float64) - mu) * np.exp(-ls.astype(np.float64))
+        sel = np.abs(m) > 1e-5  # below that the fp32 rounding of (y - mu) itself dominates
+        rel = np.abs(gr[sel, 1] - ref[sel, 1]) / np.abs(ref[sel, 1])
+        assert rel.max() < 5e-5, rel.max()
+
+
+def test_dl_closed_forms(sim):
+    for nb in (256, 65536):
+        g = load_golden(f"dl_nb{nb}")
+        N = g["raw"].shape[0]
+        lp = np.empty(N, np.float32)
+        gr = np.empty((N, 2), np.float32)
+        sim.hostsim_dl(P(np.ascontiguousarray(g["y"])), P(np.ascontiguousarray(g["raw"])), P(np.ascontiguousarray(g["gout"])),
+                       ctypes.c_int64(N), nb, ctypes.c_float(-7.0), P(lp), P(gr))
+        assert_values_close(lp, g["lp64"], "DL log-prob")
+        assert_grads_close(gr, g["graw64"], 1, np.abs(g["gout"]), "DL grads")
+
+
+def test_kl_closed_forms(sim):
+    g = load_golden("kl_free_nats")
+    ins = [np.ascontiguousarray(g[n]) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+    n = ins[0].size
+    Z = ins[0].shape[-1]
+    gout = np.ascontiguousarray(g["gout"])
+    for i, fn in enumerate(g["free_nats"]):
+        outs = [np.empty(ins[0].shape, np.float32) for _ in range(6)]
+        sim.hostsim_kl(*[P(a) for a in ins], P(gout), ctypes.c_int64(n), ctypes.c_float(fn / Z), int(fn != 0),
+                       *[P(o) for o in outs])
+        assert_values_close(outs[0], g["kl64"], "kl", atol=1e-6)
+        tie = np.zeros(ins[0].shape, bool)
+        if i == 3:
+            tie[tuple(g["tie_index"])] = True  # an exact fp32 tie of the reference's formula; not a tie in fp64
+        assert_values_close(outs[1][~tie], g[f"klfn64_{i}"][~tie], "kl_fn", atol=1e-6)
+        for o, nme in zip(outs[2:], ("mu_q", "sd_q", "mu_p", "sd_p")):
+            ref = g[f"g_{nme}64_{i}"]
+            np.testing.assert_allclose(o[~tie], ref[~tie], rtol=1e-5, atol=1e-7 * np.abs(ref).max(), err_msg=nme)
+    assert (outs[0][0, 0, :4] == 0).all()  # q == p gives exactly 0
