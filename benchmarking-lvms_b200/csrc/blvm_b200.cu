@@ -40,7 +40,8 @@ int check_launch(const char* what) {
 DmolConsts make_consts(int num_bins, float log_epsilon) {
   DmolConsts C;
   C.h = static_cast<float>(1.0 / (num_bins - 1));
-  C.two_h = static_cast<float>(2.0 / (num_bins - 1));
+  C.log_two_h = static_cast<float>(log(2.0 / (num_bins - 1)));
+  C.log_delta_thresh = static_cast<float>(log(static_cast<double>(kDeltaThresh)));
   C.lo_thresh = static_cast<float>(2.0 / num_bins - 1.0);
   C.hi_thresh = static_cast<float>(1.0 - 2.0 / num_bins);
   C.log_half_bins = static_cast<float>(log(num_bins / 2.0));

@@ -34,7 +34,8 @@ constexpr float kDeltaFloor = 1e-10f;   // log_likelihoods.py:222  `clamp(cdf_de
 // fp32 tensor (blvm_b200.cu: make_consts).
 struct DmolConsts {
   float h;              // 1/(num_bins-1)            log_likelihoods.py:206,208
-  float two_h;          // 2/(num_bins-1)
+  float log_two_h;      // log(2/(num_bins-1))
+  float log_delta_thresh;  // log(float(1e-5))
   float lo_thresh;      // 2/num_bins - 1            log_likelihoods.py:226   y <  lo  -> lower edge bin
   float hi_thresh;      // 1 - 2/num_bins            log_likelihoods.py:227   y >  hi  -> upper edge bin
   float log_half_bins;  // log(num_bins/2)           log_likelihoods.py:222
@@ -112,82 +113,93 @@ BLVM_HD int dmol_edge(float y, const DmolConsts& C) {
 
 // One (sample, component): log-prob of the discretized logistic and, if GRAD, d lp/d loc and d lp/d raw_log_scale
 // (the clamp's pass-at-equality gate included).
+//
+// With m = (y-mu)/s (mid_in), u = h/s (half bin width in scale units), a = m+u, b = m-u and E = exp(-|m|):
+//   cdf_delta = sigmoid(a) - sigmoid(b) = sinh(u) / (cosh(m) + cosh(u)) = 2 E sinh(u) / D,
+//   D = (1+E)^2 + E w,  w = 2 cosh(u) - 2,
+// hence  log cdf_delta = [-|m| - ls - 2 log(1+E)] + log(2h) + log(sinh(u)/u) - log1p(E w/(1+E)^2)
+// while the reference's fallback arm is  [-|m| - ls - 2 log(1+E)] - log(nb/2):  both arms share the bracket (one EX2,
+// one LG2, one RCP) and differ by O(u^2) corrections, so the `cdf_delta > 1e-5` selection is a branch-free select and
+// nothing cancels.  Derivatives:  d/dm = -sgn(m) (1-E^2)/D,  d/du = coth(u) - cdf_delta  (DESIGN.md §4).
+// u < 1/8 (always true for 16-bit audio: u <= 0.0167) uses short series for the u-terms; larger u (8-bit data with
+// small scales) evaluates them exactly from q = exp(-u).
+constexpr float kSmallU = 0.125f;
+
 template <bool GRAD>
 BLVM_HD void dl_component(float y, int edge, float mu, float raw_ls, const DmolConsts& C, float& lp, float& dmu,
                           float& dls) {
   const float ls = (raw_ls < C.log_eps) ? C.log_eps : raw_ls;  // clamp(min): NaN propagates like torch
   const float inv = accurate_exp(-ls);                         // exp(-log_scale)            :203
   const float c = y - mu;                                      // centered_y                 :202
-  float dm_ = 0.f, du_ = 0.f, dls_direct = 0.f, m_ = 0.f, u_ = 0.f;
 
-  if (edge == kEdgeLower) {
-    // lp = plus_in - softplus(plus_in) = log sigmoid(a)                                    :213
-    const float a = inv * (c + C.h);
-    const float e = fast_exp(-fabsf(a));
-    lp = fminf(a, 0.f) - fast_log(1.f + e);
-    if (GRAD) {
-      const float r = fast_rcp(1.f + e);
-      const float da = ((a >= 0.f) ? e : 1.f) * r;  // 1 - sigmoid(a)
-      dmu = -inv * da;
-      dls = -a * da;
-    }
-  } else if (edge == kEdgeUpper) {
-    // lp = -softplus(minus_in) = log(1 - sigmoid(b))                                       :216
-    const float b = inv * (c - C.h);
-    const float e = fast_exp(-fabsf(b));
-    lp = -fmaxf(b, 0.f) - fast_log(1.f + e);
-    if (GRAD) {
-      const float r = fast_rcp(1.f + e);
-      const float db = -((b >= 0.f) ? 1.f : e) * r;  // -sigmoid(b)
-      dmu = -inv * db;
-      dls = -b * db;
-    }
-  } else {
-    const float a = inv * (c + C.h);   // plus_in   :206
-    const float b = inv * (c - C.h);   // minus_in  :208
-    const float m = inv * c;           // mid_in    :219
-    const float ea = fast_exp(-fabsf(a));
-    const float eb = fast_exp(-fabsf(b));
-    const float pa = 1.f + ea, pb = 1.f + eb;
-    const float rab = fast_rcp(pa * pb);
-    const float t = one_minus_exp_neg(C.two_h * inv);          // 1 - exp(-(a - b))
-    const float num_sa = (a >= 0.f) ? 1.f : ea;                // numerator of sigmoid(a)
-    const float num_snb = (b >= 0.f) ? eb : 1.f;               // numerator of sigmoid(-b)
-    const float delta = t * num_sa * num_snb * rab;            // cdf_delta  :210, cancellation-free
-    if (delta > kDeltaThresh) {
-      lp = fast_log(fmaxf(delta, kDeltaFloor));                // :222 first arm
+  if (edge != kEdgeNone) {  // y in the first / last bin: rare (clipped samples), the only divergent branch
+    if (edge == kEdgeLower) {
+      // lp = plus_in - softplus(plus_in) = log sigmoid(a)                                  :213
+      const float a = inv * (c + C.h);
+      const float e = fast_exp(-fabsf(a));
+      lp = fminf(a, 0.f) - fast_log(1.f + e);
       if (GRAD) {
-        const float ra = pb * rab, rb = pa * rab;              // 1/(1+ea), 1/(1+eb)
-        const float num_sna = (a >= 0.f) ? ea : 1.f;           // numerator of sigmoid(-a)
-        const float num_sb = (b >= 0.f) ? 1.f : eb;            // numerator of sigmoid(b)
-        // sigmoid(-a) - sigmoid(b); near the bin centre (m -> 0) the two terms cancel, so use the product form
-        //   sigmoid(-a) - sigmoid(b) = -sgn(m) sigmoid(sgn(m) a) sigmoid(sgn(m) b) (1 - exp(-2|m|))
-        const float am = fabsf(m);
-        if (am < 0.125f) {
-          const float ss = (m >= 0.f) ? (num_sa * num_sb) : (num_sna * num_snb);
-          const float w = ss * ra * rb * (2.f * am) * expm1_neg_ratio_small(2.f * am);
-          dm_ = (m >= 0.f) ? -w : w;
-        } else {
-          dm_ = num_sna * ra - num_sb * rb;
-        }
-        du_ = (ea * ra * ra + eb * rb * rb) * fast_rcp(delta); // (s'(a) + s'(b)) / delta
-        m_ = m;
-        u_ = C.h * inv;
+        const float da = ((a >= 0.f) ? e : 1.f) * fast_rcp(1.f + e);  // 1 - sigmoid(a)
+        dmu = -inv * da;
+        dls = -a * da;
       }
     } else {
-      // log_pdf_mid - log(num_bins/2) = m - ls - 2 softplus(m) - log(nb/2)                 :220-222 second arm
-      const float e = fast_exp(-fabsf(m));
-      lp = -fabsf(m) - ls - 2.f * fast_log(1.f + e) - C.log_half_bins;
+      // lp = -softplus(minus_in) = log(1 - sigmoid(b))                                     :216
+      const float b = inv * (c - C.h);
+      const float e = fast_exp(-fabsf(b));
+      lp = -fmaxf(b, 0.f) - fast_log(1.f + e);
       if (GRAD) {
-        const float th = one_minus_exp_neg_given(fabsf(m), e) * fast_rcp(1.f + e);  // tanh(|m|/2), no cancellation at m -> 0
-        dm_ = (m >= 0.f) ? -th : th;                           // 1 - 2 sigmoid(m)
-        m_ = m;
-        dls_direct = -1.f;
+        const float db = -((b >= 0.f) ? 1.f : e) * fast_rcp(1.f + e);  // -sigmoid(b)
+        dmu = -inv * db;
+        dls = -b * db;
       }
     }
+  } else {
+    const float m = inv * c;                                   // mid_in                     :219
+    const float u = C.h * inv;
+    const float am = fabsf(m);
+    const float E = fast_ex2(-am * kLog2e);
+    const float p1 = 1.f + E;
+    const float r = fast_rcp(p1);
+    const float common = (-am - ls) - (2.f * kLn2) * fast_lg2(p1);   // log_pdf_mid = m - ls - 2 softplus(m)  :220
+    const float lp_fb = common - C.log_half_bins;                    // second arm of :221-223
+    // tanh(|m|/2) = (1-E)/(1+E); odd series below 1/8 so that the bin-centre gradient does not cancel
+    const float hx = 0.5f * am, hx2 = hx * hx;
+    const float th_series = hx * fmaf(hx2, fmaf(hx2, 2.0f / 15.0f, -1.0f / 3.0f), 1.0f);
+    const float th = (am < 0.25f) ? th_series : (1.f - E) * r;
+    const float dm_fb = copysignf(th, -m);                           // 1 - 2 sigmoid(m)
+    float lp_d, dm_d = 0.f, udu = 0.f;
+    bool big;
+    if (u < kSmallU) {
+      const float u2 = u * u;
+      const float er2 = E * r * r;
+      const float eps = er2 * (u2 * fmaf(u2, 1.0f / 12.0f, 1.0f));                  // E w / (1+E)^2
+      const float corr = u2 * fmaf(u2, -1.0f / 180.0f, 1.0f / 6.0f) - eps * fmaf(eps, -0.5f, 1.0f);
+      lp_d = common + (C.log_two_h + corr);                          // log cdf_delta, first arm of :221-223
+      big = lp_d > C.log_delta_thresh;                               // cdf_delta > 1e-5
+      if (GRAD) {
+        const float inv1pe = fmaf(eps, eps - 1.0f, 1.0f);            // 1/(1+eps)
+        dm_d = dm_fb * inv1pe;
+        const float udelta = 2.0f * u2 * er2 * fmaf(u2, 1.0f / 6.0f, 1.0f) * inv1pe;  // u * cdf_delta
+        udu = fmaf(u2, fmaf(u2, -1.0f / 45.0f, 1.0f / 3.0f), 1.0f) - udelta;          // u coth(u) - u cdf_delta
+      }
+    } else {
+      const float q = fast_ex2(-u * kLog2e);                         // exp(-u); everything below is overflow-free
+      const float omq = 1.f - q, omq2 = omq * (1.f + q);
+      const float rdq = fast_rcp(fmaf(q * p1, p1, E * omq * omq));   // q / D
+      const float delta = E * omq2 * rdq;                            // cdf_delta                  :210
+      big = delta > kDeltaThresh;
+      lp_d = kLn2 * fast_lg2(fmaxf(delta, kDeltaFloor));
+      if (GRAD) {
+        dm_d = dm_fb * (p1 * p1 * q * rdq);                          // -sgn(m) (1-E^2)/D
+        udu = u * (fmaf(q, q, 1.f) * fast_rcp(omq2) - delta);        // u (coth(u) - cdf_delta)
+      }
+    }
+    lp = big ? lp_d : lp_fb;
     if (GRAD) {
-      dmu = -inv * dm_;
-      dls = -(m_ * dm_ + u_ * du_) + dls_direct;
+      const float dm = big ? dm_d : dm_fb;
+      dmu = -inv * dm;
+      dls = big ? -fmaf(m, dm_d, udu) : fmaf(-m, dm_fb, -1.0f);
     }
   }
   if (GRAD) {

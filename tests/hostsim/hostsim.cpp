@@ -11,7 +11,8 @@ using namespace blvm;
 static DmolConsts make_consts(int num_bins, float log_eps) {
   DmolConsts C;
   C.h = (float)(1.0 / (num_bins - 1));
-  C.two_h = (float)(2.0 / (num_bins - 1));
+  C.log_two_h = (float)std::log(2.0 / (num_bins - 1));
+  C.log_delta_thresh = (float)std::log((double)kDeltaThresh);
   C.lo_thresh = (float)(2.0 / num_bins - 1.0);
   C.hi_thresh = (float)(1.0 - 2.0 / num_bins);
   C.log_half_bins = (float)std::log(num_bins / 2.0);
