@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Contract benchmark: waveform samples/s of one DMoL+KL ELBO forward+backward step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--T 16000] [--K 10] [--ragged]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload = BASELINE.json configs[4] ("standalone DMoL+KL ELBO kernel sweep", the configuration the metric
+"DMoL+KL ELBO fwd+bwd at 1/2/4/8 B200; % HBM roofline" is quoted on) at its first grid point: per GPU 256 utterances x
+16000 samples, DMoL K=10, 16-bit bins, one latent layer of stride 64 / width 64 (SRNN-like), beta 0.5, free nats 1/16.
+Weak scaling: every rank owns its own 256 utterances; the only collective is the all-reduce of the scalar sums.
+
+One JSON line on stdout (rank 0).  `value` times K steps with inputs resident in HBM (CUDA events, max over ranks);
+`e2e` times the same step through the public API from pinned HOST buffers (H2D of every input + D2H of the result
+inside the timed region); `roofline` is the DMoL kernel alone (CUDA events over K launches) against the measured HBM
+copy peak; `cpu_baseline` is the C port of the reference path (oracle/blvm_oracle.c) on the host cores.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "waveform samples/sec, DMoL+KL ELBO fwd+bwd"
+UNIT = "samples/s"
+NUM_BINS = 65536
+BETA, FREE_NATS = 0.5, 0.0625
+STRIDE, ZDIM = 64, 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--B", type=int, default=256, help="utterances per GPU")
+    ap.add_argument("--T", type=int, default=16000, help="samples per utterance (config 5 sweep: 16000..128000)")
+    ap.add_argument("--K", type=int, default=10, help="mixture components (config 5 sweep: 1/10/30)")
+    ap.add_argument("--ragged", action="store_true", help="x_sl ~ T*U(0.5,1) instead of full length")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph in the `value` region")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": f"config5: standalone DMoL+KL ELBO, per GPU {a.B} utterances x {a.T} samples, DMoL K={a.K}, "
+                    f"num_bins={NUM_BINS}, 1 latent layer stride {STRIDE} width {ZDIM}, beta {BETA}, free_nats {FREE_NATS}",
+        "utterances_per_gpu": a.B, "samples_per_utterance": a.T, "num_mix": a.K, "num_bins": NUM_BINS,
+        "latent_stride": STRIDE, "latent_width": ZDIM, "ragged": bool(a.ragged),
+        "global_samples_per_step": a.B * a.T * n_gpus, "parallelism": f"dp{n_gpus} (utterance sharding)",
+        "l2": "inputs+outputs ~%.2f GB per step per GPU, larger than the 126 MB L2 (no flush needed)"
+              % ((a.B * a.T * 4 * (2 + 6 * a.K) + 32 * a.B * (a.T // STRIDE) * ZDIM) / 1e9),
+    }
+
+
+def synth_numpy(B, T, K, seed, ragged):
+    """Synthetic inputs: y on the rescaled 16-bit grid, raw ~ N(0,1) with locs near y and log-scales
+    *2-4 (straddles the -7 clamp and the cdf_delta threshold), KL inputs mu ~ N(0,1), sd = softplus(N(0,1)) + 1e-6."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    y = (rng.integers(0, NUM_BINS, (B, T)).astype(np.float32) / np.float32(NUM_BINS - 1) * 2 - 1).astype(np.float32)
+    raw = rng.standard_normal((B, T, 3 * K), dtype=np.float32)
+    raw[..., K:2 * K] = y[..., None] + 0.1 * raw[..., K:2 * K]
+    raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+    Tz = T // STRIDE
+    kl = [rng.standard_normal((B, Tz, ZDIM), dtype=np.float32) for _ in range(4)]
+    for i in (1, 3):
+        kl[i] = (np.log1p(np.exp(kl[i])) + 1e-6).astype(np.float32)
+    x_sl = np.full(B, T, np.int64)
+    if ragged:
+        x_sl = (T * rng.uniform(0.5, 1.0, B)).astype(np.int64)
+    return y, raw, kl, x_sl
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the C port of the reference path on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_port_throughput(a, steps, warmup, target_step_s=1.5):
+    import numpy as np
+    from oracle import c_oracle as C
+    cores = C.num_threads()
+    # calibrate on a few utterances, then size the sample so that one step takes ~target_step_s
+    rows0 = max(1, min(a.B, cores))
+    y, raw, kl, x_sl = synth_numpy(rows0, a.T, a.K, 99, a.ragged)
+    lv = [dict(mu_q=kl[0], sd_q=kl[1], mu_p=kl[2], sd_p=kl[3], stride=STRIDE, free_nats=FREE_NATS)]
+    C.elbo_step(y, raw, x_sl, lv, BETA, a.K, NUM_BINS)
+    t0 = time.perf_counter()
+    C.elbo_step(y, raw, x_sl, lv, BETA, a.K, NUM_BINS)
+    per_row = (time.perf_counter() - t0) / rows0
+    rows = int(max(rows0, min(a.B, target_step_s / max(per_row, 1e-9))))
+    rows = max(cores, rows - rows % cores) if rows >= cores else rows
+    y, raw, kl, x_sl = synth_numpy(rows, a.T, a.K, 100, a.ragged)
+    lv = [dict(mu_q=kl[0], sd_q=kl[1], mu_p=kl[2], sd_p=kl[3], stride=STRIDE, free_nats=FREE_NATS)]
+    for _ in range(warmup):
+        C.elbo_step(y, raw, x_sl, lv, BETA, a.K, NUM_BINS)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        C.elbo_step(y, raw, x_sl, lv, BETA, a.K, NUM_BINS)
+        ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    n = float(x_sl.sum())
+    sample = (f"{rows} of {a.B} utterances x {a.T} samples (same generator), fp32, {steps} timed steps after {warmup} "
+              f"warm-up, C port of the reference path (oracle/blvm_oracle.c: fused loop, closed-form backward), OpenMP")
+    return dict(value=n / t, unit=UNIT, cores=cores, kind="port", sample=sample), t
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, a.steps), max(0, a.warmup)
+    budget = 150.0  # seconds for the whole arm
+    base, t = cpu_port_throughput(a, steps, warmup, target_step_s=min(2.0, budget / (steps + warmup + 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus), "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python/PyTorch and does not exist on the GPU box; this arm times the C port of "
+                "its path (pinned against the reference's golden vectors) on all host threads",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clocks, reasons, mx, power = [], set(), None, []
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    clocks.append(float(f[1]))
+                    mx = float(f[2])
+                    power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if clocks:
+            busy = [c for c, p in zip(clocks, power) if p >= 0.5 * max(power)] or clocks
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(clocks),
+                       power_w_max=max(power))
+        return out
+
+
+def run_gpu_arm(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import blvm_b200
+    from blvm_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a GPU (blvm_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    B, T, K = a.B, a.T, a.K
+    Tz = T // STRIDE
+
+    # ---- synthetic inputs: pinned host copies (e2e arm) and device-resident copies (value arm) -----------------------
+    y_np, raw_np, kl_np, x_sl_np = synth_numpy(B, T, K, 1234 + rank, a.ragged)
+    x_sl = torch.from_numpy(x_sl_np)
+    host = dict(y=torch.from_numpy(y_np).pin_memory(), raw=torch.from_numpy(raw_np).pin_memory(),
+                kl=[torch.from_numpy(t).pin_memory() for t in kl_np])
+    y_d = host["y"].to(dev)
+    raw_d = host["raw"].to(dev).requires_grad_(True)
+    kl_d = [t.to(dev).requires_grad_(True) for t in host["kl"]]
+    n_valid = float(x_sl.sum())
+    denom = n_valid  # per-rank normaliser; the global loss is recombined from the all-reduced sums
+    params = blvm_b200.DMoLParams(raw_d, K, 1, -7.0)
+
+    def step_device():
+        raw_d.grad = None
+        for t in kl_d:
+            t.grad = None
+        out = blvm_b200.fused_elbo(y_d, params, x_sl, [blvm_b200.KLLevel(*kl_d, stride=STRIDE)], BETA, FREE_NATS,
+                                   num_bins=NUM_BINS, denom=denom)
+        out.loss.backward()
+        sums = out.sums
+        if world > 1:
+            sums = blvm_b200.all_reduce_sums(sums)   # the path's only exchange: 5 fp64 scalars over NCCL/NVLink
+        return sums
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    runner = step_device
+    if a.graph:
+        for _ in range(3):
+            step_device()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            static_sums = step_device()
+        runner = g.replay
+
+    for _ in range(max(a.warmup, 3)):
+        runner()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(a.steps):
+        runner()
+    e1.record()
+    sync_all()
+    launches = ops.launch_count() if not a.graph else None
+    ms_total = e0.elapsed_time(e1)
+
+    # ---- the dominant kernel alone: K launches between two events on the launching stream ---------------------------
+    lp_chunks = (T + 127) // 128
+    part = torch.empty(B * lp_chunks, dtype=torch.float64, device=dev)
+    graw = torch.empty_like(raw_d)
+    x_dev = x_sl.to(dev)
+    raw_plain = raw_d.detach()
+
+    def dmol_only():
+        ops._dmol_call(y_d, raw_plain, x_dev, None, -1.0 / denom, B, T, K, 1, NUM_BINS, -7.0, 1, None, graw, part)
+
+    for _ in range(3):
+        dmol_only()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(a.steps):
+        dmol_only()
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / a.steps
+    clocks = sampler.stop() if rank == 0 else None
+    del graw, part
+
+    # ---- e2e: the public API from pinned host buffers, H2D + D2H inside the timed region -----------------------------
+    e2e = None
+    if not a.no_e2e:
+        h2d = sum(t.numel() * t.element_size() for t in [host["y"], host["raw"], *host["kl"]]) + x_sl.numel() * 8
+        d2h = 8 * 8 + 4 * B * 8
+
+        def step_e2e():
+            y = host["y"].to(dev, non_blocking=True)
+            raw = host["raw"].to(dev, non_blocking=True).requires_grad_(True)
+            kl = [t.to(dev, non_blocking=True).requires_grad_(True) for t in host["kl"]]
+            out = blvm_b200.fused_elbo(y, blvm_b200.DMoLParams(raw, K, 1, -7.0), x_sl, [blvm_b200.KLLevel(*kl, stride=STRIDE)],
+                                       BETA, FREE_NATS, num_bins=NUM_BINS, denom=denom)
+            out.loss.backward()
+            sums = out.sums
+            if world > 1:
+                sums = blvm_b200.all_reduce_sums(sums)
+            return sums.cpu(), torch.stack([out.log_prob, out.kl, out.kl_fn, out.elbo]).cpu()  # D2H (synchronises)
+
+        n_e2e = max(3, min(a.steps, 10))
+        for _ in range(2):
+            step_e2e()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            step_e2e()
+        sync_all()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.item())
+        e2e = {"value": n_valid * n_gpus / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_s * 1e3, "steps": n_e2e}
+
+    # ---- max over ranks, totals --------------------------------------------------------------------------------------
+    tot = torch.tensor([ms_total, kern_ms, n_valid], device=dev, dtype=torch.float64)
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, kern_ms, n_global = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        n_global = n_valid
+    ms_step = ms_total / a.steps
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = B * T * 4 * (2 + 6 * K)
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(f"dmol_fwd_grad_K{K}_B{B}_T{T}", {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": n_global / (ms_step * 1e-3), "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, n_gpus),
+            "roofline": {"bound": "hbm", "kernel": f"dmol_tile_kernel<K={K},128,grad>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": kern_ms * 1e3,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "e2e": e2e, "gpu_launches": launches if launches is not None else "graph replay", "clocks": clocks,
+            "step": "fused_elbo(...).loss.backward() through the Python API" + (" replayed from a CUDA graph" if a.graph else "")
+                    + ("; + 1 NCCL all-reduce of 5 fp64 sums" if world > 1 else ""),
+        }
+        if not a.no_cpu_baseline and n_gpus == 1:
+            try:
+                line["cpu_baseline"], _ = cpu_port_throughput(a, steps=5, warmup=1)
+            except Exception as ex:  # the checker must never take the measurement down
+                line["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()
