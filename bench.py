@@ -37,8 +37,11 @@ STRIDE, ZDIM = 64, 64
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--min-seconds", type=float, default=2.0,
+                    help="the K-step timed region is repeated back to back until this much time has passed (so that "
+                         "nvidia-smi can observe clocks under load); the median repeat is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--B", type=int, default=256, help="utterances per GPU")
     ap.add_argument("--T", type=int, default=16000, help="samples per utterance (config 5 sweep: 16000..128000)")
@@ -218,13 +221,15 @@ def run_gpu_arm(a):
     n_valid = float(x_sl.sum())
     denom = n_valid  # per-rank normaliser; the global loss is recombined from the all-reduced sums
     params = blvm_b200.DMoLParams(raw_d, K, 1, -7.0)
+    x_dev = x_sl.to(dev)            # `value` arm: every input, the lengths included, is resident in HBM
+    lens_dev = blvm_b200.level_lengths(x_dev, STRIDE)
 
     def step_device():
         raw_d.grad = None
         for t in kl_d:
             t.grad = None
-        out = blvm_b200.fused_elbo(y_d, params, x_sl, [blvm_b200.KLLevel(*kl_d, stride=STRIDE)], BETA, FREE_NATS,
-                                   num_bins=NUM_BINS, denom=denom)
+        out = blvm_b200.fused_elbo(y_d, params, x_sl, [blvm_b200.KLLevel(*kl_d, lens=lens_dev)], BETA, FREE_NATS,
+                                   num_bins=NUM_BINS, denom=denom, x_sl_device=x_dev)
         out.loss.backward()
         sums = out.sums
         if world > 1:
@@ -247,28 +252,38 @@ def run_gpu_arm(a):
             static_sums = step_device()
         runner = g.replay
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # nvidia-smi needs ~1 s before its first sample: start it ahead of the warm-up
     for _ in range(max(a.warmup, 3)):
         runner()
     sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ops.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for _ in range(a.steps):
-        runner()
-    e1.record()
-    sync_all()
-    launches = ops.launch_count() if not a.graph else None
-    ms_total = e0.elapsed_time(e1)
+    # Timed region: EXACTLY a.steps steps between two events, barrier + synchronize on both sides.  The region is
+    # repeated back to back until --min-seconds have passed and the median repeat is reported.
+    region_ms, launches = [], None
+    t_begin = time.perf_counter()
+    while True:
+        ops.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(a.steps):
+            runner()
+        e1.record()
+        sync_all()
+        launches = ops.launch_count() if not a.graph else None
+        region_ms.append(e0.elapsed_time(e1))
+        done = torch.tensor([1.0 if (time.perf_counter() - t_begin >= a.min_seconds or len(region_ms) >= 200) else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(done, op=dist.ReduceOp.MAX)   # all ranks leave the loop together
+        if done.item() > 0:
+            break
+    ms_total = statistics.median(region_ms)
 
     # ---- the dominant kernel alone: K launches between two events on the launching stream ---------------------------
     lp_chunks = (T + 127) // 128
     part = torch.empty(B * lp_chunks, dtype=torch.float64, device=dev)
     graw = torch.empty_like(raw_d)
-    x_dev = x_sl.to(dev)
     raw_plain = raw_d.detach()
 
     def dmol_only():
@@ -278,12 +293,13 @@ def run_gpu_arm(a):
         dmol_only()
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_kern = max(a.steps, 200)
     k0.record()
-    for _ in range(a.steps):
+    for _ in range(n_kern):
         dmol_only()
     k1.record()
     torch.cuda.synchronize()
-    kern_ms = k0.elapsed_time(k1) / a.steps
+    kern_ms = k0.elapsed_time(k1) / n_kern
     clocks = sampler.stop() if rank == 0 else None
     del graw, part
 
@@ -357,6 +373,7 @@ def run_gpu_arm(a):
                          "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": kern_ms * 1e3,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": e2e, "gpu_launches": launches if launches is not None else "graph replay", "clocks": clocks,
+            "timed_region_repeats": len(region_ms), "timed_region_ms_min_max": [min(region_ms), max(region_ms)],
             "step": "fused_elbo(...).loss.backward() through the Python API" + (" replayed from a CUDA graph" if a.graph else "")
                     + ("; + 1 NCCL all-reduce of 5 fp64 sums" if world > 1 else ""),
         }

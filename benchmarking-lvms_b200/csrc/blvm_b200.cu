@@ -15,6 +15,7 @@ using namespace blvm;
 static_assert(BLVM_DMOL_TILE == 128, "tile constant mirrors the kernel template argument");
 static_assert(BLVM_KL_TILE == kKlChunk, "tile constant mirrors the KL kernel");
 static_assert(BLVM_MAX_KL_LEVELS == kMaxLevels, "level cap");
+static_assert(BLVM_MAX_SCALE_BUFFERS == kMaxScaleBuffers, "scale buffer cap");
 static_assert(BLVM_FLAG_MASK_OUTPUT == kFlagMaskOutput && BLVM_FLAG_SKIP_PADDED == kFlagSkipPadded, "flags");
 
 namespace {
@@ -261,6 +262,25 @@ int blvm_scale_inplace(float* buf, int64_t n, const double* scale, blvm_stream_t
   const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
   scale_inplace_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(buf, n, scale);
   return check_launch("scale_inplace_kernel");
+}
+
+int blvm_scale_inplace_multi(float* const* bufs_host, const int64_t* ns_host, int count, const double* scale,
+                             blvm_stream_t stream) {
+  if (count < 0 || count > kMaxScaleBuffers) return fail(BLVM_ERR_INVALID_ARGUMENT, "count=%d out of [0, %d]", count, kMaxScaleBuffers);
+  if (count == 0) return BLVM_OK;
+  if (!scale) return fail(BLVM_ERR_INVALID_ARGUMENT, "null scale");
+  ScaleMultiArgs A{};
+  A.count = count; A.scale = scale;
+  int64_t nmax = 0;
+  for (int i = 0; i < count; ++i) {
+    if (ns_host[i] < 0 || (ns_host[i] > 0 && !bufs_host[i])) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad buffer %d", i);
+    A.buf[i] = bufs_host[i]; A.n[i] = ns_host[i];
+    nmax = ns_host[i] > nmax ? ns_host[i] : nmax;
+  }
+  const int64_t want = (nmax + 1023) / 1024;
+  dim3 grid(static_cast<unsigned>(want < 148 * 4 ? (want > 0 ? want : 1) : 148 * 4), static_cast<unsigned>(count));
+  scale_inplace_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  return check_launch("scale_inplace_multi_kernel");
 }
 
 }  // extern "C"

@@ -30,4 +30,21 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ 
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) buf[i] *= s;
 }
 
+constexpr int kMaxScaleBuffers = 36;
+struct ScaleMultiArgs {
+  float* buf[kMaxScaleBuffers];
+  int64_t n[kMaxScaleBuffers];
+  int count;
+  const double* scale;
+};
+// one launch for all gradient buffers of a fused ELBO step; blockIdx.y selects the buffer
+__global__ void __launch_bounds__(256) scale_inplace_multi_kernel(const ScaleMultiArgs A) {
+  const float s = static_cast<float>(*A.scale);
+  if (s == 1.0f) return;
+  float* __restrict__ buf = A.buf[blockIdx.y];
+  const int64_t n = A.n[blockIdx.y];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) buf[i] *= s;
+}
+
 }  // namespace blvm

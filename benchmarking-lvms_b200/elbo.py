@@ -56,10 +56,10 @@ def pack_dmol_params(parameters) -> "DMoLParams":
     return DMoLParams(raw, K, D, -math.inf)
 
 
-def _host_lengths(x_sl) -> torch.Tensor:
-    if not isinstance(x_sl, torch.Tensor):
-        x_sl = torch.as_tensor(x_sl)
-    return x_sl.to(torch.int64)
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()   # AMP hands over fp16/bf16 Linear outputs; the kernels compute in fp32
+    return t if t.is_contiguous() else t.contiguous()
 
 
 def fused_elbo(
@@ -74,6 +74,7 @@ def fused_elbo(
     denom: Optional[float] = None,
     want_twise: bool = False,
     skip_padded: bool = False,
+    x_sl_device: Optional[torch.Tensor] = None,
 ):
     """ELBO of a batch in one pass.
 
@@ -81,7 +82,8 @@ def fused_elbo(
         y: targets (B, T) or (B, T, D) in [-1, 1].
         parameters: `likelihood(x)` output (DMoLParams / DLParams / reference-style tuple) over (B, T), or None for a
             KL-only call.
-        x_sl: valid samples per utterance (B), CPU int64 like in the reference (a CUDA tensor costs one sync).
+        x_sl: valid samples per utterance (B), CPU int64 like in the reference (a CUDA tensor costs one sync unless
+            `denom` is given).
         kl_levels: the latent layers (see KLLevel).
         beta, free_nats: as in `Model.forward(x, x_sl, beta=, free_nats=)`.
         num_bins: likelihood.num_bins.
@@ -90,22 +92,40 @@ def fused_elbo(
         want_twise: also return the masked per-sample log-prob (B, T) (WaveNet returns it).
         skip_padded: do not read tiles that lie entirely in the padding (their outputs become exact zeros instead of
             `value * 0`; only differs from the reference if padded parameters are non-finite).
+        x_sl_device: the same lengths already on the device (B) int64; with `denom` given the call then does no
+            host<->device traffic at all and can be captured in a CUDA graph.
 
     Returns a namespace with fp64 tensors: loss (), elbo, log_prob, kl, kl_fn (B,), kl_levels [(B,)],
     sums (8,) = [loss, sum log_prob, sum kl, sum kl_fn, sum elbo, sum x_sl, bits-per-dim, nansum-loss] and
     log_prob_twise (B, T) fp32 or None.  Only `loss` is differentiable (w.r.t. the likelihood parameters and the
     tensors of every KLLevel); the others are detached.
     """
-    x_sl_host = _host_lengths(x_sl)
-    dev = (parameters.raw if parameters is not None and hasattr(parameters, "raw") else
-           (parameters[0] if parameters is not None else kl_levels[0].tensors[0])).device
-    if x_sl_host.is_cuda:
-        x_sl_dev = x_sl_host
-        total = float(x_sl_host.sum().item()) if denom is None else float(denom)
+    if parameters is not None:
+        dev = parameters.raw.device if hasattr(parameters, "raw") else parameters[0].device
     else:
-        total = float(x_sl_host.sum()) if denom is None else float(denom)
-        x_sl_dev = x_sl_host.to(dev, non_blocking=True)
-    B = x_sl_dev.shape[0]
+        dev = kl_levels[0].tensors[0].device
+    x_sl_t = x_sl if isinstance(x_sl, torch.Tensor) else torch.as_tensor(x_sl)
+    if x_sl_t.dtype != torch.int64:
+        x_sl_t = x_sl_t.to(torch.int64)
+    on_host = not x_sl_t.is_cuda
+    total = float(denom) if denom is not None else float(x_sl_t.sum())
+    B = x_sl_t.shape[0]
+
+    # per-level valid lengths: computed where x_sl lives; host lengths travel with x_sl in ONE small H2D copy
+    need = [lv for lv in kl_levels if lv.lens is None]
+    if x_sl_device is not None:
+        x_sl_dev = x_sl_device
+        lens_of = {id(lv): level_lengths(x_sl_dev, int(lv.stride)) for lv in need}
+    elif on_host:
+        if need:
+            packed = torch.stack([x_sl_t] + [level_lengths(x_sl_t, int(lv.stride)) for lv in need]).to(dev, non_blocking=True)
+            x_sl_dev = packed[0]
+            lens_of = {id(lv): packed[1 + i] for i, lv in enumerate(need)}
+        else:
+            x_sl_dev, lens_of = x_sl_t.to(dev, non_blocking=True), {}
+    else:
+        x_sl_dev = x_sl_t
+        lens_of = {id(lv): level_lengths(x_sl_dev, int(lv.stride)) for lv in need}
 
     likelihood, raw, K, D, log_eps = "none", None, 1, 1, -7.0
     if parameters is not None:
@@ -118,27 +138,28 @@ def fused_elbo(
             likelihood, raw, K, D, log_eps = "dmol", p.raw, p.K, p.D, p.log_epsilon
         if raw.dim() != 3 or raw.shape[0] != B:
             raise ValueError(f"likelihood parameters must be (B, T, P) with B = len(x_sl) = {B}; got {tuple(raw.shape)}")
-        if raw.dtype != torch.float32:
-            raw = raw.float()  # AMP hands over fp16/bf16 Linear outputs; the kernels compute in fp32
-        raw = raw.contiguous()
+        raw = _f32c(raw)
         T = raw.shape[1]
-        y = y.reshape(B, T, D) if y.numel() == B * T * D else y
-        if y.shape[:2] != (B, T):
-            raise ValueError(f"y {tuple(y.shape)} does not match parameters (B, T) = ({B}, {T})")
-        y = y.to(torch.float32).contiguous()
+        if y.numel() != B * T * D:
+            raise ValueError(f"y {tuple(y.shape)} does not match parameters (B, T, D) = ({B}, {T}, {D})")
+        y = _f32c(y)
 
     specs, flat = [], []
     for lv in kl_levels:
-        ts = [t.to(torch.float32).contiguous() for t in torch.broadcast_tensors(*lv.tensors)]
+        ts = lv.tensors
+        if len(ts) == 4 and not (ts[0].shape == ts[1].shape == ts[2].shape == ts[3].shape):
+            ts = torch.broadcast_tensors(*ts)
+        ts = [_f32c(t) for t in ts]
         if ts[0].dim() != 3 or ts[0].shape[0] != B:
             raise ValueError(f"KL tensors must be (B, Tz, Z) with B = {B}; got {tuple(ts[0].shape)}")
-        lens = lv.lens if lv.lens is not None else level_lengths(x_sl_dev, int(lv.stride))
-        lens = lens.to(device=dev, dtype=torch.int64)
+        lens = lv.lens if lv.lens is not None else lens_of[id(lv)]
+        if lens.device != dev or lens.dtype != torch.int64:
+            lens = lens.to(device=dev, dtype=torch.int64)
         fn = free_nats if lv.free_nats is None else lv.free_nats
         specs.append(ops.KLLevelSpec(lv.kind, float(fn or 0.0), lens, len(ts)))
         flat += ts
 
-    need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in ([raw] if raw is not None else []) + flat)
+    need_grad = torch.is_grad_enabled() and ((raw is not None and raw.requires_grad) or any(t.requires_grad for t in flat))
     spec = ops.ELBOSpec(K=K, D=D, num_bins=int(num_bins), log_epsilon=float(log_eps), beta=float(beta), denom=total,
                         levels=specs, want_twise=want_twise, skip_padded=skip_padded, need_grad=need_grad,
                         likelihood=likelihood)

@@ -245,80 +245,98 @@ class ELBOSpec:
 
 class _FusedELBO(torch.autograd.Function):
     """inputs: spec, y (B,T[,D]), x_sl_dev (B) int64, raw (B,T,P), then the KL tensors of every level, flattened.
-    outputs: loss () fp64 [differentiable], scalars (8) fp64, rows (4+L, B) fp64, log_prob_twise (B,T) or empty."""
+    outputs: loss () fp64 [differentiable], scalars (8) fp64, rows (4+L, B) fp64, log_prob_twise (B,T) or empty.
+
+    Host-side cost matters here (a step is ~200 us of GPU time): one fp64 workspace allocation holds the outputs and
+    all per-tile partial sums, and the step is 3 + L launches (DMoL, one per KL level, finalize); backward is one."""
 
     @staticmethod
     def forward(ctx, spec: ELBOSpec, y, x_sl_dev, raw, *kl_tensors):
         dev = raw.device if raw is not None else kl_tensors[0].device
+        _require_cuda(y, x_sl_dev, raw, *kl_tensors)
         B = int(x_sl_dev.shape[0])
         L = len(spec.levels)
         assert L <= _lib.BLVM_MAX_KL_LEVELS, f"at most {_lib.BLVM_MAX_KL_LEVELS} KL levels"
-        out = torch.empty(8 + (4 + L) * B, dtype=torch.float64, device=dev)
-        scalars = out[:8]
-        rows = out[8:].view(4 + L, B)
-        grads: List[Optional[torch.Tensor]] = []
-        keep = []  # partial-sum buffers must outlive the finalize launch (stream-ordered; the caching allocator is
-        #            stream-aware, but holding them until return keeps this independent of allocator behaviour)
-        twise = torch.empty(0, device=dev)
-        logp_part, logp_chunks = None, 0
-
-        if spec.likelihood != "none":
-            T = raw.shape[1]
-            flags = BLVM_FLAG_MASK_OUTPUT | (BLVM_FLAG_SKIP_PADDED if spec.skip_padded else 0)
-            logp_chunks = int(lib.blvm_dmol_chunks(T))
-            logp_part = torch.empty(B * logp_chunks, dtype=torch.float64, device=dev)
-            keep.append(logp_part)
-            if spec.want_twise:
-                twise = torch.empty(B, T, dtype=torch.float32, device=dev)
-            graw = torch.empty_like(raw) if spec.need_grad else None
-            gscale = -1.0 / spec.denom
-            lp_arg = twise if spec.want_twise else None
-            if spec.likelihood == "dmol":
-                _dmol_call(y, raw, x_sl_dev, None, gscale, B, T, spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags,
-                           lp_arg, graw, logp_part)
-            else:
-                _dl_call(y, raw, x_sl_dev, None, gscale, B, T, spec.num_bins, spec.log_epsilon, flags, lp_arg, graw,
-                         logp_part)
-            grads.append(graw)
-        else:
-            grads.append(None)
-
-        kl_parts, klfn_parts, kl_chunks = [], [], []
+        has_lik = spec.likelihood != "none"
+        T = raw.shape[1] if has_lik else 0
+        logp_chunks = int(lib.blvm_dmol_chunks(T)) if has_lik else 0
+        shapes = []
         i = 0
+        for lv in spec.levels:
+            Bz, Tz, Z = kl_tensors[i].shape
+            assert Bz == B, f"KL level batch {Bz} != {B}"
+            shapes.append((Tz, Z, int(lib.blvm_kl_chunks(Tz * Z))))
+            i += lv.n_tensors
+        n_out = 8 + (4 + L) * B
+        n_ws = n_out + B * logp_chunks + sum(2 * B * c for _, _, c in shapes)
+        ws = torch.empty(n_ws, dtype=torch.float64, device=dev)   # outputs + partial sums, one allocation
+        base = ws.data_ptr()
+        scalars = ws[:8]
+        rows = ws[8:n_out].view(4 + L, B)
+        off = n_out
+        grads: List[Optional[torch.Tensor]] = []
+        twise = torch.empty(B, T, dtype=torch.float32, device=dev) if (has_lik and spec.want_twise) else torch.empty(0, device=dev)
+        stream = _stream()
+
         with torch.cuda.device(dev):
-            for lv in spec.levels:
+            logp_ptr = None
+            if has_lik:
+                flags = BLVM_FLAG_MASK_OUTPUT | (BLVM_FLAG_SKIP_PADDED if spec.skip_padded else 0)
+                logp_ptr = base + 8 * off
+                off += B * logp_chunks
+                graw = torch.empty_like(raw) if spec.need_grad else None
+                gscale = -1.0 / spec.denom
+                lp_ptr = twise.data_ptr() if spec.want_twise else None
+                err = _err_flag(dev)
+                if spec.likelihood == "dmol":
+                    if graw is None:
+                        rc = lib.blvm_dmol_fwd(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), B, T, spec.K, spec.D,
+                                               spec.num_bins, spec.log_epsilon, flags, lp_ptr, logp_ptr, err.data_ptr(), stream)
+                    else:
+                        rc = lib.blvm_dmol_fwd_grad(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), None, gscale, B, T,
+                                                    spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags, lp_ptr,
+                                                    graw.data_ptr(), logp_ptr, err.data_ptr(), stream)
+                else:
+                    rc = lib.blvm_dl_fwd_grad(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), None, gscale, B, T,
+                                              spec.num_bins, spec.log_epsilon, flags, lp_ptr, _ptr(graw), logp_ptr,
+                                              err.data_ptr(), stream)
+                check(rc, "blvm DMoL/DL kernel")
+                _count()
+                grads.append(graw)
+            else:
+                grads.append(None)
+
+            kl_ptrs, klfn_ptrs, kl_chunks = [], [], []
+            i = 0
+            gscale = spec.beta / spec.denom
+            for lv, (Tz, Z, chunks) in zip(spec.levels, shapes):
                 ts = kl_tensors[i:i + lv.n_tensors]
                 i += lv.n_tensors
-                _require_cuda(*ts)
-                Bz, Tz, Z = ts[0].shape
-                assert Bz == B, f"KL level batch {Bz} != {B}"
-                chunks = int(lib.blvm_kl_chunks(Tz * Z))
-                pk = torch.empty(B * chunks, dtype=torch.float64, device=dev)
-                pf = torch.empty(B * chunks, dtype=torch.float64, device=dev)
-                keep += [pk, pf]
-                gscale = spec.beta / spec.denom
+                pk = base + 8 * off
+                pf = pk + 8 * B * chunks
+                off += 2 * B * chunks
                 if lv.kind == "inputs":
                     g4 = [torch.empty_like(ts[0]) for _ in range(4)] if spec.need_grad else [None] * 4
-                    rc = lib.blvm_kl_elbo_fwd_grad(*[_ptr(t) for t in ts], _ptr(lv.lens), B, Tz, Z, float(lv.free_nats),
-                                                   gscale, None, *[_ptr(g) for g in g4], _ptr(pk), _ptr(pf), _stream())
+                    rc = lib.blvm_kl_elbo_fwd_grad(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
+                                                   _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale, None,
+                                                   _ptr(g4[0]), _ptr(g4[1]), _ptr(g4[2]), _ptr(g4[3]), pk, pf, stream)
                     check(rc, "blvm_kl_elbo_fwd_grad")
                     grads += g4
                 else:
                     gk = torch.empty_like(ts[0]) if spec.need_grad else None
-                    rc = lib.blvm_kl_reduce_fwd_grad(_ptr(ts[0]), _ptr(lv.lens), B, Tz, Z, float(lv.free_nats), gscale,
-                                                     _ptr(gk), _ptr(pk), _ptr(pf), _stream())
+                    rc = lib.blvm_kl_reduce_fwd_grad(ts[0].data_ptr(), _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale,
+                                                     _ptr(gk), pk, pf, stream)
                     check(rc, "blvm_kl_reduce_fwd_grad")
                     grads.append(gk)
                 _count()
-                kl_parts.append(pk)
-                klfn_parts.append(pf)
+                kl_ptrs.append(pk)
+                klfn_ptrs.append(pf)
                 kl_chunks.append(chunks)
 
             PtrArr = ctypes.c_void_p * max(L, 1)
             I64Arr = ctypes.c_int64 * max(L, 1)
-            rc = lib.blvm_elbo_finalize(_ptr(logp_part), logp_chunks, PtrArr(*[t.data_ptr() for t in kl_parts]),
-                                        PtrArr(*[t.data_ptr() for t in klfn_parts]), I64Arr(*kl_chunks), L,
-                                        _ptr(x_sl_dev), B, float(spec.beta), _ptr(rows), _ptr(scalars), _stream())
+            rc = lib.blvm_elbo_finalize(logp_ptr, logp_chunks, PtrArr(*kl_ptrs), PtrArr(*klfn_ptrs), I64Arr(*kl_chunks), L,
+                                        x_sl_dev.data_ptr(), B, spec.beta, rows.data_ptr(), scalars.data_ptr(), stream)
             check(rc, "blvm_elbo_finalize")
             _count()
 
@@ -335,16 +353,18 @@ class _FusedELBO(torch.autograd.Function):
             raise RuntimeError("blvm_b200 fused ELBO: backward called twice (gradients are produced in the forward pass "
                                "and scaled in place; call the op again instead of retain_graph=True)")
         ctx.consumed = True
-        g = g_loss.to(torch.float64).contiguous()
-        out = [None, None, None]
-        with torch.cuda.device(g.device):
-            for buf in ctx.grads:
-                if buf is not None:
-                    check(lib.blvm_scale_inplace(_ptr(buf), buf.numel(), _ptr(g), _stream()), "blvm_scale_inplace")
-                    _count()
-                out.append(buf)
+        g = g_loss if (g_loss.dtype == torch.float64 and g_loss.is_contiguous()) else g_loss.to(torch.float64).contiguous()
+        bufs = [b for b in ctx.grads if b is not None]
+        if bufs:
+            n = len(bufs)
+            with torch.cuda.device(g.device):
+                rc = lib.blvm_scale_inplace_multi((ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs]),
+                                                  (ctypes.c_int64 * n)(*[b.numel() for b in bufs]), n, g.data_ptr(), _stream())
+                check(rc, "blvm_scale_inplace_multi")
+            _count()
+        out = (None, None, None) + tuple(ctx.grads)
         ctx.grads = None
-        return tuple(out)
+        return out
 
 
 def fused_elbo_apply(spec: ELBOSpec, y, x_sl_dev, raw, kl_tensors: Sequence[torch.Tensor]):

@@ -143,6 +143,10 @@ int blvm_quantize(const float* x, int64_t n, const float* boundaries, int64_t n_
 /* In-place `buf *= (float)*scale` (fp64 device scalar) that exits early when *scale == 1: the autograd backward of the
  * fused ELBO op uses it to apply an upstream grad_output (e.g. an AMP loss scale) without a host sync. */
 int blvm_scale_inplace(float* buf, int64_t n, const double* scale, blvm_stream_t stream);
+/* Same for up to BLVM_MAX_SCALE_BUFFERS buffers in ONE launch (bufs_host / ns_host are HOST arrays of length count). */
+#define BLVM_MAX_SCALE_BUFFERS 36
+int blvm_scale_inplace_multi(float* const* bufs_host, const int64_t* ns_host, int count, const double* scale,
+                             blvm_stream_t stream);
 
 #ifdef __cplusplus
 }
