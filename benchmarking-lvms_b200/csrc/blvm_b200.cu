@@ -231,9 +231,10 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
 
 int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
                        const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
-                       const int64_t* x_sl, int64_t B, double beta, double* rows, double* scalars, blvm_stream_t stream) {
+                       const int64_t* x_sl, int64_t B, double beta, double* rows, double* scalars,
+                       unsigned int* sync_counter, blvm_stream_t stream) {
   if (n_levels < 0 || n_levels > kMaxLevels) return fail(BLVM_ERR_INVALID_ARGUMENT, "n_levels=%d out of [0, %d]", n_levels, kMaxLevels);
-  if (B < 0 || !x_sl || !rows || !scalars) return fail(BLVM_ERR_INVALID_ARGUMENT, "null x_sl/rows/scalars");
+  if (B < 0 || !x_sl || !rows || !scalars || !sync_counter) return fail(BLVM_ERR_INVALID_ARGUMENT, "null x_sl/rows/scalars/sync_counter");
   FinalizeArgs A{};
   A.logp_part = logp_part; A.logp_chunks = logp_chunks; A.n_levels = n_levels; A.x_sl = x_sl; A.B = B; A.beta = beta;
   A.rows = rows; A.scalars = scalars;
@@ -241,7 +242,8 @@ int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const doubl
     if (!kl_part_host[l] || !klfn_part_host[l]) return fail(BLVM_ERR_INVALID_ARGUMENT, "null KL partials at level %d", l);
     A.kl_part[l] = kl_part_host[l]; A.klfn_part[l] = klfn_part_host[l]; A.kl_chunks[l] = kl_chunks_host[l];
   }
-  elbo_finalize_kernel<<<1, kFinTPB, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  const unsigned blocks = static_cast<unsigned>(B > 0 ? (B + kFinWarps - 1) / kFinWarps : 1);
+  elbo_finalize_kernel<<<blocks, kFinTPB, 0, static_cast<cudaStream_t>(stream)>>>(A, sync_counter);
   return check_launch("elbo_finalize_kernel");
 }
 

@@ -175,43 +175,66 @@ struct FinalizeArgs {
 };
 
 constexpr int kFinTPB = 256;
+constexpr int kFinWarps = kFinTPB / 32;
 
-__global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeArgs A) {
-  __shared__ double scratch[6][kFinTPB / 32];
-  const int tid = threadIdx.x;
-  double t_logp = 0, t_kl = 0, t_fn = 0, t_len = 0, t_nan_logp = 0, t_obj = 0;
-  for (int64_t b = tid; b < A.B; b += kFinTPB) {
-    double logp = 0.0;
-    if (A.logp_part)
-      for (int64_t c = 0; c < A.logp_chunks; ++c) logp += A.logp_part[b * A.logp_chunks + c];
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// lanes stride over the chunks of one utterance (coalesced), fixed-order butterfly: deterministic
+__device__ __forceinline__ double warp_row_sum(const double* __restrict__ p, int64_t n, int lane) {
+  double s = 0.0;
+  for (int64_t c = lane; c < n; c += 32) s += p[c];
+  return warp_sum_f64(s);
+}
+
+// One warp per utterance reduces its per-tile partials; the last CTA to finish (device counter, self-resetting)
+// reduces the per-utterance rows to the scalars in a fixed order.  Grid = ceil(B / 8) CTAs.
+__global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeArgs A, unsigned int* counter) {
+  __shared__ double scratch[6][kFinWarps];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * kFinWarps + warp;
+  if (b < A.B) {
+    const double logp = A.logp_part ? warp_row_sum(A.logp_part + b * A.logp_chunks, A.logp_chunks, lane) : 0.0;
     double kl = 0.0, fn = 0.0;
     for (int l = 0; l < A.n_levels; ++l) {
-      double kl_l = 0.0, fn_l = 0.0;
-      for (int64_t c = 0; c < A.kl_chunks[l]; ++c) {
-        kl_l += A.kl_part[l][b * A.kl_chunks[l] + c];
-        fn_l += A.klfn_part[l][b * A.kl_chunks[l] + c];
-      }
-      A.rows[(4 + l) * A.B + b] = kl_l;
+      const double kl_l = warp_row_sum(A.kl_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane);
+      const double fn_l = warp_row_sum(A.klfn_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane);
+      if (lane == 0) A.rows[(4 + l) * A.B + b] = kl_l;
       kl += kl_l;   // sum over levels (clockwork_vae.py:155, stcn.py:290)
       fn += fn_l;
     }
-    A.rows[0 * A.B + b] = logp;
-    A.rows[1 * A.B + b] = kl;
-    A.rows[2 * A.B + b] = fn;
-    A.rows[3 * A.B + b] = logp - kl;                     // elbo (vrnn.py:273)
+    if (lane == 0) {
+      A.rows[0 * A.B + b] = logp;
+      A.rows[1 * A.B + b] = kl;
+      A.rows[2 * A.B + b] = fn;
+      A.rows[3 * A.B + b] = logp - kl;                   // elbo (vrnn.py:273)
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double t_logp = 0, t_kl = 0, t_fn = 0, t_len = 0, t_nan_logp = 0, t_obj = 0;
+  for (int64_t r = tid; r < A.B; r += kFinTPB) {
+    const double logp = __ldcg(A.rows + 0 * A.B + r), kl = __ldcg(A.rows + 1 * A.B + r), fn = __ldcg(A.rows + 2 * A.B + r);
     t_logp += logp;
     t_kl += kl;
     t_fn += fn;
     t_obj += logp - A.beta * fn;                         // vrnn.py:277 numerator
     t_nan_logp += (logp == logp) ? logp : 0.0;           // nansum (wavenet.py:145)
-    t_len += static_cast<double>(A.x_sl[b]);
+    t_len += static_cast<double>(A.x_sl[r]);
   }
-  const double s_logp = block_sum_f64<kFinTPB / 32>(t_logp, scratch[0]);
-  const double s_kl = block_sum_f64<kFinTPB / 32>(t_kl, scratch[1]);
-  const double s_fn = block_sum_f64<kFinTPB / 32>(t_fn, scratch[2]);
-  const double s_obj = block_sum_f64<kFinTPB / 32>(t_obj, scratch[3]);
-  const double s_nan = block_sum_f64<kFinTPB / 32>(t_nan_logp, scratch[4]);
-  const double s_len = block_sum_f64<kFinTPB / 32>(t_len, scratch[5]);
+  const double s_logp = block_sum_f64<kFinWarps>(t_logp, scratch[0]);
+  const double s_kl = block_sum_f64<kFinWarps>(t_kl, scratch[1]);
+  const double s_fn = block_sum_f64<kFinWarps>(t_fn, scratch[2]);
+  const double s_obj = block_sum_f64<kFinWarps>(t_obj, scratch[3]);
+  const double s_nan = block_sum_f64<kFinWarps>(t_nan_logp, scratch[4]);
+  const double s_len = block_sum_f64<kFinWarps>(t_len, scratch[5]);
   if (tid == 0) {
     A.scalars[0] = -s_obj / s_len;                       // loss
     A.scalars[1] = s_logp;
@@ -221,6 +244,7 @@ __global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeAr
     A.scalars[5] = s_len;
     A.scalars[6] = -(s_logp - s_kl) / 0.6931471805599453 / s_len;  // bits per dim (metrics.py:456)
     A.scalars[7] = -s_nan / s_len;                       // WaveNet's nansum loss
+    *counter = 0u;                                       // ready for the next launch on this stream
   }
 }
 

@@ -54,6 +54,16 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _sync_counter(device: torch.device) -> torch.Tensor:
+    """Zero-initialised uint32 for blvm_elbo_finalize's last-block handshake, one per (device, stream)."""
+    key = ("ctr", device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ctr = _err_flags.get(key)
+    if ctr is None:
+        ctr = torch.zeros(1, dtype=torch.int32, device=device)
+        _err_flags[key] = ctr
+    return ctr
+
+
 def _err_flag(device: torch.device) -> torch.Tensor:
     key = device.index if device.index is not None else torch.cuda.current_device()
     flag = _err_flags.get(key)
@@ -72,6 +82,8 @@ def check_input_range(device=None):
     check after every call.
     """
     for key, flag in list(_err_flags.items()):
+        if isinstance(key, tuple):
+            continue
         if device is not None and torch.device(device).index not in (None, key):
             continue
         if int(flag.item()) != 0:
@@ -336,11 +348,13 @@ class _FusedELBO(torch.autograd.Function):
             PtrArr = ctypes.c_void_p * max(L, 1)
             I64Arr = ctypes.c_int64 * max(L, 1)
             rc = lib.blvm_elbo_finalize(logp_ptr, logp_chunks, PtrArr(*kl_ptrs), PtrArr(*klfn_ptrs), I64Arr(*kl_chunks), L,
-                                        x_sl_dev.data_ptr(), B, spec.beta, rows.data_ptr(), scalars.data_ptr(), stream)
+                                        x_sl_dev.data_ptr(), B, spec.beta, rows.data_ptr(), scalars.data_ptr(),
+                                        _sync_counter(dev).data_ptr(), stream)
             check(rc, "blvm_elbo_finalize")
             _count()
 
         loss = scalars[:1].view(())
+        ctx.set_materialize_grads(False)   # no zero-filled grads for the detached outputs
         ctx.grads = grads
         ctx.consumed = False
         ctx.mark_non_differentiable(scalars, rows, twise)
@@ -353,6 +367,8 @@ class _FusedELBO(torch.autograd.Function):
             raise RuntimeError("blvm_b200 fused ELBO: backward called twice (gradients are produced in the forward pass "
                                "and scaled in place; call the op again instead of retain_graph=True)")
         ctx.consumed = True
+        if g_loss is None:
+            return (None, None, None) + tuple(None for _ in ctx.grads)
         g = g_loss if (g_loss.dtype == torch.float64 and g_loss.is_contiguous()) else g_loss.to(torch.float64).contiguous()
         bufs = [b for b in ctx.grads if b is not None]
         if bufs:

@@ -128,11 +128,13 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
  *   rows     (4 + n_levels, B) fp64: logp, kl (sum over levels), kl_fn, elbo, then kl of each level
  *   scalars  (8) fp64: loss = -sum_b(logp - beta kl_fn)/sum(x_sl), sum logp, sum kl, sum kl_fn, sum elbo, sum x_sl,
  *            bits-per-dim = -sum elbo / ln 2 / sum x_sl, nansum-loss = -nansum(logp)/sum x_sl (wavenet.py:145)
+ *   sync_counter  one uint32 the caller zero-initialises ONCE per device/stream; the kernel leaves it at zero
+ *            (inter-CTA "last block reduces" handshake; launches sharing a counter must be stream-ordered)
  */
 int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
                        const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
                        const int64_t* x_sl, int64_t B, double beta, double* rows, double* scalars,
-                       blvm_stream_t stream);
+                       unsigned int* sync_counter, blvm_stream_t stream);
 
 /*
  * Quantize: torch.bucketize(x, boundaries, right=False) (blvm/data/transforms.py:257) -> int64 bin index,
