@@ -90,7 +90,7 @@ def synth_numpy(B, T, K, seed, ragged):
 def cpu_port_throughput(a, steps, warmup, target_step_s=1.5):
     import numpy as np
     from oracle import c_oracle as C
-    cores = C.num_threads()
+    cores = C.use_all_cores()
     # calibrate on a few utterances, then size the sample so that one step takes ~target_step_s
     rows0 = max(1, min(a.B, cores))
     y, raw, kl, x_sl = synth_numpy(rows0, a.T, a.K, 99, a.ragged)
@@ -224,6 +224,8 @@ def run_gpu_arm(a):
     x_dev = x_sl.to(dev)            # `value` arm: every input, the lengths included, is resident in HBM
     lens_dev = blvm_b200.level_lengths(x_dev, STRIDE)
 
+    pending = []
+
     def step_device():
         raw_d.grad = None
         for t in kl_d:
@@ -233,7 +235,11 @@ def run_gpu_arm(a):
         out.loss.backward()
         sums = out.sums
         if world > 1:
-            sums = blvm_b200.all_reduce_sums(sums)   # the path's only exchange: 5 fp64 scalars over NCCL/NVLink
+            # the path's only exchange: the fp64 scalar sums over NCCL/NVLink, asynchronous so that it overlaps the
+            # next step's kernels; the previous step's handle is waited for here (at most one in flight)
+            if pending:
+                pending.pop().wait()
+            pending.append(blvm_b200.all_reduce_sums(sums, async_op=True, inplace=True))
         return sums
 
     def sync_all():
@@ -269,6 +275,8 @@ def run_gpu_arm(a):
         e0.record()
         for _ in range(a.steps):
             runner()
+        while pending:
+            pending.pop().wait()
         e1.record()
         sync_all()
         launches = ops.launch_count() if not a.graph else None

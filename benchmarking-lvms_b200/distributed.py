@@ -28,19 +28,39 @@ def global_denominator(x_sl_local: torch.Tensor, group=None) -> float:
     return float(total.item())
 
 
-def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
-    """All-reduce(sum) of the additive part of a result's `sums` ([.. sum log_prob, sum kl, sum kl_fn, sum elbo,
-    sum x_sl ..]) and recomputation of the ratios; returns a new (8,) tensor valid on every rank."""
-    out = sums.detach().clone()
+class _Pending:
+    """Handle of an in-flight sums all-reduce: `.wait()` makes the current stream wait for it and returns the tensor."""
+
+    def __init__(self, tensor, work):
+        self.tensor, self.work = tensor, work
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        return self.tensor
+
+
+def all_reduce_sums(sums: torch.Tensor, group=None, async_op: bool = False, inplace: bool = False):
+    """All-reduce(sum) of a `fused_elbo` result's `sums` (8,) over the ranks — the path's only exchange.  Every entry
+    is summed; the ratio entries (loss, bits-per-dim, nansum-loss) must afterwards be recomputed with `combine_sums`.
+    `async_op=True` returns a handle (`.wait()`), so the collective (NCCL runs it on its own stream) overlaps the next
+    step's kernels; `inplace=True` reduces into `sums` itself instead of a copy."""
+    out = sums.detach() if inplace else sums.detach().clone()
+    work = None
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(out[1:6], op=dist.ReduceOp.SUM, group=group)
+        work = dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    if async_op:
+        return _Pending(out, work)
     return out
 
 
 def combine_sums(sums: torch.Tensor, beta: float) -> torch.Tensor:
-    """Recompute loss / bits-per-dim from globally reduced additive sums (indices as in blvm_elbo_finalize)."""
+    """Recompute the ratio entries (loss, bits-per-dim; indices as in blvm_elbo_finalize) from globally reduced additive
+    sums [.., sum log_prob, sum kl, sum kl_fn, sum elbo, sum x_sl, ..]; the nansum-loss entry is set to the loss."""
     out = sums.clone()
     s_logp, s_kl, s_klfn, s_elbo, s_len = out[1], out[2], out[3], out[4], out[5]
     out[0] = -(s_logp - beta * s_klfn) / s_len
     out[6] = -s_elbo / 0.6931471805599453 / s_len
+    out[7] = out[0]
     return out

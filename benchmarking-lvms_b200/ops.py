@@ -50,8 +50,38 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-def _stream():
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _stream(device_index: Optional[int] = None):
+    """Raw cudaStream_t of torch's current stream (fast path avoids building a torch.cuda.Stream object)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device() if device_index is None else device_index)
     return torch.cuda.current_stream().cuda_stream
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs ~10 us)."""
+
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, dev: torch.device):
+        self.dev = dev
+
+    def __enter__(self):
+        idx = self.dev.index
+        cur = torch.cuda.current_device()
+        if idx is None or idx == cur:
+            self.prev = None
+        else:
+            self.prev = cur
+            torch.cuda.set_device(idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _sync_counter(device: torch.device) -> torch.Tensor:
@@ -107,7 +137,7 @@ def _as_f32c(t: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------------
 def _dmol_call(y, raw, x_sl_dev, gout, gscale, B, T, K, D, num_bins, log_eps, flags, lp, graw, partials):
     _require_cuda(y, raw, x_sl_dev, gout, lp, graw, partials)
-    with torch.cuda.device(raw.device):
+    with _on_device(raw.device):
         err = _err_flag(raw.device)
         if graw is None:
             rc = lib.blvm_dmol_fwd(_ptr(y), _ptr(raw), _ptr(x_sl_dev), B, T, K, D, num_bins, log_eps, flags, _ptr(lp),
@@ -122,7 +152,7 @@ def _dmol_call(y, raw, x_sl_dev, gout, gscale, B, T, K, D, num_bins, log_eps, fl
 
 def _dl_call(y, raw, x_sl_dev, gout, gscale, B, T, num_bins, log_eps, flags, lp, graw, partials):
     _require_cuda(y, raw, x_sl_dev, gout, lp, graw, partials)
-    with torch.cuda.device(raw.device):
+    with _on_device(raw.device):
         err = _err_flag(raw.device)
         rc = lib.blvm_dl_fwd_grad(_ptr(y), _ptr(raw), _ptr(x_sl_dev), _ptr(gout), gscale, B, T, num_bins, log_eps, flags,
                                   _ptr(lp), _ptr(graw), _ptr(partials), _ptr(err), _stream())
@@ -205,7 +235,7 @@ class _KLGaussian(torch.autograd.Function):
         ins = [t.contiguous() for t in (mu_q, sd_q, mu_p, sd_p)]
         _require_cuda(*ins)
         kl = torch.empty_like(ins[0])
-        with torch.cuda.device(kl.device):
+        with _on_device(kl.device):
             check(lib.blvm_kl_gaussian_fwd(*[_ptr(t) for t in ins], kl.numel(), _ptr(kl), _stream()), "blvm_kl_gaussian_fwd")
         _count()
         ctx.save_for_backward(*ins)
@@ -217,7 +247,7 @@ class _KLGaussian(torch.autograd.Function):
         ins = ctx.saved_tensors
         g = _as_f32c(g)
         outs = [torch.empty_like(ins[0]) for _ in range(4)]
-        with torch.cuda.device(g.device):
+        with _on_device(g.device):
             check(lib.blvm_kl_gaussian_bwd(*[_ptr(t) for t in ins], _ptr(g), g.numel(), *[_ptr(t) for t in outs], _stream()),
                   "blvm_kl_gaussian_bwd")
         _count()
@@ -288,9 +318,9 @@ class _FusedELBO(torch.autograd.Function):
         off = n_out
         grads: List[Optional[torch.Tensor]] = []
         twise = torch.empty(B, T, dtype=torch.float32, device=dev) if (has_lik and spec.want_twise) else torch.empty(0, device=dev)
-        stream = _stream()
 
-        with torch.cuda.device(dev):
+        with _on_device(dev):
+            stream = _stream(dev.index)
             logp_ptr = None
             if has_lik:
                 flags = BLVM_FLAG_MASK_OUTPUT | (BLVM_FLAG_SKIP_PADDED if spec.skip_padded else 0)
@@ -373,7 +403,7 @@ class _FusedELBO(torch.autograd.Function):
         bufs = [b for b in ctx.grads if b is not None]
         if bufs:
             n = len(bufs)
-            with torch.cuda.device(g.device):
+            with _on_device(g.device):
                 rc = lib.blvm_scale_inplace_multi((ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs]),
                                                   (ctypes.c_int64 * n)(*[b.numel() for b in bufs]), n, g.data_ptr(), _stream())
                 check(rc, "blvm_scale_inplace_multi")
@@ -395,7 +425,7 @@ def quantize_indices(x: torch.Tensor, boundaries: torch.Tensor) -> torch.Tensor:
     x = _as_f32c(x)
     boundaries = _as_f32c(boundaries)
     out = torch.empty(x.shape, dtype=torch.int64, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         check(lib.blvm_quantize(_ptr(x), x.numel(), _ptr(boundaries), boundaries.numel(), _ptr(out), _stream()), "blvm_quantize")
     _count()
     return out

@@ -28,6 +28,13 @@ def num_threads() -> int:
     return int(load().oracle_num_threads())
 
 
+def use_all_cores() -> int:
+    """Use every host core regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    load().oracle_set_num_threads(int(n))
+    return num_threads()
+
+
 def _p(a, ct):
     return None if a is None else a.ctypes.data_as(ctypes.POINTER(ct))
 
