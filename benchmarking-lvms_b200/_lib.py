@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libblvm_b200.so")
+LIB_PATH = os.environ.get("BLVM_B200_LIB") or os.path.join(_HERE, "lib", "libblvm_b200.so")  # override = A/B builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -52,10 +52,10 @@ DmolConsts make_consts(int num_bins, float log_epsilon) {
 
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <int K, bool GRAD>
-int launch_tile(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
+template <int K, bool GRAD, int UMODE>
+int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
   constexpr size_t smem = dmol_tile_smem_bytes<K, kTile>();
-  auto kern = dmol_tile_kernel<K, kTile, GRAD>;
+  auto kern = dmol_tile_kernel<K, kTile, GRAD, UMODE>;
   static bool configured = false;  // per instantiation; benign race (idempotent attribute)
   if (!configured) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -64,6 +64,15 @@ int launch_tile(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
   }
   kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
   return check_launch("dmol_tile_kernel");
+}
+
+// u = h / s <= h * exp(-log_epsilon) for every element: if that bound is tiny (16-bit bins with the -7 clamp: 0.0167)
+// the kernel specialisation without the large-u code is exact to O(u^4) ~ 1e-7 (blvm_math.cuh).
+template <int K, bool GRAD>
+int launch_tile(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
+  const double u_max = static_cast<double>(A.C.h) * exp(-static_cast<double>(A.C.log_eps));
+  if (u_max < static_cast<double>(kTinyU)) return launch_tile_mode<K, GRAD, kUTiny>(A, tiles, st);
+  return launch_tile_mode<K, GRAD, kUGeneral>(A, tiles, st);
 }
 
 template <bool GRAD>

@@ -72,6 +72,9 @@ BLVM_HD float fast_rcp(float x) {
 BLVM_HD float fast_exp(float x) { return fast_ex2(x * kLog2e); }
 // exp(x) with the rounding of the scaled argument compensated: x*log2(e) = p_hi + p_lo exactly (to ~2^-48),
 // exp(x) = 2^p_hi * (1 + ln2 * p_lo).  Leaves only the MUFU.EX2 error (~2^-22.5); 3 extra FMA-pipe ops.
+#ifndef BLVM_COMPENSATED_EXP
+#define BLVM_COMPENSATED_EXP 1
+#endif
 BLVM_HD float accurate_exp(float x) {
   constexpr float kLog2eLo = 1.925963033500011e-08f;  // log2(e) - float(log2(e))
   const float p_hi = x * kLog2e;
@@ -103,6 +106,15 @@ BLVM_HD float one_minus_exp_neg_given(float x, float e) {
   return (x < 0.25f) ? x * expm1_neg_ratio_small(x) : 1.0f - e;
 }
 
+// exp(-log_scale): compensated by default (build with -DBLVM_COMPENSATED_EXP=0 to measure the plain MUFU path)
+BLVM_HD float stable_exp(float x) {
+#if BLVM_COMPENSATED_EXP
+  return accurate_exp(x);
+#else
+  return fast_exp(x);
+#endif
+}
+
 enum : int { kEdgeNone = 0, kEdgeLower = 1, kEdgeUpper = 2 };
 
 // Which of the two y-predicates fires (bit-exact fp32 compares against fp32-rounded constants; upper wins because it
@@ -121,90 +133,117 @@ BLVM_HD int dmol_edge(float y, const DmolConsts& C) {
 // while the reference's fallback arm is  [-|m| - ls - 2 log(1+E)] - log(nb/2):  both arms share the bracket (one EX2,
 // one LG2, one RCP) and differ by O(u^2) corrections, so the `cdf_delta > 1e-5` selection is a branch-free select and
 // nothing cancels.  Derivatives:  d/dm = -sgn(m) (1-E^2)/D,  d/du = coth(u) - cdf_delta  (DESIGN.md §4).
-// u < 1/8 (always true for 16-bit audio: u <= 0.0167) uses short series for the u-terms; larger u (8-bit data with
-// small scales) evaluates them exactly from q = exp(-u).
+//
+// UMODE selects how the u-terms are evaluated (the host picks it from num_bins and log_epsilon, which bound
+// u <= h exp(-log_epsilon)):
+//   kUTiny    u < 0.02 guaranteed (16-bit audio with the -7 clamp: u <= 0.0167): first-order series, O(u^4) ~ 1e-7 dropped
+//   kUGeneral any u: second-order series below 1/8, exact evaluation from q = exp(-u) above (8-bit data, small scales)
+enum : int { kUTiny = 0, kUGeneral = 1 };
+constexpr float kTinyU = 0.02f;
 constexpr float kSmallU = 0.125f;
+
+// Non-edge sample (neither y-predicate fires): the common case, no divergent branch in kUTiny mode.
+template <bool GRAD, int UMODE>
+BLVM_HD void dl_mid(float y, float mu, float raw_ls, const DmolConsts& C, float& lp, float& dmu, float& dls) {
+  const float ls = (raw_ls < C.log_eps) ? C.log_eps : raw_ls;  // clamp(min): NaN propagates like torch
+  const float inv = stable_exp(-ls);                           // exp(-log_scale)            :203
+  const float m = inv * (y - mu);                              // mid_in                     :202,219
+  const float u = C.h * inv;
+  const float am = fabsf(m);
+  const float E = fast_ex2(-am * kLog2e);
+  const float p1 = 1.f + E;
+  const float r = fast_rcp(p1);
+  const float common = (-am - ls) - (2.f * kLn2) * fast_lg2(p1);   // log_pdf_mid = m - ls - 2 softplus(m)  :220
+  const float lp_fb = common - C.log_half_bins;                    // second arm of :221-223
+  // tanh(|m|/2) = (1-E)/(1+E); odd series below 1/8 so that the bin-centre gradient does not cancel
+  float dm_fb = 0.f;
+  if (GRAD) {
+    const float hx = 0.5f * am, hx2 = hx * hx;
+    const float th_series = hx * fmaf(hx2, fmaf(hx2, 2.0f / 15.0f, -1.0f / 3.0f), 1.0f);
+    const float th = (am < 0.25f) ? th_series : (1.f - E) * r;
+    dm_fb = copysignf(th, -m);                                     // 1 - 2 sigmoid(m)
+  }
+  float lp_d, dm_d = 0.f, udu = 0.f;
+  bool big;
+  if (UMODE == kUTiny) {
+    const float u2 = u * u;
+    const float er2 = E * r * r;
+    const float eps = er2 * u2;                                    // E w / (1+E)^2,  w = u^2 + O(u^4)
+    lp_d = common + (fmaf(u2, 1.0f / 6.0f, C.log_two_h) - eps);    // log cdf_delta, first arm of :221-223
+    big = lp_d > C.log_delta_thresh;                               // cdf_delta > 1e-5
+    if (GRAD) {
+      dm_d = fmaf(-eps, dm_fb, dm_fb);                             // dm_fb / (1 + eps)
+      udu = fmaf(u2, 1.0f / 3.0f - 2.0f * er2, 1.0f);              // u coth(u) - u cdf_delta
+    }
+  } else if (u < kSmallU) {
+    const float u2 = u * u;
+    const float er2 = E * r * r;
+    const float eps = er2 * (u2 * fmaf(u2, 1.0f / 12.0f, 1.0f));
+    const float corr = u2 * fmaf(u2, -1.0f / 180.0f, 1.0f / 6.0f) - eps * fmaf(eps, -0.5f, 1.0f);
+    lp_d = common + (C.log_two_h + corr);
+    big = lp_d > C.log_delta_thresh;
+    if (GRAD) {
+      const float inv1pe = fmaf(eps, eps - 1.0f, 1.0f);            // 1/(1+eps)
+      dm_d = dm_fb * inv1pe;
+      const float udelta = 2.0f * u2 * er2 * fmaf(u2, 1.0f / 6.0f, 1.0f) * inv1pe;  // u * cdf_delta
+      udu = fmaf(u2, fmaf(u2, -1.0f / 45.0f, 1.0f / 3.0f), 1.0f) - udelta;
+    }
+  } else {
+    const float q = fast_ex2(-u * kLog2e);                         // exp(-u); everything below is overflow-free
+    const float omq = 1.f - q, omq2 = omq * (1.f + q);
+    const float rdq = fast_rcp(fmaf(q * p1, p1, E * omq * omq));   // q / D
+    const float delta = E * omq2 * rdq;                            // cdf_delta                  :210
+    big = delta > kDeltaThresh;
+    lp_d = kLn2 * fast_lg2(fmaxf(delta, kDeltaFloor));
+    if (GRAD) {
+      dm_d = dm_fb * (p1 * p1 * q * rdq);                          // -sgn(m) (1-E^2)/D
+      udu = u * (fmaf(q, q, 1.f) * fast_rcp(omq2) - delta);        // u (coth(u) - cdf_delta)
+    }
+  }
+  lp = big ? lp_d : lp_fb;
+  if (GRAD) {
+    const float dm = big ? dm_d : dm_fb;
+    dmu = -inv * dm;
+    dls = big ? -fmaf(m, dm_d, udu) : fmaf(-m, dm_fb, -1.0f);
+    if (raw_ls < C.log_eps) dls = 0.f;  // clamp(min=eps) blocks the gradient strictly below eps, passes at equality
+  }
+}
+
+// y in the first / last bin (clipped samples): log sigmoid(a) resp. log(1 - sigmoid(b))   :213,216,226-227
+template <bool GRAD>
+BLVM_HD void dl_edge(float y, int edge, float mu, float raw_ls, const DmolConsts& C, float& lp, float& dmu, float& dls) {
+  const float ls = (raw_ls < C.log_eps) ? C.log_eps : raw_ls;
+  const float inv = stable_exp(-ls);
+  const float c = y - mu;
+  if (edge == kEdgeLower) {
+    const float a = inv * (c + C.h);                                 // plus_in :206
+    const float e = fast_exp(-fabsf(a));
+    lp = fminf(a, 0.f) - fast_log(1.f + e);                          // a - softplus(a)
+    if (GRAD) {
+      const float da = ((a >= 0.f) ? e : 1.f) * fast_rcp(1.f + e);   // 1 - sigmoid(a)
+      dmu = -inv * da;
+      dls = -a * da;
+    }
+  } else {
+    const float b = inv * (c - C.h);                                 // minus_in :208
+    const float e = fast_exp(-fabsf(b));
+    lp = -fmaxf(b, 0.f) - fast_log(1.f + e);                         // -softplus(b)
+    if (GRAD) {
+      const float db = -((b >= 0.f) ? 1.f : e) * fast_rcp(1.f + e);  // -sigmoid(b)
+      dmu = -inv * db;
+      dls = -b * db;
+    }
+  }
+  if (GRAD) {
+    if (raw_ls < C.log_eps) dls = 0.f;
+  }
+}
 
 template <bool GRAD>
 BLVM_HD void dl_component(float y, int edge, float mu, float raw_ls, const DmolConsts& C, float& lp, float& dmu,
                           float& dls) {
-  const float ls = (raw_ls < C.log_eps) ? C.log_eps : raw_ls;  // clamp(min): NaN propagates like torch
-  const float inv = accurate_exp(-ls);                         // exp(-log_scale)            :203
-  const float c = y - mu;                                      // centered_y                 :202
-
-  if (edge != kEdgeNone) {  // y in the first / last bin: rare (clipped samples), the only divergent branch
-    if (edge == kEdgeLower) {
-      // lp = plus_in - softplus(plus_in) = log sigmoid(a)                                  :213
-      const float a = inv * (c + C.h);
-      const float e = fast_exp(-fabsf(a));
-      lp = fminf(a, 0.f) - fast_log(1.f + e);
-      if (GRAD) {
-        const float da = ((a >= 0.f) ? e : 1.f) * fast_rcp(1.f + e);  // 1 - sigmoid(a)
-        dmu = -inv * da;
-        dls = -a * da;
-      }
-    } else {
-      // lp = -softplus(minus_in) = log(1 - sigmoid(b))                                     :216
-      const float b = inv * (c - C.h);
-      const float e = fast_exp(-fabsf(b));
-      lp = -fmaxf(b, 0.f) - fast_log(1.f + e);
-      if (GRAD) {
-        const float db = -((b >= 0.f) ? 1.f : e) * fast_rcp(1.f + e);  // -sigmoid(b)
-        dmu = -inv * db;
-        dls = -b * db;
-      }
-    }
-  } else {
-    const float m = inv * c;                                   // mid_in                     :219
-    const float u = C.h * inv;
-    const float am = fabsf(m);
-    const float E = fast_ex2(-am * kLog2e);
-    const float p1 = 1.f + E;
-    const float r = fast_rcp(p1);
-    const float common = (-am - ls) - (2.f * kLn2) * fast_lg2(p1);   // log_pdf_mid = m - ls - 2 softplus(m)  :220
-    const float lp_fb = common - C.log_half_bins;                    // second arm of :221-223
-    // tanh(|m|/2) = (1-E)/(1+E); odd series below 1/8 so that the bin-centre gradient does not cancel
-    const float hx = 0.5f * am, hx2 = hx * hx;
-    const float th_series = hx * fmaf(hx2, fmaf(hx2, 2.0f / 15.0f, -1.0f / 3.0f), 1.0f);
-    const float th = (am < 0.25f) ? th_series : (1.f - E) * r;
-    const float dm_fb = copysignf(th, -m);                           // 1 - 2 sigmoid(m)
-    float lp_d, dm_d = 0.f, udu = 0.f;
-    bool big;
-    if (u < kSmallU) {
-      const float u2 = u * u;
-      const float er2 = E * r * r;
-      const float eps = er2 * (u2 * fmaf(u2, 1.0f / 12.0f, 1.0f));                  // E w / (1+E)^2
-      const float corr = u2 * fmaf(u2, -1.0f / 180.0f, 1.0f / 6.0f) - eps * fmaf(eps, -0.5f, 1.0f);
-      lp_d = common + (C.log_two_h + corr);                          // log cdf_delta, first arm of :221-223
-      big = lp_d > C.log_delta_thresh;                               // cdf_delta > 1e-5
-      if (GRAD) {
-        const float inv1pe = fmaf(eps, eps - 1.0f, 1.0f);            // 1/(1+eps)
-        dm_d = dm_fb * inv1pe;
-        const float udelta = 2.0f * u2 * er2 * fmaf(u2, 1.0f / 6.0f, 1.0f) * inv1pe;  // u * cdf_delta
-        udu = fmaf(u2, fmaf(u2, -1.0f / 45.0f, 1.0f / 3.0f), 1.0f) - udelta;          // u coth(u) - u cdf_delta
-      }
-    } else {
-      const float q = fast_ex2(-u * kLog2e);                         // exp(-u); everything below is overflow-free
-      const float omq = 1.f - q, omq2 = omq * (1.f + q);
-      const float rdq = fast_rcp(fmaf(q * p1, p1, E * omq * omq));   // q / D
-      const float delta = E * omq2 * rdq;                            // cdf_delta                  :210
-      big = delta > kDeltaThresh;
-      lp_d = kLn2 * fast_lg2(fmaxf(delta, kDeltaFloor));
-      if (GRAD) {
-        dm_d = dm_fb * (p1 * p1 * q * rdq);                          // -sgn(m) (1-E^2)/D
-        udu = u * (fmaf(q, q, 1.f) * fast_rcp(omq2) - delta);        // u (coth(u) - cdf_delta)
-      }
-    }
-    lp = big ? lp_d : lp_fb;
-    if (GRAD) {
-      const float dm = big ? dm_d : dm_fb;
-      dmu = -inv * dm;
-      dls = big ? -fmaf(m, dm_d, udu) : fmaf(-m, dm_fb, -1.0f);
-    }
-  }
-  if (GRAD) {
-    if (raw_ls < C.log_eps) dls = 0.f;  // clamp(min=eps) blocks the gradient strictly below eps, passes at equality
-  }
+  if (edge != kEdgeNone) dl_edge<GRAD>(y, edge, mu, raw_ls, C, lp, dmu, dls);
+  else dl_mid<GRAD, kUGeneral>(y, mu, raw_ls, C, lp, dmu, dls);
 }
 
 // ---- Gaussian KL, std-dev parametrisation (variational.py:67-70), cancellation-free around q == p ----------------
@@ -262,18 +301,31 @@ namespace blvm {
 //   out: returns log p(y) = logsumexp_k(lp_k + log_softmax(logits)_k)    (log_likelihoods.py:229-231)
 //        if GRAD, r[] is overwritten with g * d log p / d r[]
 // d/d logit_k = resp_k - softmax_k,  d/d loc_k = resp_k * dlp_k/dloc,  d/d ls_k = resp_k * dlp_k/dls.
-template <int K, bool GRAD>
+template <int K, bool GRAD, int UMODE = kUGeneral>
 BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts& C) {
   const int edge = dmol_edge(y, C);
   float v[K];
+  if (edge == kEdgeNone) {   // hoisted out of the component loop: the hot loop below has no edge test
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    float lp, dmu = 0.f, dls = 0.f;
-    dl_component<GRAD>(y, edge, r[K + k], r[2 * K + k], C, lp, dmu, dls);
-    v[k] = lp + r[k];
-    if (GRAD) {
-      r[K + k] = dmu;
-      r[2 * K + k] = dls;
+    for (int k = 0; k < K; ++k) {
+      float lp, dmu = 0.f, dls = 0.f;
+      dl_mid<GRAD, UMODE>(y, r[K + k], r[2 * K + k], C, lp, dmu, dls);
+      v[k] = lp + r[k];
+      if (GRAD) {
+        r[K + k] = dmu;
+        r[2 * K + k] = dls;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {  // (unrolled too: r[] must stay in registers)
+      float lp, dmu = 0.f, dls = 0.f;
+      dl_edge<GRAD>(y, edge, r[K + k], r[2 * K + k], C, lp, dmu, dls);
+      v[k] = lp + r[k];
+      if (GRAD) {
+        r[K + k] = dmu;
+        r[2 * K + k] = dls;
+      }
     }
   }
   float m1 = v[0], m2 = r[0];

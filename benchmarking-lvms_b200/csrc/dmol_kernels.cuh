@@ -1,6 +1,6 @@
 // DMoL kernels for sm_100a.
 //
-// dmol_tile_kernel<K, TPB, GRAD>: the hot kernel.  One CTA = one tile of up to TPB consecutive waveform samples of ONE
+// dmol_tile_kernel<K, TPB, GRAD, UMODE>: the hot kernel (UMODE: see blvm_math.cuh, chosen on the host).  One CTA = one tile of up to TPB consecutive waveform samples of ONE
 // utterance (row b), one thread per sample.  The tile's K-mixture parameters are the contiguous slab
 // raw[b, t0:t0+n, 0:3K] (3K*n floats): it is pulled into shared memory with one 1-D TMA bulk copy
 // (cp.async.bulk -> SASS UBLKCP) signalled on an mbarrier, each thread lifts its own 3K-float row into registers with
@@ -94,7 +94,7 @@ constexpr size_t dmol_tile_smem_bytes() {
   return size_t(TPB) * 3 * K * sizeof(float) + 16 /*mbarrier*/ + (TPB / 32) * sizeof(double);
 }
 
-template <int K, int TPB, bool GRAD>
+template <int K, int TPB, bool GRAD, int UMODE>
 __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
   constexpr int P = 3 * K;
   constexpr int NW = TPB / 32;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
     float* row = tile + tid * P;
     if (!skip) {
       row_load<P>(row, r);
-      L = dmol_sample<K, GRAD>(yv, r, g, A.C);
+      L = dmol_sample<K, GRAD, UMODE>(yv, r, g, A.C);
     } else {
 #pragma unroll
       for (int i = 0; i < P; ++i) r[i] = 0.f;

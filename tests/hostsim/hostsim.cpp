@@ -21,12 +21,13 @@ static DmolConsts make_consts(int num_bins, float log_eps) {
 }
 
 template <int K>
-static void run_fixed(const float* y, const float* raw, const float* gout, int64_t N, const DmolConsts& C, float* lp,
-                      float* graw) {
+static void run_fixed(const float* y, const float* raw, const float* gout, int64_t N, const DmolConsts& C, int tiny,
+                      float* lp, float* graw) {
   for (int64_t n = 0; n < N; ++n) {
     float r[3 * K];
     for (int i = 0; i < 3 * K; ++i) r[i] = raw[n * 3 * K + i];
-    lp[n] = dmol_sample<K, true>(y[n], r, gout ? gout[n] : 1.f, C);
+    lp[n] = tiny ? dmol_sample<K, true, kUTiny>(y[n], r, gout ? gout[n] : 1.f, C)
+                 : dmol_sample<K, true, kUGeneral>(y[n], r, gout ? gout[n] : 1.f, C);
     for (int i = 0; i < 3 * K; ++i) graw[n * 3 * K + i] = r[i];
   }
 }
@@ -34,20 +35,22 @@ static void run_fixed(const float* y, const float* raw, const float* gout, int64
 extern "C" int hostsim_dmol(const float* y, const float* raw, const float* gout, int64_t N, int K, int D, int num_bins,
                             float log_eps, int force_generic, float* lp, float* graw) {
   const DmolConsts C = make_consts(num_bins, log_eps);
+  // same rule as blvm_b200.cu: the tiny-u specialisation is used iff h * exp(-log_eps) < kTinyU
+  const int tiny = (double)C.h * std::exp(-(double)log_eps) < (double)kTinyU;
   if (D == 1 && !force_generic) {
     switch (K) {
-      case 1: run_fixed<1>(y, raw, gout, N, C, lp, graw); return 0;
-      case 2: run_fixed<2>(y, raw, gout, N, C, lp, graw); return 0;
-      case 5: run_fixed<5>(y, raw, gout, N, C, lp, graw); return 0;
-      case 10: run_fixed<10>(y, raw, gout, N, C, lp, graw); return 0;
-      case 30: run_fixed<30>(y, raw, gout, N, C, lp, graw); return 0;
+      case 1: run_fixed<1>(y, raw, gout, N, C, tiny, lp, graw); return tiny;
+      case 2: run_fixed<2>(y, raw, gout, N, C, tiny, lp, graw); return tiny;
+      case 5: run_fixed<5>(y, raw, gout, N, C, tiny, lp, graw); return tiny;
+      case 10: run_fixed<10>(y, raw, gout, N, C, tiny, lp, graw); return tiny;
+      case 30: run_fixed<30>(y, raw, gout, N, C, tiny, lp, graw); return tiny;
       default: break;
     }
   }
   const int P = K * (2 * D + 1);
   for (int64_t n = 0; n < N; ++n)
     lp[n] = dmol_sample_generic<true>(y + n * D, raw + n * P, K, D, gout ? gout[n] : 1.f, C, graw + n * P);
-  return 1;
+  return 2;
 }
 
 extern "C" void hostsim_dl(const float* y, const float* raw, const float* gout, int64_t N, int num_bins, float log_eps,

@@ -37,7 +37,9 @@ def run_dmol(sim, g, force_generic=0):
     N = raw.shape[0]
     lp = np.empty(N, np.float32)
     gr = np.empty_like(raw)
-    sim.hostsim_dmol(P(y), P(raw), P(gout), ctypes.c_int64(N), K, D, nb, ctypes.c_float(-7.0), force_generic, P(lp), P(gr))
+    mode = sim.hostsim_dmol(P(y), P(raw), P(gout), ctypes.c_int64(N), K, D, nb, ctypes.c_float(-7.0), force_generic, P(lp), P(gr))
+    if not force_generic and D == 1:
+        assert mode == (1 if nb == 65536 else 0)  # 16-bit bins + the -7 clamp select the tiny-u specialisation
     return lp, gr
 
 
