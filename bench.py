@@ -308,8 +308,7 @@ def run_gpu_arm(a):
     ms_total = statistics.median(region_ms)
 
     # ---- the dominant kernel alone: K launches between two events on the launching stream ---------------------------
-    lp_chunks = (T + 127) // 128
-    part = torch.empty(B * lp_chunks, dtype=torch.float64, device=dev)
+    part = torch.empty(B * int(blvm_b200._lib.lib.blvm_dmol_chunks(T, K, 1)), dtype=torch.float64, device=dev)
     graw = torch.empty_like(raw_d)
     raw_plain = raw_d.detach()
 

@@ -24,7 +24,8 @@ _f64 = ctypes.c_double
 SIGNATURES = {
     "blvm_version": (_i32, []),
     "blvm_last_error_string": (ctypes.c_char_p, []),
-    "blvm_dmol_chunks": (_i64, [_i64]),
+    "blvm_dmol_chunks": (_i64, [_i64, _i32, _i32]),
+    "blvm_dl_chunks": (_i64, [_i64]),
     "blvm_kl_chunks": (_i64, [_i64]),
     "blvm_dmol_fwd": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p]),
     "blvm_dmol_fwd_grad": (_i32, [_p, _p, _p, _p, _f32, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p, _p]),

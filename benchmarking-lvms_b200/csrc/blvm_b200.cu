@@ -121,7 +121,26 @@ extern "C" {
 
 int blvm_version(void) { return BLVM_B200_VERSION; }
 const char* blvm_last_error_string(void) { return g_err; }
-int64_t blvm_dmol_chunks(int64_t T) { return (T + kTile - 1) / kTile; }
+// samples per partial sum: the register kernel's tile (128 * samples-per-thread, a function of K) or 128 (generic / DL)
+static int64_t dmol_tile_samples(int K, int D) {
+  if (D == 1) {
+    switch (K) {
+#define BLVM_CASE(KK) \
+  case KK:            \
+    return static_cast<int64_t>(kTile) * DmolSpt<KK>::value;
+      BLVM_CASE(1) BLVM_CASE(2) BLVM_CASE(3) BLVM_CASE(4) BLVM_CASE(5) BLVM_CASE(6) BLVM_CASE(8) BLVM_CASE(10)
+      BLVM_CASE(12) BLVM_CASE(16) BLVM_CASE(20) BLVM_CASE(30)
+#undef BLVM_CASE
+      default: break;
+    }
+  }
+  return kTile;
+}
+int64_t blvm_dmol_chunks(int64_t T, int K, int D) {
+  const int64_t ts = dmol_tile_samples(K, D);
+  return (T + ts - 1) / ts;
+}
+int64_t blvm_dl_chunks(int64_t T) { return (T + kTile - 1) / kTile; }
 int64_t blvm_kl_chunks(int64_t row_elems) { return (row_elems + kKlChunk - 1) / kKlChunk; }
 
 int blvm_dmol_fwd(const float* y, const float* raw, const int64_t* x_sl, int64_t B, int64_t T, int K, int D, int num_bins,
@@ -129,7 +148,7 @@ int blvm_dmol_fwd(const float* y, const float* raw, const int64_t* x_sl, int64_t
   if (int rc = validate_dmol(y, raw, B, T, K, D, num_bins)) return rc;
   DmolArgs A{};
   A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = nullptr; A.gscale = 0.f; A.lp = lp; A.graw = nullptr;
-  A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T); A.K = K; A.D = D;
+  A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T, K, D); A.K = K; A.D = D;
   A.flags = flags; A.C = make_consts(num_bins, log_epsilon);
   return dispatch_dmol<false>(A, static_cast<cudaStream_t>(stream));
 }
@@ -142,7 +161,7 @@ int blvm_dmol_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, co
   if (!aligned(graw, 4)) return fail(BLVM_ERR_INVALID_ARGUMENT, "graw must be 4-byte aligned");
   DmolArgs A{};
   A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = gout; A.gscale = gscale; A.lp = lp; A.graw = graw;
-  A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T); A.K = K; A.D = D;
+  A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T, K, D); A.K = K; A.D = D;
   A.flags = flags; A.C = make_consts(num_bins, log_epsilon);
   return dispatch_dmol<true>(A, static_cast<cudaStream_t>(stream));
 }
@@ -154,7 +173,7 @@ int blvm_dl_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, cons
   if (!aligned(raw, 8) || !aligned(graw, 8)) return fail(BLVM_ERR_INVALID_ARGUMENT, "raw/graw must be 8-byte aligned");
   DmolArgs A{};
   A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = gout; A.gscale = gscale; A.lp = lp; A.graw = graw;
-  A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T); A.K = 1; A.D = 1;
+  A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dl_chunks(T); A.K = 1; A.D = 1;
   A.flags = flags; A.C = make_consts(num_bins, log_epsilon);
   const int64_t tiles = A.B * A.chunks;
   if (tiles == 0) return BLVM_OK;

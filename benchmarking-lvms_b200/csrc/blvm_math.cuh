@@ -310,7 +310,7 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     for (int k = 0; k < K; ++k) {
       float lp, dmu = 0.f, dls = 0.f;
       dl_mid<GRAD, UMODE>(y, r[K + k], r[2 * K + k], C, lp, dmu, dls);
-      v[k] = lp + r[k];
+      v[k] = (K == 1) ? lp : lp + r[k];
       if (GRAD) {
         r[K + k] = dmu;
         r[2 * K + k] = dls;
@@ -321,12 +321,23 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     for (int k = 0; k < K; ++k) {  // (unrolled too: r[] must stay in registers)
       float lp, dmu = 0.f, dls = 0.f;
       dl_edge<GRAD>(y, edge, r[K + k], r[2 * K + k], C, lp, dmu, dls);
-      v[k] = lp + r[k];
+      v[k] = (K == 1) ? lp : lp + r[k];
       if (GRAD) {
         r[K + k] = dmu;
         r[2 * K + k] = dls;
       }
     }
+  }
+  if constexpr (K == 1) {
+    // one component: log_softmax(logit) = 0, responsibility = softmax = 1, d/d logit = 0 (NaN/inf logits still propagate)
+    const float z = r[0] - r[0];   // 0, or NaN for a non-finite logit
+    const float L1 = v[0] + z;
+    if (GRAD) {
+      r[0] = g * z;
+      r[1] *= g;
+      r[2] *= g;
+    }
+    return L1;
   }
   float m1 = v[0], m2 = r[0];
 #pragma unroll

@@ -89,27 +89,36 @@ __device__ __forceinline__ void row_store(float* p, const float (&r)[P]) {
   }
 }
 
+// Samples per thread: small K means small rows, so a 128-sample tile would be a 1.5 KB slab (K = 1) and the per-CTA
+// fixed cost (mbarrier, barriers, bulk-store drain) dominates; each thread then walks SPT samples of a 128*SPT tile.
+template <int K>
+struct DmolSpt {
+  static constexpr int value = K <= 2 ? 8 : (K <= 5 ? 4 : (K <= 8 ? 2 : 1));
+};
+
 template <int K, int TPB>
 constexpr size_t dmol_tile_smem_bytes() {
-  return size_t(TPB) * 3 * K * sizeof(float) + 16 /*mbarrier*/ + (TPB / 32) * sizeof(double);
+  return size_t(TPB) * DmolSpt<K>::value * 3 * K * sizeof(float) + 16 /*mbarrier*/ + (TPB / 32) * sizeof(double);
 }
 
 template <int K, int TPB, bool GRAD, int UMODE>
 __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
   constexpr int P = 3 * K;
   constexpr int NW = TPB / 32;
+  constexpr int SPT = DmolSpt<K>::value;
+  constexpr int TILE = TPB * SPT;
   extern __shared__ __align__(128) unsigned char smem[];
   float* tile = reinterpret_cast<float*>(smem);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + size_t(TPB) * P * sizeof(float));
-  double* scratch = reinterpret_cast<double*>(smem + size_t(TPB) * P * sizeof(float) + 16);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + size_t(TILE) * P * sizeof(float));
+  double* scratch = reinterpret_cast<double*>(smem + size_t(TILE) * P * sizeof(float) + 16);
 
   const int tid = threadIdx.x;
   const int64_t tile_id = blockIdx.x;
   const int64_t b = tile_id / A.chunks;
   const int64_t c = tile_id - b * A.chunks;
-  const int64_t t0 = c * TPB;
-  const int n = static_cast<int>(min(static_cast<int64_t>(TPB), A.T - t0));  // samples of this tile
-  const int64_t s0 = b * A.T + t0;                                           // first flat sample
+  const int64_t t0 = c * TILE;
+  const int n = static_cast<int>(min(static_cast<int64_t>(TILE), A.T - t0));  // samples of this tile
+  const int64_t s0 = b * A.T + t0;                                            // first flat sample
   int64_t len = A.x_sl ? A.x_sl[b] : A.T;
   len = len < 0 ? 0 : (len > A.T ? A.T : len);
   const int nvalid = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(n), len - t0)));
@@ -135,36 +144,47 @@ __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
     }
   }
 
-  const bool in_tile = tid < n;
-  const bool valid = tid < nvalid;
-  float yv = 0.f, g = 0.f;
-  if (in_tile) {
-    yv = ptx::ldg_stream(A.y + s0 + tid);
-    if (!(yv <= 1.0f && yv >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
-    if (GRAD) {
-      g = valid ? A.gscale : 0.f;
-      if (A.gout) g *= ptx::ldg_stream(A.gout + s0 + tid);
+  // sample j of this thread is tile-local index j*TPB + tid: coalesced y / log-prob accesses, conflict-free smem rows
+  float yv[SPT], g[SPT];
+#pragma unroll
+  for (int j = 0; j < SPT; ++j) {
+    const int i = j * TPB + tid;
+    yv[j] = 0.f;
+    g[j] = 0.f;
+    if (i < n) {
+      yv[j] = ptx::ldg_stream(A.y + s0 + i);
+      if (!(yv[j] <= 1.0f && yv[j] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
+      if (GRAD) {
+        g[j] = (i < nvalid) ? A.gscale : 0.f;
+        if (A.gout) g[j] *= ptx::ldg_stream(A.gout + s0 + i);
+      }
     }
   }
   __syncthreads();  // mbarrier init / plain loads visible to everyone
   if (!skip && bulk_in) ptx::mbar_wait(bar, 0);
 
-  float L = 0.f;
-  if (in_tile) {
-    float r[P];
-    float* row = tile + tid * P;
-    if (!skip) {
-      row_load<P>(row, r);
-      L = dmol_sample<K, GRAD, UMODE>(yv, r, g, A.C);
-    } else {
+  double acc = 0.0;
 #pragma unroll
-      for (int i = 0; i < P; ++i) r[i] = 0.f;
+  for (int j = 0; j < SPT; ++j) {
+    const int i = j * TPB + tid;
+    if (i < n) {
+      float L = 0.f;
+      float r[P];
+      float* row = tile + i * P;
+      if (!skip) {
+        row_load<P>(row, r);
+        L = dmol_sample<K, GRAD, UMODE>(yv[j], r, g[j], A.C);
+      } else {
+#pragma unroll
+        for (int q = 0; q < P; ++q) r[q] = 0.f;
+      }
+      if (GRAD) row_store<P>(row, r);
+      // reference semantics: log_prob * mask (NaN/inf in the padding propagate like `* 0`), vrnn.py:268
+      const float Lm = (i < nvalid) ? L : L * 0.0f;
+      if (A.lp) A.lp[s0 + i] = (A.flags & kFlagMaskOutput) ? Lm : L;
+      acc += static_cast<double>(Lm);
     }
-    if (GRAD) row_store<P>(row, r);
   }
-  // reference semantics: log_prob * mask (NaN/inf in the padding propagate like `* 0`), vrnn.py:268
-  const float Lm = valid ? L : L * 0.0f;
-  if (A.lp && in_tile) A.lp[s0 + tid] = (A.flags & kFlagMaskOutput) ? Lm : L;
 
   if (GRAD) {
     if (bulk_out) {
@@ -180,7 +200,7 @@ __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
     }
   }
   if (A.partials) {
-    const double s = block_sum_f64<NW>(static_cast<double>(Lm), scratch);
+    const double s = block_sum_f64<NW>(acc, scratch);
     if (tid == 0) A.partials[tile_id] = s;
   }
   if (GRAD && bulk_out && tid == 0) ptx::bulk_wait_read0();  // smem must outlive the bulk store's read

@@ -301,7 +301,9 @@ class _FusedELBO(torch.autograd.Function):
         assert L <= _lib.BLVM_MAX_KL_LEVELS, f"at most {_lib.BLVM_MAX_KL_LEVELS} KL levels"
         has_lik = spec.likelihood != "none"
         T = raw.shape[1] if has_lik else 0
-        logp_chunks = int(lib.blvm_dmol_chunks(T)) if has_lik else 0
+        logp_chunks = 0
+        if has_lik:
+            logp_chunks = int(lib.blvm_dmol_chunks(T, spec.K, spec.D)) if spec.likelihood == "dmol" else int(lib.blvm_dl_chunks(T))
         shapes = []
         i = 0
         for lv in spec.levels:

@@ -40,7 +40,7 @@ enum {
 };
 
 #define BLVM_MAX_KL_LEVELS 8
-#define BLVM_DMOL_TILE 128   /* samples per partial sum of the DMoL / DL kernels  */
+#define BLVM_DMOL_TILE 128   /* threads per CTA of the DMoL / DL kernels (tile = 128 x samples-per-thread) */
 #define BLVM_KL_TILE 1024    /* latent elements per partial sum of the KL kernels */
 
 typedef void* blvm_stream_t;
@@ -48,8 +48,10 @@ typedef void* blvm_stream_t;
 int blvm_version(void);
 const char* blvm_last_error_string(void);
 
-/* Number of fp64 partial sums per utterance the kernels write: ceil(T / BLVM_DMOL_TILE), ceil(Tz*Z / BLVM_KL_TILE). */
-int64_t blvm_dmol_chunks(int64_t T);
+/* Number of fp64 partial sums per utterance the kernels write (one per CTA tile; the DMoL tile is BLVM_DMOL_TILE
+ * samples times a K-dependent samples-per-thread factor, the DL tile BLVM_DMOL_TILE, the KL tile BLVM_KL_TILE). */
+int64_t blvm_dmol_chunks(int64_t T, int K, int D);
+int64_t blvm_dl_chunks(int64_t T);
 int64_t blvm_kl_chunks(int64_t row_elems);
 
 /*
@@ -62,7 +64,7 @@ int64_t blvm_kl_chunks(int64_t row_elems);
  *                              at log_epsilon inside the kernel
  *   x_sl     (B) int64, nullable: valid samples per utterance (None = all T)
  *   lp       (B, T), nullable: per-sample log-prob out
- *   partials (B, blvm_dmol_chunks(T)) fp64, nullable: masked per-tile sums of log-prob
+ *   partials (B, blvm_dmol_chunks(T, K, D)) fp64, nullable: masked per-tile sums of log-prob
  *   err_flag int32, nullable: set to 1 if some y is outside [-1, 1] (the reference's assert, log_likelihoods.py:195)
  */
 int blvm_dmol_fwd(const float* y, const float* raw, const int64_t* x_sl, int64_t B, int64_t T, int K, int D,

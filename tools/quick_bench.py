@@ -50,7 +50,7 @@ def main():
         x_dev = x_sl.to(dev)
         lp = torch.empty(B, T, device=dev)
         graw = torch.empty_like(raw)
-        part = torch.empty(B * ((T + 127) // 128), dtype=torch.float64, device=dev)
+        part = torch.empty(B * int(blvm_b200._lib.lib.blvm_dmol_chunks(T, K, 1)), dtype=torch.float64, device=dev)
         N = B * T
         g = -1.0 / float(x_sl.sum())
         med, best = timeit(lambda: ops._dmol_call(y, raw, x_dev, None, g, B, T, K, 1, nb, -7.0, 1, lp, graw, part))
