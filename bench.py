@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--ragged", action="store_true", help="x_sl ~ T*U(0.5,1) instead of full length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph in the `value` region")
+    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "eager"],
+                    help="`value` region: replay the step's kernels from CUDA graphs (auto/graph) or call the API eagerly")
     return ap.parse_args()
 
 
@@ -226,56 +227,67 @@ def run_gpu_arm(a):
 
     pending = []
 
-    def step_device():
+    def compute_step():
+        """One step of the path through the public API: forward (values + gradients) and backward."""
         raw_d.grad = None
         for t in kl_d:
             t.grad = None
         out = blvm_b200.fused_elbo(y_d, params, x_sl, [blvm_b200.KLLevel(*kl_d, lens=lens_dev)], BETA, FREE_NATS,
                                    num_bins=NUM_BINS, denom=denom, x_sl_device=x_dev)
         out.loss.backward()
-        sums = out.sums
+        return out.sums
+
+    def exchange(sums):
+        # the path's only exchange: the fp64 scalar sums over NCCL/NVLink, asynchronous (NCCL's own stream) so that it
+        # overlaps the next step's kernels
         if world > 1:
-            # the path's only exchange: the fp64 scalar sums over NCCL/NVLink, asynchronous so that it overlaps the
-            # next step's kernels; the previous step's handle is waited for here (at most one in flight)
-            if pending:
-                pending.pop().wait()
             pending.append(blvm_b200.all_reduce_sums(sums, async_op=True, inplace=True))
-        return sums
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+    def step_eager():
+        while pending:
+            pending.pop(0).wait()
+        exchange(compute_step())
+
+    mode = a.mode
+    runner = step_eager
+    if mode in ("auto", "graph"):
+        # Capture the compute part of the step (fused_elbo + backward: 4 kernels) in two CUDA graphs with separate
+        # output workspaces and replay them alternately; the exchange stays an eager NCCL call on the previous replay's
+        # sums.  Removes ~190 us/step of Python + launch overhead (the GPU work is ~200 us/step).
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    compute_step()
+            torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            graphs = []
+            for _ in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    sums_static = compute_step()
+                graphs.append((g, sums_static))
+            torch.cuda.synchronize()
+            state = {"i": 0}
 
-    runner = step_device
-    if a.graph and world > 1:
-        raise SystemExit("--graph is single-GPU only (NCCL inside a captured graph hung on this stack; the N>1 arm runs eagerly)")
-    if a.graph:
-        # capture ONE step (fused_elbo + backward [+ the sums all-reduce]) and replay it: removes the Python/launch
-        # overhead (~190 us/step on the host vs ~215 us of GPU work) from the timed region
-        def step_for_capture():
-            raw_d.grad = None
-            for t in kl_d:
-                t.grad = None
-            out = blvm_b200.fused_elbo(y_d, params, x_sl, [blvm_b200.KLLevel(*kl_d, lens=lens_dev)], BETA, FREE_NATS,
-                                       num_bins=NUM_BINS, denom=denom, x_sl_device=x_dev)
-            out.loss.backward()
-            if world > 1:
-                dist.all_reduce(out.sums.detach())
-            return out.sums
+            def step_graph():
+                g, sums_static = graphs[state["i"] & 1]
+                state["i"] += 1
+                while len(pending) >= 2:       # this graph's previous exchange must be done before it rewrites its sums
+                    pending.pop(0).wait()
+                g.replay()
+                exchange(sums_static)
 
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                step_for_capture()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            static_sums = step_for_capture()
-        runner = g.replay
+            runner = step_graph
+            mode = "graph"
+        except Exception as ex:  # capture not possible on this stack: fall back to the eager step
+            if a.mode == "graph":
+                raise
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({ex!r}); running eagerly\n")
+            mode = "eager"
+    else:
+        mode = "eager"
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -298,7 +310,7 @@ def run_gpu_arm(a):
             pending.pop().wait()
         e1.record()
         sync_all()
-        launches = ops.launch_count() if not a.graph else None
+        launches = ops.launch_count() if mode == "eager" else 4 * a.steps
         region_ms.append(e0.elapsed_time(e1))
         done = torch.tensor([1.0 if (time.perf_counter() - t_begin >= a.min_seconds or len(region_ms) >= 200) else 0.0], device=dev)
         if world > 1:
@@ -398,9 +410,9 @@ def run_gpu_arm(a):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": kern_ms * 1e3,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
-            "e2e": e2e, "gpu_launches": launches if launches is not None else "graph replay", "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "mode": mode,
             "timed_region_repeats": len(region_ms), "timed_region_ms_min_max": [min(region_ms), max(region_ms)],
-            "step": "fused_elbo(...).loss.backward() through the Python API" + (" replayed from a CUDA graph" if a.graph else "")
+            "step": "fused_elbo(...).loss.backward() through the Python API" + (" (4 kernels, replayed from CUDA graphs)" if mode == "graph" else "")
                     + ("; + 1 NCCL all-reduce of 5 fp64 sums" if world > 1 else ""),
         }
         if not a.no_cpu_baseline and n_gpus == 1:
