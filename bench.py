@@ -227,6 +227,12 @@ def run_gpu_arm(a):
 
     pending = []
 
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     def compute_step():
         """One step of the path through the public API: forward (values + gradients) and backward."""
         raw_d.grad = None
