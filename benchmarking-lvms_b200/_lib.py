@@ -27,8 +27,9 @@ SIGNATURES = {
     "blvm_dmol_chunks": (_i64, [_i64, _i32, _i32]),
     "blvm_dl_chunks": (_i64, [_i64]),
     "blvm_kl_chunks": (_i64, [_i64]),
-    "blvm_dmol_fwd": (_i32, [_p, _p, _p, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p]),
-    "blvm_dmol_fwd_grad": (_i32, [_p, _p, _p, _p, _f32, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p, _p]),
+    "blvm_dmol_has_fast_path": (_i32, [_i32, _i32]),
+    "blvm_dmol_fwd": (_i32, [_p, _p, _i32, _p, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p]),
+    "blvm_dmol_fwd_grad": (_i32, [_p, _p, _i32, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p, _p]),
     "blvm_dl_fwd_grad": (_i32, [_p, _p, _p, _p, _f32, _i64, _i64, _i32, _f32, _i32, _p, _p, _p, _p, _p]),
     "blvm_kl_gaussian_fwd": (_i32, [_p, _p, _p, _p, _i64, _p, _p]),
     "blvm_kl_gaussian_bwd": (_i32, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
@@ -37,7 +38,7 @@ SIGNATURES = {
     "blvm_elbo_finalize": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64, _f64, _p, _p, _p, _p]),
     "blvm_quantize": (_i32, [_p, _i64, _p, _i64, _p, _p]),
     "blvm_scale_inplace": (_i32, [_p, _i64, _p, _p]),
-    "blvm_scale_inplace_multi": (_i32, [ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _p]),
+    "blvm_scale_inplace_multi": (_i32, [ctypes.POINTER(_p), ctypes.POINTER(_i64), ctypes.POINTER(_i32), _i32, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -45,6 +46,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
+BLVM_DTYPE_F32, BLVM_DTYPE_F16, BLVM_DTYPE_BF16 = 0, 1, 2
 BLVM_FLAG_MASK_OUTPUT = 1
 BLVM_FLAG_SKIP_PADDED = 2
 BLVM_MAX_KL_LEVELS = 8

@@ -52,10 +52,10 @@ DmolConsts make_consts(int num_bins, float log_epsilon) {
 
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <int K, bool GRAD, int UMODE>
+template <int K, bool GRAD, int UMODE, typename TP>
 int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
-  constexpr size_t smem = dmol_tile_smem_bytes<K, kTile>();
-  auto kern = dmol_tile_kernel<K, kTile, GRAD, UMODE>;
+  constexpr size_t smem = dmol_tile_smem_bytes<K, kTile, TP>();
+  auto kern = dmol_tile_kernel<K, kTile, GRAD, UMODE, TP>;
   static bool configured = false;  // per instantiation; benign race (idempotent attribute)
   if (!configured) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -68,50 +68,81 @@ int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
 
 // u = h / s <= h * exp(-log_epsilon) for every element: if that bound is tiny (16-bit bins with the -7 clamp: 0.0167)
 // the kernel specialisation without the large-u code is exact to O(u^4) ~ 1e-7 (blvm_math.cuh).
-template <int K, bool GRAD>
-int launch_tile(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
+template <int K, bool GRAD, typename TP>
+int launch_tile_dtype(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
   const double u_max = static_cast<double>(A.C.h) * exp(-static_cast<double>(A.C.log_eps));
-  if (u_max < static_cast<double>(kTinyU)) return launch_tile_mode<K, GRAD, kUTiny>(A, tiles, st);
-  return launch_tile_mode<K, GRAD, kUGeneral>(A, tiles, st);
+  if (u_max < static_cast<double>(kTinyU)) return launch_tile_mode<K, GRAD, kUTiny, TP>(A, tiles, st);
+  return launch_tile_mode<K, GRAD, kUGeneral, TP>(A, tiles, st);
+}
+
+template <int K, bool GRAD>
+int launch_tile(const DmolArgs& A, int raw_dtype, int64_t tiles, cudaStream_t st) {
+  switch (raw_dtype) {
+    case BLVM_DTYPE_F32: return launch_tile_dtype<K, GRAD, float>(A, tiles, st);
+    case BLVM_DTYPE_F16: return launch_tile_dtype<K, GRAD, __half>(A, tiles, st);
+    case BLVM_DTYPE_BF16: return launch_tile_dtype<K, GRAD, __nv_bfloat16>(A, tiles, st);
+    default: return fail(BLVM_ERR_INVALID_ARGUMENT, "raw_dtype=%d", raw_dtype);
+  }
+}
+
+#define BLVM_FOR_EACH_K(X) X(1) X(2) X(3) X(4) X(5) X(6) X(8) X(10) X(12) X(16) X(20) X(30)
+
+// samples per partial sum: the register kernel's tile (128 * samples-per-thread, a function of K) or 128 (generic / DL)
+int64_t dmol_tile_samples(int K, int D) {
+  if (D == 1) {
+    switch (K) {
+#define BLVM_CASE(KK) \
+  case KK:            \
+    return static_cast<int64_t>(kTile) * DmolSpt<KK>::value;
+      BLVM_FOR_EACH_K(BLVM_CASE)
+#undef BLVM_CASE
+      default: break;
+    }
+  }
+  return kTile;
+}
+
+bool dmol_has_register_kernel(int K, int D) {
+  if (D != 1) return false;
+  switch (K) {
+#define BLVM_CASE(KK) case KK:
+    BLVM_FOR_EACH_K(BLVM_CASE)
+#undef BLVM_CASE
+    return true;
+    default: return false;
+  }
 }
 
 template <bool GRAD>
-int dispatch_dmol(const DmolArgs& A, cudaStream_t st) {
+int dispatch_dmol(const DmolArgs& A, int raw_dtype, cudaStream_t st) {
+  const int64_t ts = dmol_tile_samples(A.K, A.D);
   const int64_t tiles = A.B * A.chunks;
+  (void)ts;
   if (tiles == 0) return BLVM_OK;
   if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)tiles);
   if (A.D == 1) {
     switch (A.K) {
 #define BLVM_CASE(KK) \
   case KK:            \
-    return launch_tile<KK, GRAD>(A, tiles, st);
-      BLVM_CASE(1)
-      BLVM_CASE(2)
-      BLVM_CASE(3)
-      BLVM_CASE(4)
-      BLVM_CASE(5)
-      BLVM_CASE(6)
-      BLVM_CASE(8)
-      BLVM_CASE(10)
-      BLVM_CASE(12)
-      BLVM_CASE(16)
-      BLVM_CASE(20)
-      BLVM_CASE(30)
+    return launch_tile<KK, GRAD>(A, raw_dtype, tiles, st);
+      BLVM_FOR_EACH_K(BLVM_CASE)
 #undef BLVM_CASE
       default:
         break;
     }
   }
+  if (raw_dtype != BLVM_DTYPE_F32)
+    return fail(BLVM_ERR_UNSUPPORTED, "fp16/bf16 parameters need a register kernel (K=%d D=%d has none): upcast to fp32", A.K, A.D);
   dmol_generic_kernel<kTile, GRAD><<<static_cast<unsigned>(tiles), kTile, 0, st>>>(A);
   return check_launch("dmol_generic_kernel");
 }
 
-int validate_dmol(const float* y, const float* raw, int64_t B, int64_t T, int K, int D, int num_bins) {
+int validate_dmol(const float* y, const void* raw, int64_t B, int64_t T, int K, int D, int num_bins) {
   if (B < 0 || T < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "negative size B=%lld T=%lld", (long long)B, (long long)T);
   if (K < 1 || D < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "K=%d D=%d must be >= 1", K, D);
   if (num_bins < 2) return fail(BLVM_ERR_INVALID_ARGUMENT, "num_bins=%d must be >= 2", num_bins);
   if (B * T > 0 && (!y || !raw)) return fail(BLVM_ERR_INVALID_ARGUMENT, "null y/raw");
-  if (!aligned(y, 4) || !aligned(raw, 4)) return fail(BLVM_ERR_INVALID_ARGUMENT, "y/raw must be 4-byte aligned");
+  if (!aligned(y, 4) || !aligned(raw, 2)) return fail(BLVM_ERR_INVALID_ARGUMENT, "y must be 4-byte, raw element aligned");
   return BLVM_OK;
 }
 
@@ -121,49 +152,36 @@ extern "C" {
 
 int blvm_version(void) { return BLVM_B200_VERSION; }
 const char* blvm_last_error_string(void) { return g_err; }
-// samples per partial sum: the register kernel's tile (128 * samples-per-thread, a function of K) or 128 (generic / DL)
-static int64_t dmol_tile_samples(int K, int D) {
-  if (D == 1) {
-    switch (K) {
-#define BLVM_CASE(KK) \
-  case KK:            \
-    return static_cast<int64_t>(kTile) * DmolSpt<KK>::value;
-      BLVM_CASE(1) BLVM_CASE(2) BLVM_CASE(3) BLVM_CASE(4) BLVM_CASE(5) BLVM_CASE(6) BLVM_CASE(8) BLVM_CASE(10)
-      BLVM_CASE(12) BLVM_CASE(16) BLVM_CASE(20) BLVM_CASE(30)
-#undef BLVM_CASE
-      default: break;
-    }
-  }
-  return kTile;
-}
 int64_t blvm_dmol_chunks(int64_t T, int K, int D) {
   const int64_t ts = dmol_tile_samples(K, D);
   return (T + ts - 1) / ts;
 }
 int64_t blvm_dl_chunks(int64_t T) { return (T + kTile - 1) / kTile; }
+int blvm_dmol_has_fast_path(int K, int D) { return dmol_has_register_kernel(K, D) ? 1 : 0; }
 int64_t blvm_kl_chunks(int64_t row_elems) { return (row_elems + kKlChunk - 1) / kKlChunk; }
 
-int blvm_dmol_fwd(const float* y, const float* raw, const int64_t* x_sl, int64_t B, int64_t T, int K, int D, int num_bins,
-                  float log_epsilon, int flags, float* lp, double* partials, int* err_flag, blvm_stream_t stream) {
+int blvm_dmol_fwd(const float* y, const void* raw, int raw_dtype, const int64_t* x_sl, int64_t B, int64_t T, int K, int D,
+                  int num_bins, float log_epsilon, int flags, float* lp, double* partials, int* err_flag,
+                  blvm_stream_t stream) {
   if (int rc = validate_dmol(y, raw, B, T, K, D, num_bins)) return rc;
   DmolArgs A{};
   A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = nullptr; A.gscale = 0.f; A.lp = lp; A.graw = nullptr;
   A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T, K, D); A.K = K; A.D = D;
   A.flags = flags; A.C = make_consts(num_bins, log_epsilon);
-  return dispatch_dmol<false>(A, static_cast<cudaStream_t>(stream));
+  return dispatch_dmol<false>(A, raw_dtype, static_cast<cudaStream_t>(stream));
 }
 
-int blvm_dmol_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale, int64_t B,
-                       int64_t T, int K, int D, int num_bins, float log_epsilon, int flags, float* lp, float* graw,
-                       double* partials, int* err_flag, blvm_stream_t stream) {
+int blvm_dmol_fwd_grad(const float* y, const void* raw, int raw_dtype, const int64_t* x_sl, const float* gout, float gscale,
+                       const double* gscale_dev, int64_t B, int64_t T, int K, int D, int num_bins, float log_epsilon,
+                       int flags, float* lp, void* graw, double* partials, int* err_flag, blvm_stream_t stream) {
   if (int rc = validate_dmol(y, raw, B, T, K, D, num_bins)) return rc;
   if (B * T > 0 && !graw) return fail(BLVM_ERR_INVALID_ARGUMENT, "null graw");
-  if (!aligned(graw, 4)) return fail(BLVM_ERR_INVALID_ARGUMENT, "graw must be 4-byte aligned");
+  if (!aligned(graw, 2)) return fail(BLVM_ERR_INVALID_ARGUMENT, "graw must be element aligned");
   DmolArgs A{};
-  A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = gout; A.gscale = gscale; A.lp = lp; A.graw = graw;
+  A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = gout; A.gscale = gscale; A.gscale_dev = gscale_dev; A.lp = lp; A.graw = graw;
   A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T, K, D); A.K = K; A.D = D;
   A.flags = flags; A.C = make_consts(num_bins, log_epsilon);
-  return dispatch_dmol<true>(A, static_cast<cudaStream_t>(stream));
+  return dispatch_dmol<true>(A, raw_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int blvm_dl_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale, int64_t B,
@@ -294,8 +312,8 @@ int blvm_scale_inplace(float* buf, int64_t n, const double* scale, blvm_stream_t
   return check_launch("scale_inplace_kernel");
 }
 
-int blvm_scale_inplace_multi(float* const* bufs_host, const int64_t* ns_host, int count, const double* scale,
-                             blvm_stream_t stream) {
+int blvm_scale_inplace_multi(void* const* bufs_host, const int64_t* ns_host, const int* dtypes_host, int count,
+                             const double* scale, blvm_stream_t stream) {
   if (count < 0 || count > kMaxScaleBuffers) return fail(BLVM_ERR_INVALID_ARGUMENT, "count=%d out of [0, %d]", count, kMaxScaleBuffers);
   if (count == 0) return BLVM_OK;
   if (!scale) return fail(BLVM_ERR_INVALID_ARGUMENT, "null scale");
@@ -304,7 +322,8 @@ int blvm_scale_inplace_multi(float* const* bufs_host, const int64_t* ns_host, in
   int64_t nmax = 0;
   for (int i = 0; i < count; ++i) {
     if (ns_host[i] < 0 || (ns_host[i] > 0 && !bufs_host[i])) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad buffer %d", i);
-    A.buf[i] = bufs_host[i]; A.n[i] = ns_host[i];
+    A.buf[i] = bufs_host[i]; A.n[i] = ns_host[i]; A.dtype[i] = dtypes_host ? dtypes_host[i] : 0;
+    if (A.dtype[i] < 0 || A.dtype[i] > 2) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad dtype for buffer %d", i);
     nmax = ns_host[i] > nmax ? ns_host[i] : nmax;
   }
   const int64_t want = (nmax + 1023) / 1024;

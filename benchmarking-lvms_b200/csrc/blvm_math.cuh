@@ -274,7 +274,8 @@ BLVM_HD KlTerms kl_gaussian_terms(float mu_q, float sd_q, float mu_p, float sd_p
   p = fmaf(p, s2, 1.0f / 5.0f);
   p = fmaf(p, s2, 1.0f / 3.0f);
   p = fmaf(p, s2, 1.0f);
-  const float log_rho = (fabsf(s) < 0.2f) ? 2.0f * s * p : kLn2 * fast_lg2(sd_q * t.inv_sp);
+  const float log_series = 2.0f * s * p, log_mufu = kLn2 * fast_lg2(sd_q * t.inv_sp);   // both evaluated: a select, no branch
+  const float log_rho = (fabsf(s) < 0.2f) ? log_series : log_mufu;
   t.kl = 0.5f * t.q - log_rho;
   return t;
 }

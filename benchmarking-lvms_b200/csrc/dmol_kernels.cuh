@@ -11,6 +11,8 @@
 //
 // Algorithmic traffic per sample: read 4 (y) + 12K (params), write 4 (log-prob) + 12K (grads) = 4(2+6K) bytes.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -26,12 +28,13 @@ enum : int {
 
 struct DmolArgs {
   const float* y;          // (B*T*D)
-  const float* raw;        // (B*T, P)  P = K(2D+1)
+  const void* raw;         // (B*T, P)  P = K(2D+1); fp32, or fp16/bf16 in the register kernels (AMP Linear output)
   const int64_t* x_sl;     // (B) valid samples per row, device; nullptr = all valid
   const float* gout;       // (B*T) upstream gradient per sample, nullptr = 1
   float gscale;            // scalar multiplier of every gradient (e.g. -1/sum(x_sl))
+  const double* gscale_dev;  // optional device scalar multiplied into gscale (an upstream grad_output), nullptr = 1
   float* lp;               // (B*T) per-sample log-prob out, nullptr = not wanted
-  float* graw;             // (B*T, P) gradient out (GRAD kernels)
+  void* graw;              // (B*T, P) gradient out (GRAD kernels), same element type as raw
   double* partials;        // (B, chunks) masked per-tile sums of log-prob, nullptr = not wanted
   int* err_flag;           // set to 1 if any y is outside [-1, 1] (the reference's assert, log_likelihoods.py:195)
   int64_t B, T, chunks;
@@ -55,39 +58,94 @@ __device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
   return s;  // valid in thread 0
 }
 
-// Lift / drop one P-float row between shared memory and registers with the widest aligned vector the row stride allows.
+// Lift / drop one P-element row between shared memory and registers (as fp32) with the widest aligned vector the
+// row stride allows.  fp32 rows: 128/64/32-bit; fp16/bf16 rows: 32-bit pairs when P is even.
+template <typename TP, int P>
+struct RowIO;
+
 template <int P>
-__device__ __forceinline__ void row_load(const float* p, float (&r)[P]) {
-  if constexpr (P % 4 == 0) {
+struct RowIO<float, P> {
+  static __device__ __forceinline__ void load(const float* p, float (&r)[P]) {
+    if constexpr (P % 4 == 0) {
 #pragma unroll
-    for (int i = 0; i < P / 4; ++i) {
-      const float4 v = reinterpret_cast<const float4*>(p)[i];
-      r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+      for (int i = 0; i < P / 4; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(p)[i];
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+      }
+    } else if constexpr (P % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        const float2 v = reinterpret_cast<const float2*>(p)[i];
+        r[2 * i] = v.x; r[2 * i + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) r[i] = p[i];
     }
-  } else if constexpr (P % 2 == 0) {
-#pragma unroll
-    for (int i = 0; i < P / 2; ++i) {
-      const float2 v = reinterpret_cast<const float2*>(p)[i];
-      r[2 * i] = v.x; r[2 * i + 1] = v.y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < P; ++i) r[i] = p[i];
   }
-}
+  static __device__ __forceinline__ void store(float* p, const float (&r)[P]) {
+    if constexpr (P % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    } else if constexpr (P % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(r[2 * i], r[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) p[i] = r[i];
+    }
+  }
+};
+
 template <int P>
-__device__ __forceinline__ void row_store(float* p, const float (&r)[P]) {
-  if constexpr (P % 4 == 0) {
+struct RowIO<__half, P> {
+  static __device__ __forceinline__ void load(const __half* p, float (&r)[P]) {
+    if constexpr (P % 2 == 0) {
 #pragma unroll
-    for (int i = 0; i < P / 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-  } else if constexpr (P % 2 == 0) {
+      for (int i = 0; i < P / 2; ++i) {
+        const float2 v = __half22float2(reinterpret_cast<const __half2*>(p)[i]);
+        r[2 * i] = v.x; r[2 * i + 1] = v.y;
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < P / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(r[2 * i], r[2 * i + 1]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < P; ++i) p[i] = r[i];
+      for (int i = 0; i < P; ++i) r[i] = __half2float(p[i]);
+    }
   }
-}
+  static __device__ __forceinline__ void store(__half* p, const float (&r)[P]) {
+    if constexpr (P % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) reinterpret_cast<__half2*>(p)[i] = __floats2half2_rn(r[2 * i], r[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) p[i] = __float2half_rn(r[i]);
+    }
+  }
+};
+
+template <int P>
+struct RowIO<__nv_bfloat16, P> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[P]) {
+    if constexpr (P % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        const float2 v = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(p)[i]);
+        r[2 * i] = v.x; r[2 * i + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) r[i] = __bfloat162float(p[i]);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&r)[P]) {
+    if constexpr (P % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) reinterpret_cast<__nv_bfloat162*>(p)[i] = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < P; ++i) p[i] = __float2bfloat16_rn(r[i]);
+    }
+  }
+};
 
 // Samples per thread: small K means small rows, so a 128-sample tile would be a 1.5 KB slab (K = 1) and the per-CTA
 // fixed cost (mbarrier, barriers, bulk-store drain) dominates; each thread then walks SPT samples of a 128*SPT tile.
@@ -96,21 +154,22 @@ struct DmolSpt {
   static constexpr int value = K <= 2 ? 8 : (K <= 5 ? 4 : (K <= 8 ? 2 : 1));
 };
 
-template <int K, int TPB>
+template <int K, int TPB, typename TP>
 constexpr size_t dmol_tile_smem_bytes() {
-  return size_t(TPB) * DmolSpt<K>::value * 3 * K * sizeof(float) + 16 /*mbarrier*/ + (TPB / 32) * sizeof(double);
+  return ((size_t(TPB) * DmolSpt<K>::value * 3 * K * sizeof(TP) + 15) / 16) * 16 + 16 /*mbarrier*/ + (TPB / 32) * sizeof(double);
 }
 
-template <int K, int TPB, bool GRAD, int UMODE>
+template <int K, int TPB, bool GRAD, int UMODE, typename TP>
 __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
   constexpr int P = 3 * K;
   constexpr int NW = TPB / 32;
   constexpr int SPT = DmolSpt<K>::value;
   constexpr int TILE = TPB * SPT;
+  constexpr size_t kTileBytes = ((size_t(TILE) * P * sizeof(TP) + 15) / 16) * 16;
   extern __shared__ __align__(128) unsigned char smem[];
-  float* tile = reinterpret_cast<float*>(smem);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + size_t(TILE) * P * sizeof(float));
-  double* scratch = reinterpret_cast<double*>(smem + size_t(TILE) * P * sizeof(float) + 16);
+  TP* tile = reinterpret_cast<TP*>(smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kTileBytes);
+  double* scratch = reinterpret_cast<double*>(smem + kTileBytes + 16);
 
   const int tid = threadIdx.x;
   const int64_t tile_id = blockIdx.x;
@@ -123,9 +182,9 @@ __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
   len = len < 0 ? 0 : (len > A.T ? A.T : len);
   const int nvalid = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(n), len - t0)));
 
-  const float* gsrc = A.raw + s0 * P;
-  float* gdst = GRAD ? A.graw + s0 * P : nullptr;
-  const uint32_t bytes = static_cast<uint32_t>(n) * P * sizeof(float);
+  const TP* gsrc = static_cast<const TP*>(A.raw) + s0 * P;
+  TP* gdst = GRAD ? static_cast<TP*>(A.graw) + s0 * P : nullptr;
+  const uint32_t bytes = static_cast<uint32_t>(n) * P * sizeof(TP);
   const bool skip = (A.flags & kFlagSkipPadded) && nvalid == 0;
   const bool bulk_in = ((reinterpret_cast<uintptr_t>(gsrc) | bytes) & 15u) == 0;
   const bool bulk_out = GRAD && ((reinterpret_cast<uintptr_t>(gdst) | bytes) & 15u) == 0;
@@ -139,13 +198,15 @@ __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
         ptx::mbar_arrive_expect_tx(bar, bytes);
         ptx::bulk_g2s(tile, gsrc, bytes, bar, pol);
       }
-    } else {  // unaligned slab (odd T with even K, or an offset view): coalesced 32-bit loads
-      for (int i = tid; i < n * P; i += TPB) tile[i] = ptx::ldg_stream(gsrc + i);
+    } else {  // unaligned slab (odd T with even K, or an offset view): coalesced element-wise loads
+      for (int i = tid; i < n * P; i += TPB) tile[i] = gsrc[i];
     }
   }
 
   // sample j of this thread is tile-local index j*TPB + tid: coalesced y / log-prob accesses, conflict-free smem rows
   float yv[SPT], g[SPT];
+  float gs = A.gscale;
+  if (GRAD && A.gscale_dev) gs *= static_cast<float>(*A.gscale_dev);
 #pragma unroll
   for (int j = 0; j < SPT; ++j) {
     const int i = j * TPB + tid;
@@ -155,7 +216,7 @@ __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
       yv[j] = ptx::ldg_stream(A.y + s0 + i);
       if (!(yv[j] <= 1.0f && yv[j] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
       if (GRAD) {
-        g[j] = (i < nvalid) ? A.gscale : 0.f;
+        g[j] = (i < nvalid) ? gs : 0.f;
         if (A.gout) g[j] *= ptx::ldg_stream(A.gout + s0 + i);
       }
     }
@@ -170,15 +231,15 @@ __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
     if (i < n) {
       float L = 0.f;
       float r[P];
-      float* row = tile + i * P;
+      TP* row = tile + i * P;
       if (!skip) {
-        row_load<P>(row, r);
+        RowIO<TP, P>::load(row, r);
         L = dmol_sample<K, GRAD, UMODE>(yv[j], r, g[j], A.C);
       } else {
 #pragma unroll
         for (int q = 0; q < P; ++q) r[q] = 0.f;
       }
-      if (GRAD) row_store<P>(row, r);
+      if (GRAD) RowIO<TP, P>::store(row, r);
       // reference semantics: log_prob * mask (NaN/inf in the padding propagate like `* 0`), vrnn.py:268
       const float Lm = (i < nvalid) ? L : L * 0.0f;
       if (A.lp) A.lp[s0 + i] = (A.flags & kFlagMaskOutput) ? Lm : L;
@@ -196,7 +257,7 @@ __global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
       }
     } else {
       __syncthreads();
-      for (int i = tid; i < n * P; i += TPB) ptx::stg_stream(gdst + i, tile[i]);
+      for (int i = tid; i < n * P; i += TPB) gdst[i] = tile[i];
     }
   }
   if (A.partials) {
@@ -233,12 +294,14 @@ __global__ void __launch_bounds__(TPB) dmol_generic_kernel(const DmolArgs A) {
     float g = 0.f;
     if (GRAD) {
       g = valid ? A.gscale : 0.f;
+      if (A.gscale_dev) g *= static_cast<float>(*A.gscale_dev);
       if (A.gout) g *= A.gout[s];
     }
     if (!skip) {
-      L = dmol_sample_generic<GRAD>(yv, A.raw + s * P, A.K, A.D, g, A.C, GRAD ? A.graw + s * P : nullptr);
+      L = dmol_sample_generic<GRAD>(yv, static_cast<const float*>(A.raw) + s * P, A.K, A.D, g, A.C,
+                                    GRAD ? static_cast<float*>(A.graw) + s * P : nullptr);
     } else if (GRAD) {
-      for (int i = 0; i < P; ++i) A.graw[s * P + i] = 0.f;
+      for (int i = 0; i < P; ++i) static_cast<float*>(A.graw)[s * P + i] = 0.f;
     }
   }
   const float Lm = valid ? L : L * 0.0f;
@@ -274,14 +337,15 @@ __global__ void __launch_bounds__(TPB) dl_kernel(const DmolArgs A) {
     float g = 0.f;
     if (GRAD) {
       g = valid ? A.gscale : 0.f;
+      if (A.gscale_dev) g *= static_cast<float>(*A.gscale_dev);
       if (A.gout) g *= A.gout[s];
     }
     float dmu = 0.f, dls = 0.f;
     if (!skip) {
-      const float2 p = reinterpret_cast<const float2*>(A.raw)[s];
+      const float2 p = static_cast<const float2*>(A.raw)[s];
       dl_component<GRAD>(yv, dmol_edge(yv, A.C), p.x, p.y, A.C, L, dmu, dls);
     }
-    if (GRAD) reinterpret_cast<float2*>(A.graw)[s] = make_float2(g * dmu, g * dls);
+    if (GRAD) static_cast<float2*>(A.graw)[s] = make_float2(g * dmu, g * dls);
   }
   const float Lm = valid ? L : L * 0.0f;
   if (A.lp && in_tile) A.lp[s0 + tid] = (A.flags & kFlagMaskOutput) ? Lm : L;

@@ -32,15 +32,18 @@ constexpr int kKlTPB = 256;
 constexpr int kKlVec = 4;
 constexpr int kKlChunk = kKlTPB * kKlVec;  // elements per CTA
 
+// s_kl / s_fn accumulate the (at most 4) elements of one thread in fp32 — KL terms are non-negative, so the 4-term fp32
+// sum is good to ~1e-7 relative — and are widened to fp64 once per thread for the block reduction (fp32->fp64
+// conversions run on the 16-lane XU pipe; per element they were 2 of ~6 XU operations).
 template <bool GRAD>
 __device__ __forceinline__ void kl_element(const KlArgs& A, int64_t idx, bool valid, float mq, float sq, float mp, float sp,
-                                           float& kl, float& gmq, float& gsq, float& gmp, float& gsp, double& s_kl,
-                                           double& s_fn) {
+                                           float& kl, float& gmq, float& gsq, float& gmp, float& gsp, float& s_kl,
+                                           float& s_fn) {
   const KlTerms t = kl_gaussian_terms(mq, sq, mp, sp);
   kl = t.kl;
   const float klfn = (A.fn_enabled && kl < A.min_kl) ? A.min_kl : kl;  // torch.maximum; NaN propagates
-  s_kl += static_cast<double>(valid ? kl : kl * 0.0f);                 // `kld * mask` semantics (vrnn.py:272)
-  s_fn += static_cast<double>(valid ? klfn : klfn * 0.0f);
+  s_kl += valid ? kl : kl * 0.0f;                                      // `kld * mask` semantics (vrnn.py:272)
+  s_fn += valid ? klfn : klfn * 0.0f;
   if (GRAD) {
     float g = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
     if (A.gout) g *= A.gout[idx];
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(kKlTPB) kl_kernel(const KlArgs A) {
   len = len < 0 ? 0 : (len > max_steps ? max_steps : len);
   const int64_t nvalid_row = len * A.Z;
   const int64_t base = b * A.row_elems;
-  double s_kl = 0.0, s_fn = 0.0;
+  float s_kl = 0.f, s_fn = 0.f;
 
   if (VEC) {
     const int64_t e = e0 + static_cast<int64_t>(tid) * kKlVec;
@@ -103,8 +106,8 @@ __global__ void __launch_bounds__(kKlTPB) kl_kernel(const KlArgs A) {
     }
   }
   if (A.part_kl) {
-    const double a = block_sum_f64<kKlTPB / 32>(s_kl, scratch[0]);
-    const double f = block_sum_f64<kKlTPB / 32>(s_fn, scratch[1]);
+    const double a = block_sum_f64<kKlTPB / 32>(static_cast<double>(s_kl), scratch[0]);
+    const double f = block_sum_f64<kKlTPB / 32>(static_cast<double>(s_fn), scratch[1]);
     if (tid == 0) {
       A.part_kl[tile_id] = a;
       A.part_klfn[tile_id] = f;

@@ -1,5 +1,7 @@
 // Small helpers around the hot path: the integer Quantize transform and an early-exit in-place scale.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,8 +34,9 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ 
 
 constexpr int kMaxScaleBuffers = 36;
 struct ScaleMultiArgs {
-  float* buf[kMaxScaleBuffers];
+  void* buf[kMaxScaleBuffers];
   int64_t n[kMaxScaleBuffers];
+  int dtype[kMaxScaleBuffers];   // 0 fp32, 1 fp16, 2 bf16
   int count;
   const double* scale;
 };
@@ -41,10 +44,19 @@ struct ScaleMultiArgs {
 __global__ void __launch_bounds__(256) scale_inplace_multi_kernel(const ScaleMultiArgs A) {
   const float s = static_cast<float>(*A.scale);
   if (s == 1.0f) return;
-  float* __restrict__ buf = A.buf[blockIdx.y];
   const int64_t n = A.n[blockIdx.y];
   const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) buf[i] *= s;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (A.dtype[blockIdx.y] == 0) {
+    float* __restrict__ buf = static_cast<float*>(A.buf[blockIdx.y]);
+    for (int64_t i = i0; i < n; i += stride) buf[i] *= s;
+  } else if (A.dtype[blockIdx.y] == 1) {
+    __half* __restrict__ buf = static_cast<__half*>(A.buf[blockIdx.y]);
+    for (int64_t i = i0; i < n; i += stride) buf[i] = __float2half_rn(__half2float(buf[i]) * s);
+  } else {
+    __nv_bfloat16* __restrict__ buf = static_cast<__nv_bfloat16*>(A.buf[blockIdx.y]);
+    for (int64_t i = i0; i < n; i += stride) buf[i] = __float2bfloat16_rn(__bfloat162float(buf[i]) * s);
+  }
 }
 
 }  // namespace blvm

@@ -138,7 +138,7 @@ def fused_elbo(
             likelihood, raw, K, D, log_eps = "dmol", p.raw, p.K, p.D, p.log_epsilon
         if raw.dim() != 3 or raw.shape[0] != B:
             raise ValueError(f"likelihood parameters must be (B, T, P) with B = len(x_sl) = {B}; got {tuple(raw.shape)}")
-        raw = _f32c(raw)
+        raw = ops.param_tensor(raw, K, D) if likelihood == "dmol" else _f32c(raw)   # fp16/bf16 AMP outputs are read as is
         T = raw.shape[1]
         if y.numel() != B * T * D:
             raise ValueError(f"y {tuple(y.shape)} does not match parameters (B, T, D) = ({B}, {T}, {D})")

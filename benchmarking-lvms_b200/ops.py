@@ -126,6 +126,17 @@ def _maybe_strict(device):
         check_input_range(device)
 
 
+_DTYPE_CODE = {torch.float32: _lib.BLVM_DTYPE_F32, torch.float16: _lib.BLVM_DTYPE_F16, torch.bfloat16: _lib.BLVM_DTYPE_BF16}
+
+
+def param_tensor(raw: torch.Tensor, K: int, D: int) -> torch.Tensor:
+    """Contiguous likelihood parameters in a dtype the kernels read directly: fp32 always, fp16/bf16 (the AMP Linear
+    output) where a register kernel exists for (K, D); anything else is upcast to fp32 once."""
+    if raw.dtype not in _DTYPE_CODE or (raw.dtype != torch.float32 and not lib.blvm_dmol_has_fast_path(K, D)):
+        raw = raw.float()
+    return raw if raw.is_contiguous() else raw.contiguous()
+
+
 def _as_f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
@@ -135,17 +146,19 @@ def _as_f32c(t: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------------
 # raw kernel calls
 # ----------------------------------------------------------------------------------------------------------------------
-def _dmol_call(y, raw, x_sl_dev, gout, gscale, B, T, K, D, num_bins, log_eps, flags, lp, graw, partials):
-    _require_cuda(y, raw, x_sl_dev, gout, lp, graw, partials)
+def _dmol_call(y, raw, x_sl_dev, gout, gscale, B, T, K, D, num_bins, log_eps, flags, lp, graw, partials, gscale_dev=None):
+    _require_cuda(y, raw, x_sl_dev, gout, lp, graw, partials, gscale_dev)
+    dt = _DTYPE_CODE[raw.dtype]
     with _on_device(raw.device):
         err = _err_flag(raw.device)
         if graw is None:
-            rc = lib.blvm_dmol_fwd(_ptr(y), _ptr(raw), _ptr(x_sl_dev), B, T, K, D, num_bins, log_eps, flags, _ptr(lp),
+            rc = lib.blvm_dmol_fwd(_ptr(y), _ptr(raw), dt, _ptr(x_sl_dev), B, T, K, D, num_bins, log_eps, flags, _ptr(lp),
                                    _ptr(partials), _ptr(err), _stream())
             check(rc, "blvm_dmol_fwd")
         else:
-            rc = lib.blvm_dmol_fwd_grad(_ptr(y), _ptr(raw), _ptr(x_sl_dev), _ptr(gout), gscale, B, T, K, D, num_bins,
-                                        log_eps, flags, _ptr(lp), _ptr(graw), _ptr(partials), _ptr(err), _stream())
+            assert graw.dtype == raw.dtype
+            rc = lib.blvm_dmol_fwd_grad(_ptr(y), _ptr(raw), dt, _ptr(x_sl_dev), _ptr(gout), gscale, _ptr(gscale_dev), B, T, K,
+                                        D, num_bins, log_eps, flags, _ptr(lp), _ptr(graw), _ptr(partials), _ptr(err), _stream())
             check(rc, "blvm_dmol_fwd_grad")
     _count()
 
@@ -165,10 +178,10 @@ def _dl_call(y, raw, x_sl_dev, gout, gscale, B, T, num_bins, log_eps, flags, lp,
 # ----------------------------------------------------------------------------------------------------------------------
 class _DMoLLogProb(torch.autograd.Function):
     @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @custom_fwd(device_type="cuda")
     def forward(ctx, y, raw, K, D, num_bins, log_eps):
-        y = y.contiguous()
-        raw = raw.contiguous()
+        y = _as_f32c(y)
+        raw = param_tensor(raw, K, D)   # fp16/bf16 Linear outputs (AMP) are read as they are; arithmetic is fp32
         P = K * (2 * D + 1)
         assert raw.shape[-1] == P, f"raw last dim {raw.shape[-1]} != K(2D+1) = {P}"
         N = raw.numel() // P
@@ -328,18 +341,26 @@ class _FusedELBO(torch.autograd.Function):
                 flags = BLVM_FLAG_MASK_OUTPUT | (BLVM_FLAG_SKIP_PADDED if spec.skip_padded else 0)
                 logp_ptr = base + 8 * off
                 off += B * logp_chunks
-                graw = torch.empty_like(raw) if spec.need_grad else None
+                # fp16 parameters (AMP with a GradScaler): gradients of magnitude ~1/sum(x_sl) would underflow in fp16
+                # before the loss scale is applied, so the gradient is produced in backward (second launch, with the
+                # upstream grad_output read from the device); fp32 / bf16 parameters get it in this pass.
+                deferred = spec.need_grad and raw.dtype == torch.float16
+                graw = torch.empty_like(raw) if (spec.need_grad and not deferred) else None
                 gscale = -1.0 / spec.denom
                 lp_ptr = twise.data_ptr() if spec.want_twise else None
                 err = _err_flag(dev)
                 if spec.likelihood == "dmol":
+                    dt = _DTYPE_CODE[raw.dtype]
                     if graw is None:
-                        rc = lib.blvm_dmol_fwd(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), B, T, spec.K, spec.D,
+                        rc = lib.blvm_dmol_fwd(y.data_ptr(), raw.data_ptr(), dt, x_sl_dev.data_ptr(), B, T, spec.K, spec.D,
                                                spec.num_bins, spec.log_epsilon, flags, lp_ptr, logp_ptr, err.data_ptr(), stream)
                     else:
-                        rc = lib.blvm_dmol_fwd_grad(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), None, gscale, B, T,
-                                                    spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags, lp_ptr,
+                        rc = lib.blvm_dmol_fwd_grad(y.data_ptr(), raw.data_ptr(), dt, x_sl_dev.data_ptr(), None, gscale, None,
+                                                    B, T, spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags, lp_ptr,
                                                     graw.data_ptr(), logp_ptr, err.data_ptr(), stream)
+                    if deferred:
+                        ctx.save_for_backward(y, raw, x_sl_dev)
+                        ctx.deferred = (B, T, spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags, gscale)
                 else:
                     rc = lib.blvm_dl_fwd_grad(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), None, gscale, B, T,
                                               spec.num_bins, spec.log_epsilon, flags, lp_ptr, _ptr(graw), logp_ptr,
@@ -387,6 +408,8 @@ class _FusedELBO(torch.autograd.Function):
 
         loss = scalars[:1].view(())
         ctx.set_materialize_grads(False)   # no zero-filled grads for the detached outputs
+        if not hasattr(ctx, "deferred"):
+            ctx.deferred = None
         ctx.grads = grads
         ctx.consumed = False
         ctx.mark_non_differentiable(scalars, rows, twise)
@@ -402,17 +425,25 @@ class _FusedELBO(torch.autograd.Function):
         if g_loss is None:
             return (None, None, None) + tuple(None for _ in ctx.grads)
         g = g_loss if (g_loss.dtype == torch.float64 and g_loss.is_contiguous()) else g_loss.to(torch.float64).contiguous()
-        bufs = [b for b in ctx.grads if b is not None]
+        grads = list(ctx.grads)
+        bufs = [b for b in grads if b is not None]
         if bufs:
             n = len(bufs)
             with _on_device(g.device):
                 rc = lib.blvm_scale_inplace_multi((ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs]),
-                                                  (ctypes.c_int64 * n)(*[b.numel() for b in bufs]), n, g.data_ptr(), _stream())
+                                                  (ctypes.c_int64 * n)(*[b.numel() for b in bufs]),
+                                                  (ctypes.c_int * n)(*[_DTYPE_CODE[b.dtype] for b in bufs]), n, g.data_ptr(),
+                                                  _stream())
                 check(rc, "blvm_scale_inplace_multi")
             _count()
-        out = (None, None, None) + tuple(ctx.grads)
+        if ctx.deferred is not None:   # fp16 parameters: value+gradient launch now, scaled by the device-side grad_output
+            y, raw, x_sl_dev = ctx.saved_tensors
+            B, T, K, D, num_bins, log_eps, flags, gscale = ctx.deferred
+            graw = torch.empty_like(raw)
+            _dmol_call(y, raw, x_sl_dev, None, gscale, B, T, K, D, num_bins, log_eps, flags, None, graw, None, gscale_dev=g)
+            grads[0] = graw
         ctx.grads = None
-        return out
+        return (None, None, None) + tuple(grads)
 
 
 def fused_elbo_apply(spec: ELBOSpec, y, x_sl_dev, raw, kl_tensors: Sequence[torch.Tensor]):

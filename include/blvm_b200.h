@@ -39,6 +39,13 @@ enum {
   BLVM_FLAG_SKIP_PADDED = 2, /* tiles entirely inside the padding are not read; their outputs are exact zeros */
 };
 
+/* element type of the likelihood parameters `raw` (and of their gradient): the AMP Linear output can be consumed as is */
+enum {
+  BLVM_DTYPE_F32 = 0,
+  BLVM_DTYPE_F16 = 1,
+  BLVM_DTYPE_BF16 = 2,
+};
+
 #define BLVM_MAX_KL_LEVELS 8
 #define BLVM_DMOL_TILE 128   /* threads per CTA of the DMoL / DL kernels (tile = 128 x samples-per-thread) */
 #define BLVM_KL_TILE 1024    /* latent elements per partial sum of the KL kernels */
@@ -52,6 +59,9 @@ const char* blvm_last_error_string(void);
  * samples times a K-dependent samples-per-thread factor, the DL tile BLVM_DMOL_TILE, the KL tile BLVM_KL_TILE). */
 int64_t blvm_dmol_chunks(int64_t T, int K, int D);
 int64_t blvm_dl_chunks(int64_t T);
+/* 1 if (K, D) has a register-resident TMA kernel (D == 1 and K in {1,2,3,4,5,6,8,10,12,16,20,30}); other shapes run the
+ * generic fp32 kernel. */
+int blvm_dmol_has_fast_path(int K, int D);
 int64_t blvm_kl_chunks(int64_t row_elems);
 
 /*
@@ -61,26 +71,29 @@ int64_t blvm_kl_chunks(int64_t row_elems);
  * sum of compute_elbo (blvm/models/vrnn.py:266-269).
  *   y        (B, T, D)         targets in [-1, 1]
  *   raw      (B, T, K(2D+1))   the Linear output: [logits K | per d: locs K, log_scales K]; log-scales are clamped
- *                              at log_epsilon inside the kernel
+ *                              at log_epsilon inside the kernel; element type `raw_dtype` (BLVM_DTYPE_*; fp16/bf16
+ *                              only where blvm_dmol_has_fast_path), arithmetic is fp32 either way
  *   x_sl     (B) int64, nullable: valid samples per utterance (None = all T)
  *   lp       (B, T), nullable: per-sample log-prob out
  *   partials (B, blvm_dmol_chunks(T, K, D)) fp64, nullable: masked per-tile sums of log-prob
  *   err_flag int32, nullable: set to 1 if some y is outside [-1, 1] (the reference's assert, log_likelihoods.py:195)
  */
-int blvm_dmol_fwd(const float* y, const float* raw, const int64_t* x_sl, int64_t B, int64_t T, int K, int D,
-                  int num_bins, float log_epsilon, int flags, float* lp, double* partials, int* err_flag,
+int blvm_dmol_fwd(const float* y, const void* raw, int raw_dtype, const int64_t* x_sl, int64_t B, int64_t T, int K,
+                  int D, int num_bins, float log_epsilon, int flags, float* lp, double* partials, int* err_flag,
                   blvm_stream_t stream);
 
 /*
- * Single pass forward + gradient: additionally writes
- *   graw (B, T, K(2D+1)) = gscale * gout[b,t] * mask[b,t] * d log p(y[b,t]) / d raw[b,t,:]
+ * Single pass forward + gradient: additionally writes (in the element type of raw)
+ *   graw (B, T, K(2D+1)) = gscale * (*gscale_dev) * gout[b,t] * mask[b,t] * d log p(y[b,t]) / d raw[b,t,:]
  * which is what autograd produces through log_likelihoods.py:198-231 and the clamp of distributions.py:386
- * (gradient passes at raw == log_epsilon).  `gout` (B, T) nullable = 1.  With gscale = -1/sum(x_sl) this is
+ * (gradient passes at raw == log_epsilon).  `gout` (B, T) nullable = 1; `gscale_dev` nullable fp64 device scalar (an
+ * upstream grad_output, e.g. an AMP loss scale, applied without a host sync).  With gscale = -1/sum(x_sl) this is
  * d loss / d raw of vrnn.py:277.  Also serves as the backward of a generic log_prob call (lp = NULL).
  */
-int blvm_dmol_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale,
-                       int64_t B, int64_t T, int K, int D, int num_bins, float log_epsilon, int flags, float* lp,
-                       float* graw, double* partials, int* err_flag, blvm_stream_t stream);
+int blvm_dmol_fwd_grad(const float* y, const void* raw, int raw_dtype, const int64_t* x_sl, const float* gout,
+                       float gscale, const double* gscale_dev, int64_t B, int64_t T, int K, int D, int num_bins,
+                       float log_epsilon, int flags, float* lp, void* graw, double* partials, int* err_flag,
+                       blvm_stream_t stream);
 
 /*
  * Single discretized logistic (K = 1, no mixture weights), packed raw (B, T, 2) = [mu | log_scale].
@@ -147,10 +160,11 @@ int blvm_quantize(const float* x, int64_t n, const float* boundaries, int64_t n_
 /* In-place `buf *= (float)*scale` (fp64 device scalar) that exits early when *scale == 1: the autograd backward of the
  * fused ELBO op uses it to apply an upstream grad_output (e.g. an AMP loss scale) without a host sync. */
 int blvm_scale_inplace(float* buf, int64_t n, const double* scale, blvm_stream_t stream);
-/* Same for up to BLVM_MAX_SCALE_BUFFERS buffers in ONE launch (bufs_host / ns_host are HOST arrays of length count). */
+/* Same for up to BLVM_MAX_SCALE_BUFFERS buffers in ONE launch (bufs_host / ns_host / dtypes_host are HOST arrays of
+ * length count; dtypes_host nullable = all fp32, else BLVM_DTYPE_* per buffer). */
 #define BLVM_MAX_SCALE_BUFFERS 36
-int blvm_scale_inplace_multi(float* const* bufs_host, const int64_t* ns_host, int count, const double* scale,
-                             blvm_stream_t stream);
+int blvm_scale_inplace_multi(void* const* bufs_host, const int64_t* ns_host, const int* dtypes_host, int count,
+                             const double* scale, blvm_stream_t stream);
 
 #ifdef __cplusplus
 }

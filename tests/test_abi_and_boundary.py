@@ -45,7 +45,7 @@ def test_library_has_sm100a_code_and_tma():
         pytest.skip("cuobjdump not available")
     out = subprocess.run(["cuobjdump", "-lelf", blvm_b200.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4blvm16dmol_tile_kernelILi10ELi128ELb1ELi0EEEvNS_8DmolArgsE",
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4blvm16dmol_tile_kernelILi10ELi128ELb1ELi0EfEEvNS_8DmolArgsE",
                            blvm_b200.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass
 

@@ -420,16 +420,66 @@ def test_no_grad_eval_path(B):
     assert math.isclose(m.bpd, -g["logp64"].sum() / math.log(2) / g["x_sl"].sum(), rel_tol=1e-6)
 
 
-def test_autocast_inputs(B):
-    """Under AMP the Linear output arrives in bf16/fp16: it is upcast once, results equal the fp32 call on the rounded
-    parameters."""
-    g = load_golden("dmol_K10_nb65536")
-    raw16 = cu(g["raw"]).to(torch.bfloat16)
-    lik = B.DiscretizedLogisticMixtureDense(3, 1, 10, 65536)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        lp16 = lik.log_prob(cu(g["y"]), B.DMoLParams(raw16, 10, 1, -7.0))
-    lp32 = lik.log_prob(cu(g["y"]), B.DMoLParams(raw16.float(), 10, 1, -7.0))
-    assert lp16.dtype == torch.float32 and torch.equal(lp16, lp32)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("K", [10, 5, 30])
+def test_half_precision_parameters(dtype, K, B, O):
+    """Under AMP the Linear output arrives in bf16/fp16 and the kernels read it as it is (arithmetic stays fp32): values
+    equal the fp32 call on the same rounded parameters bit for bit, gradients come back in the parameter dtype and match
+    the oracle on the rounded parameters to the dtype's resolution."""
+    rng = np.random.default_rng(K)
+    Bn, T, nb = 3, 300, 65536
+    y = (rng.integers(0, nb, (Bn, T)) / (nb - 1) * 2 - 1).astype(np.float32)
+    raw = rng.normal(size=(Bn, T, 3 * K)).astype(np.float32)
+    raw[..., K:2 * K] = y[..., None] + 0.1 * raw[..., K:2 * K]
+    raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+    raw_h = cu(raw).to(dtype)
+    x_sl = torch.tensor([300, 211, 17])
+    lik = B.DiscretizedLogisticMixtureDense(3, 1, K, nb)
+    with torch.autocast("cuda", dtype=dtype):
+        lp_h = lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(raw_h, K, 1, -7.0))
+    lp_f = lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(raw_h.float(), K, 1, -7.0))
+    assert lp_h.dtype == torch.float32 and torch.equal(lp_h, lp_f)
+    # fused op: loss * scale backward (GradScaler-style), gradient dtype == parameter dtype
+    scale = 4096.0
+    r = raw_h.clone().requires_grad_(True)
+    out = B.fused_elbo(cu(y), B.DMoLParams(r, K, 1, -7.0), x_sl, (), num_bins=nb)
+    (out.loss * scale).backward()
+    assert r.grad.dtype == dtype
+    ref = O.fused_elbo_value_and_grad(y, raw_h.float().cpu().numpy(), x_sl.numpy(), [], 1.0, K, nb)
+    assert_sums_close(out.loss.item(), ref["loss"], "loss on rounded parameters")
+    g = r.grad.float().cpu().numpy().astype(np.float64) / scale
+    gref = ref["graw"]
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    tol = eps * np.abs(gref) + 1e-4 * np.abs(gref).max(-1, keepdims=True) + (6e-8 / scale if dtype == torch.float16 else 0)
+    assert (np.abs(g - gref) <= tol).all()
+    # generic autograd path (recompute backward) in the same dtype
+    r2 = raw_h.clone().requires_grad_(True)
+    lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(r2, K, 1, -7.0)).sum().backward()
+    assert r2.grad.dtype == dtype and torch.isfinite(r2.grad.float()).all()
+    # a K without a register kernel is upcast transparently
+    r7 = torch.randn(2, 50, 21, device="cuda").to(dtype).requires_grad_(True)
+    lp7 = B.DiscretizedLogisticMixtureDense(3, 1, 7, nb).log_prob(torch.zeros(2, 50, 1, device="cuda"), B.DMoLParams(r7, 7, 1, -7.0))
+    lp7.sum().backward()
+    assert r7.grad.dtype == dtype
+
+
+def test_fp16_gradients_do_not_underflow_with_loss_scale(B, O):
+    """fp16 parameters: d loss/d raw ~ 1/sum(x_sl) ~ 1e-7 is below fp16's subnormal range; with the GradScaler's loss
+    scale applied inside the backward launch (device scalar) the scaled gradients are representable."""
+    g = load_golden("elbo_wavenet")
+    K, nb = 10, 65536
+    x_sl = torch.full((4,), 80)
+    raw = cu(np.tile(g["raw"], (1, 1, 1))).to(torch.float16).requires_grad_(True)
+    out = B.fused_elbo(cu(g["y"]), B.DMoLParams(raw, K, 1, -7.0), x_sl, (), num_bins=nb, denom=4.0e6)
+    scale = torch.tensor(65536.0, device="cuda", dtype=torch.float64)
+    (out.loss * scale).backward()
+    gr = raw.grad.float()
+    ref = O.fused_elbo_value_and_grad(g["y"], raw.detach().float().cpu().numpy(), x_sl.numpy(), [], 1.0, K, nb)
+    gref = ref["graw"] * (float(x_sl.sum()) / 4.0e6) * 65536.0
+    big = np.abs(gref) > 1e-3
+    assert big.sum() > 1000
+    np.testing.assert_allclose(gr.cpu().numpy()[big], gref[big], rtol=2e-3)
+    assert (gr != 0).float().mean().item() > 0.5
 
 
 # ---- full benchmark size: size-independent properties ---------------------------------------------------------------
