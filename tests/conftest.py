@@ -10,6 +10,20 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _ensure_native_library():
+    """The CUDA library is git-ignored (built artefact): build it if this checkout does not have it yet (nvcc
+    cross-compiles sm_100a without a GPU, ~1 min)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("blvm_b200_build", os.path.join(ROOT, "benchmarking-lvms_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if not mod.up_to_date():
+        mod.build_library()
+
+
+_ensure_native_library()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

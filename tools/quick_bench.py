@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--T", type=int, default=16000)
     ap.add_argument("--Ks", type=int, nargs="+", default=[10])
     ap.add_argument("--ragged", action="store_true")
+    ap.add_argument("--dtypes", nargs="+", default=["float32"])
     args = ap.parse_args()
     dev = "cuda"
     B, T = args.B, args.T
@@ -39,11 +40,14 @@ def main():
     med, best = timeit(lambda: b.copy_(a))
     print(f"copy 1GiB fp32: {2 * a.numel() * 4 / best / 1e6:.0f} GB/s best, {2 * a.numel() * 4 / med / 1e6:.0f} median")
     del a, b
-    for K in args.Ks:
+    for K, dtn in [(K, d) for K in args.Ks for d in args.dtypes]:
+        dt = getattr(torch, dtn)
+        esz = torch.empty(0, dtype=dt).element_size()
         y = torch.randint(0, nb, (B, T), device=dev).float() / (nb - 1) * 2 - 1
         raw = torch.randn(B, T, 3 * K, device=dev)
         raw[..., K:2 * K] = y.unsqueeze(-1) + 0.1 * torch.randn(B, T, K, device=dev)
         raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+        raw = raw.to(dt)
         x_sl = torch.full((B,), T, dtype=torch.int64)
         if args.ragged:
             x_sl = (T * (0.5 + 0.5 * torch.rand(B))).long()
@@ -54,12 +58,12 @@ def main():
         N = B * T
         g = -1.0 / float(x_sl.sum())
         med, best = timeit(lambda: ops._dmol_call(y, raw, x_dev, None, g, B, T, K, 1, nb, -7.0, 1, lp, graw, part))
-        byt = N * 4 * (2 + 6 * K)
-        print(f"K={K:2d} dmol fwd+grad: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
+        byt = N * (8 + 6 * K * esz)
+        print(f"K={K:2d} {dtn:8s} dmol fwd+grad: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
               f"{byt / med / 1e6:7.0f} GB/s algorithmic")
         med, best = timeit(lambda: ops._dmol_call(y, raw, x_dev, None, 0.0, B, T, K, 1, nb, -7.0, 1, lp, None, part))
-        byt = N * 4 * (2 + 3 * K)
-        print(f"K={K:2d} dmol fwd only: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
+        byt = N * (8 + 3 * K * esz)
+        print(f"K={K:2d} {dtn:8s} dmol fwd only: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
               f"{byt / med / 1e6:7.0f} GB/s algorithmic")
         del raw, graw
     # KL fused
