@@ -149,9 +149,23 @@ struct RowIO<__nv_bfloat16, P> {
 
 // Samples per thread: small K means small rows, so a 128-sample tile would be a 1.5 KB slab (K = 1) and the per-CTA
 // fixed cost (mbarrier, barriers, bulk-store drain) dominates; each thread then walks SPT samples of a 128*SPT tile.
+#ifndef BLVM_SPT_2
+#define BLVM_SPT_2 8    // K <= 2
+#define BLVM_SPT_5 4    // K <= 5
+#define BLVM_SPT_8 2    // K <= 8
+#define BLVM_SPT_12 1   // K <= 12
+#endif
+#ifndef BLVM_MINB_BIGK
+#define BLVM_MINB_BIGK 4  // __launch_bounds__ min blocks/SM for K > 12: caps registers at 128 so that 4 CTAs (16 warps, 4 slabs
+                          // of 46 KB at K = 30) are resident per SM; measured 543 -> 471 us at K = 30 (5.5 -> 6.3 TB/s)
+#endif
 template <int K>
 struct DmolSpt {
-  static constexpr int value = K <= 2 ? 8 : (K <= 5 ? 4 : (K <= 8 ? 2 : 1));
+  static constexpr int value = K <= 2 ? BLVM_SPT_2 : (K <= 5 ? BLVM_SPT_5 : (K <= 8 ? BLVM_SPT_8 : (K <= 12 ? BLVM_SPT_12 : 1)));
+};
+template <int K>
+struct DmolMinBlocks {
+  static constexpr int value = K > 12 ? BLVM_MINB_BIGK : 0;   // 0 = no constraint
 };
 
 template <int K, int TPB, typename TP>
@@ -160,7 +174,7 @@ constexpr size_t dmol_tile_smem_bytes() {
 }
 
 template <int K, int TPB, bool GRAD, int UMODE, typename TP>
-__global__ void __launch_bounds__(TPB) dmol_tile_kernel(const DmolArgs A) {
+__global__ void __launch_bounds__(TPB, DmolMinBlocks<K>::value) dmol_tile_kernel(const DmolArgs A) {
   constexpr int P = 3 * K;
   constexpr int NW = TPB / 32;
   constexpr int SPT = DmolSpt<K>::value;

@@ -541,3 +541,41 @@ def test_full_size_properties(B, O):
     scale = float(x_sl[rows].sum()) / float(x_sl.sum())  # oracle normalised by the subset's length
     gabs = np.full(len(rows) * T, 1.0 / float(x_sl.sum()))
     assert_grads_close(g1[rows].cpu().numpy().reshape(-1, 3 * K), ref["graw"].reshape(-1, 3 * K) * scale, K, gabs)
+
+
+def test_config5_top_end_64bit_indexing(B, O):
+    """BASELINE config 5's largest point: 256 x 128000 samples, K = 30 -> 2.95 G parameter elements (> 2^31), 11.8 GB of
+    parameters + 11.8 GB of gradients.  Checks the last utterance (highest addresses) against the oracle, the sums
+    against the per-sample values, and exact zeros in the padding."""
+    Bn, T, K, nb = 256, 128000, 30, 65536
+    dev = "cuda"
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~30 GB of free HBM")
+    gen = torch.Generator(device=dev).manual_seed(7)
+    y = torch.randint(0, nb, (Bn, T), device=dev, generator=gen).float() / (nb - 1) * 2 - 1
+    raw = torch.empty(Bn, T, 3 * K, device=dev)
+    for b0 in range(0, Bn, 32):  # fill in slices: keeps the temporary small
+        sl = slice(b0, b0 + 32)
+        raw[sl].normal_(generator=gen)
+        raw[sl, :, K:2 * K] = y[sl].unsqueeze(-1) + 0.1 * raw[sl, :, K:2 * K]
+        raw[sl, :, 2 * K:] = raw[sl, :, 2 * K:] * 2 - 4
+    assert raw.numel() > 2 ** 31
+    x_sl = torch.full((Bn,), T)
+    x_sl[-1] = T - 12345
+    raw.requires_grad_(True)
+    out = B.fused_elbo(y, B.DMoLParams(raw, K, 1, -7.0), x_sl, (), num_bins=nb, want_twise=True)
+    out.loss.backward()
+    torch.testing.assert_close(out.log_prob_twise.double().sum(1), out.log_prob, rtol=1e-9, atol=0)
+    last = Bn - 1
+    sub = slice(T - 20000, T)   # the tail of the last utterance: highest addresses, straddles the mask edge
+    ref_lp, ref_g = O.dmol_value_and_grad(y[last, sub].cpu().numpy().astype(np.float64),
+                                          raw[last, sub].detach().cpu().numpy().astype(np.float64), K, 1, nb)
+    m = (np.arange(T)[sub] < int(x_sl[last])).astype(np.float64)
+    assert_values_close(out.log_prob_twise[last, sub].cpu().numpy(), ref_lp * m, "twise at the top of the address range")
+    gs = -m / float(x_sl.sum())
+    g = raw.grad[last, sub].cpu().numpy()
+    assert_grads_close(g, ref_g * gs[:, None], K, np.abs(gs) + 1e-30, "grads at the top of the address range")
+    assert (g[m == 0] == 0).all() and (out.log_prob_twise[last, sub].cpu().numpy()[m == 0] == 0).all()
+    del raw, out
+    torch.cuda.empty_cache()
