@@ -9,6 +9,7 @@
 #include "dmol_kernels.cuh"
 #include "kl_kernels.cuh"
 #include "misc_kernels.cuh"
+#include "sample_kernels.cuh"
 
 using namespace blvm;
 
@@ -301,6 +302,27 @@ int blvm_quantize(const float* x, int64_t n, const float* boundaries, int64_t n_
   if (blocks > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many elements");
   quantize_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, boundaries, n_bins, out);
   return check_launch("quantize_kernel");
+}
+
+int blvm_dmol_sample_mode(const void* raw, int raw_dtype, int64_t N, int K, int D, float log_epsilon, uint64_t seed,
+                          uint64_t offset, float* sample, float* mode, int32_t* mode_index, blvm_stream_t stream) {
+  if (N < 0 || K < 1 || D < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad shape N=%lld K=%d D=%d", (long long)N, K, D);
+  if (N > 0 && !raw) return fail(BLVM_ERR_INVALID_ARGUMENT, "null raw");
+  if (N == 0) return BLVM_OK;
+  const int64_t blocks = (N + 255) / 256;
+  if (blocks > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many samples");
+  SampleArgs A{};
+  A.raw = raw; A.N = N; A.K = K; A.D = D; A.log_eps = log_epsilon; A.seed = seed; A.offset = offset;
+  A.sample = sample; A.mode = mode; A.mode_index = mode_index;
+  const unsigned g = static_cast<unsigned>(blocks);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (raw_dtype) {
+    case BLVM_DTYPE_F32: dmol_sample_mode_kernel<float><<<g, 256, 0, st>>>(A); break;
+    case BLVM_DTYPE_F16: dmol_sample_mode_kernel<__half><<<g, 256, 0, st>>>(A); break;
+    case BLVM_DTYPE_BF16: dmol_sample_mode_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(A); break;
+    default: return fail(BLVM_ERR_INVALID_ARGUMENT, "raw_dtype=%d", raw_dtype);
+  }
+  return check_launch("dmol_sample_mode_kernel");
 }
 
 int blvm_scale_inplace(float* buf, int64_t n, const double* scale, blvm_stream_t stream) {

@@ -189,12 +189,29 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
         log_scale = torch.gather(log_scales, index=index, dim=-1).squeeze(-1)
         return _rsample_logistic(loc, log_scale)
 
+    def _fused_sample_mode(self, params):
+        """One kernel reads the packed parameters once and produces both the sample and the mode; the result is cached
+        on the parameter container because the models call sample() and mode() back to back (vrnn.py:332-333)."""
+        cached = params._cache.get("sample_mode")
+        if cached is None:
+            cached = ops.dmol_sample_mode(params.raw, params.K, params.D, params.log_epsilon)
+            params._cache["sample_mode"] = cached
+        return cached
+
     @torch.no_grad()
     def sample(self, params):
+        """A sample of the mixture, clamped to [-1, 1] (distributions.py:359-361, variational.py:309-349)."""
+        if isinstance(params, DMoLParams) and params.raw.is_cuda:
+            return self._fused_sample_mode(params)[0]
         return self.rsample(params)
 
     def mode(self, params):
         """Mean of the most probable component (distributions.py:363-368)."""
+        if isinstance(params, DMoLParams) and params.raw.is_cuda:
+            _, mode, index = self._fused_sample_mode(params)
+            if torch.is_grad_enabled() and params.raw.requires_grad:
+                return ops.mode_with_grad(params.raw, mode, index, params.K, params.D)
+            return mode if params.raw.dtype == torch.float32 else mode.to(params.raw.dtype)
         component = params[0].argmax(-1, keepdim=True).unsqueeze(-2)
         component = component.expand(*component.shape[:-2], params[1].size(-2), 1)
         return torch.gather(params[1], index=component, dim=-1).squeeze(-1).contiguous()

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import BLVM_FLAG_MASK_OUTPUT, BLVM_FLAG_SKIP_PADDED, check, lib
 
 __all__ = [
-    "dmol_log_prob", "dl_log_prob", "kl_gaussian", "KLLevelSpec", "ELBOSpec", "fused_elbo_apply", "quantize_indices",
+    "dmol_log_prob", "dl_log_prob", "kl_gaussian", "KLLevelSpec", "ELBOSpec", "fused_elbo_apply", "quantize_indices", "dmol_sample_mode", "mode_with_grad",
     "check_input_range", "launch_count", "reset_launch_count",
 ]
 
@@ -448,6 +448,65 @@ class _FusedELBO(torch.autograd.Function):
 
 def fused_elbo_apply(spec: ELBOSpec, y, x_sl_dev, raw, kl_tensors: Sequence[torch.Tensor]):
     return _FusedELBO.apply(spec, y, x_sl_dev, raw, *kl_tensors)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fused sample() + mode()
+# ----------------------------------------------------------------------------------------------------------------------
+_rng_state = {"seed": None, "offset": 0}
+
+
+def _next_rng():
+    """Philox key / offset derived from torch's global seed: `torch.manual_seed(s)` makes the sample stream reproducible."""
+    seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    if _rng_state["seed"] != seed:
+        _rng_state["seed"], _rng_state["offset"] = seed, 0
+    _rng_state["offset"] += 1
+    return seed, _rng_state["offset"]
+
+
+def dmol_sample_mode(raw: torch.Tensor, K: int, D: int, log_epsilon: float, want_sample=True, want_mode=True):
+    """One launch: (sample (*, D), mode (*, D), mode_index (*)) from packed parameters raw (*, K(2D+1)); detached."""
+    _require_cuda(raw)
+    raw = raw.detach()
+    if raw.dtype not in _DTYPE_CODE:
+        raw = raw.float()
+    raw = raw if raw.is_contiguous() else raw.contiguous()
+    batch = raw.shape[:-1]
+    N = raw.numel() // raw.shape[-1] if raw.numel() else 0
+    sample = torch.empty(*batch, D, dtype=torch.float32, device=raw.device) if want_sample else None
+    mode = torch.empty(*batch, D, dtype=torch.float32, device=raw.device) if want_mode else None
+    index = torch.empty(batch, dtype=torch.int32, device=raw.device) if want_mode else None
+    seed, offset = _next_rng()
+    with _on_device(raw.device):
+        rc = lib.blvm_dmol_sample_mode(_ptr(raw), _DTYPE_CODE[raw.dtype], N, K, D, float(log_epsilon), seed, offset,
+                                       _ptr(sample), _ptr(mode), _ptr(index), _stream())
+        check(rc, "blvm_dmol_sample_mode")
+    _count()
+    return sample, mode, index
+
+
+class _ModeWithGrad(torch.autograd.Function):
+    """mode() is differentiable w.r.t. the chosen component's loc in the reference (a gather); the backward scatters."""
+
+    @staticmethod
+    def forward(ctx, raw, mode, index, K, D):
+        ctx.save_for_backward(index)
+        ctx.cfg = (K, D, raw.shape, raw.dtype)
+        return mode.to(raw.dtype) if raw.dtype != torch.float32 else mode
+
+    @staticmethod
+    def backward(ctx, g):
+        (index,) = ctx.saved_tensors
+        K, D, shape, dtype = ctx.cfg
+        graw = torch.zeros(shape, dtype=dtype, device=g.device)
+        cols = (K + index.long().unsqueeze(-1) + 2 * K * torch.arange(D, device=g.device)).reshape(*shape[:-1], D)
+        graw.scatter_(-1, cols, g.to(dtype))
+        return graw, None, None, None, None
+
+
+def mode_with_grad(raw, mode, index, K, D):
+    return _ModeWithGrad.apply(raw, mode, index, K, D)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

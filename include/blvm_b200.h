@@ -157,6 +157,17 @@ int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const doubl
  */
 int blvm_quantize(const float* x, int64_t n, const float* boundaries, int64_t n_bins, int64_t* out, blvm_stream_t stream);
 
+/*
+ * Fused sample() + mode() of the mixture, one read of the parameters.
+ * Replaces rsample_discretized_logistic_mixture (blvm/utils/variational.py:309-349: Gumbel-max over the logits with
+ * u ~ U(1e-5, 1-1e-5), gather, logistic inverse CDF with u ~ U(1e-8, 1-1e-8), clamp to [-1, 1]) and
+ * DiscretizedLogisticMixtureDense.mode (blvm/modules/distributions.py:363-368: loc of the arg-max logit).
+ *   raw (N, K(2D+1)) in raw_dtype; sample, mode (N, D) fp32, nullable; mode_index (N) int32, nullable
+ *   seed / offset: Philox4x32-10 key and stream offset (same seed + offset => same samples)
+ */
+int blvm_dmol_sample_mode(const void* raw, int raw_dtype, int64_t N, int K, int D, float log_epsilon, uint64_t seed,
+                          uint64_t offset, float* sample, float* mode, int32_t* mode_index, blvm_stream_t stream);
+
 /* In-place `buf *= (float)*scale` (fp64 device scalar) that exits early when *scale == 1: the autograd backward of the
  * fused ELBO op uses it to apply an upstream grad_output (e.g. an AMP loss scale) without a host sync. */
 int blvm_scale_inplace(float* buf, int64_t n, const double* scale, blvm_stream_t stream);

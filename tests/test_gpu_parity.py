@@ -579,3 +579,60 @@ def test_config5_top_end_64bit_indexing(B, O):
     assert (g[m == 0] == 0).all() and (out.log_prob_twise[last, sub].cpu().numpy()[m == 0] == 0).all()
     del raw, out
     torch.cuda.empty_cache()
+
+
+def test_fused_sample_and_mode(B):
+    """sample() + mode() from one read of the parameters.  mode is exact (argmax + gather, with the
+    gather's gradient); the sample stream is Philox-based, so parity with the reference's torch RNG is distributional:
+    mixture frequencies follow softmax(logits), each component is a logistic(loc, exp(log_scale)), values are clamped to
+    [-1, 1] (blvm/utils/variational.py:282-349)."""
+    from scipy import stats
+    K, nb = 4, 65536
+    lik = B.DiscretizedLogisticMixtureDense(3, 1, K, nb)
+    # --- mode: exact, differentiable like the reference's gather
+    raw = torch.randn(6, 50, 3 * K, device="cuda", requires_grad=True)
+    p = B.DMoLParams(raw, K, 1, -7.0)
+    n0 = B.launch_count()
+    smp = lik.sample(p)
+    mode = lik.mode(p)
+    assert B.launch_count() - n0 == 1                      # one kernel served both calls
+    assert smp.shape == (6, 50, 1) and mode.shape == (6, 50, 1) and not smp.requires_grad
+    idx = raw[..., :K].argmax(-1, keepdim=True)
+    ref_mode = torch.gather(raw[..., K:2 * K], -1, idx)
+    assert torch.equal(mode.detach(), ref_mode.detach())
+    w = torch.randn_like(mode)
+    (g_ours,) = torch.autograd.grad((mode * w).sum(), raw)
+    (g_ref,) = torch.autograd.grad((ref_mode * w).sum(), raw)
+    assert torch.equal(g_ours, g_ref)
+    assert float(smp.abs().max()) <= 1.0
+    # --- sample statistics on one parameter row replicated N times
+    N = 400000
+    logits = torch.tensor([0.5, -1.0, 2.0, 0.0])
+    locs = torch.tensor([-0.6, -0.2, 0.2, 0.6])
+    ls = torch.tensor([-5.0, -4.5, -5.5, -4.0])
+    row = torch.cat([logits, locs, ls]).cuda()
+    torch.manual_seed(123)
+    x = lik.sample(B.DMoLParams(row.expand(N, 3 * K).contiguous(), K, 1, -7.0)).squeeze(-1).double().cpu()
+    comp = (x.unsqueeze(-1) - locs.double()).abs().argmin(-1)       # components are ~20 scales apart
+    freq = torch.bincount(comp, minlength=K).double() / N
+    pi = torch.softmax(logits.double(), -1)
+    assert ((freq - pi).abs() < 5 * torch.sqrt(pi * (1 - pi) / N)).all(), (freq, pi)
+    for k in range(K):
+        z = ((x[comp == k] - locs[k].double()) / math.exp(float(ls[k]))).numpy()
+        z = z[np.abs(z) < 15]                                        # drop the rare cross-assigned tail points
+        assert stats.kstest(z[:50000], "logistic").pvalue > 1e-4
+    # --- reproducibility: torch.manual_seed controls the Philox key, successive calls advance the offset
+    prm = B.DMoLParams(row.expand(1000, 3 * K).contiguous(), K, 1, -7.0)
+    torch.manual_seed(7)
+    a1 = lik.sample(B.DMoLParams(prm.raw, K, 1, -7.0))
+    a2 = lik.sample(B.DMoLParams(prm.raw, K, 1, -7.0))
+    torch.manual_seed(7)
+    b1 = lik.sample(B.DMoLParams(prm.raw, K, 1, -7.0))
+    assert torch.equal(a1, b1) and not torch.equal(a1, a2)
+    # --- clamp: a wide component next to the upper edge
+    wide = torch.tensor([0.0, 0.0, 0.0, 0.0, 0.99, 0.99, 0.99, 0.99, -1.0, -1.0, -1.0, -1.0]).cuda()
+    xs = lik.sample(B.DMoLParams(wide.expand(20000, 12).contiguous(), K, 1, -7.0))
+    assert float(xs.max()) == 1.0 and float(xs.min()) >= -1.0 and (xs == 1.0).float().mean().item() > 0.3
+    # --- bf16 parameters are read directly
+    xs16 = lik.sample(B.DMoLParams(wide.expand(64, 12).contiguous().to(torch.bfloat16), K, 1, -7.0))
+    assert xs16.dtype == torch.float32 and float(xs16.abs().max()) <= 1.0
