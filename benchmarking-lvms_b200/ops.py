@@ -453,16 +453,14 @@ def fused_elbo_apply(spec: ELBOSpec, y, x_sl_dev, raw, kl_tensors: Sequence[torc
 # ----------------------------------------------------------------------------------------------------------------------
 # fused sample() + mode()
 # ----------------------------------------------------------------------------------------------------------------------
-_rng_state = {"seed": None, "offset": 0}
-
-
-def _next_rng():
-    """Philox key / offset derived from torch's global seed: `torch.manual_seed(s)` makes the sample stream reproducible."""
-    seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
-    if _rng_state["seed"] != seed:
-        _rng_state["seed"], _rng_state["offset"] = seed, 0
-    _rng_state["offset"] += 1
-    return seed, _rng_state["offset"]
+def _next_rng(device: torch.device):
+    """Philox key / offset taken from (and advanced on) torch's CUDA generator of the device, the way torch's own
+    kernels consume it: `torch.manual_seed(s)` makes the sample stream reproducible."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed = int(gen.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    offset = int(gen.get_offset())
+    gen.set_offset(offset + 4)
+    return seed, offset // 4 + 1
 
 
 def dmol_sample_mode(raw: torch.Tensor, K: int, D: int, log_epsilon: float, want_sample=True, want_mode=True):
@@ -477,7 +475,7 @@ def dmol_sample_mode(raw: torch.Tensor, K: int, D: int, log_epsilon: float, want
     sample = torch.empty(*batch, D, dtype=torch.float32, device=raw.device) if want_sample else None
     mode = torch.empty(*batch, D, dtype=torch.float32, device=raw.device) if want_mode else None
     index = torch.empty(batch, dtype=torch.int32, device=raw.device) if want_mode else None
-    seed, offset = _next_rng()
+    seed, offset = _next_rng(raw.device)
     with _on_device(raw.device):
         rc = lib.blvm_dmol_sample_mode(_ptr(raw), _DTYPE_CODE[raw.dtype], N, K, D, float(log_epsilon), seed, offset,
                                        _ptr(sample), _ptr(mode), _ptr(index), _stream())
