@@ -636,3 +636,69 @@ def test_fused_sample_and_mode(B):
     # --- bf16 parameters are read directly
     xs16 = lik.sample(B.DMoLParams(wide.expand(64, 12).contiguous().to(torch.bfloat16), K, 1, -7.0))
     assert xs16.dtype == torch.float32 and float(xs16.abs().max()) <= 1.0
+
+
+@pytest.mark.parametrize("T,K", [(127, 10), (1000, 1), (333, 5), (130, 30), (64, 7)])
+def test_no_out_of_bounds_writes(T, K, B):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are checked with canaries: every output of the
+    DMoL / KL kernels lives inside one arena with poisoned guard bands on both sides (tail tiles, unaligned slabs,
+    multi-sample tiles and the generic kernel are all covered by the shapes above)."""
+    from blvm_b200 import ops
+    lib = B._lib.lib
+    dev, Bn, nb, G = "cuda", 3, 65536, 4096
+    P = 3 * K
+    y = torch.rand(Bn, T, device=dev) * 2 - 1
+    raw = torch.randn(Bn, T, P, device=dev)
+    x_sl = torch.tensor([T, T // 2, 1], device=dev)
+    chunks = int(lib.blvm_dmol_chunks(T, K, 1))
+    ev = lambda n: n + (n & 1)                                            # keep every view 8-byte aligned
+    sizes = {"lp": ev(Bn * T), "graw": ev(Bn * T * P), "part": 2 * Bn * chunks}   # partials are fp64 = 2 floats each
+    arena = torch.full((sum(sizes.values()) + G * (len(sizes) + 1),), 1234.5, device=dev)
+    views, off = {}, G
+    for name, n in sizes.items():
+        views[name] = arena[off:off + n]
+        off += n + G
+    used = {"lp": Bn * T, "graw": Bn * T * P}
+    part = views["part"].view(torch.float64)
+    lp_v, graw_v = views["lp"][:used["lp"]], views["graw"][:used["graw"]]
+    ops._dmol_call(y, raw, x_sl, None, -1e-3, Bn, T, K, 1, nb, -7.0, 1, lp_v.view(Bn, T), graw_v.view(Bn, T, P), part)
+    torch.cuda.synchronize()
+    off = 0
+    for name, n in sizes.items():
+        assert (arena[off:off + G] == 1234.5).all(), f"guard before {name} overwritten"
+        off += G + n
+    assert (arena[off:off + G] == 1234.5).all(), "trailing guard overwritten"
+    assert torch.isfinite(lp_v).all() and torch.isfinite(graw_v).all() and torch.isfinite(part).all()
+    assert (lp_v != 1234.5).all() and (graw_v != 1234.5).all()                     # every output element was written
+    for name in used:                                                              # alignment padding untouched
+        assert (views[name][used[name]:] == 1234.5).all()
+    # KL kernel with a row length that is not a multiple of the vector width / tile
+    Tz, Z = 37, 3
+    ins = [torch.randn(Bn, Tz, Z, device=dev), torch.rand(Bn, Tz, Z, device=dev) + 0.1, torch.randn(Bn, Tz, Z, device=dev),
+           torch.rand(Bn, Tz, Z, device=dev) + 0.1]
+    n = Bn * Tz * Z
+    kc = int(lib.blvm_kl_chunks(Tz * Z))
+    npad = n + (n & 1)
+    arena2 = torch.full((4 * npad + 4 * Bn * kc + 7 * G,), 77.0, device=dev)
+    outs, off = [], G
+    for _ in range(4):
+        outs.append(arena2[off:off + n])
+        off += npad + G
+    pk = arena2[off:off + 2 * Bn * kc].view(torch.float64)
+    off += 2 * Bn * kc + G
+    pf = arena2[off:off + 2 * Bn * kc].view(torch.float64)
+    lens = torch.tensor([Tz, 5, 0], device=dev)
+    rc = lib.blvm_kl_elbo_fwd_grad(*[t.data_ptr() for t in ins], lens.data_ptr(), Bn, Tz, Z, 0.5, 1e-3, None,
+                                   *[o.data_ptr() for o in outs], pk.data_ptr(), pf.data_ptr(), ops._stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    guard_mask = torch.ones_like(arena2, dtype=torch.bool)
+    off = G
+    for _ in range(4):
+        guard_mask[off:off + n] = False
+        off += npad + G
+    guard_mask[off:off + 2 * Bn * kc] = False
+    off += 2 * Bn * kc + G
+    guard_mask[off:off + 2 * Bn * kc] = False
+    assert (arena2[guard_mask] == 77.0).all(), "KL kernel wrote outside its outputs"
+    assert all(torch.isfinite(o).all() for o in outs) and (outs[0].view(Bn, Tz, Z)[2] == 0).all()
