@@ -1,0 +1,141 @@
+"""Drop-in glue, end to end, on CPU (build container only — needs the reference tree): every reference audio model
+(VRNN, SRNN, Clockwork-VAE, STCN, WaveNet, LSTM) is run with `patch_blvm()` applied and the three kernel entry points
+of `blvm_b200.ops` swapped for oracle-backed fakes (numpy, fp64 -> the test is about plumbing, not arithmetic).  The
+patched model must produce the same loss / ELBO / log-prob / KL, with the same dtypes and output structure, as the
+unpatched reference model with identical weights and inputs.  This exercises: DMoLParams travelling through the model
+body (sample / mode / outputs), the compute_elbo / compute_loss signatures, the stride / mask -> length conversion, the
+per-level free-nats scaling and the float64 quirk."""
+import copy
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/blvm"), reason="reference tree not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def env():
+    os.environ.setdefault("BLVM_DATA_ROOT_DIRECTORY", "/tmp/blvmdata")
+    os.makedirs(os.environ["BLVM_DATA_ROOT_DIRECTORY"], exist_ok=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden", "_ref_shims"))
+    sys.path.insert(0, "/root/reference")
+    import blvm.models as M
+    import blvm_b200 as B
+    from oracle import blvm_oracle as O
+    return M, B, O
+
+
+def install_fakes(monkeypatch, B, O):
+    """Oracle-backed stand-ins for the CUDA entry points (tests only)."""
+    from blvm_b200 import ops
+
+    def fake_dmol_log_prob(y, raw, K, D, num_bins, log_epsilon):
+        yv = y.detach().double().numpy().reshape(-1, D)
+        r = raw.detach().double().numpy().reshape(-1, raw.shape[-1])
+        lp, _ = O.dmol_value_and_grad(yv, r, K, D, num_bins, log_epsilon)
+        return torch.from_numpy(lp.reshape(raw.shape[:-1])).float()
+
+    def fake_kl(mu_q, sd_q, mu_p, sd_p):
+        a = [t.detach().double().numpy() for t in torch.broadcast_tensors(mu_q, sd_q, mu_p, sd_p)]
+        return torch.from_numpy(O.kl_divergence_gaussian(*a)).float()
+
+    def fake_fused(spec, y, x_sl_dev, raw, kl_tensors):
+        x_sl = x_sl_dev.numpy()
+        B_ = len(x_sl)
+        levels, i = [], 0
+        kl_rows, fn_rows = [], []
+        for lv in spec.levels:
+            ts = [t.detach().double().numpy() for t in kl_tensors[i:i + lv.n_tensors]]
+            i += lv.n_tensors
+            kl = O.kl_divergence_gaussian(*ts) if lv.kind == "inputs" else ts[0]
+            m = O.sequence_mask(lv.lens.numpy(), max_len=kl.shape[1])[..., None].astype(np.float64)
+            kl_rows.append((kl * m).sum((1, 2)))
+            fn_rows.append((O.discount_free_nats(kl, lv.free_nats, -1) * m).sum((1, 2)))
+        logp = np.zeros(B_)
+        twise = torch.empty(0)
+        if spec.likelihood != "none":
+            T = raw.shape[1]
+            lp, _ = O.dmol_value_and_grad(y.detach().double().numpy().reshape(-1, spec.D),
+                                          raw.detach().double().numpy().reshape(B_ * T, -1), spec.K, spec.D, spec.num_bins,
+                                          spec.log_epsilon)
+            lp = lp.reshape(B_, T) * O.sequence_mask(x_sl, max_len=T)
+            logp = lp.sum(1)
+            twise = torch.from_numpy(lp).float()
+        kl_tot, fn_tot = sum(kl_rows, np.zeros(B_)), sum(fn_rows, np.zeros(B_))
+        loss = -(logp - spec.beta * fn_tot).sum() / spec.denom
+        rows = torch.from_numpy(np.stack([logp, kl_tot, fn_tot, logp - kl_tot] + kl_rows))
+        nan_loss = -np.nansum(logp) / spec.denom
+        sums = torch.tensor([loss, logp.sum(), kl_tot.sum(), fn_tot.sum(), (logp - kl_tot).sum(), spec.denom,
+                             -(logp - kl_tot).sum() / np.log(2) / spec.denom, nan_loss], dtype=torch.float64)
+        return sums[0], sums, rows, twise
+
+    monkeypatch.setattr(ops, "dmol_log_prob", fake_dmol_log_prob)
+    monkeypatch.setattr(ops, "kl_gaussian", fake_kl)
+    monkeypatch.setattr(ops, "fused_elbo_apply", fake_fused)
+    monkeypatch.setattr(ops, "param_tensor", lambda raw, K, D: raw.float().contiguous())
+
+
+def build(M, name):
+    torch.manual_seed(3)
+    lik = importlib.import_module("blvm.modules.distributions").DiscretizedLogisticMixtureDense
+    if name == "vrnn":
+        return M.VRNNAudio(input_size=200, hidden_size=32, latent_size=8, likelihood="DMoL")
+    if name == "srnn":
+        return M.SRNNAudio(likelihood="DMoL", input_size=64, hidden_size=32, latent_size=8, num_bins=2 ** 16)
+    if name == "cwvae":
+        return M.CWVAEAudio(z_size=[8, 4], h_size=[16, 16], strides=[16, 4], num_level_layers=2, stride_per_layer=4, likelihood="DMoL", num_bins=2 ** 16)
+    if name == "stcn":
+        return M.STCN(likelihood="DMoL", n_layers=2, latent_size=[8, 4], res_channels=16)
+    if name == "wavenet":
+        return M.WaveNet(likelihood=lik(x_dim=16, y_dim=1, num_mix=10, num_bins=2 ** 16), n_layers=2, n_stacks=1, res_channels=16)
+    if name == "lstm":
+        return M.LSTMAudio(stack_size=64, hidden_size=16, num_bins=2 ** 16)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["vrnn", "srnn", "cwvae", "stcn", "wavenet", "lstm"])
+def test_patched_model_matches_reference_model(name, env, monkeypatch):
+    M, B, O = env
+    T = 1600 if name != "cwvae" else 1024
+    x_sl = torch.tensor([T, T - 37 * 8])  # second utterance is padded
+    torch.manual_seed(1)
+    x = (torch.randint(0, 65536, (2, T)).float() / 65535 * 2 - 1)
+    kwargs = {} if name in ("wavenet", "lstm") else dict(beta=0.5, free_nats=0.25)
+
+    def run(model):
+        model.eval()
+        torch.manual_seed(5)   # sample() inside forward consumes RNG: same stream for both runs
+        with torch.no_grad():
+            return model(x, x_sl, **kwargs)
+
+    ref_model = build(M, name)
+    state = copy.deepcopy(ref_model.state_dict())
+    loss_ref, metrics_ref, out_ref = run(ref_model)
+
+    try:
+        B.patch_blvm()
+        install_fakes(monkeypatch, B, O)
+        ours_model = build(M, name)
+        assert set(ours_model.state_dict()) == set(state)              # checkpoint keys unchanged
+        ours_model.load_state_dict(state)
+        lik = [m for m in ours_model.modules() if isinstance(m, B.DiscretizedLogisticMixtureDense)]
+        assert len(lik) == 1
+        loss, metrics, out = run(ours_model)
+    finally:
+        B.unpatch_blvm()
+
+    assert loss.dtype == loss_ref.dtype, (loss.dtype, loss_ref.dtype)   # float64 for VRNN/SRNN, float32 elsewhere
+    np.testing.assert_allclose(float(loss), float(loss_ref), rtol=2e-5)
+    for key in ("elbo", "log_prob", "kl"):
+        if hasattr(out_ref, key):
+            a, b = getattr(out, key), getattr(out_ref, key)
+            assert a.dtype == b.dtype and a.shape == b.shape, key
+            np.testing.assert_allclose(a.double().numpy(), b.double().numpy(), rtol=5e-5, err_msg=key)
+    assert [type(m).__name__ for m in metrics] == [type(m).__name__ for m in metrics_ref]
+    assert sorted(vars(out)) == sorted(vars(out_ref))
