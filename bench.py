@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--ragged", action="store_true", help="x_sl ~ T*U(0.5,1) instead of full length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1: scalar-sum exchange fused into the finalize kernel over NVLink peer memory (p2p) or an "
+                         "asynchronous NCCL all-reduce (nccl)")
     ap.add_argument("--mode", default="auto", choices=["auto", "graph", "eager"],
                     help="`value` region: replay the step's kernels from CUDA graphs (auto/graph) or call the API eagerly")
     return ap.parse_args()
@@ -226,6 +229,17 @@ def run_gpu_arm(a):
     lens_dev = blvm_b200.level_lengths(x_dev, STRIDE)
 
     pending = []
+    ex, gsums = None, None
+    if world > 1 and a.exchange in ("auto", "p2p"):
+        try:
+            ex = blvm_b200.SumsExchange()
+            gsums = torch.zeros(8, dtype=torch.float64, device=dev)
+        except Exception as err:   # no symmetric memory on this stack: NCCL all-reduce instead
+            if a.exchange == "p2p":
+                raise
+            sys.stderr.write(f"[bench] symmetric-memory exchange unavailable ({err!r}); using NCCL\n")
+            ex = None
+    exchange_kind = "none" if world == 1 else ("p2p (fused into finalize, NVLink peer stores)" if ex is not None else "nccl all-reduce (async)")
 
     def sync_all():
         torch.cuda.synchronize()
@@ -239,14 +253,18 @@ def run_gpu_arm(a):
         for t in kl_d:
             t.grad = None
         out = blvm_b200.fused_elbo(y_d, params, x_sl, [blvm_b200.KLLevel(*kl_d, lens=lens_dev)], BETA, FREE_NATS,
-                                   num_bins=NUM_BINS, denom=denom, x_sl_device=x_dev)
+                                   num_bins=NUM_BINS, denom=denom, x_sl_device=x_dev, exchange=ex)
         out.loss.backward()
+        if ex is not None:
+            # the sums were published to every rank by the finalize kernel; this one-warp kernel adds the previous
+            # step's slots (lag 1: never stalls) — the whole exchange is device-side and part of the captured graph
+            ex.consume(beta=BETA, lag=1, out=gsums)
         return out.sums
 
     def exchange(sums):
         # the path's only exchange: the fp64 scalar sums over NCCL/NVLink, asynchronous (NCCL's own stream) so that it
         # overlaps the next step's kernels
-        if world > 1:
+        if world > 1 and ex is None:
             pending.append(blvm_b200.all_reduce_sums(sums, async_op=True, inplace=True))
 
     def step_eager():
@@ -316,7 +334,7 @@ def run_gpu_arm(a):
             pending.pop().wait()
         e1.record()
         sync_all()
-        launches = ops.launch_count() if mode == "eager" else 4 * a.steps
+        launches = ops.launch_count() if mode == "eager" else (5 if ex is not None else 4) * a.steps
         region_ms.append(e0.elapsed_time(e1))
         done = torch.tensor([1.0 if (time.perf_counter() - t_begin >= a.min_seconds or len(region_ms) >= 200) else 0.0], device=dev)
         if world > 1:
@@ -416,10 +434,10 @@ def run_gpu_arm(a):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": kern_ms * 1e3,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "mode": mode,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "mode": mode, "exchange": exchange_kind,
             "timed_region_repeats": len(region_ms), "timed_region_ms_min_max": [min(region_ms), max(region_ms)],
             "step": "fused_elbo(...).loss.backward() through the Python API" + (" (4 kernels, replayed from CUDA graphs)" if mode == "graph" else "")
-                    + ("; + 1 NCCL all-reduce of 5 fp64 sums" if world > 1 else ""),
+                    + (("; sums exchange: " + exchange_kind) if world > 1 else ""),
         }
         if not a.no_cpu_baseline and n_gpus == 1:
             try:

@@ -12,7 +12,7 @@ or, with the reference tree importable, `blvm_b200.patch_blvm()` and run `experi
 The CUDA library is mandatory: importing this package without `lib/libblvm_b200.so` raises (no CPU fallback).
 """
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is not built)
-from .distributed import all_reduce_sums, combine_sums, global_denominator, shard_rows
+from .distributed import SumsExchange, all_reduce_sums, combine_sums, global_denominator, shard_rows
 from .distributions import (ConditionalDistribution, DiscretizedLogisticDense, DiscretizedLogisticMixtureDense, DLParams,
                             DMoLParams)
 from .elbo import (KLLevel, cwvae_compute_elbo, fused_elbo, pack_dmol_params, srnn_compute_elbo, stcn_compute_loss,

@@ -276,22 +276,59 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
   return check_launch("kl_reduce_kernel");
 }
 
-int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
-                       const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
-                       const int64_t* x_sl, int64_t B, double beta, double* rows, double* scalars,
-                       unsigned int* sync_counter, blvm_stream_t stream) {
+static int finalize_impl(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
+                         const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
+                         const int64_t* x_sl, int64_t B, double beta, double denom, double* rows, double* scalars,
+                         unsigned int* sync_counter, const ExchangeArgs& X, blvm_stream_t stream) {
   if (n_levels < 0 || n_levels > kMaxLevels) return fail(BLVM_ERR_INVALID_ARGUMENT, "n_levels=%d out of [0, %d]", n_levels, kMaxLevels);
   if (B < 0 || !x_sl || !rows || !scalars || !sync_counter) return fail(BLVM_ERR_INVALID_ARGUMENT, "null x_sl/rows/scalars/sync_counter");
   FinalizeArgs A{};
   A.logp_part = logp_part; A.logp_chunks = logp_chunks; A.n_levels = n_levels; A.x_sl = x_sl; A.B = B; A.beta = beta;
-  A.rows = rows; A.scalars = scalars;
+  A.denom = denom; A.rows = rows; A.scalars = scalars;
   for (int l = 0; l < n_levels; ++l) {
     if (!kl_part_host[l] || !klfn_part_host[l]) return fail(BLVM_ERR_INVALID_ARGUMENT, "null KL partials at level %d", l);
     A.kl_part[l] = kl_part_host[l]; A.klfn_part[l] = klfn_part_host[l]; A.kl_chunks[l] = kl_chunks_host[l];
   }
   const unsigned blocks = static_cast<unsigned>(B > 0 ? (B + kFinWarps - 1) / kFinWarps : 1);
-  elbo_finalize_kernel<<<blocks, kFinTPB, 0, static_cast<cudaStream_t>(stream)>>>(A, sync_counter);
+  elbo_finalize_kernel<<<blocks, kFinTPB, 0, static_cast<cudaStream_t>(stream)>>>(A, sync_counter, X);
   return check_launch("elbo_finalize_kernel");
+}
+
+int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
+                       const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
+                       const int64_t* x_sl, int64_t B, double beta, double denom, double* rows, double* scalars,
+                       unsigned int* sync_counter, blvm_stream_t stream) {
+  ExchangeArgs X{};
+  return finalize_impl(logp_part, logp_chunks, kl_part_host, klfn_part_host, kl_chunks_host, n_levels, x_sl, B, beta, denom,
+                       rows, scalars, sync_counter, X, stream);
+}
+
+int blvm_elbo_finalize_publish(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
+                               const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
+                               const int64_t* x_sl, int64_t B, double beta, double denom, double* rows, double* scalars,
+                               unsigned int* sync_counter, void* const* peer_bases_host, int rank, int world,
+                               unsigned long long* exchange_counters, blvm_stream_t stream) {
+  if (world < 1 || world > kExMaxWorld || rank < 0 || rank >= world) return fail(BLVM_ERR_INVALID_ARGUMENT, "rank=%d world=%d (max %d)", rank, world, kExMaxWorld);
+  if (!peer_bases_host || !exchange_counters) return fail(BLVM_ERR_INVALID_ARGUMENT, "null exchange buffers");
+  ExchangeArgs X{};
+  X.rank = rank; X.world = world; X.counters = exchange_counters;
+  for (int p = 0; p < world; ++p) {
+    if (!peer_bases_host[p]) return fail(BLVM_ERR_INVALID_ARGUMENT, "null peer buffer %d", p);
+    X.peer_base[p] = static_cast<double*>(peer_bases_host[p]);
+  }
+  return finalize_impl(logp_part, logp_chunks, kl_part_host, klfn_part_host, kl_chunks_host, n_levels, x_sl, B, beta, denom,
+                       rows, scalars, sync_counter, X, stream);
+}
+
+int64_t blvm_exchange_buffer_bytes(void) { return static_cast<int64_t>(kExBufferBytes); }
+
+int blvm_exchange_consume(void* local_base, int world, unsigned long long* exchange_counters, int lag, double beta,
+                          double* out_sums, int* err_flag, blvm_stream_t stream) {
+  if (!local_base || !exchange_counters || !out_sums) return fail(BLVM_ERR_INVALID_ARGUMENT, "null pointer");
+  if (world < 1 || world > kExMaxWorld || lag < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "world=%d lag=%d", world, lag);
+  exchange_consume_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<double*>(local_base), world,
+                                                                          exchange_counters, lag, beta, out_sums, err_flag);
+  return check_launch("exchange_consume_kernel");
 }
 
 int blvm_quantize(const float* x, int64_t n, const float* boundaries, int64_t n_bins, int64_t* out, blvm_stream_t stream) {

@@ -173,12 +173,44 @@ struct FinalizeArgs {
   const int64_t* x_sl;              // (B) device
   int64_t B;
   double beta;
+  double denom;                     // normaliser of the loss; <= 0 means sum(x_sl) (data-parallel callers pass global/world)
   double* rows;                     // (4 + n_levels, B): logp, kl, kl_fn, elbo, kl_level_l...
   double* scalars;                  // (8): loss, sum logp, sum kl, sum kl_fn, sum elbo, sum x_sl, bpd, nan-safe loss
 };
 
 constexpr int kFinTPB = 256;
 constexpr int kFinWarps = kFinTPB / 32;
+
+// ---- scalar-sum exchange over NVLink peer memory (fused into the finalize kernel) -----------------------------------
+// Every rank owns one symmetric buffer (torch symmetric memory: the same allocation mapped into all ranks of the node):
+//   values [kExNbuf][kExMaxWorld][8] fp64   slot (buf, r) = the 8 scalars rank r published for step seq, buf = seq % kExNbuf
+//   flags  [kExNbuf][kExMaxWorld]    u64    = seq once the slot is complete
+// The last CTA of finalize writes its scalars into slot (buf, my_rank) of EVERY rank's buffer with plain peer stores
+// (NVLink P2P), fences system-wide, then releases the flags: the all-gather costs no extra launch and no host call.
+// A one-warp consumer kernel (exchange_consume_kernel) waits for the W flags of a step and adds the slots in rank
+// order (deterministic).  4 buffers + the consumer's wait bound the rank skew to < 4 steps.
+constexpr int kExNbuf = 4;
+constexpr int kExMaxWorld = 8;
+constexpr int kExValues = 8;
+constexpr size_t kExBufferBytes = sizeof(double) * kExNbuf * kExMaxWorld * kExValues + sizeof(unsigned long long) * kExNbuf * kExMaxWorld;
+
+struct ExchangeArgs {
+  int rank, world;                         // world == 0: no exchange
+  double* peer_base[kExMaxWorld];          // every rank's buffer as mapped in this process (peer_base[rank] is local)
+  unsigned long long* counters;            // local, not symmetric: [0] steps published, [1] steps consumed
+};
+__device__ __forceinline__ double* ex_slot(double* base, int buf, int r) { return base + (buf * kExMaxWorld + r) * kExValues; }
+__device__ __forceinline__ unsigned long long* ex_flag(double* base, int buf, int r) {
+  return reinterpret_cast<unsigned long long*>(base + kExNbuf * kExMaxWorld * kExValues) + buf * kExMaxWorld + r;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -194,7 +226,7 @@ __device__ __forceinline__ double warp_row_sum(const double* __restrict__ p, int
 
 // One warp per utterance reduces its per-tile partials; the last CTA to finish (device counter, self-resetting)
 // reduces the per-utterance rows to the scalars in a fixed order.  Grid = ceil(B / 8) CTAs.
-__global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeArgs A, unsigned int* counter) {
+__global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeArgs A, unsigned int* counter, const ExchangeArgs X) {
   __shared__ double scratch[6][kFinWarps];
   __shared__ bool is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -239,15 +271,70 @@ __global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeAr
   const double s_nan = block_sum_f64<kFinWarps>(t_nan_logp, scratch[4]);
   const double s_len = block_sum_f64<kFinWarps>(t_len, scratch[5]);
   if (tid == 0) {
-    A.scalars[0] = -s_obj / s_len;                       // loss
+    const double dn = A.denom > 0.0 ? A.denom : s_len;
+    A.scalars[0] = -s_obj / dn;                          // loss (vrnn.py:277), consistent with the gradients' 1/denom
     A.scalars[1] = s_logp;
     A.scalars[2] = s_kl;
     A.scalars[3] = s_fn;
     A.scalars[4] = s_logp - s_kl;                        // sum elbo
     A.scalars[5] = s_len;
     A.scalars[6] = -(s_logp - s_kl) / 0.6931471805599453 / s_len;  // bits per dim (metrics.py:456)
-    A.scalars[7] = -s_nan / s_len;                       // WaveNet's nansum loss
+    A.scalars[7] = -s_nan / dn;                          // WaveNet's nansum loss
     *counter = 0u;                                       // ready for the next launch on this stream
+    if (X.world > 0) {                                   // publish this rank's scalars to every rank of the node
+      const unsigned long long seq = ++X.counters[0];
+      const int buf = static_cast<int>(seq % kExNbuf);
+      for (int p = 0; p < X.world; ++p) {
+        volatile double* dst = ex_slot(X.peer_base[p], buf, X.rank);
+#pragma unroll
+        for (int i = 0; i < kExValues; ++i) dst[i] = A.scalars[i];
+      }
+      __threadfence_system();
+      for (int p = 0; p < X.world; ++p) st_release_sys(ex_flag(X.peer_base[p], buf, X.rank), seq);
+    }
+  }
+}
+
+// Consume one published step: wait until all W ranks' slots of step `seq = published - lag` have landed in the LOCAL
+// buffer, add them in rank order and recompute the ratio entries.  No-op if that step does not exist yet or was already
+// consumed.  err: bit 0 = timeout (a peer never published), bit 1 = slot overrun (a peer ran >= kExNbuf steps ahead).
+__global__ void __launch_bounds__(32) exchange_consume_kernel(double* local_base, int world, unsigned long long* counters,
+                                                              int lag, double beta, double* out, int* err) {
+  const int lane = threadIdx.x;
+  const unsigned long long published = counters[0], consumed = counters[1];
+  if (published < static_cast<unsigned long long>(lag) + 1) return;
+  const unsigned long long seq = published - lag;
+  if (seq <= consumed) return;
+  const int buf = static_cast<int>(seq % kExNbuf);
+  if (lane < world) {
+    const unsigned long long* f = ex_flag(local_base, buf, lane);
+    unsigned long long v = ld_acquire_sys(f);
+    long long spins = 0;
+    while (v < seq) {
+      __nanosleep(100);
+      v = ld_acquire_sys(f);
+      if (++spins > (1LL << 26)) {   // ~10 s: a peer died or never reached this step
+        if (err) atomicOr(err, 1);
+        break;
+      }
+    }
+    if (v > seq && err) atomicOr(err, 2);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    double s[kExValues];
+#pragma unroll
+    for (int i = 0; i < kExValues; ++i) s[i] = 0.0;
+    for (int r = 0; r < world; ++r) {
+      const volatile double* src = ex_slot(local_base, buf, r);
+#pragma unroll
+      for (int i = 0; i < kExValues; ++i) s[i] += src[i];
+    }
+    out[1] = s[1]; out[2] = s[2]; out[3] = s[3]; out[4] = s[4]; out[5] = s[5];
+    out[0] = -(s[1] - beta * s[3]) / s[5];                        // global loss (vrnn.py:277)
+    out[6] = -s[4] / 0.6931471805599453 / s[5];                   // global bits per dim
+    out[7] = static_cast<double>(seq);                            // which step these sums belong to
+    counters[1] = seq;
   }
 }
 

@@ -6,7 +6,7 @@ from typing import Optional, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_rows", "global_denominator", "all_reduce_sums", "combine_sums"]
+__all__ = ["shard_rows", "global_denominator", "all_reduce_sums", "combine_sums", "SumsExchange"]
 
 
 def shard_rows(n_rows: int, rank: int, world_size: int):
@@ -64,3 +64,56 @@ def combine_sums(sums: torch.Tensor, beta: float) -> torch.Tensor:
     out[6] = -s_elbo / 0.6931471805599453 / s_len
     out[7] = out[0]
     return out
+
+
+class SumsExchange:
+    """The scalar-sum exchange fused into the finalize kernel over NVLink peer memory (single node, <= 8 ranks).
+
+    Each rank owns a small symmetric buffer (torch symmetric memory: one allocation mapped into every rank).  With
+    `fused_elbo(..., exchange=ex)` the last CTA of the finalize kernel stores the step's 8 fp64 sums into this rank's
+    slot of EVERY rank's buffer and releases a flag — no NCCL call, no extra launch, nothing on the host.  `consume()`
+    launches a one-warp kernel that waits for all ranks' slots of a step and adds them in rank order (bit-reproducible)
+    into an (8,) tensor [global loss, sum log_prob, sum kl, sum kl_fn, sum elbo, sum x_sl, global bpd, step].  With
+    `lag=1` (default) it consumes the previous step, so the wait never stalls the stream; it also bounds the skew between
+    ranks, which is what makes the 4-deep slot ring safe.  All state is on the device: the calls can be graph-captured.
+    """
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+
+        from ._lib import lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("SumsExchange is a single-node exchange (<= 8 ranks); use all_reduce_sums across nodes")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        n = int(lib.blvm_exchange_buffer_bytes()) // 8
+        self.buffer = symm.empty(n, dtype=torch.float64, device=self.device)
+        self.buffer.zero_()
+        self.handle = symm.rendezvous(self.buffer, self.group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        self.handle.barrier()              # every buffer is zeroed before anyone publishes
+        torch.cuda.synchronize(self.device)
+
+    def consume(self, beta: float = 1.0, lag: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Global sums of step (published - lag); `out[7]` tells which step they belong to (0 = nothing consumed yet)."""
+        from . import ops
+        from ._lib import check, lib
+        if out is None:
+            out = torch.zeros(8, dtype=torch.float64, device=self.device)
+        with ops._on_device(self.device):
+            rc = lib.blvm_exchange_consume(self.buffer.data_ptr(), self.world, self.counters.data_ptr(), int(lag), float(beta),
+                                           out.data_ptr(), self.err.data_ptr(), ops._stream(self.device.index))
+            check(rc, "blvm_exchange_consume")
+        ops._count()
+        return out
+
+    def check(self):
+        """One sync: raise if a consume timed out (a peer never published) or a slot was overrun."""
+        e = int(self.err.item())
+        if e:
+            self.err.zero_()
+            raise RuntimeError(f"blvm_b200 SumsExchange error flags {e:#x} (1 = timeout waiting for a peer, 2 = slot overrun)")

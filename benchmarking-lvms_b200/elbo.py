@@ -75,6 +75,7 @@ def fused_elbo(
     want_twise: bool = False,
     skip_padded: bool = False,
     x_sl_device: Optional[torch.Tensor] = None,
+    exchange=None,
 ):
     """ELBO of a batch in one pass.
 
@@ -94,6 +95,8 @@ def fused_elbo(
             `value * 0`; only differs from the reference if padded parameters are non-finite).
         x_sl_device: the same lengths already on the device (B) int64; with `denom` given the call then does no
             host<->device traffic at all and can be captured in a CUDA graph.
+        exchange: a `blvm_b200.SumsExchange`: the finalize kernel then also publishes this rank's sums to every rank
+            over NVLink peer memory (`exchange.consume()` returns the global sums).
 
     Returns a namespace with fp64 tensors: loss (), elbo, log_prob, kl, kl_fn (B,), kl_levels [(B,)],
     sums (8,) = [loss, sum log_prob, sum kl, sum kl_fn, sum elbo, sum x_sl, bits-per-dim, nansum-loss] and
@@ -162,7 +165,7 @@ def fused_elbo(
     need_grad = torch.is_grad_enabled() and ((raw is not None and raw.requires_grad) or any(t.requires_grad for t in flat))
     spec = ops.ELBOSpec(K=K, D=D, num_bins=int(num_bins), log_epsilon=float(log_eps), beta=float(beta), denom=total,
                         levels=specs, want_twise=want_twise, skip_padded=skip_padded, need_grad=need_grad,
-                        likelihood=likelihood)
+                        likelihood=likelihood, exchange=exchange)
     loss, sums, rows, twise = ops.fused_elbo_apply(spec, y, x_sl_dev, raw, flat)
     return SimpleNamespace(loss=loss, log_prob=rows[0], kl=rows[1], kl_fn=rows[2], elbo=rows[3],
                            kl_levels=[rows[4 + l] for l in range(len(specs))], sums=sums,

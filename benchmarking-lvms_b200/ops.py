@@ -296,6 +296,7 @@ class ELBOSpec:
     skip_padded: bool = False
     need_grad: bool = True
     likelihood: str = "dmol"       # "dmol" | "dl" | "none"
+    exchange: object = None        # distributed.SumsExchange: publish the sums to all ranks from the finalize kernel
 
 
 class _FusedELBO(torch.autograd.Function):
@@ -400,9 +401,17 @@ class _FusedELBO(torch.autograd.Function):
 
             PtrArr = ctypes.c_void_p * max(L, 1)
             I64Arr = ctypes.c_int64 * max(L, 1)
-            rc = lib.blvm_elbo_finalize(logp_ptr, logp_chunks, PtrArr(*kl_ptrs), PtrArr(*klfn_ptrs), I64Arr(*kl_chunks), L,
-                                        x_sl_dev.data_ptr(), B, spec.beta, rows.data_ptr(), scalars.data_ptr(),
-                                        _sync_counter(dev).data_ptr(), stream)
+            ex = spec.exchange
+            if ex is None:
+                rc = lib.blvm_elbo_finalize(logp_ptr, logp_chunks, PtrArr(*kl_ptrs), PtrArr(*klfn_ptrs), I64Arr(*kl_chunks), L,
+                                            x_sl_dev.data_ptr(), B, spec.beta, spec.denom, rows.data_ptr(), scalars.data_ptr(),
+                                            _sync_counter(dev).data_ptr(), stream)
+            else:   # finalize + all-gather of the sums over NVLink peer memory, one kernel
+                rc = lib.blvm_elbo_finalize_publish(logp_ptr, logp_chunks, PtrArr(*kl_ptrs), PtrArr(*klfn_ptrs),
+                                                    I64Arr(*kl_chunks), L, x_sl_dev.data_ptr(), B, spec.beta, spec.denom,
+                                                    rows.data_ptr(), scalars.data_ptr(), _sync_counter(dev).data_ptr(),
+                                                    (ctypes.c_void_p * ex.world)(*ex.peer_ptrs), ex.rank, ex.world,
+                                                    ex.counters.data_ptr(), stream)
             check(rc, "blvm_elbo_finalize")
             _count()
 

@@ -141,15 +141,40 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
  * the BitsPerDimMetric arithmetic (blvm/evaluation/metrics.py:443-468).
  *   kl_part_host / klfn_part_host / kl_chunks_host: HOST arrays of n_levels device pointers / chunk counts
  *   rows     (4 + n_levels, B) fp64: logp, kl (sum over levels), kl_fn, elbo, then kl of each level
- *   scalars  (8) fp64: loss = -sum_b(logp - beta kl_fn)/sum(x_sl), sum logp, sum kl, sum kl_fn, sum elbo, sum x_sl,
+ *   denom    normaliser of the loss (<= 0: sum(x_sl)); data-parallel ranks pass sum_global(x_sl)/world, the value their
+ *            gradients were scaled with
+ *   scalars  (8) fp64: loss = -sum_b(logp - beta kl_fn)/denom, sum logp, sum kl, sum kl_fn, sum elbo, sum x_sl,
  *            bits-per-dim = -sum elbo / ln 2 / sum x_sl, nansum-loss = -nansum(logp)/sum x_sl (wavenet.py:145)
  *   sync_counter  one uint32 the caller zero-initialises ONCE per device/stream; the kernel leaves it at zero
  *            (inter-CTA "last block reduces" handshake; launches sharing a counter must be stream-ordered)
  */
 int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
                        const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
-                       const int64_t* x_sl, int64_t B, double beta, double* rows, double* scalars,
+                       const int64_t* x_sl, int64_t B, double beta, double denom, double* rows, double* scalars,
                        unsigned int* sync_counter, blvm_stream_t stream);
+
+/*
+ * Multi-GPU: the same finalize with the scalar exchange fused in.  After computing `scalars` the last
+ * CTA stores them into this rank's slot of EVERY rank's exchange buffer over NVLink peer memory and releases a
+ * per-slot flag — an all-gather of 8 fp64 values with no extra launch and no host call.
+ *   peer_bases_host   HOST array of `world` device pointers: every rank's exchange buffer (blvm_exchange_buffer_bytes()
+ *                     bytes, zero-initialised, symmetric memory / peer-mapped) as mapped in THIS process; entry `rank`
+ *                     is the local buffer
+ *   exchange_counters 2 x uint64 device memory, zero-initialised once: steps published / consumed by this rank
+ */
+int blvm_elbo_finalize_publish(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
+                               const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
+                               const int64_t* x_sl, int64_t B, double beta, double denom, double* rows, double* scalars,
+                               unsigned int* sync_counter, void* const* peer_bases_host, int rank, int world,
+                               unsigned long long* exchange_counters, blvm_stream_t stream);
+int64_t blvm_exchange_buffer_bytes(void);
+/*
+ * Consume step `published - lag` (no-op if it does not exist or was consumed): wait for all ranks' slots in the LOCAL
+ * buffer, add them in rank order -> out_sums (8) fp64 = [global loss, sum log_prob, sum kl, sum kl_fn, sum elbo,
+ * sum x_sl, global bits-per-dim, step number].  err_flag (nullable int32): bit 0 timeout, bit 1 slot overrun.
+ */
+int blvm_exchange_consume(void* local_base, int world, unsigned long long* exchange_counters, int lag, double beta,
+                          double* out_sums, int* err_flag, blvm_stream_t stream);
 
 /*
  * Quantize: torch.bucketize(x, boundaries, right=False) (blvm/data/transforms.py:257) -> int64 bin index,

@@ -1,0 +1,87 @@
+"""Multi-GPU tests (need >= 2 GPUs on one node: run under `gpurun --gpus 2`; skipped on the single-GPU box).
+Two ranks (one process per GPU, NCCL for rendezvous) run the fused ELBO on their shard with the scalar exchange fused
+into the finalize kernel over NVLink peer memory; the consumed global sums must equal the single-process values."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import blvm_b200 as B
+    g = load_golden("elbo_srnn_a")
+    K, nb, S = int(g["K"]), int(g["num_bins"]), int(g["stride"])
+    beta, fn = float(g["beta"]), float(g["free_nats"])
+    lo, hi = B.shard_rows(len(g["x_sl"]), rank, world)
+    dev = torch.device("cuda", rank)
+    cu = lambda a: torch.as_tensor(np.asarray(a)[lo:hi]).float().to(dev)
+    x_sl = torch.as_tensor(g["x_sl"][lo:hi])
+    denom = B.global_denominator(x_sl)
+    ex = B.SumsExchange()
+    results = []
+    for step in range(6):      # several steps: exercises the 4-deep slot ring and the lagged consume
+        raw = cu(g["raw"]).requires_grad_(True)
+        ins = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+        out = B.fused_elbo(cu(g["y"]), B.DMoLParams(raw, K, 1, -7.0), x_sl, [B.KLLevel(*ins, stride=S)], beta, fn,
+                           num_bins=nb, denom=denom, exchange=ex)
+        out.loss.backward()
+        results.append(ex.consume(beta=beta, lag=1).clone())
+    last = ex.consume(beta=beta, lag=0)
+    torch.cuda.synchronize()
+    ex.check()
+    # NCCL path for comparison
+    ref = B.combine_sums(B.all_reduce_sums(out.sums), beta)
+    q.put((rank, [r.cpu().numpy() for r in results], last.cpu().numpy(), ref.cpu().numpy(), out.loss.item(), denom))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node")
+@pytest.mark.timeout(300)
+def test_fused_finalize_exchange_two_gpus():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = load_golden("elbo_srnn_a")
+    for rank, results, last, ref, loss_local, denom in got:
+        assert results[0][7] == 0                      # lag 1: nothing to consume after the first step
+        for i, r in enumerate(results[1:], start=1):
+            assert r[7] == i                           # step i consumed after step i+1 was published
+        assert last[7] == 6
+        for r in results[1:] + [last]:
+            np.testing.assert_allclose(r[0], g["loss64"], rtol=1e-6)          # global loss on every rank
+            np.testing.assert_allclose(r[4], g["elbo64"].sum(), rtol=1e-6)
+            np.testing.assert_allclose(r[5], g["x_sl"].sum(), rtol=0)
+            np.testing.assert_allclose(r[6], -g["elbo64"].sum() / np.log(2) / g["x_sl"].sum(), rtol=1e-6)
+        np.testing.assert_allclose(last[:7], ref[:7], rtol=1e-12)             # identical to the NCCL all-reduce path
+    assert np.array_equal(got[0][2], got[1][2])                              # bit-identical on both ranks
+    np.testing.assert_allclose(np.mean([x[4] for x in got]), g["loss64"], rtol=1e-6)   # mean of rank losses == global
