@@ -255,10 +255,8 @@ def run_gpu_arm(a):
         out = blvm_b200.fused_elbo(y_d, params, x_sl, [blvm_b200.KLLevel(*kl_d, lens=lens_dev)], BETA, FREE_NATS,
                                    num_bins=NUM_BINS, denom=denom, x_sl_device=x_dev, exchange=ex)
         out.loss.backward()
-        if ex is not None:
-            # the sums were published to every rank by the finalize kernel; this one-warp kernel adds the previous
-            # step's slots (lag 1: never stalls) — the whole exchange is device-side and part of the captured graph
-            ex.consume(beta=BETA, lag=1, out=gsums)
+        # with `exchange=ex` the finalize kernel itself publishes this step's sums to every rank over NVLink peer memory
+        # and adds up the previous step's slots into ex.global_sums: the exchange costs no launch and no host call
         return out.sums
 
     def exchange(sums):
@@ -334,7 +332,7 @@ def run_gpu_arm(a):
             pending.pop().wait()
         e1.record()
         sync_all()
-        launches = ops.launch_count() if mode == "eager" else (5 if ex is not None else 4) * a.steps
+        launches = ops.launch_count() if mode == "eager" else 4 * a.steps
         region_ms.append(e0.elapsed_time(e1))
         done = torch.tensor([1.0 if (time.perf_counter() - t_begin >= a.min_seconds or len(region_ms) >= 200) else 0.0], device=dev)
         if world > 1:

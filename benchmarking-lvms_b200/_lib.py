@@ -37,7 +37,7 @@ SIGNATURES = {
     "blvm_kl_reduce_fwd_grad": (_i32, [_p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _p]),
     "blvm_elbo_finalize": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64, _f64, _f64, _p, _p, _p, _p]),
     "blvm_elbo_finalize_publish": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64,
-                                          _f64, _f64, _p, _p, _p, ctypes.POINTER(_p), _i32, _i32, _p, _p]),
+                                          _f64, _f64, _p, _p, _p, ctypes.POINTER(_p), _i32, _i32, _p, _p, _p, _p]),
     "blvm_exchange_buffer_bytes": (_i64, []),
     "blvm_exchange_consume": (_i32, [_p, _i32, _p, _i32, _f64, _p, _p, _p]),
     "blvm_quantize": (_i32, [_p, _i64, _p, _i64, _p, _p]),

@@ -307,11 +307,12 @@ int blvm_elbo_finalize_publish(const double* logp_part, int64_t logp_chunks, con
                                const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
                                const int64_t* x_sl, int64_t B, double beta, double denom, double* rows, double* scalars,
                                unsigned int* sync_counter, void* const* peer_bases_host, int rank, int world,
-                               unsigned long long* exchange_counters, blvm_stream_t stream) {
+                               unsigned long long* exchange_counters, double* prev_global_sums, int* err_flag,
+                               blvm_stream_t stream) {
   if (world < 1 || world > kExMaxWorld || rank < 0 || rank >= world) return fail(BLVM_ERR_INVALID_ARGUMENT, "rank=%d world=%d (max %d)", rank, world, kExMaxWorld);
   if (!peer_bases_host || !exchange_counters) return fail(BLVM_ERR_INVALID_ARGUMENT, "null exchange buffers");
   ExchangeArgs X{};
-  X.rank = rank; X.world = world; X.counters = exchange_counters;
+  X.rank = rank; X.world = world; X.counters = exchange_counters; X.global_out = prev_global_sums; X.err = err_flag;
   for (int p = 0; p < world; ++p) {
     if (!peer_bases_host[p]) return fail(BLVM_ERR_INVALID_ARGUMENT, "null peer buffer %d", p);
     X.peer_base[p] = static_cast<double*>(peer_bases_host[p]);

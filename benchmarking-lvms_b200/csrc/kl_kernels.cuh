@@ -198,18 +198,61 @@ struct ExchangeArgs {
   int rank, world;                         // world == 0: no exchange
   double* peer_base[kExMaxWorld];          // every rank's buffer as mapped in this process (peer_base[rank] is local)
   unsigned long long* counters;            // local, not symmetric: [0] steps published, [1] steps consumed
+  double* global_out;                      // nullable (8): the PREVIOUS step's global sums, consumed in the same kernel
+  int* err;                                // nullable: bit 0 timeout, bit 1 slot overrun
 };
 __device__ __forceinline__ double* ex_slot(double* base, int buf, int r) { return base + (buf * kExMaxWorld + r) * kExValues; }
 __device__ __forceinline__ unsigned long long* ex_flag(double* base, int buf, int r) {
   return reinterpret_cast<unsigned long long*>(base + kExNbuf * kExMaxWorld * kExValues) + buf * kExMaxWorld + r;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+
+// Wait for the W slots of step `seq` in the local buffer and add them in rank order.  Called by a full warp: lane r
+// polls / reads rank r's slot (parallel over ranks), lane 0 accumulates through shuffles in a fixed order.
+__device__ __forceinline__ void ex_consume_step(double* local_base, int world, unsigned long long seq, double beta, double* out,
+                                                int* err) {
+  const int lane = threadIdx.x & 31;
+  const int buf = static_cast<int>(seq % kExNbuf);
+  double v[kExValues];
+#pragma unroll
+  for (int i = 0; i < kExValues; ++i) v[i] = 0.0;
+  if (lane < world) {
+    const unsigned long long* f = ex_flag(local_base, buf, lane);
+    unsigned long long got = ld_acquire_sys(f);
+    long long spins = 0;
+    while (got < seq) {
+      __nanosleep(100);
+      got = ld_acquire_sys(f);
+      if (++spins > (1LL << 26)) {   // ~10 s: a peer died or never reached this step
+        if (err) atomicOr(err, 1);
+        break;
+      }
+    }
+    if (got > seq && err) atomicOr(err, 2);
+    const volatile double* src = ex_slot(local_base, buf, lane);
+#pragma unroll
+    for (int i = 0; i < kExValues; ++i) v[i] = src[i];
+  }
+  double s[kExValues];
+#pragma unroll
+  for (int i = 0; i < kExValues; ++i) s[i] = 0.0;
+  for (int r = 0; r < world; ++r) {
+#pragma unroll
+    for (int i = 0; i < kExValues; ++i) s[i] += __shfl_sync(0xffffffffu, v[i], r);
+  }
+  if (lane == 0) {
+    out[1] = s[1]; out[2] = s[2]; out[3] = s[3]; out[4] = s[4]; out[5] = s[5];
+    out[0] = -(s[1] - beta * s[3]) / s[5];                        // global loss (vrnn.py:277)
+    out[6] = -s[4] / 0.6931471805599453 / s[5];                   // global bits per dim
+    out[7] = static_cast<double>(seq);                            // which step these sums belong to
+  }
 }
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
@@ -281,16 +324,32 @@ __global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeAr
     A.scalars[6] = -(s_logp - s_kl) / 0.6931471805599453 / s_len;  // bits per dim (metrics.py:456)
     A.scalars[7] = -s_nan / dn;                          // WaveNet's nansum loss
     *counter = 0u;                                       // ready for the next launch on this stream
-    if (X.world > 0) {                                   // publish this rank's scalars to every rank of the node
-      const unsigned long long seq = ++X.counters[0];
-      const int buf = static_cast<int>(seq % kExNbuf);
-      for (int p = 0; p < X.world; ++p) {
-        volatile double* dst = ex_slot(X.peer_base[p], buf, X.rank);
+  }
+  // ---- fused exchange (warp 0 of the last CTA): publish this step's scalars into every rank's buffer over NVLink peer
+  // memory, then add up the previous step's slots.  Lane p talks to rank p.
+  if (X.world > 0 && tid < 32) {
+    __syncwarp();
+    unsigned long long seq = 0;
+    if (tid == 0) {
+      __threadfence();                                   // scalars[] written above are visible to the lanes below
+      seq = ++X.counters[0];
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    const int buf = static_cast<int>(seq % kExNbuf);
+    if (tid < X.world) {
+      volatile double* dst = ex_slot(X.peer_base[tid], buf, X.rank);
 #pragma unroll
-        for (int i = 0; i < kExValues; ++i) dst[i] = A.scalars[i];
-      }
-      __threadfence_system();
-      for (int p = 0; p < X.world; ++p) st_release_sys(ex_flag(X.peer_base[p], buf, X.rank), seq);
+      for (int i = 0; i < kExValues; ++i) dst[i] = __ldcg(A.scalars + i);
+      __threadfence_system();                            // the slot is complete before its flag
+      st_relaxed_sys(ex_flag(X.peer_base[tid], buf, X.rank), seq);
+    }
+    // the PREVIOUS step's slots landed a whole step ago: no stall, no extra launch; this wait is also what bounds the
+    // skew between ranks to < kExNbuf steps
+    unsigned long long consumed = (tid == 0) ? X.counters[1] : 0;
+    consumed = __shfl_sync(0xffffffffu, consumed, 0);
+    if (X.global_out && seq >= 2 && consumed < seq - 1) {
+      ex_consume_step(X.peer_base[X.rank], X.world, seq - 1, A.beta, X.global_out, X.err);
+      if (tid == 0) X.counters[1] = seq - 1;
     }
   }
 }
@@ -305,37 +364,8 @@ __global__ void __launch_bounds__(32) exchange_consume_kernel(double* local_base
   if (published < static_cast<unsigned long long>(lag) + 1) return;
   const unsigned long long seq = published - lag;
   if (seq <= consumed) return;
-  const int buf = static_cast<int>(seq % kExNbuf);
-  if (lane < world) {
-    const unsigned long long* f = ex_flag(local_base, buf, lane);
-    unsigned long long v = ld_acquire_sys(f);
-    long long spins = 0;
-    while (v < seq) {
-      __nanosleep(100);
-      v = ld_acquire_sys(f);
-      if (++spins > (1LL << 26)) {   // ~10 s: a peer died or never reached this step
-        if (err) atomicOr(err, 1);
-        break;
-      }
-    }
-    if (v > seq && err) atomicOr(err, 2);
-  }
-  __syncwarp();
-  if (lane == 0) {
-    double s[kExValues];
-#pragma unroll
-    for (int i = 0; i < kExValues; ++i) s[i] = 0.0;
-    for (int r = 0; r < world; ++r) {
-      const volatile double* src = ex_slot(local_base, buf, r);
-#pragma unroll
-      for (int i = 0; i < kExValues; ++i) s[i] += src[i];
-    }
-    out[1] = s[1]; out[2] = s[2]; out[3] = s[3]; out[4] = s[4]; out[5] = s[5];
-    out[0] = -(s[1] - beta * s[3]) / s[5];                        // global loss (vrnn.py:277)
-    out[6] = -s[4] / 0.6931471805599453 / s[5];                   // global bits per dim
-    out[7] = static_cast<double>(seq);                            // which step these sums belong to
-    counters[1] = seq;
-  }
+  ex_consume_step(local_base, world, seq, beta, out, err);
+  if (lane == 0) counters[1] = seq;
 }
 
 }  // namespace blvm

@@ -71,11 +71,12 @@ class SumsExchange:
 
     Each rank owns a small symmetric buffer (torch symmetric memory: one allocation mapped into every rank).  With
     `fused_elbo(..., exchange=ex)` the last CTA of the finalize kernel stores the step's 8 fp64 sums into this rank's
-    slot of EVERY rank's buffer and releases a flag — no NCCL call, no extra launch, nothing on the host.  `consume()`
-    launches a one-warp kernel that waits for all ranks' slots of a step and adds them in rank order (bit-reproducible)
-    into an (8,) tensor [global loss, sum log_prob, sum kl, sum kl_fn, sum elbo, sum x_sl, global bpd, step].  With
-    `lag=1` (default) it consumes the previous step, so the wait never stalls the stream; it also bounds the skew between
-    ranks, which is what makes the 4-deep slot ring safe.  All state is on the device: the calls can be graph-captured.
+    slot of EVERY rank's buffer and releases a flag — no NCCL call, no extra launch, nothing on the host.  The same
+    kernel also adds up (in rank order: bit-reproducible) the slots all ranks published for the PREVIOUS step into
+    `self.global_sums` (8,) = [global loss, sum log_prob, sum kl, sum kl_fn, sum elbo, sum x_sl, global bpd, step]: they
+    landed a whole step ago, so this never stalls, and it bounds the skew between ranks, which makes the 4-deep slot ring
+    safe.  `consume(lag=0)` (a one-warp kernel) fetches the sums of the latest step, e.g. after the last step of an
+    epoch.  All state is on the device: the calls can be captured in a CUDA graph.
     """
 
     def __init__(self, group=None, device=None):
@@ -93,12 +94,13 @@ class SumsExchange:
         self.handle = symm.rendezvous(self.buffer, self.group)
         self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self.counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.global_sums = torch.zeros(8, dtype=torch.float64, device=self.device)   # previous step's global sums
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize(self.device)
         self.handle.barrier()              # every buffer is zeroed before anyone publishes
         torch.cuda.synchronize(self.device)
 
-    def consume(self, beta: float = 1.0, lag: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def consume(self, beta: float = 1.0, lag: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Global sums of step (published - lag); `out[7]` tells which step they belong to (0 = nothing consumed yet)."""
         from . import ops
         from ._lib import check, lib

@@ -411,7 +411,7 @@ class _FusedELBO(torch.autograd.Function):
                                                     I64Arr(*kl_chunks), L, x_sl_dev.data_ptr(), B, spec.beta, spec.denom,
                                                     rows.data_ptr(), scalars.data_ptr(), _sync_counter(dev).data_ptr(),
                                                     (ctypes.c_void_p * ex.world)(*ex.peer_ptrs), ex.rank, ex.world,
-                                                    ex.counters.data_ptr(), stream)
+                                                    ex.counters.data_ptr(), ex.global_sums.data_ptr(), ex.err.data_ptr(), stream)
             check(rc, "blvm_elbo_finalize")
             _count()
 

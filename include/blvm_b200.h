@@ -161,12 +161,16 @@ int blvm_elbo_finalize(const double* logp_part, int64_t logp_chunks, const doubl
  *                     bytes, zero-initialised, symmetric memory / peer-mapped) as mapped in THIS process; entry `rank`
  *                     is the local buffer
  *   exchange_counters 2 x uint64 device memory, zero-initialised once: steps published / consumed by this rank
+ *   prev_global_sums  nullable (8) fp64: the same kernel also consumes the PREVIOUS step (all ranks' slots landed a step
+ *                     ago) -> [global loss, sum log_prob, sum kl, sum kl_fn, sum elbo, sum x_sl, global bpd, step number]
+ *   err_flag          nullable int32: bit 0 timeout waiting for a peer, bit 1 slot overrun
  */
 int blvm_elbo_finalize_publish(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
                                const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
                                const int64_t* x_sl, int64_t B, double beta, double denom, double* rows, double* scalars,
                                unsigned int* sync_counter, void* const* peer_bases_host, int rank, int world,
-                               unsigned long long* exchange_counters, blvm_stream_t stream);
+                               unsigned long long* exchange_counters, double* prev_global_sums, int* err_flag,
+                               blvm_stream_t stream);
 int64_t blvm_exchange_buffer_bytes(void);
 /*
  * Consume step `published - lag` (no-op if it does not exist or was consumed): wait for all ranks' slots in the LOCAL
