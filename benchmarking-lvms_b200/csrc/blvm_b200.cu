@@ -116,9 +116,7 @@ bool dmol_has_register_kernel(int K, int D) {
 
 template <bool GRAD>
 int dispatch_dmol(const DmolArgs& A, int raw_dtype, cudaStream_t st) {
-  const int64_t ts = dmol_tile_samples(A.K, A.D);
   const int64_t tiles = A.B * A.chunks;
-  (void)ts;
   if (tiles == 0) return BLVM_OK;
   if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)tiles);
   if (A.D == 1) {

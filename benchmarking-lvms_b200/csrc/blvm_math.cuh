@@ -7,12 +7,12 @@
 //   blvm/utils/log_likelihoods.py:198-231   the four-branch discretized logistic, log_softmax, logsumexp
 //   blvm/utils/variational.py:67-70,86-122  Gaussian KL (std-dev parametrisation), free nats
 //
-// Numerical design (DESIGN.md §4): the reference evaluates cdf_delta = sigmoid(a) - sigmoid(b) in fp32, which loses
+// Numerical design (DESIGN.md §3.2): the reference evaluates cdf_delta = sigmoid(a) - sigmoid(b) in fp32, which loses
 // up to 3 digits to cancellation when the bin is narrow (16-bit audio: half width 1.5e-5).  We evaluate the same
-// quantity without cancellation,
-//     sigmoid(a) - sigmoid(b) = sigmoid(a) * sigmoid(-b) * (1 - exp(-(a - b))),   a - b = 2 h / s,
-// and its derivatives as  d/dm = sigmoid(-a) - sigmoid(b),  d/du = (s'(a) + s'(b)) / delta  (a = m + u, b = m - u),
-// so results track the reference run in fp64 to ~1e-6 relative, inside the fp32 reference's own error band.
+// quantity without cancellation and without a divergent branch through
+//     sigmoid(m+u) - sigmoid(m-u) = sinh(u) / (cosh(m) + cosh(u))            (a = m + u, b = m - u)
+// (see dl_mid below), so results track the reference run in fp64 to ~3e-7 relative, well inside the fp32 reference's
+// own error band (1e-3).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -83,28 +83,6 @@ BLVM_HD float accurate_exp(float x) {
   return fmaf(e, p_lo * kLn2, e);
 }
 BLVM_HD float fast_log(float x) { return fast_lg2(x) * kLn2; }
-
-// (1 - exp(-x)) / x for 0 <= x < 0.25:  1 - x/2 + x^2/6 - x^3/24 + x^4/120 - x^5/720 + x^6/5040
-// (next term x^7/40320 < 1.6e-9 relative at 0.25).  FMA pipe only.
-BLVM_HD float expm1_neg_ratio_small(float x) {
-  float p = 1.0f / 5040.0f;
-  p = fmaf(p, x, -1.0f / 720.0f);
-  p = fmaf(p, x, 1.0f / 120.0f);
-  p = fmaf(p, x, -1.0f / 24.0f);
-  p = fmaf(p, x, 1.0f / 6.0f);
-  p = fmaf(p, x, -0.5f);
-  p = fmaf(p, x, 1.0f);
-  return p;
-}
-// 1 - exp(-x) for x >= 0 without cancellation.
-BLVM_HD float one_minus_exp_neg(float x) {
-  if (x < 0.25f) return x * expm1_neg_ratio_small(x);
-  return 1.0f - fast_exp(-x);
-}
-// same, when e = exp(-x) is already at hand
-BLVM_HD float one_minus_exp_neg_given(float x, float e) {
-  return (x < 0.25f) ? x * expm1_neg_ratio_small(x) : 1.0f - e;
-}
 
 // exp(-log_scale): compensated by default (build with -DBLVM_COMPENSATED_EXP=0 to measure the plain MUFU path)
 BLVM_HD float stable_exp(float x) {
