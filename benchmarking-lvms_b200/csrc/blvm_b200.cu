@@ -155,7 +155,7 @@ int64_t blvm_dmol_chunks(int64_t T, int K, int D) {
   const int64_t ts = dmol_tile_samples(K, D);
   return (T + ts - 1) / ts;
 }
-int64_t blvm_dl_chunks(int64_t T) { return (T + kTile - 1) / kTile; }
+int64_t blvm_dl_chunks(int64_t T) { return (T + kTile * kDlSpt - 1) / (kTile * kDlSpt); }
 int blvm_dmol_has_fast_path(int K, int D) { return dmol_has_register_kernel(K, D) ? 1 : 0; }
 int64_t blvm_kl_chunks(int64_t row_elems) { return (row_elems + kKlChunk - 1) / kKlChunk; }
 

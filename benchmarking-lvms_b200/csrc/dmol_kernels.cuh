@@ -326,46 +326,66 @@ __global__ void __launch_bounds__(TPB) dmol_generic_kernel(const DmolArgs A) {
   }
 }
 
-// Single discretized logistic (DiscretizedLogisticDense, distributions.py:268-307): raw (B*T, 2) = [mu | log_scale],
-// one thread per sample with a 64-bit load/store; same tiling, mask and partial-sum contract as the mixture kernel.
+// Single discretized logistic (DiscretizedLogisticDense, distributions.py:268-307): raw (B*T, 2) = [mu | log_scale].
+// One CTA = kDlSpt * TPB consecutive samples of one utterance; each thread issues its kDlSpt coalesced 64-bit parameter
+// loads and 32-bit target loads up front (memory-level parallelism), then evaluates and stores; same mask and
+// partial-sum contract as the mixture kernel.  24 B/sample fwd+grad.
+constexpr int kDlSpt = 8;
+
 template <int TPB, bool GRAD>
 __global__ void __launch_bounds__(TPB) dl_kernel(const DmolArgs A) {
   __shared__ double scratch[TPB / 32];
+  constexpr int TILE = TPB * kDlSpt;
   const int tid = threadIdx.x;
   const int64_t tile_id = blockIdx.x;
   const int64_t b = tile_id / A.chunks;
   const int64_t c = tile_id - b * A.chunks;
-  const int64_t t0 = c * TPB;
-  const int n = static_cast<int>(min(static_cast<int64_t>(TPB), A.T - t0));
+  const int64_t t0 = c * TILE;
+  const int n = static_cast<int>(min(static_cast<int64_t>(TILE), A.T - t0));
   const int64_t s0 = b * A.T + t0;
   int64_t len = A.x_sl ? A.x_sl[b] : A.T;
   len = len < 0 ? 0 : (len > A.T ? A.T : len);
   const int nvalid = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(n), len - t0)));
-  const bool in_tile = tid < n, valid = tid < nvalid;
   const bool skip = (A.flags & kFlagSkipPadded) && nvalid == 0;
-  float L = 0.f;
-  if (in_tile) {
-    const int64_t s = s0 + tid;
-    const float yv = A.y[s];
-    if (!(yv <= 1.0f && yv >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
-    float g = 0.f;
-    if (GRAD) {
-      g = valid ? A.gscale : 0.f;
-      if (A.gscale_dev) g *= static_cast<float>(*A.gscale_dev);
-      if (A.gout) g *= A.gout[s];
+  const float2* raw = static_cast<const float2*>(A.raw);
+  float2* graw = static_cast<float2*>(A.graw);
+  float gs = A.gscale;
+  if (GRAD && A.gscale_dev) gs *= static_cast<float>(*A.gscale_dev);
+
+  float yv[kDlSpt];
+  float2 p[kDlSpt];
+#pragma unroll
+  for (int j = 0; j < kDlSpt; ++j) {
+    const int i = j * TPB + tid;
+    yv[j] = 0.f;
+    p[j] = make_float2(0.f, 0.f);
+    if (i < n) {
+      yv[j] = ptx::ldg_stream(A.y + s0 + i);
+      if (!skip) p[j] = raw[s0 + i];
     }
-    float dmu = 0.f, dls = 0.f;
-    if (!skip) {
-      const float2 p = static_cast<const float2*>(A.raw)[s];
-      dl_component<GRAD>(yv, dmol_edge(yv, A.C), p.x, p.y, A.C, L, dmu, dls);
-    }
-    if (GRAD) static_cast<float2*>(A.graw)[s] = make_float2(g * dmu, g * dls);
   }
-  const float Lm = valid ? L : L * 0.0f;
-  if (A.lp && in_tile) A.lp[s0 + tid] = (A.flags & kFlagMaskOutput) ? Lm : L;
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < kDlSpt; ++j) {
+    const int i = j * TPB + tid;
+    if (i < n) {
+      const int64_t s = s0 + i;
+      if (!(yv[j] <= 1.0f && yv[j] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
+      float L = 0.f, dmu = 0.f, dls = 0.f;
+      if (!skip) dl_component<GRAD>(yv[j], dmol_edge(yv[j], A.C), p[j].x, p[j].y, A.C, L, dmu, dls);
+      if (GRAD) {
+        float g = (i < nvalid) ? gs : 0.f;
+        if (A.gout) g *= A.gout[s];
+        graw[s] = make_float2(g * dmu, g * dls);
+      }
+      const float Lm = (i < nvalid) ? L : L * 0.0f;
+      if (A.lp) A.lp[s] = (A.flags & kFlagMaskOutput) ? Lm : L;
+      acc += static_cast<double>(Lm);
+    }
+  }
   if (A.partials) {
-    const double s = block_sum_f64<TPB / 32>(static_cast<double>(Lm), scratch);
-    if (tid == 0) A.partials[tile_id] = s;
+    const double sum = block_sum_f64<TPB / 32>(acc, scratch);
+    if (tid == 0) A.partials[tile_id] = sum;
   }
 }
 

@@ -66,6 +66,19 @@ def main():
         print(f"K={K:2d} {dtn:8s} dmol fwd only: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
               f"{byt / med / 1e6:7.0f} GB/s algorithmic")
         del raw, graw
+    # single discretized logistic (DiscretizedLogisticDense): packed (B, T, 2)
+    y = torch.randint(0, nb, (B, T), device=dev).float() / (nb - 1) * 2 - 1
+    raw2 = torch.randn(B, T, 2, device=dev)
+    raw2[..., 0] = y + 0.1 * raw2[..., 0]
+    raw2[..., 1] = raw2[..., 1] * 2 - 4
+    x_dev = torch.full((B,), T, dtype=torch.int64, device=dev)
+    lp = torch.empty(B, T, device=dev)
+    g2 = torch.empty_like(raw2)
+    part = torch.empty(B * int(blvm_b200._lib.lib.blvm_dl_chunks(T)), dtype=torch.float64, device=dev)
+    med, best = timeit(lambda: ops._dl_call(y, raw2, x_dev, None, -1e-6, B, T, nb, -7.0, 1, lp, g2, part))
+    print(f"DL fwd+grad: {med * 1e3:8.1f} us median; {B * T * 24 / med / 1e6:7.0f} GB/s algorithmic")
+    med, best = timeit(lambda: ops._dl_call(y, raw2, x_dev, None, 0.0, B, T, nb, -7.0, 1, lp, None, part))
+    print(f"DL fwd only: {med * 1e3:8.1f} us median; {B * T * 16 / med / 1e6:7.0f} GB/s algorithmic")
     # KL fused
     S, Z = 64, 64
     Tz = T // S
