@@ -203,19 +203,22 @@ int blvm_dl_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, cons
   return check_launch("dl_kernel");
 }
 
+static bool kl_vec_ok(const KlArgs& A, bool grad) {
+  bool vec = (A.row_elems % 4 == 0) && aligned(A.mu_q, 16) && aligned(A.sd_q, 16) && aligned(A.mu_p, 16) &&
+             aligned(A.sd_p, 16) && aligned(A.kl, 16);
+  if (grad) vec = vec && aligned(A.g_mu_q, 16) && aligned(A.g_sd_q, 16) && aligned(A.g_mu_p, 16) && aligned(A.g_sd_p, 16);
+  return vec;
+}
+
 static int launch_kl(KlArgs& A, bool grad, cudaStream_t st) {
   A.chunks = blvm_kl_chunks(A.row_elems);
   const int64_t tiles = A.B * A.chunks;
   if (tiles == 0) return BLVM_OK;
   if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
-  bool vec = (A.row_elems % 4 == 0) && aligned(A.mu_q, 16) && aligned(A.sd_q, 16) && aligned(A.mu_p, 16) &&
-             aligned(A.sd_p, 16) && aligned(A.kl, 16);
-  if (grad) vec = vec && aligned(A.g_mu_q, 16) && aligned(A.g_sd_q, 16) && aligned(A.g_mu_p, 16) && aligned(A.g_sd_p, 16);
+  A.vec = kl_vec_ok(A, grad) ? 1 : 0;
   const unsigned g = static_cast<unsigned>(tiles);
-  if (vec && grad) kl_kernel<true, true><<<g, kKlTPB, 0, st>>>(A);
-  else if (vec) kl_kernel<true, false><<<g, kKlTPB, 0, st>>>(A);
-  else if (grad) kl_kernel<false, true><<<g, kKlTPB, 0, st>>>(A);
-  else kl_kernel<false, false><<<g, kKlTPB, 0, st>>>(A);
+  if (grad) kl_kernel<true><<<g, kKlTPB, 0, st>>>(A);
+  else kl_kernel<false><<<g, kKlTPB, 0, st>>>(A);
   return check_launch("kl_kernel");
 }
 
@@ -262,16 +265,16 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
   if (B < 0 || Tz < 0 || Z < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad shape");
   if (B * Tz > 0 && !kl) return fail(BLVM_ERR_INVALID_ARGUMENT, "null kl");
   if (!part_kl || !part_klfn) return fail(BLVM_ERR_INVALID_ARGUMENT, "null partials");
-  KlReduceArgs A{};
-  A.kl = kl; A.lens = lens; A.gscale = gscale; A.fn_enabled = (free_nats != 0.0) ? 1 : 0;
+  KlArgs A{};
+  A.kl_in = kl; A.lens = lens; A.gscale = gscale; A.fn_enabled = (free_nats != 0.0) ? 1 : 0;
   A.min_kl = static_cast<float>(free_nats / static_cast<double>(Z));
   A.gkl = gkl; A.part_kl = part_kl; A.part_klfn = part_klfn; A.B = B; A.row_elems = Tz * Z; A.Z = Z;
   A.chunks = blvm_kl_chunks(A.row_elems);
   const int64_t tiles = B * A.chunks;
   if (tiles == 0) return BLVM_OK;
   if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
-  kl_reduce_kernel<<<static_cast<unsigned>(tiles), kKlTPB, 0, static_cast<cudaStream_t>(stream)>>>(A);
-  return check_launch("kl_reduce_kernel");
+  kl_kernel<false><<<static_cast<unsigned>(tiles), kKlTPB, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  return check_launch("kl_kernel (materialised KL)");
 }
 
 static int finalize_impl(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,

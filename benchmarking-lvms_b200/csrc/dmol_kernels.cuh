@@ -173,20 +173,20 @@ constexpr size_t dmol_tile_smem_bytes() {
   return ((size_t(TPB) * DmolSpt<K>::value * 3 * K * sizeof(TP) + 15) / 16) * 16 + 16 /*mbarrier*/ + (TPB / 32) * sizeof(double);
 }
 
+// The body of one tile; returns true if a bulk store is still reading the tile's shared memory (the caller must execute
+// ptx::bulk_wait_read0() in thread 0 before the CTA exits or reuses it).  Shared by dmol_tile_kernel and elbo_step_kernel.
 template <int K, int TPB, bool GRAD, int UMODE, typename TP>
-__global__ void __launch_bounds__(TPB, DmolMinBlocks<K>::value) dmol_tile_kernel(const DmolArgs A) {
+__device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t tile_id, unsigned char* smem) {
   constexpr int P = 3 * K;
   constexpr int NW = TPB / 32;
   constexpr int SPT = DmolSpt<K>::value;
   constexpr int TILE = TPB * SPT;
   constexpr size_t kTileBytes = ((size_t(TILE) * P * sizeof(TP) + 15) / 16) * 16;
-  extern __shared__ __align__(128) unsigned char smem[];
   TP* tile = reinterpret_cast<TP*>(smem);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kTileBytes);
   double* scratch = reinterpret_cast<double*>(smem + kTileBytes + 16);
 
   const int tid = threadIdx.x;
-  const int64_t tile_id = blockIdx.x;
   const int64_t b = tile_id / A.chunks;
   const int64_t c = tile_id - b * A.chunks;
   const int64_t t0 = c * TILE;
@@ -278,7 +278,14 @@ __global__ void __launch_bounds__(TPB, DmolMinBlocks<K>::value) dmol_tile_kernel
     const double s = block_sum_f64<NW>(acc, scratch);
     if (tid == 0) A.partials[tile_id] = s;
   }
-  if (GRAD && bulk_out && tid == 0) ptx::bulk_wait_read0();  // smem must outlive the bulk store's read
+  return GRAD && bulk_out;
+}
+
+template <int K, int TPB, bool GRAD, int UMODE, typename TP>
+__global__ void __launch_bounds__(TPB, DmolMinBlocks<K>::value) dmol_tile_kernel(const DmolArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const bool pending = dmol_tile_body<K, TPB, GRAD, UMODE, TP>(A, blockIdx.x, smem);
+  if (pending && threadIdx.x == 0) ptx::bulk_wait_read0();  // smem must outlive the bulk store's read
 }
 
 // Generic shapes (any K, D >= 1): one thread per sample straight from global memory, two-pass recompute.

@@ -26,6 +26,9 @@ struct KlArgs {
   double* part_kl;       // (B, chunks) masked sums of kl (nullable)
   double* part_klfn;     // (B, chunks) masked sums of max(kl, min_kl) (nullable)
   int64_t B, row_elems, Z, chunks;
+  const float* kl_in;    // non-null: the level's KL is already materialised (compute_elbo's `kld_twise`); reduce it
+  float* gkl;            // with kl_in: d/d kl out (nullable)
+  int vec;               // 1: 128-bit accesses are legal for every pointer and row (set by the host)
 };
 
 constexpr int kKlTPB = 256;
@@ -51,46 +54,64 @@ __device__ __forceinline__ void kl_element(const KlArgs& A, int64_t idx, bool va
   }
 }
 
-template <bool VEC, bool GRAD>
-__global__ void __launch_bounds__(kKlTPB) kl_kernel(const KlArgs A) {
-  __shared__ double scratch[2][kKlTPB / 32];
+// One tile (kKlChunk elements of one utterance) with TPB threads; writes the two fp64 partial sums of the tile.
+// `scratch` = 2 x (TPB/32) doubles of shared memory.
+template <int TPB, bool GRAD>
+__device__ __forceinline__ void kl_tile_body(const KlArgs& A, const int64_t tile_id, double* scratch) {
+  constexpr int EPT = kKlChunk / TPB;                    // elements per thread (4 at 256 threads, 8 at 128)
   const int tid = threadIdx.x;
-  const int64_t tile_id = blockIdx.x;
   const int64_t b = tile_id / A.chunks;
   const int64_t c = tile_id - b * A.chunks;
   const int64_t e0 = c * kKlChunk;                       // first element of this chunk within the row
-  int64_t len = A.lens ? A.lens[b] : (A.row_elems / A.Z);
   const int64_t max_steps = A.row_elems / A.Z;
+  int64_t len = A.lens ? A.lens[b] : max_steps;
   len = len < 0 ? 0 : (len > max_steps ? max_steps : len);
   const int64_t nvalid_row = len * A.Z;
   const int64_t base = b * A.row_elems;
   float s_kl = 0.f, s_fn = 0.f;
 
-  if (VEC) {
-    const int64_t e = e0 + static_cast<int64_t>(tid) * kKlVec;
-    if (e < A.row_elems) {  // row_elems % 4 == 0 on this path, so the whole vector is inside the row
-      const int64_t i = base + e;
-      const float4 mq = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.mu_q + i));
-      const float4 sq = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.sd_q + i));
-      const float4 mp = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.mu_p + i));
-      const float4 sp = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.sd_p + i));
-      float4 kl, gmq, gsq, gmp, gsp;
-      kl_element<GRAD>(A, i + 0, e + 0 < nvalid_row, mq.x, sq.x, mp.x, sp.x, kl.x, gmq.x, gsq.x, gmp.x, gsp.x, s_kl, s_fn);
-      kl_element<GRAD>(A, i + 1, e + 1 < nvalid_row, mq.y, sq.y, mp.y, sp.y, kl.y, gmq.y, gsq.y, gmp.y, gsp.y, s_kl, s_fn);
-      kl_element<GRAD>(A, i + 2, e + 2 < nvalid_row, mq.z, sq.z, mp.z, sp.z, kl.z, gmq.z, gsq.z, gmp.z, gsp.z, s_kl, s_fn);
-      kl_element<GRAD>(A, i + 3, e + 3 < nvalid_row, mq.w, sq.w, mp.w, sp.w, kl.w, gmq.w, gsq.w, gmp.w, gsp.w, s_kl, s_fn);
-      if (A.kl) ptx::stg_stream4(reinterpret_cast<float4*>(A.kl + i), kl);
-      if (GRAD) {
-        ptx::stg_stream4(reinterpret_cast<float4*>(A.g_mu_q + i), gmq);
-        ptx::stg_stream4(reinterpret_cast<float4*>(A.g_sd_q + i), gsq);
-        ptx::stg_stream4(reinterpret_cast<float4*>(A.g_mu_p + i), gmp);
-        ptx::stg_stream4(reinterpret_cast<float4*>(A.g_sd_p + i), gsp);
+  if (A.kl_in) {                                         // materialised KL: mask, free nats, sums, d/d kl
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const int64_t e = e0 + static_cast<int64_t>(j) * TPB + tid;
+      if (e < A.row_elems) {
+        const int64_t i = base + e;
+        const bool valid = e < nvalid_row;
+        const float kl = A.kl_in[i];
+        const float klfn = (A.fn_enabled && kl < A.min_kl) ? A.min_kl : kl;
+        s_kl += valid ? kl : kl * 0.0f;
+        s_fn += valid ? klfn : klfn * 0.0f;
+        if (A.gkl) A.gkl[i] = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
+      }
+    }
+  } else if (A.vec) {
+#pragma unroll
+    for (int j = 0; j < EPT / kKlVec; ++j) {
+      const int64_t e = e0 + (static_cast<int64_t>(j) * TPB + tid) * kKlVec;
+      if (e < A.row_elems) {  // row_elems % 4 == 0 on this path, so the whole vector is inside the row
+        const int64_t i = base + e;
+        const float4 mq = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.mu_q + i));
+        const float4 sq = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.sd_q + i));
+        const float4 mp = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.mu_p + i));
+        const float4 sp = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.sd_p + i));
+        float4 kl, gmq, gsq, gmp, gsp;
+        kl_element<GRAD>(A, i + 0, e + 0 < nvalid_row, mq.x, sq.x, mp.x, sp.x, kl.x, gmq.x, gsq.x, gmp.x, gsp.x, s_kl, s_fn);
+        kl_element<GRAD>(A, i + 1, e + 1 < nvalid_row, mq.y, sq.y, mp.y, sp.y, kl.y, gmq.y, gsq.y, gmp.y, gsp.y, s_kl, s_fn);
+        kl_element<GRAD>(A, i + 2, e + 2 < nvalid_row, mq.z, sq.z, mp.z, sp.z, kl.z, gmq.z, gsq.z, gmp.z, gsp.z, s_kl, s_fn);
+        kl_element<GRAD>(A, i + 3, e + 3 < nvalid_row, mq.w, sq.w, mp.w, sp.w, kl.w, gmq.w, gsq.w, gmp.w, gsp.w, s_kl, s_fn);
+        if (A.kl) ptx::stg_stream4(reinterpret_cast<float4*>(A.kl + i), kl);
+        if (GRAD) {
+          ptx::stg_stream4(reinterpret_cast<float4*>(A.g_mu_q + i), gmq);
+          ptx::stg_stream4(reinterpret_cast<float4*>(A.g_sd_q + i), gsq);
+          ptx::stg_stream4(reinterpret_cast<float4*>(A.g_mu_p + i), gmp);
+          ptx::stg_stream4(reinterpret_cast<float4*>(A.g_sd_p + i), gsp);
+        }
       }
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < kKlVec; ++j) {
-      const int64_t e = e0 + static_cast<int64_t>(j) * kKlTPB + tid;
+    for (int j = 0; j < EPT; ++j) {
+      const int64_t e = e0 + static_cast<int64_t>(j) * TPB + tid;
       if (e < A.row_elems) {
         const int64_t i = base + e;
         float kl, gmq, gsq, gmp, gsp;
@@ -106,8 +127,8 @@ __global__ void __launch_bounds__(kKlTPB) kl_kernel(const KlArgs A) {
     }
   }
   if (A.part_kl) {
-    const double a = block_sum_f64<kKlTPB / 32>(static_cast<double>(s_kl), scratch[0]);
-    const double f = block_sum_f64<kKlTPB / 32>(static_cast<double>(s_fn), scratch[1]);
+    const double a = block_sum_f64<TPB / 32>(static_cast<double>(s_kl), scratch);
+    const double f = block_sum_f64<TPB / 32>(static_cast<double>(s_fn), scratch + TPB / 32);
     if (tid == 0) {
       A.part_kl[tile_id] = a;
       A.part_klfn[tile_id] = f;
@@ -115,50 +136,10 @@ __global__ void __launch_bounds__(kKlTPB) kl_kernel(const KlArgs A) {
   }
 }
 
-// KL already materialised by the caller (the reference's compute_elbo receives `kld_twise`): masked sums of kl and
-// max(kl, min_kl) plus d/d kl = gscale * gate * mask.  8 B per latent element.
-struct KlReduceArgs {
-  const float* kl;
-  const int64_t* lens;
-  float gscale, min_kl;
-  int fn_enabled;
-  float* gkl;  // nullable
-  double *part_kl, *part_klfn;
-  int64_t B, row_elems, Z, chunks;
-};
-
-__global__ void __launch_bounds__(kKlTPB) kl_reduce_kernel(const KlReduceArgs A) {
-  __shared__ double scratch[2][kKlTPB / 32];
-  const int tid = threadIdx.x;
-  const int64_t tile_id = blockIdx.x;
-  const int64_t b = tile_id / A.chunks;
-  const int64_t c = tile_id - b * A.chunks;
-  const int64_t e0 = c * kKlChunk;
-  const int64_t max_steps = A.row_elems / A.Z;
-  int64_t len = A.lens ? A.lens[b] : max_steps;
-  len = len < 0 ? 0 : (len > max_steps ? max_steps : len);
-  const int64_t nvalid_row = len * A.Z;
-  const int64_t base = b * A.row_elems;
-  double s_kl = 0.0, s_fn = 0.0;
-#pragma unroll
-  for (int j = 0; j < kKlVec; ++j) {
-    const int64_t e = e0 + static_cast<int64_t>(j) * kKlTPB + tid;
-    if (e < A.row_elems) {
-      const int64_t i = base + e;
-      const bool valid = e < nvalid_row;
-      const float kl = A.kl[i];
-      const float klfn = (A.fn_enabled && kl < A.min_kl) ? A.min_kl : kl;
-      s_kl += static_cast<double>(valid ? kl : kl * 0.0f);
-      s_fn += static_cast<double>(valid ? klfn : klfn * 0.0f);
-      if (A.gkl) A.gkl[i] = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
-    }
-  }
-  const double a = block_sum_f64<kKlTPB / 32>(s_kl, scratch[0]);
-  const double f = block_sum_f64<kKlTPB / 32>(s_fn, scratch[1]);
-  if (tid == 0) {
-    A.part_kl[tile_id] = a;
-    A.part_klfn[tile_id] = f;
-  }
+template <bool GRAD>
+__global__ void __launch_bounds__(kKlTPB) kl_kernel(const KlArgs A) {
+  __shared__ double scratch[2 * (kKlTPB / 32)];
+  kl_tile_body<kKlTPB, GRAD>(A, blockIdx.x, scratch);
 }
 
 // ---- finalize: per-tile partials -> per-utterance sums -> loss / ELBO / bits-per-dim --------------------------------
