@@ -8,11 +8,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libblvm_b200.so")
-SOURCES = ["blvm_b200.cu"]
-HEADERS = ["blvm_math.cuh", "ptx_sm100.cuh", "dmol_kernels.cuh", "kl_kernels.cuh", "misc_kernels.cuh", "sample_kernels.cuh",
+SOURCES = ["blvm_b200.cu"]   # one object per source, compiled in parallel
+HEADERS = ["blvm_math.cuh", "ptx_sm100.cuh", "dmol_kernels.cuh", "kl_kernels.cuh", "misc_kernels.cuh", "sample_kernels.cuh", "host_common.h",
            os.path.join("..", "..", "include", "blvm_b200.h")]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-shared"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -30,18 +29,29 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
-        return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
+def _run(cmd):
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    return res.stderr
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return LIB
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(HERE, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    objs = [os.path.join(obj_dir, os.path.splitext(s)[0] + ".o") for s in SOURCES]
+    cmds = [[_nvcc()] + NVCC_FLAGS + extra + ["-c", "-o", o, os.path.join(CSRC, s)] for s, o in zip(SOURCES, objs)]
+    with ThreadPoolExecutor(max_workers=len(cmds)) as pool:
+        logs = list(pool.map(_run, cmds))
+    _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
     if verbose:
-        sys.stderr.write(res.stderr)
+        sys.stderr.write("".join(logs))
     return LIB
 
 

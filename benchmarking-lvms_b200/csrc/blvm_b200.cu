@@ -6,6 +6,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include "host_common.h"
+
 #include "dmol_kernels.cuh"
 #include "kl_kernels.cuh"
 #include "misc_kernels.cuh"
@@ -22,36 +24,10 @@ static_assert(BLVM_FLAG_MASK_OUTPUT == kFlagMaskOutput && BLVM_FLAG_SKIP_PADDED 
 namespace {
 
 constexpr int kTile = BLVM_DMOL_TILE;
-thread_local char g_err[512] = "";
-
-int fail(int code, const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
-  va_end(ap);
-  return code;
-}
-
-int check_launch(const char* what) {
-  const cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-  return BLVM_OK;
-}
-
-// fp32 constants rounded from double exactly like torch rounds a Python scalar that meets an fp32 tensor.
-DmolConsts make_consts(int num_bins, float log_epsilon) {
-  DmolConsts C;
-  C.h = static_cast<float>(1.0 / (num_bins - 1));
-  C.log_two_h = static_cast<float>(log(2.0 / (num_bins - 1)));
-  C.log_delta_thresh = static_cast<float>(log(static_cast<double>(kDeltaThresh)));
-  C.lo_thresh = static_cast<float>(2.0 / num_bins - 1.0);
-  C.hi_thresh = static_cast<float>(1.0 - 2.0 / num_bins);
-  C.log_half_bins = static_cast<float>(log(num_bins / 2.0));
-  C.log_eps = log_epsilon;
-  return C;
-}
-
-bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+using blvm_host::aligned;
+using blvm_host::check_launch;
+using blvm_host::fail;
+using blvm_host::make_consts;
 
 template <int K, bool GRAD, int UMODE, typename TP>
 int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
@@ -71,8 +47,7 @@ int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
 // the kernel specialisation without the large-u code is exact to O(u^4) ~ 1e-7 (blvm_math.cuh).
 template <int K, bool GRAD, typename TP>
 int launch_tile_dtype(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
-  const double u_max = static_cast<double>(A.C.h) * exp(-static_cast<double>(A.C.log_eps));
-  if (u_max < static_cast<double>(kTinyU)) return launch_tile_mode<K, GRAD, kUTiny, TP>(A, tiles, st);
+  if (blvm_host::u_is_tiny(A.C)) return launch_tile_mode<K, GRAD, kUTiny, TP>(A, tiles, st);
   return launch_tile_mode<K, GRAD, kUGeneral, TP>(A, tiles, st);
 }
 
@@ -147,10 +122,27 @@ int validate_dmol(const float* y, const void* raw, int64_t B, int64_t T, int K, 
 
 }  // namespace
 
+namespace blvm_host {
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return BLVM_OK;
+}
+const char* last_error() { return g_err; }
+}  // namespace blvm_host
+
 extern "C" {
 
 int blvm_version(void) { return BLVM_B200_VERSION; }
-const char* blvm_last_error_string(void) { return g_err; }
+const char* blvm_last_error_string(void) { return blvm_host::last_error(); }
 int64_t blvm_dmol_chunks(int64_t T, int K, int D) {
   const int64_t ts = dmol_tile_samples(K, D);
   return (T + ts - 1) / ts;

@@ -1,0 +1,36 @@
+// Host-side helpers shared by the translation units of libblvm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/blvm_b200.h"
+#include "blvm_math.cuh"
+
+namespace blvm_host {
+
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+const char* last_error();
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// fp32 constants rounded from double exactly like torch rounds a Python scalar that meets an fp32 tensor.
+inline blvm::DmolConsts make_consts(int num_bins, float log_epsilon) {
+  blvm::DmolConsts C;
+  C.h = static_cast<float>(1.0 / (num_bins - 1));
+  C.log_two_h = static_cast<float>(log(2.0 / (num_bins - 1)));
+  C.log_delta_thresh = static_cast<float>(log(static_cast<double>(blvm::kDeltaThresh)));
+  C.lo_thresh = static_cast<float>(2.0 / num_bins - 1.0);
+  C.hi_thresh = static_cast<float>(1.0 - 2.0 / num_bins);
+  C.log_half_bins = static_cast<float>(log(num_bins / 2.0));
+  C.log_eps = log_epsilon;
+  return C;
+}
+
+// u = h / s <= h * exp(-log_epsilon): tiny for 16-bit bins with the -7 clamp (blvm_math.cuh: kUTiny)
+inline bool u_is_tiny(const blvm::DmolConsts& C) {
+  return static_cast<double>(C.h) * exp(-static_cast<double>(C.log_eps)) < static_cast<double>(blvm::kTinyU);
+}
+
+}  // namespace blvm_host

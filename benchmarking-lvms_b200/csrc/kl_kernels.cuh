@@ -244,42 +244,37 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 // lanes stride over the chunks of one utterance (coalesced), fixed-order butterfly: deterministic
 __device__ __forceinline__ double warp_row_sum(const double* __restrict__ p, int64_t n, int lane) {
   double s = 0.0;
-  for (int64_t c = lane; c < n; c += 32) s += p[c];
+  for (int64_t c = lane; c < n; c += 32) s += __ldcg(p + c);   // written by other CTAs: read through L2
   return warp_sum_f64(s);
 }
 
-// One warp per utterance reduces its per-tile partials; the last CTA to finish (device counter, self-resetting)
-// reduces the per-utterance rows to the scalars in a fixed order.  Grid = ceil(B / 8) CTAs.
-__global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeArgs A, unsigned int* counter, const ExchangeArgs X) {
-  __shared__ double scratch[6][kFinWarps];
-  __shared__ bool is_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t b = static_cast<int64_t>(blockIdx.x) * kFinWarps + warp;
-  if (b < A.B) {
-    const double logp = A.logp_part ? warp_row_sum(A.logp_part + b * A.logp_chunks, A.logp_chunks, lane) : 0.0;
-    double kl = 0.0, fn = 0.0;
-    for (int l = 0; l < A.n_levels; ++l) {
-      const double kl_l = warp_row_sum(A.kl_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane);
-      const double fn_l = warp_row_sum(A.klfn_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane);
-      if (lane == 0) A.rows[(4 + l) * A.B + b] = kl_l;
-      kl += kl_l;   // sum over levels (clockwork_vae.py:155, stcn.py:290)
-      fn += fn_l;
-    }
-    if (lane == 0) {
-      A.rows[0 * A.B + b] = logp;
-      A.rows[1 * A.B + b] = kl;
-      A.rows[2 * A.B + b] = fn;
-      A.rows[3 * A.B + b] = logp - kl;                   // elbo (vrnn.py:273)
-    }
+// Reduce the per-tile partials of utterance b (called by ONE warp; lane 0 writes the row entries).
+__device__ __forceinline__ void finalize_row(const FinalizeArgs& A, int64_t b, int lane) {
+  const double logp = A.logp_part ? warp_row_sum(A.logp_part + b * A.logp_chunks, A.logp_chunks, lane) : 0.0;
+  double kl = 0.0, fn = 0.0;
+  for (int l = 0; l < A.n_levels; ++l) {
+    const double kl_l = warp_row_sum(A.kl_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane);
+    const double fn_l = warp_row_sum(A.klfn_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane);
+    if (lane == 0) A.rows[(4 + l) * A.B + b] = kl_l;
+    kl += kl_l;   // sum over levels (clockwork_vae.py:155, stcn.py:290)
+    fn += fn_l;
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+  if (lane == 0) {
+    A.rows[0 * A.B + b] = logp;
+    A.rows[1 * A.B + b] = kl;
+    A.rows[2 * A.B + b] = fn;
+    A.rows[3 * A.B + b] = logp - kl;                     // elbo (vrnn.py:273)
+  }
+}
+
+// Rows -> scalars (+ the fused NVLink exchange), executed by ONE whole CTA of TPB threads after every row is final.
+// `scratch` = 6 x (TPB/32) doubles of shared memory.
+template <int TPB>
+__device__ __forceinline__ void finalize_scalars(const FinalizeArgs& A, const ExchangeArgs& X, double* scratch) {
+  constexpr int NW = TPB / 32;
+  const int tid = threadIdx.x;
   double t_logp = 0, t_kl = 0, t_fn = 0, t_len = 0, t_nan_logp = 0, t_obj = 0;
-  for (int64_t r = tid; r < A.B; r += kFinTPB) {
+  for (int64_t r = tid; r < A.B; r += TPB) {
     const double logp = __ldcg(A.rows + 0 * A.B + r), kl = __ldcg(A.rows + 1 * A.B + r), fn = __ldcg(A.rows + 2 * A.B + r);
     t_logp += logp;
     t_kl += kl;
@@ -288,12 +283,12 @@ __global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeAr
     t_nan_logp += (logp == logp) ? logp : 0.0;           // nansum (wavenet.py:145)
     t_len += static_cast<double>(A.x_sl[r]);
   }
-  const double s_logp = block_sum_f64<kFinWarps>(t_logp, scratch[0]);
-  const double s_kl = block_sum_f64<kFinWarps>(t_kl, scratch[1]);
-  const double s_fn = block_sum_f64<kFinWarps>(t_fn, scratch[2]);
-  const double s_obj = block_sum_f64<kFinWarps>(t_obj, scratch[3]);
-  const double s_nan = block_sum_f64<kFinWarps>(t_nan_logp, scratch[4]);
-  const double s_len = block_sum_f64<kFinWarps>(t_len, scratch[5]);
+  const double s_logp = block_sum_f64<NW>(t_logp, scratch + 0 * NW);
+  const double s_kl = block_sum_f64<NW>(t_kl, scratch + 1 * NW);
+  const double s_fn = block_sum_f64<NW>(t_fn, scratch + 2 * NW);
+  const double s_obj = block_sum_f64<NW>(t_obj, scratch + 3 * NW);
+  const double s_nan = block_sum_f64<NW>(t_nan_logp, scratch + 4 * NW);
+  const double s_len = block_sum_f64<NW>(t_len, scratch + 5 * NW);
   if (tid == 0) {
     const double dn = A.denom > 0.0 ? A.denom : s_len;
     A.scalars[0] = -s_obj / dn;                          // loss (vrnn.py:277), consistent with the gradients' 1/denom
@@ -304,10 +299,9 @@ __global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeAr
     A.scalars[5] = s_len;
     A.scalars[6] = -(s_logp - s_kl) / 0.6931471805599453 / s_len;  // bits per dim (metrics.py:456)
     A.scalars[7] = -s_nan / dn;                          // WaveNet's nansum loss
-    *counter = 0u;                                       // ready for the next launch on this stream
   }
-  // ---- fused exchange (warp 0 of the last CTA): publish this step's scalars into every rank's buffer over NVLink peer
-  // memory, then add up the previous step's slots.  Lane p talks to rank p.
+  // ---- fused exchange (warp 0): publish this step's scalars into every rank's buffer over NVLink peer memory, then
+  // add up the previous step's slots.  Lane p talks to rank p.
   if (X.world > 0 && tid < 32) {
     __syncwarp();
     unsigned long long seq = 0;
@@ -335,10 +329,28 @@ __global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeAr
   }
 }
 
+// One warp per utterance reduces its per-tile partials; the last CTA to finish (device counter, self-resetting)
+// reduces the per-utterance rows to the scalars in a fixed order.  Grid = ceil(B / 8) CTAs.
+static __global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const FinalizeArgs A, unsigned int* counter, const ExchangeArgs X) {
+  __shared__ double scratch[6 * kFinWarps];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * kFinWarps + warp;
+  if (b < A.B) finalize_row(A, b, lane);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid == 0) *counter = 0u;                           // ready for the next launch on this stream
+  finalize_scalars<kFinTPB>(A, X, scratch);
+}
+
 // Consume one published step: wait until all W ranks' slots of step `seq = published - lag` have landed in the LOCAL
 // buffer, add them in rank order and recompute the ratio entries.  No-op if that step does not exist yet or was already
 // consumed.  err: bit 0 = timeout (a peer never published), bit 1 = slot overrun (a peer ran >= kExNbuf steps ahead).
-__global__ void __launch_bounds__(32) exchange_consume_kernel(double* local_base, int world, unsigned long long* counters,
+static __global__ void __launch_bounds__(32) exchange_consume_kernel(double* local_base, int world, unsigned long long* counters,
                                                               int lag, double beta, double* out, int* err) {
   const int lane = threadIdx.x;
   const unsigned long long published = counters[0], consumed = counters[1];
