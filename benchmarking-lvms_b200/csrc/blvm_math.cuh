@@ -134,14 +134,15 @@ BLVM_HD void dl_mid(float y, float mu, float raw_ls, const DmolConsts& C, float&
   const float common = (-am - ls) - (2.f * kLn2) * fast_lg2(p1);   // log_pdf_mid = m - ls - 2 softplus(m)  :220
   const float lp_fb = common - C.log_half_bins;                    // second arm of :221-223
   // tanh(|m|/2) = (1-E)/(1+E); odd series below 1/8 so that the bin-centre gradient does not cancel
-  float dm_fb = 0.f;
+  // Derivatives are carried as magnitudes: d lp/d m = -sgn(m) th, so d lp/d loc = -inv * d/dm = copysign(inv th, m) and
+  // m * d/dm = -|m| th; the sign of m is applied once at the end.
+  float th = 0.f;                                                  // tanh(|m|/2) = |1 - 2 sigmoid(m)|
   if (GRAD) {
     const float hx = 0.5f * am, hx2 = hx * hx;
     const float th_series = hx * fmaf(hx2, fmaf(hx2, 2.0f / 15.0f, -1.0f / 3.0f), 1.0f);
-    const float th = (am < 0.25f) ? th_series : (1.f - E) * r;
-    dm_fb = copysignf(th, -m);                                     // 1 - 2 sigmoid(m)
+    th = (am < 0.25f) ? th_series : (1.f - E) * r;
   }
-  float lp_d, dm_d = 0.f, udu = 0.f;
+  float lp_d, th_d = 0.f, udu = 0.f;
   bool big;
   if (UMODE == kUTiny) {
     const float u2 = u * u;
@@ -150,8 +151,8 @@ BLVM_HD void dl_mid(float y, float mu, float raw_ls, const DmolConsts& C, float&
     lp_d = common + (fmaf(u2, 1.0f / 6.0f, C.log_two_h) - eps);    // log cdf_delta, first arm of :221-223
     big = lp_d > C.log_delta_thresh;                               // cdf_delta > 1e-5
     if (GRAD) {
-      dm_d = fmaf(-eps, dm_fb, dm_fb);                             // dm_fb / (1 + eps)
-      udu = fmaf(u2, 1.0f / 3.0f - 2.0f * er2, 1.0f);              // u coth(u) - u cdf_delta
+      th_d = fmaf(-eps, th, th);                                   // th / (1 + eps)
+      udu = fmaf(u2, fmaf(er2, -2.0f, 1.0f / 3.0f), 1.0f);         // u coth(u) - u cdf_delta
     }
   } else if (u < kSmallU) {
     const float u2 = u * u;
@@ -162,7 +163,7 @@ BLVM_HD void dl_mid(float y, float mu, float raw_ls, const DmolConsts& C, float&
     big = lp_d > C.log_delta_thresh;
     if (GRAD) {
       const float inv1pe = fmaf(eps, eps - 1.0f, 1.0f);            // 1/(1+eps)
-      dm_d = dm_fb * inv1pe;
+      th_d = th * inv1pe;
       const float udelta = 2.0f * u2 * er2 * fmaf(u2, 1.0f / 6.0f, 1.0f) * inv1pe;  // u * cdf_delta
       udu = fmaf(u2, fmaf(u2, -1.0f / 45.0f, 1.0f / 3.0f), 1.0f) - udelta;
     }
@@ -174,15 +175,15 @@ BLVM_HD void dl_mid(float y, float mu, float raw_ls, const DmolConsts& C, float&
     big = delta > kDeltaThresh;
     lp_d = kLn2 * fast_lg2(fmaxf(delta, kDeltaFloor));
     if (GRAD) {
-      dm_d = dm_fb * (p1 * p1 * q * rdq);                          // -sgn(m) (1-E^2)/D
+      th_d = th * (p1 * p1 * q * rdq);                             // (1-E^2)/D
       udu = u * (fmaf(q, q, 1.f) * fast_rcp(omq2) - delta);        // u (coth(u) - cdf_delta)
     }
   }
   lp = big ? lp_d : lp_fb;
   if (GRAD) {
-    const float dm = big ? dm_d : dm_fb;
-    dmu = -inv * dm;
-    dls = big ? -fmaf(m, dm_d, udu) : fmaf(-m, dm_fb, -1.0f);
+    const float th_sel = big ? th_d : th;
+    dmu = copysignf(inv * th_sel, m);                              // -inv * d lp/d m
+    dls = fmaf(am, th_sel, big ? -udu : -1.0f);                    // -(m d/dm + u d/du)  resp.  -m d/dm - 1
     if (raw_ls < C.log_eps) dls = 0.f;  // clamp(min=eps) blocks the gradient strictly below eps, passes at equality
   }
 }
@@ -325,10 +326,11 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     m2 = fmaxf(m2, r[k]);
   }
   float s1 = 0.f, s2 = 0.f;
+  const float nm1 = -m1 * kLog2e, nm2 = -m2 * kLog2e;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    v[k] = fast_ex2((v[k] - m1) * kLog2e);
-    r[k] = fast_ex2((r[k] - m2) * kLog2e);
+    v[k] = fast_ex2(fmaf(v[k], kLog2e, nm1));   // exp(v_k - max), one FFMA per argument
+    r[k] = fast_ex2(fmaf(r[k], kLog2e, nm2));
     s1 += v[k];
     s2 += r[k];
   }
