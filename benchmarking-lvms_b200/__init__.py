@@ -13,17 +13,17 @@ The CUDA library is mandatory: importing this package without `lib/libblvm_b200.
 """
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is not built)
 from .distributed import SumsExchange, all_reduce_sums, combine_sums, global_denominator, shard_rows
-from .distributions import (ConditionalDistribution, DiscretizedLogisticDense, DiscretizedLogisticMixtureDense, DLParams,
-                            DMoLParams)
+from .distributions import (ConditionalDistribution, DiagonalGaussianMixtureDense, DiscretizedLogisticDense,
+                            DiscretizedLogisticMixtureDense, DLParams, DMoLParams, GMMParams)
 from .elbo import (KLLevel, cwvae_compute_elbo, fused_elbo, pack_dmol_params, srnn_compute_elbo, stcn_compute_loss,
                    vrnn_compute_elbo, wavenet_compute_loss)
-from .log_likelihoods import discretized_logistic_ll, discretized_logistic_mixture_ll
+from .log_likelihoods import discretized_logistic_ll, discretized_logistic_mixture_ll, gaussian_ll, gaussian_mixture_ll
 from .metrics import RunningMean, bits_per_dim, elbo_metrics
 from .operations import level_lengths, sequence_mask
 from .ops import check_input_range, launch_count, reset_launch_count
 from .patch import patch_blvm, unpatch_blvm
 from .transforms import Quantize
-from .variational import discount_free_nats, kl_divergence_gaussian
+from .variational import discount_free_nats, kl_divergence_gaussian, kl_divergence_gaussian_mc
 
 __version__ = "0.1.0"
 LIB_PATH = _lib.LIB_PATH

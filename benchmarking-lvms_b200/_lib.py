@@ -30,6 +30,9 @@ SIGNATURES = {
     "blvm_dmol_has_fast_path": (_i32, [_i32, _i32]),
     "blvm_dmol_fwd": (_i32, [_p, _p, _i32, _p, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p]),
     "blvm_dmol_fwd_grad": (_i32, [_p, _p, _i32, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p, _p]),
+    "blvm_gmm_chunks": (_i64, [_i64, _i32, _i32]),
+    "blvm_gmm_fwd_grad": (_i32, [_p, _p, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _f64, _f64, _f64, _i32, _p, _p, _p, _p]),
+    "blvm_gaussian_ll": (_i32, [_p, _p, _p, _p, _i64, _f64, _p, _p, _p, _p]),
     "blvm_dl_fwd_grad": (_i32, [_p, _p, _p, _p, _f32, _i64, _i64, _i32, _f32, _i32, _p, _p, _p, _p, _p]),
     "blvm_kl_gaussian_fwd": (_i32, [_p, _p, _p, _p, _i64, _p, _p]),
     "blvm_kl_gaussian_bwd": (_i32, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),

@@ -111,6 +111,55 @@ int dispatch_dmol(const DmolArgs& A, int raw_dtype, cudaStream_t st) {
   return check_launch("dmol_generic_kernel");
 }
 
+// ---- Gaussian mixture: same tile kernel, different component density; fp32 parameters, K in {1, 5, 10, 20} in
+// registers, anything else through the generic kernel
+#define BLVM_FOR_EACH_GMM_K(X) X(1) X(5) X(10) X(20)
+
+template <int K, bool GRAD, int LIK>
+int launch_gmm_tile(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
+  constexpr size_t smem = dmol_tile_smem_bytes<K, kTile, float>();
+  auto kern = dmol_tile_kernel<K, kTile, GRAD, kUGeneral, float, LIK>;
+  static bool configured = false;
+  if (!configured) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
+  return check_launch("dmol_tile_kernel<gmm>");
+}
+
+bool gmm_has_register_kernel(int K, int D) {
+  if (D != 1) return false;
+  switch (K) {
+#define BLVM_CASE(KK) case KK:
+    BLVM_FOR_EACH_GMM_K(BLVM_CASE)
+#undef BLVM_CASE
+    return true;
+    default: return false;
+  }
+}
+
+template <bool GRAD>
+int dispatch_gmm(const DmolArgs& A, cudaStream_t st) {
+  const int64_t tiles = A.B * A.chunks;
+  if (tiles == 0) return BLVM_OK;
+  if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)tiles);
+  if (A.D == 1) {
+    switch (A.K) {
+#define BLVM_CASE(KK)                                                                          \
+  case KK:                                                                                     \
+    return A.lik == kLikGmmRaw ? launch_gmm_tile<KK, GRAD, kLikGmmRaw>(A, tiles, st)           \
+                               : launch_gmm_tile<KK, GRAD, kLikGmmSd>(A, tiles, st);
+      BLVM_FOR_EACH_GMM_K(BLVM_CASE)
+#undef BLVM_CASE
+      default: break;
+    }
+  }
+  dmol_generic_kernel<kTile, GRAD><<<static_cast<unsigned>(tiles), kTile, 0, st>>>(A);
+  return check_launch("dmol_generic_kernel<gmm>");
+}
+
 int validate_dmol(const float* y, const void* raw, int64_t B, int64_t T, int K, int D, int num_bins) {
   if (B < 0 || T < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "negative size B=%lld T=%lld", (long long)B, (long long)T);
   if (K < 1 || D < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "K=%d D=%d must be >= 1", K, D);
@@ -173,6 +222,44 @@ int blvm_dmol_fwd_grad(const float* y, const void* raw, int raw_dtype, const int
   A.partials = partials; A.err_flag = err_flag; A.B = B; A.T = T; A.chunks = blvm_dmol_chunks(T, K, D); A.K = K; A.D = D;
   A.flags = flags; A.C = make_consts(num_bins, log_epsilon);
   return dispatch_dmol<true>(A, raw_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int64_t blvm_gmm_chunks(int64_t T, int K, int D) {
+  const int64_t ts = gmm_has_register_kernel(K, D) ? dmol_tile_samples(K, D) : kTile;
+  return (T + ts - 1) / ts;
+}
+
+int blvm_gmm_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale,
+                      const double* gscale_dev, int64_t B, int64_t T, int K, int D, int from_raw, double softplus_beta,
+                      double sd_add, double sd_floor, int flags, float* lp, float* graw, double* partials,
+                      blvm_stream_t stream) {
+  if (int rc = validate_dmol(y, raw, B, T, K, D, 2)) return rc;
+  if (from_raw && !(softplus_beta > 0.0)) return fail(BLVM_ERR_INVALID_ARGUMENT, "softplus_beta=%g must be > 0", softplus_beta);
+  DmolArgs A{};
+  A.y = y; A.raw = raw; A.x_sl = x_sl; A.gout = gout; A.gscale = gscale; A.gscale_dev = gscale_dev; A.lp = lp; A.graw = graw;
+  A.partials = partials; A.err_flag = nullptr; A.B = B; A.T = T; A.chunks = blvm_gmm_chunks(T, K, D); A.K = K; A.D = D;
+  A.flags = flags; A.lik = from_raw ? kLikGmmRaw : kLikGmmSd;
+  A.C = make_consts(256, -7.0f);
+  A.C.sp_beta = static_cast<float>(softplus_beta); A.C.sp_inv_beta = static_cast<float>(1.0 / (from_raw ? softplus_beta : 1.0));
+  A.C.sd_add = static_cast<float>(sd_add); A.C.sd_floor = static_cast<float>(sd_floor);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return graw ? dispatch_gmm<true>(A, st) : dispatch_gmm<false>(A, st);
+}
+
+int blvm_gaussian_ll(const float* y, const float* mu, const float* sd, const float* gout, int64_t n, double sd_floor,
+                     float* lp, float* g_mu, float* g_sd, blvm_stream_t stream) {
+  if (n < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "negative n");
+  if (n > 0 && (!y || !mu || !sd)) return fail(BLVM_ERR_INVALID_ARGUMENT, "null input");
+  if ((g_mu == nullptr) != (g_sd == nullptr)) return fail(BLVM_ERR_INVALID_ARGUMENT, "g_mu and g_sd must be given together");
+  if (n == 0) return BLVM_OK;
+  DmolConsts C = make_consts(256, -7.0f);
+  C.sd_floor = static_cast<float>(sd_floor);
+  const int64_t want = (n + 1023) / 1024;
+  const unsigned blocks = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_mu) gaussian_ll_kernel<true><<<blocks, 256, 0, st>>>(y, mu, sd, gout, n, C, lp, g_mu, g_sd);
+  else gaussian_ll_kernel<false><<<blocks, 256, 0, st>>>(y, mu, sd, gout, n, C, lp, nullptr, nullptr);
+  return check_launch("gaussian_ll_kernel");
 }
 
 int blvm_dl_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale, int64_t B,

@@ -33,6 +33,11 @@ constexpr float kDeltaFloor = 1e-10f;   // log_likelihoods.py:222  `clamp(cdf_de
 // Constants derived on the host in double and rounded to fp32 exactly like torch rounds Python scalars that meet an
 // fp32 tensor (blvm_b200.cu: make_consts).
 struct DmolConsts {
+  // Gaussian-mixture variant (sibling likelihood, same packed layout [logits | mu | log_sd]); unused by the DMoL path
+  float sp_beta;        // softplus beta of the sd activation: ln2/initial_sd     distributions.py:167-170
+  float sp_inv_beta;
+  float sd_add;         // epsilon added after the softplus (AddConstant)          distributions.py:168
+  float sd_floor;       // gaussian_ll's `epsilon` clamp under no_grad (0 = none)  log_likelihoods.py:33-35
   float h;              // 1/(num_bins-1)            log_likelihoods.py:206,208
   float log_two_h;      // log(2/(num_bins-1))
   float log_delta_thresh;  // log(float(1e-5))
@@ -42,13 +47,36 @@ struct DmolConsts {
   float log_eps;        // log_epsilon (-7)          distributions.py:386
 };
 
+// Host build (tests/hostsim): libm stands in for the MUFU unit.  With -DBLVM_HOSTSIM_MUFU_BITS=n the result is degraded
+// to the precision class of the approximate instruction (rounded to 2^n ulps, i.e. a relative error up to 2^(n-24)),
+// so that the CPU suite exercises the closed forms under MUFU-like error as well.
+#if !defined(__CUDA_ARCH__) && defined(BLVM_HOSTSIM_MUFU_BITS)
+inline float hostsim_degrade(float v, int bits) {
+  uint32_t u;
+  __builtin_memcpy(&u, &v, 4);
+  u = (u + (1u << (bits - 1))) & ~((1u << bits) - 1u);   // nearest multiple of 2^bits ulps: |error| <= 2^(bits-1) ulps
+  __builtin_memcpy(&v, &u, 4);
+  return v;
+}
+// lg2.approx: absolute error 2^-22 for results in (-1, 1), relative 2^-22 outside
+inline float hostsim_degrade_lg2(float v, int bits) {
+  if (fabsf(v) < 1.0f) return ldexpf(rintf(ldexpf(v, 23 - bits)), bits - 23);
+  return hostsim_degrade(v, bits);
+}
+#define BLVM_MUFU(v, bits) hostsim_degrade((v), (bits))
+#define BLVM_MUFU_LG2(v, bits) hostsim_degrade_lg2((v), (bits))
+#else
+#define BLVM_MUFU(v, bits) (v)
+#define BLVM_MUFU_LG2(v, bits) (v)
+#endif
+
 BLVM_HD float fast_ex2(float x) {
 #if defined(__CUDA_ARCH__)
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 #else
-  return exp2f(x);
+  return BLVM_MUFU(exp2f(x), BLVM_HOSTSIM_MUFU_BITS);
 #endif
 }
 BLVM_HD float fast_lg2(float x) {
@@ -57,7 +85,7 @@ BLVM_HD float fast_lg2(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 #else
-  return log2f(x);
+  return BLVM_MUFU_LG2(log2f(x), BLVM_HOSTSIM_MUFU_BITS);
 #endif
 }
 BLVM_HD float fast_rcp(float x) {
@@ -66,7 +94,7 @@ BLVM_HD float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 #else
-  return 1.0f / x;
+  return BLVM_MUFU(1.0f / x, BLVM_HOSTSIM_MUFU_BITS - 1);
 #endif
 }
 BLVM_HD float fast_exp(float x) { return fast_ex2(x * kLog2e); }
@@ -225,17 +253,62 @@ BLVM_HD void dl_component(float y, int edge, float mu, float raw_ls, const DmolC
   else dl_mid<GRAD, kUGeneral>(y, mu, raw_ls, C, lp, dmu, dls);
 }
 
+// 1/x to ~1 ulp: MUFU.RCP + one Newton step (2 FMA) instead of the ~10-instruction IEEE division sequence
+BLVM_HD float rcp_nr(float x) {
+  const float r = fast_rcp(x);
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
+// ---- Gaussian (mixture) likelihood: the sibling of the DMoL behind the same boundary --------------
+//   gaussian_ll  blvm/utils/log_likelihoods.py:17-39:  -(y-mu)^2/(2 sd^2) - log sd - 0.5 log(2 pi)
+// FROM_RAW: the third parameter is the Linear output; sd = softplus_beta(p) + sd_add (DiagonalGaussianMixtureDense.forward,
+// distributions.py:198-203) is applied here and the chain rule d sd/d p = sigmoid(beta p) folded into the gradient.
+// Otherwise it is sd itself; with sd_floor > 0 (the functional's `epsilon`) sd is clamped under no_grad, which in the
+// reference detaches it: no gradient reaches sd at all in that case (kept).
+constexpr float kHalfLog2Pi = 0.9189385332046727f;
+template <bool GRAD, bool FROM_RAW>
+BLVM_HD void gauss_component(float y, float mu, float p, const DmolConsts& C, float& lp, float& dmu, float& dp) {
+  float sd, dsd_dp = 1.f;
+  if (FROM_RAW) {
+    const float bx = C.sp_beta * p;
+    const float e = fast_exp(-fabsf(bx));                    // softplus(bx) = max(bx, 0) + log1p(exp(-|bx|)), threshold 20
+    // log1p(e) on e in (0, 1] as e * P9(e) (minimax fit of log1p(e)/e, 1.3e-7 relative): sd ~ sd_add + exp(bx)/beta must keep
+    // RELATIVE accuracy when e is small, which lg2(1 + e) cannot give (1 + e rounds) and a short series only gives below ~1/32
+    float q = -0.003214032156392932f;
+    q = fmaf(q, e, 0.019649142399430275f);
+    q = fmaf(q, e, -0.05643497034907341f);
+    q = fmaf(q, e, 0.10533220320940018f);
+    q = fmaf(q, e, -0.15251445770263672f);
+    q = fmaf(q, e, 0.19651488959789276f);
+    q = fmaf(q, e, -0.24947808682918549f);
+    q = fmaf(q, e, 0.3332909941673279f);
+    q = fmaf(q, e, -0.4999985098838806f);
+    const float l1p = e * fmaf(q, e, 1.0f);
+    const float sp = (bx > 20.f) ? bx : fmaxf(bx, 0.f) + l1p;
+    sd = fmaf(sp, C.sp_inv_beta, C.sd_add);
+    if (GRAD) dsd_dp = (bx > 20.f) ? 1.f : ((bx >= 0.f) ? 1.f : e) * fast_rcp(1.f + e);   // sigmoid(bx)
+  } else {
+    sd = p;
+    if (C.sd_floor > 0.f) {
+      sd = (p < C.sd_floor) ? C.sd_floor : p;
+      dsd_dp = 0.f;
+    }
+  }
+  const float inv = rcp_nr(sd);
+  const float z = (y - mu) * inv;
+  lp = fmaf(-0.5f * z, z, -kLn2 * fast_lg2(sd) - kHalfLog2Pi);
+  if (GRAD) {
+    dmu = z * inv;                                           // (y - mu)/sd^2
+    dp = fmaf(z, z, -1.f) * inv * dsd_dp;                    // ((y-mu)^2/sd^3 - 1/sd) d sd/d p
+  }
+}
+
 // ---- Gaussian KL, std-dev parametrisation (variational.py:67-70), cancellation-free around q == p ----------------
 //   kl = log sd_p - log sd_q + (sd_q^2 + (mu_q-mu_p)^2) / (2 sd_p^2) - 1/2
 //      = -log1p(rho-1) + ((rho-1)(rho+1) + z^2)/2,   rho = sd_q/sd_p,  z = (mu_q-mu_p)/sd_p
 struct KlTerms {
   float kl, z, rho_m1, rho_p1, inv_sp, q;  // q = (rho-1)(rho+1) + z^2
 };
-// 1/x to ~1 ulp: MUFU.RCP + one Newton step (2 FMA) instead of the ~10-instruction IEEE division sequence
-BLVM_HD float rcp_nr(float x) {
-  const float r = fast_rcp(x);
-  return fmaf(r, fmaf(-x, r, 1.0f), r);
-}
 BLVM_HD KlTerms kl_gaussian_terms(float mu_q, float sd_q, float mu_p, float sd_p) {
   KlTerms t;
   t.inv_sp = rcp_nr(sd_p);
@@ -281,11 +354,24 @@ namespace blvm {
 //   out: returns log p(y) = logsumexp_k(lp_k + log_softmax(logits)_k)    (log_likelihoods.py:229-231)
 //        if GRAD, r[] is overwritten with g * d log p / d r[]
 // d/d logit_k = resp_k - softmax_k,  d/d loc_k = resp_k * dlp_k/dloc,  d/d ls_k = resp_k * dlp_k/dls.
-template <int K, bool GRAD, int UMODE = kUGeneral>
+enum : int { kLikDmol = 0, kLikGmmRaw = 1, kLikGmmSd = 2 };
+
+template <int K, bool GRAD, int UMODE = kUGeneral, int LIK = kLikDmol>
 BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts& C) {
-  const int edge = dmol_edge(y, C);
+  const int edge = (LIK == kLikDmol) ? dmol_edge(y, C) : kEdgeNone;
   float v[K];
-  if (edge == kEdgeNone) {   // hoisted out of the component loop: the hot loop below has no edge test
+  if (LIK != kLikDmol) {   // Gaussian mixture: same layout and mixture algebra, different component density
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float lp, dmu = 0.f, dp = 0.f;
+      gauss_component<GRAD, LIK == kLikGmmRaw>(y, r[K + k], r[2 * K + k], C, lp, dmu, dp);
+      v[k] = (K == 1) ? lp : lp + r[k];
+      if (GRAD) {
+        r[K + k] = dmu;
+        r[2 * K + k] = dp;
+      }
+    }
+  } else if (edge == kEdgeNone) {   // hoisted out of the component loop: the hot loop below has no edge test
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       float lp, dmu = 0.f, dls = 0.f;
@@ -351,14 +437,23 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
 // Generic (runtime K, D >= 1) sample, two passes with recomputation; `p` is the sample's K(2D+1) parameters laid
 // out [logits K | d=0: locs K, log_scales K | d=1: ...] (distributions.py:383-385), `yv` its D targets, `o` the
 // gradient row (may alias nothing; written only if GRAD).  Used for shapes the register kernel is not instantiated for.
+// component dispatch for the generic (runtime K, D) path
 template <bool GRAD>
-BLVM_HD float dmol_sample_generic(const float* yv, const float* p, int K, int D, float g, const DmolConsts& C, float* o) {
+BLVM_HD void any_component(int lik, float y, float mu, float p, const DmolConsts& C, float& lp, float& dmu, float& dp) {
+  if (lik == kLikDmol) dl_component<GRAD>(y, dmol_edge(y, C), mu, p, C, lp, dmu, dp);
+  else if (lik == kLikGmmRaw) gauss_component<GRAD, true>(y, mu, p, C, lp, dmu, dp);
+  else gauss_component<GRAD, false>(y, mu, p, C, lp, dmu, dp);
+}
+
+template <bool GRAD>
+BLVM_HD float dmol_sample_generic(const float* yv, const float* p, int K, int D, float g, const DmolConsts& C, float* o,
+                                  int lik = kLikDmol) {
   float m1 = -INFINITY, m2 = -INFINITY;
   for (int k = 0; k < K; ++k) {
     float lpk = 0.f;
     for (int d = 0; d < D; ++d) {
       float lp, a, b;
-      dl_component<false>(yv[d], dmol_edge(yv[d], C), p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, a, b);
+      any_component<false>(lik, yv[d], p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, a, b);
       lpk += lp;
     }
     const float vk = lpk + p[k];
@@ -371,7 +466,7 @@ BLVM_HD float dmol_sample_generic(const float* yv, const float* p, int K, int D,
     float lpk = 0.f;
     for (int d = 0; d < D; ++d) {
       float lp, a, b;
-      dl_component<false>(yv[d], dmol_edge(yv[d], C), p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, a, b);
+      any_component<false>(lik, yv[d], p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, a, b);
       lpk += lp;
     }
     s1 += fast_ex2((lpk + p[k] - m1) * kLog2e);
@@ -384,7 +479,7 @@ BLVM_HD float dmol_sample_generic(const float* yv, const float* p, int K, int D,
       float lpk = 0.f;
       for (int d = 0; d < D; ++d) {
         float lp, dmu, dls;
-        dl_component<true>(yv[d], dmol_edge(yv[d], C), p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, dmu, dls);
+        any_component<true>(lik, yv[d], p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, dmu, dls);
         lpk += lp;
         o[K + d * 2 * K + k] = dmu;
         o[K + d * 2 * K + K + k] = dls;

@@ -40,6 +40,7 @@ struct DmolArgs {
   int64_t B, T, chunks;
   int K, D;
   int flags;
+  int lik;                 // kLikDmol / kLikGmmRaw / kLikGmmSd (generic kernel; the register kernels take it as a template argument)
   DmolConsts C;
 };
 
@@ -175,7 +176,7 @@ constexpr size_t dmol_tile_smem_bytes() {
 
 // The body of one tile; returns true if a bulk store is still reading the tile's shared memory (the caller must execute
 // ptx::bulk_wait_read0() in thread 0 before the CTA exits or reuses it).  Shared by dmol_tile_kernel and elbo_step_kernel.
-template <int K, int TPB, bool GRAD, int UMODE, typename TP>
+template <int K, int TPB, bool GRAD, int UMODE, typename TP, int LIK = kLikDmol>
 __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t tile_id, unsigned char* smem) {
   constexpr int P = 3 * K;
   constexpr int NW = TPB / 32;
@@ -228,7 +229,7 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
     g[j] = 0.f;
     if (i < n) {
       yv[j] = ptx::ldg_stream(A.y + s0 + i);
-      if (!(yv[j] <= 1.0f && yv[j] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
+      if (LIK == kLikDmol && !(yv[j] <= 1.0f && yv[j] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
       if (GRAD) {
         g[j] = (i < nvalid) ? gs : 0.f;
         if (A.gout) g[j] *= ptx::ldg_stream(A.gout + s0 + i);
@@ -248,7 +249,7 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
       TP* row = tile + i * P;
       if (!skip) {
         RowIO<TP, P>::load(row, r);
-        L = dmol_sample<K, GRAD, UMODE>(yv[j], r, g[j], A.C);
+        L = dmol_sample<K, GRAD, UMODE, LIK>(yv[j], r, g[j], A.C);
       } else {
 #pragma unroll
         for (int q = 0; q < P; ++q) r[q] = 0.f;
@@ -281,10 +282,10 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
   return GRAD && bulk_out;
 }
 
-template <int K, int TPB, bool GRAD, int UMODE, typename TP>
+template <int K, int TPB, bool GRAD, int UMODE, typename TP, int LIK = kLikDmol>
 __global__ void __launch_bounds__(TPB, DmolMinBlocks<K>::value) dmol_tile_kernel(const DmolArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const bool pending = dmol_tile_body<K, TPB, GRAD, UMODE, TP>(A, blockIdx.x, smem);
+  const bool pending = dmol_tile_body<K, TPB, GRAD, UMODE, TP, LIK>(A, blockIdx.x, smem);
   if (pending && threadIdx.x == 0) ptx::bulk_wait_read0();  // smem must outlive the bulk store's read
 }
 
@@ -310,8 +311,9 @@ __global__ void __launch_bounds__(TPB) dmol_generic_kernel(const DmolArgs A) {
   if (in_tile) {
     const int64_t s = s0 + tid;
     const float* yv = A.y + s * A.D;
-    for (int d = 0; d < A.D; ++d)
-      if (!(yv[d] <= 1.0f && yv[d] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
+    if (A.lik == kLikDmol)
+      for (int d = 0; d < A.D; ++d)
+        if (!(yv[d] <= 1.0f && yv[d] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
     float g = 0.f;
     if (GRAD) {
       g = valid ? A.gscale : 0.f;
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(TPB) dmol_generic_kernel(const DmolArgs A) {
     }
     if (!skip) {
       L = dmol_sample_generic<GRAD>(yv, static_cast<const float*>(A.raw) + s * P, A.K, A.D, g, A.C,
-                                    GRAD ? static_cast<float*>(A.graw) + s * P : nullptr);
+                                    GRAD ? static_cast<float*>(A.graw) + s * P : nullptr, A.lik);
     } else if (GRAD) {
       for (int i = 0; i < P; ++i) static_cast<float*>(A.graw)[s * P + i] = 0.f;
     }

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "blvm_math.cuh"
+
 namespace blvm {
 
 // torch.bucketize(x, boundaries, right=False) (blvm/data/transforms.py:257): lower bound, i.e. the first index i with
@@ -30,6 +32,26 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ 
   if (s == 1.0f) return;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) buf[i] *= s;
+}
+
+// Elementwise gaussian_ll (blvm/utils/log_likelihoods.py:17-39) on separate y / mu / sd arrays: value, and with GRAD
+// gout * d/d mu and gout * d/d sd (sd is detached when sd_floor > 0, like the reference's no_grad clamp).
+template <bool GRAD>
+__global__ void __launch_bounds__(256) gaussian_ll_kernel(const float* __restrict__ y, const float* __restrict__ mu,
+                                                          const float* __restrict__ sd, const float* __restrict__ gout,
+                                                          int64_t n, DmolConsts C, float* __restrict__ lp,
+                                                          float* __restrict__ g_mu, float* __restrict__ g_sd) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) {
+    float l, dmu = 0.f, dsd = 0.f;
+    gauss_component<GRAD, false>(y[i], mu[i], sd[i], C, l, dmu, dsd);
+    if (lp) lp[i] = l;
+    if (GRAD) {
+      const float g = gout ? gout[i] : 1.f;
+      g_mu[i] = g * dmu;
+      g_sd[i] = g * dsd;
+    }
+  }
 }
 
 constexpr int kMaxScaleBuffers = 36;

@@ -11,10 +11,12 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .log_likelihoods import discretized_logistic_ll, discretized_logistic_mixture_ll
+import math
+
+from .log_likelihoods import discretized_logistic_ll, discretized_logistic_mixture_ll, gaussian_mixture_ll
 
 __all__ = ["ConditionalDistribution", "DiscretizedLogisticMixtureDense", "DiscretizedLogisticDense", "DMoLParams",
-           "DLParams"]
+           "DLParams", "DiagonalGaussianMixtureDense", "GMMParams"]
 
 
 class ConditionalDistribution(nn.Module):
@@ -225,3 +227,81 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
 
     def forward(self, x):
         return DMoLParams(self.params(x), self.num_mix, self.y_dim, self.log_epsilon)
+
+
+class GMMParams:
+    """What DiagonalGaussianMixtureDense.forward returns: indexes like the reference's `(logit_probs (*, K),
+    mu (*, D, K), sd (*, D, K))` with sd = softplus_beta(log_sd) + epsilon, and carries the packed Linear output so that
+    log_prob / fused_elbo apply the activation (and its chain rule) inside the kernel."""
+
+    __slots__ = ("raw", "K", "D", "beta", "sd_add", "_cache")
+
+    def __init__(self, raw, K, D, beta, sd_add):
+        self.raw, self.K, self.D, self.beta, self.sd_add = raw, K, D, beta, sd_add
+        self._cache = {}
+
+    def __len__(self):
+        return 3
+
+    def __iter__(self):
+        return iter((self[0], self[1], self[2]))
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += 3
+        if i not in self._cache:
+            raw, K, D = self.raw, self.K, self.D
+            if i == 0:
+                t = raw[..., :K]                                                            # distributions.py:198
+            elif i in (1, 2):
+                mls = raw[..., K:].view(*raw.shape[:-1], D, 2 * K)                          # :199
+                if i == 1:
+                    t = mls[..., :K]
+                else:                                                                       # :201 sd activation
+                    t = torch.nn.functional.softplus(mls[..., K:], beta=self.beta) + self.sd_add
+            else:
+                raise IndexError(i)
+            t._blvm_packed_gmm = (self.raw, self.K, self.D, self.beta, self.sd_add)
+            self._cache[i] = t
+        return self._cache[i]
+
+
+class DiagonalGaussianMixtureDense(ConditionalDistribution):
+    """Drop-in for blvm/modules/distributions.py:153-204 (`--likelihood GMM`): same constructor, attributes and
+    state-dict keys; the sd activation Softplus(beta = ln2/initial_sd) + epsilon runs inside the likelihood kernel."""
+
+    def __init__(self, x_dim, y_dim, num_mix: int, initial_sd: float = 1, epsilon: float = 1e-6):
+        super().__init__()
+        self.x_dim, self.y_dim, self.num_mix = x_dim, y_dim, num_mix
+        self.initial_sd, self.epsilon = initial_sd, epsilon
+        self.out_features = num_mix * (2 * y_dim + 1)
+        self.params = nn.Linear(x_dim, self.out_features)
+        # distributions.py:167-170: beta = ln2/initial_sd when epsilon > 0, ln2/(initial_sd - epsilon) otherwise
+        self.softplus_beta = math.log(2) / (initial_sd if epsilon > 0 else (initial_sd - epsilon))
+        self.reset_parameters()
+
+    def rsample(self, params):
+        """Gumbel-max component choice, then mu + sd * N(0, 1) (blvm/utils/variational.py:156-196); plain torch."""
+        logits, mu, sd = params[0], params[1], params[2]
+        u = torch.empty_like(logits).uniform_(1e-6, 1.0 - 1e-6)
+        choice = torch.argmax(logits - torch.log(-torch.log(u)), dim=-1, keepdim=True)
+        index = choice.expand(*choice.shape[:-1], mu.size(-2)).unsqueeze(-1)
+        m = torch.gather(mu, index=index, dim=-1).squeeze(-1)
+        s = torch.gather(sd, index=index, dim=-1).squeeze(-1)
+        return torch.randn_like(m).mul(s).add(m)
+
+    @torch.no_grad()
+    def sample(self, params):
+        return self.rsample(params)
+
+    def mode(self, params):
+        component = params[0].argmax(-1, keepdim=True).unsqueeze(-2)
+        return torch.gather(params[1], index=component, dim=-1).squeeze(-1)
+
+    def log_prob(self, y, params, reduce_dim: int = -1):
+        if isinstance(params, GMMParams) and y.shape == params.raw.shape[:-1] + (self.y_dim,) and reduce_dim in (-1, y.ndim - 1):
+            return ops.gmm_log_prob(y, params.raw, self.num_mix, self.y_dim, True, params.beta, params.sd_add, 0.0)
+        return gaussian_mixture_ll(y, params[0], params[1], params[2], epsilon=0, reduce_dim=reduce_dim)
+
+    def forward(self, x):
+        return GMMParams(self.params(x), self.num_mix, self.y_dim, self.softplus_beta, self.epsilon if self.epsilon > 0 else 0.0)

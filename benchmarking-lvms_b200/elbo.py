@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Union
 import torch
 
 from . import ops
-from .distributions import DLParams, DMoLParams
+from .distributions import DLParams, DMoLParams, GMMParams
 from .operations import level_lengths, sequence_mask
 
 __all__ = ["KLLevel", "fused_elbo", "vrnn_compute_elbo", "srnn_compute_elbo", "cwvae_compute_elbo", "stcn_compute_loss",
@@ -130,9 +130,11 @@ def fused_elbo(
         x_sl_dev = x_sl_t
         lens_of = {id(lv): level_lengths(x_sl_dev, int(lv.stride)) for lv in need}
 
-    likelihood, raw, K, D, log_eps = "none", None, 1, 1, -7.0
+    likelihood, raw, K, D, log_eps, gmm = "none", None, 1, 1, -7.0, (1.0, 0.0)
     if parameters is not None:
-        if isinstance(parameters, DLParams):
+        if isinstance(parameters, GMMParams):
+            likelihood, raw, K, D, gmm = "gmm", parameters.raw, parameters.K, parameters.D, (parameters.beta, parameters.sd_add)
+        elif isinstance(parameters, DLParams):
             likelihood, raw, log_eps = "dl", parameters.raw, parameters.log_epsilon
             if parameters.D != 1:
                 raise NotImplementedError("fused_elbo supports DiscretizedLogisticDense with y_dim == 1")
@@ -165,7 +167,7 @@ def fused_elbo(
     need_grad = torch.is_grad_enabled() and ((raw is not None and raw.requires_grad) or any(t.requires_grad for t in flat))
     spec = ops.ELBOSpec(K=K, D=D, num_bins=int(num_bins), log_epsilon=float(log_eps), beta=float(beta), denom=total,
                         levels=specs, want_twise=want_twise, skip_padded=skip_padded, need_grad=need_grad,
-                        likelihood=likelihood, exchange=exchange)
+                        likelihood=likelihood, exchange=exchange, gmm=gmm)
     loss, sums, rows, twise = ops.fused_elbo_apply(spec, y, x_sl_dev, raw, flat)
     return SimpleNamespace(loss=loss, log_prob=rows[0], kl=rows[1], kl_fn=rows[2], elbo=rows[3],
                            kl_levels=[rows[4 + l] for l in range(len(specs))], sums=sums,

@@ -7,7 +7,7 @@ import torch
 
 from . import ops
 
-__all__ = ["discretized_logistic_mixture_ll", "discretized_logistic_ll", "reduce"]
+__all__ = ["discretized_logistic_mixture_ll", "discretized_logistic_ll", "gaussian_ll", "gaussian_mixture_ll", "reduce"]
 
 _NO_CLAMP = -math.inf  # log-scales handed to the functional API are used as they are (the module clamps, not the function)
 
@@ -85,3 +85,29 @@ def discretized_logistic_ll(y: torch.Tensor, loc: torch.Tensor, log_scale: torch
         raw = torch.stack([loc_b, ls_b], dim=-1)
         log_prob = ops.dl_log_prob(y_b, raw, num_bins, _NO_CLAMP)
     return reduce(log_prob, reduce_dim) if reduce_dim else log_prob
+
+
+def gaussian_ll(y, mu, sd, epsilon: float = 1e-6, reduce_dim: Optional[int] = -1):
+    """Elementwise Gaussian log-likelihood — drop-in for blvm/utils/log_likelihoods.py:17-39.  The standard deviation is
+    clamped at `epsilon`; the reference does that under no_grad, which detaches sd, so with epsilon != 0 no gradient
+    reaches sd (kept).  `reduce_dim` falsy => no reduction."""
+    if not isinstance(sd, torch.Tensor):
+        sd = torch.as_tensor(float(sd), device=mu.device)
+    log_prob = ops.gaussian_ll_elementwise(y, mu, sd, sd_floor=float(epsilon or 0.0))
+    return reduce(log_prob, reduce_dim) if reduce_dim else log_prob
+
+
+def gaussian_mixture_ll(y, logits, mu, sd, epsilon: float = 1e-6, reduce_dim: int = -1):
+    """Gaussian-mixture log-likelihood — drop-in for blvm/utils/log_likelihoods.py:42-60.
+    y (*, D); logits (*, K); mu, sd (*, D, K) -> (*).  Runs the DMoL tile kernel with the Gaussian component density."""
+    if reduce_dim not in (-1, y.ndim - 1):
+        raise NotImplementedError("blvm_b200.gaussian_mixture_ll reduces over the last (D) axis of y only")
+    packed = getattr(sd, "_blvm_packed_gmm", None)
+    if packed is not None and getattr(logits, "_blvm_packed_gmm", (None,))[0] is packed[0] and not epsilon \
+            and y.shape[:-1] == packed[0].shape[:-1]:
+        raw, K, D, beta, sd_add = packed
+        return ops.gmm_log_prob(y, raw, K, D, True, beta, sd_add, 0.0)
+    K, D = logits.size(-1), y.size(-1)
+    batch = torch.broadcast_shapes(y.shape[:-1], logits.shape[:-1], mu.shape[:-2], sd.shape[:-2])
+    raw = torch.cat([logits.expand(*batch, K), torch.cat([mu.expand(*batch, D, K), sd.expand(*batch, D, K)], dim=-1).flatten(-2)], dim=-1)
+    return ops.gmm_log_prob(y.expand(*batch, D), raw, K, D, False, 1.0, 0.0, float(epsilon or 0.0))

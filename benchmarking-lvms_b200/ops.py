@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import BLVM_FLAG_MASK_OUTPUT, BLVM_FLAG_SKIP_PADDED, check, lib
 
 __all__ = [
-    "dmol_log_prob", "dl_log_prob", "kl_gaussian", "KLLevelSpec", "ELBOSpec", "fused_elbo_apply", "quantize_indices", "dmol_sample_mode", "mode_with_grad",
+    "dmol_log_prob", "dl_log_prob", "kl_gaussian", "KLLevelSpec", "ELBOSpec", "fused_elbo_apply", "quantize_indices", "dmol_sample_mode", "mode_with_grad", "gmm_log_prob", "gaussian_ll_elementwise",
     "check_input_range", "launch_count", "reset_launch_count",
 ]
 
@@ -239,6 +239,84 @@ def dl_log_prob(y: torch.Tensor, raw: torch.Tensor, num_bins: int, log_epsilon: 
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# sibling likelihoods: Gaussian mixture (packed layout) and elementwise Gaussian
+# ----------------------------------------------------------------------------------------------------------------------
+def _gmm_call(y, raw, x_sl_dev, gout, gscale, B, T, K, D, from_raw, beta, sd_add, sd_floor, flags, lp, graw, partials,
+              gscale_dev=None):
+    _require_cuda(y, raw, x_sl_dev, gout, lp, graw, partials, gscale_dev)
+    with _on_device(raw.device):
+        rc = lib.blvm_gmm_fwd_grad(_ptr(y), _ptr(raw), _ptr(x_sl_dev), _ptr(gout), gscale, _ptr(gscale_dev), B, T, K, D,
+                                   1 if from_raw else 0, float(beta), float(sd_add), float(sd_floor), flags, _ptr(lp),
+                                   _ptr(graw), _ptr(partials), _stream())
+        check(rc, "blvm_gmm_fwd_grad")
+    _count()
+
+
+class _GMMLogProb(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, y, raw, K, D, from_raw, beta, sd_add, sd_floor):
+        y = y.contiguous()
+        raw = raw.contiguous()
+        P = K * (2 * D + 1)
+        assert raw.shape[-1] == P, f"raw last dim {raw.shape[-1]} != K(2D+1) = {P}"
+        N = raw.numel() // P
+        assert y.numel() == N * D
+        lp = torch.empty(raw.shape[:-1], dtype=torch.float32, device=raw.device)
+        _gmm_call(y, raw, None, None, 0.0, 1, N, K, D, from_raw, beta, sd_add, sd_floor, 0, lp, None, None)
+        ctx.save_for_backward(y, raw)
+        ctx.cfg = (K, D, from_raw, beta, sd_add, sd_floor, N)
+        return lp
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        y, raw = ctx.saved_tensors
+        K, D, from_raw, beta, sd_add, sd_floor, N = ctx.cfg
+        graw = torch.empty_like(raw)
+        _gmm_call(y, raw, None, _as_f32c(g), 1.0, 1, N, K, D, from_raw, beta, sd_add, sd_floor, 0, None, graw, None)
+        return None, graw, None, None, None, None, None, None
+
+
+def gmm_log_prob(y, raw, K, D, from_raw=True, beta=1.0, sd_add=0.0, sd_floor=0.0):
+    """Gaussian-mixture log p(y) per element of `raw.shape[:-1]` from packed raw (*, K(2D+1)) = [logits | mu | s]."""
+    return _GMMLogProb.apply(y, raw, K, D, bool(from_raw), float(beta), float(sd_add), float(sd_floor))
+
+
+class _GaussianLL(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, y, mu, sd, sd_floor):
+        y, mu, sd = (t.contiguous() for t in (y, mu, sd))
+        _require_cuda(y, mu, sd)
+        lp = torch.empty_like(mu)
+        with _on_device(mu.device):
+            check(lib.blvm_gaussian_ll(_ptr(y), _ptr(mu), _ptr(sd), None, mu.numel(), sd_floor, _ptr(lp), None, None, _stream()),
+                  "blvm_gaussian_ll")
+        _count()
+        ctx.save_for_backward(y, mu, sd)
+        ctx.sd_floor = sd_floor
+        return lp
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        y, mu, sd = ctx.saved_tensors
+        g = _as_f32c(g)
+        g_mu, g_sd = torch.empty_like(mu), torch.empty_like(mu)
+        with _on_device(mu.device):
+            check(lib.blvm_gaussian_ll(_ptr(y), _ptr(mu), _ptr(sd), _ptr(g), mu.numel(), ctx.sd_floor, None, _ptr(g_mu), _ptr(g_sd),
+                                       _stream()), "blvm_gaussian_ll (backward)")
+        _count()
+        return -g_mu, g_mu, (g_sd if ctx.sd_floor == 0 else None), None   # d/dy = -d/dmu
+
+
+def gaussian_ll_elementwise(y, mu, sd, sd_floor: float = 0.0):
+    y, mu, sd = torch.broadcast_tensors(y, mu, sd)
+    return _GaussianLL.apply(y, mu, sd, float(sd_floor))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # elementwise Gaussian KL
 # ----------------------------------------------------------------------------------------------------------------------
 class _KLGaussian(torch.autograd.Function):
@@ -295,7 +373,8 @@ class ELBOSpec:
     want_twise: bool = False
     skip_padded: bool = False
     need_grad: bool = True
-    likelihood: str = "dmol"       # "dmol" | "dl" | "none"
+    likelihood: str = "dmol"       # "dmol" | "dl" | "gmm" | "none"
+    gmm: tuple = (1.0, 0.0)        # (softplus beta, sd epsilon) of the Gaussian-mixture sd activation
     exchange: object = None        # distributed.SumsExchange: publish the sums to all ranks from the finalize kernel
 
 
@@ -317,7 +396,8 @@ class _FusedELBO(torch.autograd.Function):
         T = raw.shape[1] if has_lik else 0
         logp_chunks = 0
         if has_lik:
-            logp_chunks = int(lib.blvm_dmol_chunks(T, spec.K, spec.D)) if spec.likelihood == "dmol" else int(lib.blvm_dl_chunks(T))
+            logp_chunks = int({"dmol": lambda: lib.blvm_dmol_chunks(T, spec.K, spec.D), "dl": lambda: lib.blvm_dl_chunks(T),
+                               "gmm": lambda: lib.blvm_gmm_chunks(T, spec.K, spec.D)}[spec.likelihood]())
         shapes = []
         i = 0
         for lv in spec.levels:
@@ -362,6 +442,10 @@ class _FusedELBO(torch.autograd.Function):
                     if deferred:
                         ctx.save_for_backward(y, raw, x_sl_dev)
                         ctx.deferred = (B, T, spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags, gscale)
+                elif spec.likelihood == "gmm":
+                    rc = lib.blvm_gmm_fwd_grad(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), None, gscale, None, B, T,
+                                               spec.K, spec.D, 1, spec.gmm[0], spec.gmm[1], 0.0, flags, lp_ptr, _ptr(graw),
+                                               logp_ptr, stream)
                 else:
                     rc = lib.blvm_dl_fwd_grad(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), None, gscale, B, T,
                                               spec.num_bins, spec.log_epsilon, flags, lp_ptr, _ptr(graw), logp_ptr,

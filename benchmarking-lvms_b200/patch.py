@@ -39,7 +39,12 @@ def patch_blvm():
     before = len(_saved)
     _rebind_everywhere(ref_ll.discretized_logistic_mixture_ll, log_likelihoods.discretized_logistic_mixture_ll)
     _rebind_everywhere(ref_ll.discretized_logistic_ll, log_likelihoods.discretized_logistic_ll)
+    _rebind_everywhere(ref_ll.gaussian_mixture_ll, log_likelihoods.gaussian_mixture_ll)
     _rebind_everywhere(ref_var.kl_divergence_gaussian, variational.kl_divergence_gaussian)
+    _rebind_everywhere(ref_dist.DiagonalGaussianMixtureDense, distributions.DiagonalGaussianMixtureDense)
+    # gaussian_ll / DiagonalGaussianDense are NOT rebound: the model bodies use them for the latent layers
+    # (vrnn.py:81,91), which are outside this path; blvm_b200.gaussian_ll / kl_divergence_gaussian_mc exist for callers
+    # that want the kernels (e.g. bottom-up STCN).
     _rebind_everywhere(ref_dist.DiscretizedLogisticMixtureDense, distributions.DiscretizedLogisticMixtureDense)
     _rebind_everywhere(ref_dist.DiscretizedLogisticDense, distributions.DiscretizedLogisticDense)
 

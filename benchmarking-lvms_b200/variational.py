@@ -1,12 +1,12 @@
 """Variational helpers with the reference's names (blvm/utils/variational.py): analytic Gaussian KL and free nats."""
 import math
-from typing import Tuple, Union
+from typing import Optional, Tuple, Union
 
 import torch
 
 from . import ops
 
-__all__ = ["kl_divergence_gaussian", "discount_free_nats"]
+__all__ = ["kl_divergence_gaussian", "kl_divergence_gaussian_mc", "discount_free_nats"]
 
 
 def kl_divergence_gaussian(mu_q: torch.Tensor, sd_q: torch.Tensor, mu_p: torch.Tensor, sd_p: torch.Tensor):
@@ -14,6 +14,12 @@ def kl_divergence_gaussian(mu_q: torch.Tensor, sd_q: torch.Tensor, mu_p: torch.T
     blvm/utils/variational.py:67-70.  One kernel forward, one backward; evaluated as
     -log1p(rho-1) + ((rho-1)(rho+1) + z^2)/2 so that q ~ p does not cancel."""
     return ops.kl_gaussian(mu_q, sd_q, mu_p, sd_p)
+
+
+def kl_divergence_gaussian_mc(mu_q, sd_q, mu_p, sd_p, z, epsilon: float = 0, reduce_dim: Optional[int] = None):
+    """Elementwise Monte-Carlo KL log q(z) - log p(z) — drop-in for blvm/utils/variational.py:73-83 (bottom-up STCN)."""
+    from .log_likelihoods import gaussian_ll
+    return gaussian_ll(z, mu_q, sd_q, epsilon, reduce_dim) - gaussian_ll(z, mu_p, sd_p, epsilon, reduce_dim)
 
 
 def discount_free_nats(kld: torch.Tensor, free_nats: float = None, shared_dims: Union[Tuple[int], int] = None):

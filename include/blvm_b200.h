@@ -105,6 +105,24 @@ int blvm_dl_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, cons
                      int* err_flag, blvm_stream_t stream);
 
 /*
+ * Sibling likelihood: Gaussian mixture with the DMoL's packed layout raw (B, T, K(2D+1)) = [logits | per d: mu K, s K]
+ * (SURVEY.md §8f row 4).  Replaces DiagonalGaussianMixtureDense.forward's split + sd activation
+ * (blvm/modules/distributions.py:198-203) and gaussian_mixture_ll (blvm/utils/log_likelihoods.py:42-60) + autograd.
+ *   from_raw = 1: s is the Linear output, sd = softplus_{softplus_beta}(s) + sd_add is applied inside (chain rule folded
+ *                 into graw);  from_raw = 0: s is sd itself, clamped at sd_floor if > 0 (then detached, like the
+ *                 reference's no_grad clamp, log_likelihoods.py:33-35)
+ *   graw nullable (forward only); partials (B, blvm_gmm_chunks(T, K, D)) nullable; mask / gout / gscale as for the DMoL
+ */
+int64_t blvm_gmm_chunks(int64_t T, int K, int D);
+int blvm_gmm_fwd_grad(const float* y, const float* raw, const int64_t* x_sl, const float* gout, float gscale,
+                      const double* gscale_dev, int64_t B, int64_t T, int K, int D, int from_raw, double softplus_beta,
+                      double sd_add, double sd_floor, int flags, float* lp, float* graw, double* partials,
+                      blvm_stream_t stream);
+/* Elementwise gaussian_ll (log_likelihoods.py:17-39): lp nullable; g_mu, g_sd nullable together (= gout * d lp/d .). */
+int blvm_gaussian_ll(const float* y, const float* mu, const float* sd, const float* gout, int64_t n, double sd_floor,
+                     float* lp, float* g_mu, float* g_sd, blvm_stream_t stream);
+
+/*
  * Diagonal-Gaussian KL(q||p), std-dev parametrisation, elementwise over n elements.
  * Replaces kl_divergence_gaussian (blvm/utils/variational.py:67-70).
  */

@@ -24,6 +24,8 @@ __all__ = [
     "sequence_mask", "discretized_logistic_ll", "discretized_logistic_mixture_ll", "split_dmol_params",
     "dmol_branches", "dmol_value_and_grad", "dl_value_and_grad", "kl_divergence_gaussian", "kl_value_and_grad",
     "discount_free_nats", "elbo_vrnn", "elbo_srnn", "elbo_cwvae", "elbo_stcn", "loss_wavenet", "quantize", "bits_per_dim", "fused_elbo_value_and_grad",
+    "softplus_beta", "gaussian_ll", "gaussian_mixture_ll", "gmm_value_and_grad", "gaussian_ll_value_and_grad",
+    "kl_divergence_gaussian_mc",
 ]
 
 
@@ -196,6 +198,78 @@ def dl_value_and_grad(y, raw, num_bins=256, log_epsilon=-7.0, gout=None):
     grad[:, 0] = gout * (-aux["inv"] * (da + db + dm))
     grad[:, 1] = gout * (-(aux["a"] * da + aux["b"] * db + aux["m"] * dm) + dls_direct) * (raw_ls >= log_epsilon)
     return lp, grad
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sibling likelihoods: Gaussian and Gaussian mixture
+# ---------------------------------------------------------------------------------------------------------------
+def softplus_beta(x, beta, threshold=20.0):
+    """nn.Softplus(beta): log1p(exp(beta x))/beta, linear above beta*x > threshold."""
+    with np.errstate(over="ignore"):
+        return np.where(x * beta > threshold, x, np.log1p(np.exp(np.minimum(beta * x, threshold))) / beta)
+
+
+def gaussian_ll(y, mu, sd, epsilon=1e-6, reduce_dim=-1):
+    """blvm/utils/log_likelihoods.py:17-39 (sd clamped at epsilon; the clamp is under no_grad in the reference)."""
+    if epsilon:
+        sd = np.maximum(sd, epsilon)
+    log_prob = -((y - mu) ** 2) / (2 * sd ** 2) - np.log(sd) - 0.5 * math.log(2 * math.pi)
+    if reduce_dim:
+        return log_prob.squeeze(reduce_dim) if log_prob.shape[reduce_dim] == 1 else log_prob.sum(reduce_dim)
+    return log_prob
+
+
+def gaussian_mixture_ll(y, logits, mu, sd, epsilon=1e-6, reduce_dim=-1):
+    """blvm/utils/log_likelihoods.py:42-60. y (*, D); logits (*, K); mu, sd (*, D, K) -> (*)."""
+    log_prob_y = gaussian_ll(np.asarray(y)[..., None], mu, sd, epsilon=epsilon, reduce_dim=reduce_dim - 1)
+    return _logsumexp(log_prob_y + _log_softmax(np.asarray(logits), -1), -1)
+
+
+def gmm_value_and_grad(y, raw, K, D=1, beta=math.log(2), sd_add=1e-4, gout=None):
+    """GMM log-prob from the packed Linear output (DiagonalGaussianMixtureDense.forward + log_prob,
+    blvm/modules/distributions.py:189-204) and d(sum gout*lp)/d raw.  sd = softplus_beta(log_sd) + sd_add."""
+    raw = np.asarray(raw)
+    y = np.asarray(y).reshape(raw.shape[0], D)
+    logits = raw[..., :K]
+    mls = raw[..., K:].reshape(raw.shape[0], D, 2 * K)
+    mu, p = mls[..., :K], mls[..., K:]
+    sd = softplus_beta(p, beta) + sd_add
+    z = (y[..., None] - mu) / sd
+    lp_dk = -0.5 * z * z - np.log(sd) - 0.5 * math.log(2 * math.pi)
+    v = lp_dk.sum(-2) + _log_softmax(logits, -1)
+    L = _logsumexp(v, -1)
+    if gout is None:
+        gout = np.ones_like(L)
+    r = np.exp(v - L[..., None])
+    pi = np.exp(_log_softmax(logits, -1))
+    with np.errstate(over="ignore"):
+        dsd_dp = np.where(p * beta > 20.0, 1.0, 1 / (1 + np.exp(-beta * p)))
+    g = np.asarray(gout)[..., None]
+    grad = np.empty_like(raw)
+    grad[..., :K] = g * (r - pi)
+    gm = grad[..., K:].reshape(raw.shape[0], D, 2 * K)
+    gm[..., :K] = (g * r)[:, None, :] * (z / sd)
+    gm[..., K:] = (g * r)[:, None, :] * ((z * z - 1) / sd) * dsd_dp
+    grad[..., K:] = gm.reshape(raw.shape[0], -1)
+    return L, grad
+
+
+def gaussian_ll_value_and_grad(y, mu, sd, epsilon=0.0, gout=None):
+    """Elementwise gaussian_ll with gradients w.r.t. mu and sd (no gradient reaches sd when epsilon != 0: the reference
+    clamps under no_grad, which detaches it, log_likelihoods.py:33-35)."""
+    sd_c = np.maximum(sd, epsilon) if epsilon else sd
+    z = (y - mu) / sd_c
+    lp = -0.5 * z * z - np.log(sd_c) - 0.5 * math.log(2 * math.pi)
+    if gout is None:
+        gout = np.ones_like(lp)
+    g_mu = gout * z / sd_c
+    g_sd = gout * (z * z - 1) / sd_c * (0.0 if epsilon else 1.0)
+    return lp, g_mu, g_sd
+
+
+def kl_divergence_gaussian_mc(mu_q, sd_q, mu_p, sd_p, z, epsilon=0):
+    """blvm/utils/variational.py:73-83: log q(z) - log p(z), elementwise."""
+    return gaussian_ll(z, mu_q, sd_q, epsilon, None) - gaussian_ll(z, mu_p, sd_p, epsilon, None)
 
 
 # ---------------------------------------------------------------------------------------------------------------

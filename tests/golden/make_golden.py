@@ -368,9 +368,74 @@ def make_quantize():
     save("quantize", **out)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# (v) sibling likelihoods: GMM (distributions.py:153-204 + log_likelihoods.py:42-60), Gaussian (:17-39), MC KL
+# ----------------------------------------------------------------------------------------------------------------
+def make_gmm():
+    from blvm.modules.distributions import DiagonalGaussianMixtureDense
+    from blvm.utils.log_likelihoods import gaussian_ll, gaussian_mixture_ll
+    from blvm.utils.variational import kl_divergence_gaussian_mc
+    for K in (1, 5, 10, 20, 7):
+        gen = torch.Generator().manual_seed(6000 + K)
+        N, D = 320, 1
+        mod = DiagonalGaussianMixtureDense(x_dim=3 * K, y_dim=D, num_mix=K, initial_sd=1, epsilon=1e-4)
+        y = torch.rand(N, D, generator=gen) * 2 - 1
+        raw = torch.randn(N, 3 * K, generator=gen)
+        raw[:, K:2 * K] = y + 0.3 * torch.randn(N, K, generator=gen)
+        raw[:, 2 * K:] = raw[:, 2 * K:] * 4 - 4            # softplus regime from ~exp(-20) to linear
+        raw[0, 2 * K] = 40.0                               # beta*x > threshold: linear branch
+        raw[1, 2 * K] = -60.0                              # sd == epsilon
+        gout = torch.randn(N, generator=gen)
+        out = dict(y=y.numpy(), raw=raw.numpy(), gout=gout.numpy(), K=K, D=D, beta=math.log(2) / 1.0, sd_add=1e-4)
+        for tag, dt in (("32", torch.float32), ("64", torch.float64)):
+            r = raw.to(dt).clone().requires_grad_(True)
+            logits = r[..., :K]
+            mls = r[..., K:].view(N, D, 2 * K)
+            mu, log_sd = mls.chunk(2, dim=-1)
+            sd = mod.sd_activation(log_sd)                  # distributions.py:203
+            lp = gaussian_mixture_ll(y.to(dt), logits, mu, sd, epsilon=0)
+            (lp * gout.to(dt)).sum().backward()
+            out["lp" + tag] = lp.detach().numpy()
+            out["graw" + tag] = r.grad.numpy()
+            if tag == "64":
+                out["sd64"] = sd.detach().numpy()
+        save(f"gmm_K{K}", **out)
+    # elementwise gaussian_ll (epsilon = 0 as the modules call it, and 1e-2: clamp under no_grad) and the MC KL
+    gen = torch.Generator().manual_seed(6100)
+    shape = (5, 9, 4)
+    y = torch.randn(shape, generator=gen)
+    mu_q, mu_p = torch.randn(shape, generator=gen), torch.randn(shape, generator=gen)
+    sd_q = torch.nn.functional.softplus(torch.randn(shape, generator=gen)) + 1e-3
+    sd_p = torch.nn.functional.softplus(torch.randn(shape, generator=gen)) + 1e-3
+    sd_q[0, 0, 0] = 1e-3
+    gout = torch.randn(shape, generator=gen)
+    out = dict(y=y.numpy(), mu_q=mu_q.numpy(), sd_q=sd_q.numpy(), mu_p=mu_p.numpy(), sd_p=sd_p.numpy(), gout=gout.numpy())
+    for tag, dt in (("32", torch.float32), ("64", torch.float64)):
+        for eps in (0.0, 1e-2):
+            m = mu_q.to(dt).clone().requires_grad_(True)
+            s_ = sd_q.to(dt).clone().requires_grad_(True)
+            lp = gaussian_ll(y.to(dt), m, s_, epsilon=eps, reduce_dim=None)
+            (lp * gout.to(dt)).sum().backward()
+            e = "0" if eps == 0 else "1"
+            out[f"lp{tag}_{e}"] = lp.detach().numpy()
+            out[f"g_mu{tag}_{e}"] = m.grad.numpy()
+            out[f"g_sd{tag}_{e}"] = s_.grad.numpy() if s_.grad is not None else np.zeros(shape)
+        ins = [t.to(dt).clone().requires_grad_(True) for t in (mu_q, sd_q, mu_p, sd_p)]
+        kl = kl_divergence_gaussian_mc(*ins, y.to(dt))
+        (kl * gout.to(dt)).sum().backward()
+        out["klmc" + tag] = kl.detach().numpy()
+        for nme, t in zip(("mu_q", "sd_q", "mu_p", "sd_p"), ins):
+            out[f"klmc_g_{nme}{tag}"] = t.grad.numpy()
+    save("gaussian_ll", **out)
+
+
 if __name__ == "__main__":
+    if "--gmm-only" in sys.argv:
+        make_gmm()
+        sys.exit(0)
     make_dmol()
     make_dl()
     make_kl()
     make_elbo_models()
     make_quantize()
+    make_gmm()

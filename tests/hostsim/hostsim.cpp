@@ -76,3 +76,51 @@ extern "C" void hostsim_kl(const float* mu_q, const float* sd_q, const float* mu
     kl_gaussian_grads(t, sd_q[i], g, g_mu_q[i], g_sd_q[i], g_mu_p[i], g_sd_p[i]);
   }
 }
+
+
+// ---- Gaussian mixture (sibling likelihood) ---------------------------------------------------------------------------
+template <int K>
+static void run_gmm_fixed(const float* y, const float* raw, const float* gout, int64_t N, const DmolConsts& C, int from_raw,
+                          float* lp, float* graw) {
+  for (int64_t n = 0; n < N; ++n) {
+    float r[3 * K];
+    for (int i = 0; i < 3 * K; ++i) r[i] = raw[n * 3 * K + i];
+    const float g = gout ? gout[n] : 1.f;
+    lp[n] = from_raw ? dmol_sample<K, true, kUGeneral, kLikGmmRaw>(y[n], r, g, C)
+                     : dmol_sample<K, true, kUGeneral, kLikGmmSd>(y[n], r, g, C);
+    for (int i = 0; i < 3 * K; ++i) graw[n * 3 * K + i] = r[i];
+  }
+}
+
+extern "C" int hostsim_gmm(const float* y, const float* raw, const float* gout, int64_t N, int K, float beta, float sd_add,
+                           float sd_floor, int from_raw, int force_generic, float* lp, float* graw) {
+  DmolConsts C = make_consts(256, -7.0f);
+  C.sp_beta = beta; C.sp_inv_beta = 1.0f / beta; C.sd_add = sd_add; C.sd_floor = sd_floor;
+  if (!force_generic) {
+    switch (K) {
+      case 1: run_gmm_fixed<1>(y, raw, gout, N, C, from_raw, lp, graw); return 0;
+      case 5: run_gmm_fixed<5>(y, raw, gout, N, C, from_raw, lp, graw); return 0;
+      case 10: run_gmm_fixed<10>(y, raw, gout, N, C, from_raw, lp, graw); return 0;
+      case 20: run_gmm_fixed<20>(y, raw, gout, N, C, from_raw, lp, graw); return 0;
+      default: break;
+    }
+  }
+  const int P = 3 * K;
+  for (int64_t n = 0; n < N; ++n)
+    lp[n] = dmol_sample_generic<true>(y + n, raw + n * P, K, 1, gout ? gout[n] : 1.f, C, graw + n * P,
+                                      from_raw ? kLikGmmRaw : kLikGmmSd);
+  return 2;
+}
+
+extern "C" void hostsim_gauss(const float* y, const float* mu, const float* sd, const float* gout, int64_t n, float sd_floor,
+                              float* lp, float* g_mu, float* g_sd) {
+  DmolConsts C = make_consts(256, -7.0f);
+  C.sd_floor = sd_floor;
+  for (int64_t i = 0; i < n; ++i) {
+    float dmu, dsd;
+    gauss_component<true, false>(y[i], mu[i], sd[i], C, lp[i], dmu, dsd);
+    const float g = gout ? gout[i] : 1.f;
+    g_mu[i] = g * dmu;
+    g_sd[i] = g * dsd;
+  }
+}

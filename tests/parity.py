@@ -29,7 +29,20 @@ def assert_values_close(ours, ref64, what="value", rtol=RTOL, atol=ATOL_LP, mask
                            f"{(err / tol)[bad].max():.3g} at {np.argwhere(bad)[0]}")
 
 
-def assert_grads_close(ours, ref64, K, gout_abs, what="grad", rtol=RTOL, rows=None):
+def gmm_row_factor(y, raw, K, beta, sd_add):
+    """fp32 conditioning of a Gaussian-mixture gradient: responsibilities are exp(lp_k - max) and lp_k carries an
+    absolute rounding error of ~|lp_k| * 6e-8 in fp32 (for the reference as well), so their relative accuracy is bounded
+    by that; with sd down to 1e-4, |lp_k| reaches 1e7.  Returns max(1, max_k |lp_k| * 1.2e-7 / RTOL) per sample."""
+    y = np.asarray(y, np.float64).reshape(-1, 1)
+    raw = np.asarray(raw, np.float64)
+    mu, p = raw[:, K:2 * K], raw[:, 2 * K:]
+    with np.errstate(over="ignore"):
+        sd = np.where(p * beta > 20, p, np.log1p(np.exp(np.minimum(beta * p, 20))) / beta) + sd_add
+    lp = -0.5 * ((y - mu) / sd) ** 2 - np.log(sd) - 0.9189385332046727
+    return np.maximum(1.0, np.abs(lp).max(-1) * 1.2e-7 / RTOL)
+
+
+def assert_grads_close(ours, ref64, K, gout_abs, what="grad", rtol=RTOL, rows=None, row_factor=None):
     """ours/ref64 (N, P) with P = K(2D+1) laid out [logits K | per d: locs K, log-scales K]; gout_abs (N,) = |upstream
     gradient| of each sample (sets the absolute floor: d/d logit is bounded by it)."""
     ours = np.asarray(ours, dtype=np.float64).reshape(-1, np.asarray(ref64).shape[-1])
@@ -40,7 +53,8 @@ def assert_grads_close(ours, ref64, K, gout_abs, what="grad", rtol=RTOL, rows=No
     for g0 in range(0, P, K):
         o, r = ours[:, g0:g0 + K], ref64[:, g0:g0 + K]
         gmax = np.abs(r).max(-1, keepdims=True)
-        tol = rtol * np.abs(r) + rtol * gmax + 1e-6 * gout_abs + 1e-30
+        rt = rtol if row_factor is None else rtol * np.asarray(row_factor, dtype=np.float64).reshape(-1, 1)
+        tol = rt * np.abs(r) + rt * gmax + 1e-6 * gout_abs + 1e-30
         ratio = np.abs(o - r) / tol
         if rows is not None:
             ratio = ratio[rows]

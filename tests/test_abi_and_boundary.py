@@ -45,8 +45,11 @@ def test_library_has_sm100a_code_and_tma():
         pytest.skip("cuobjdump not available")
     out = subprocess.run(["cuobjdump", "-lelf", blvm_b200.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4blvm16dmol_tile_kernelILi10ELi128ELb1ELi0EfEEvNS_8DmolArgsE",
-                           blvm_b200.LIB_PATH], capture_output=True, text=True).stdout
+    syms = subprocess.run(["cuobjdump", "-elf", blvm_b200.LIB_PATH], capture_output=True, text=True).stdout
+    import re as _re
+    names = sorted(set(_re.findall(r"_ZN4blvm16dmol_tile_kernelILi10ELi128ELb1ELi0EfLi0EE\w*DmolArgsE\b", syms)))
+    assert names, "K=10 fp32 fwd+grad tile kernel not found in the library"
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", names[0], blvm_b200.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass
 
 

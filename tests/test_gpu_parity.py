@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from parity import RTOL, assert_grads_close, assert_sums_close, assert_values_close
+from parity import RTOL, assert_grads_close, assert_sums_close, assert_values_close, gmm_row_factor
 
 pytestmark = pytest.mark.gpu
 
@@ -702,3 +702,68 @@ def test_no_out_of_bounds_writes(T, K, B):
     guard_mask[off:off + 2 * Bn * kc] = False
     assert (arena2[guard_mask] == 77.0).all(), "KL kernel wrote outside its outputs"
     assert all(torch.isfinite(o).all() for o in outs) and (outs[0].view(Bn, Tz, Z)[2] == 0).all()
+
+
+# ---- sibling likelihoods behind the same boundary ---------------------------------------------------
+@pytest.mark.parametrize("K", [1, 5, 10, 20, 7])
+def test_gmm_module_golden(K, B, O):
+    """DiagonalGaussianMixtureDense (`--likelihood GMM`): the sd activation + gaussian_mixture_ll + autograd of the
+    reference (blvm/modules/distributions.py:153-204, blvm/utils/log_likelihoods.py:42-60) against the fused kernel."""
+    g = load_golden(f"gmm_K{K}")
+    lik = B.DiagonalGaussianMixtureDense(3 * K, 1, num_mix=K, initial_sd=1, epsilon=1e-4)
+    assert lik.out_features == 3 * K and list(lik.state_dict().keys()) == ["params.weight", "params.bias"]
+    assert math.isclose(lik.softplus_beta, float(g["beta"]))
+    raw = cu(g["raw"]).requires_grad_(True)
+    params = B.GMMParams(raw, K, 1, lik.softplus_beta, lik.epsilon)
+    lp = lik.log_prob(cu(g["y"]), params)
+    (lp * cu(g["gout"])).sum().backward()
+    fac = gmm_row_factor(g["y"], g["raw"], K, float(g["beta"]), float(g["sd_add"]))
+    assert_values_close(lp.detach().cpu().numpy(), g["lp64"], "GMM log-prob")
+    assert_grads_close(raw.grad.cpu().numpy(), g["graw64"], K, np.abs(g["gout"]), "GMM grads", row_factor=fac)
+    # the container indexes like the reference's (logits, mu, sd) tuple
+    np.testing.assert_allclose(params[2].detach().cpu().numpy(), g["sd64"], rtol=1e-5)
+    # functional form with separate, already activated tensors (sd given)
+    t = [cu(g["raw"][:, :K]).requires_grad_(True), cu(g["raw"][:, K:2 * K]).unsqueeze(1).requires_grad_(True),
+         cu(g["sd64"]).requires_grad_(True)]
+    lp2 = B.gaussian_mixture_ll(cu(g["y"]), *t, epsilon=0)
+    lp2.sum().backward()
+    assert_values_close(lp2.detach().cpu().numpy(), g["lp64"], "GMM functional", rtol=2e-5)
+    assert torch.isfinite(t[2].grad).all() and t[2].grad.abs().sum() > 0
+    # fused ELBO with the GMM likelihood (WaveNet-style: no latents)
+    Bn, T = 4, raw.shape[0] // 4
+    x_sl = torch.tensor([T, T - 3, T // 2, 1])
+    r = cu(g["raw"]).view(Bn, T, 3 * K).clone().requires_grad_(True)
+    out = B.fused_elbo(cu(g["y"]).view(Bn, T), B.GMMParams(r, K, 1, lik.softplus_beta, lik.epsilon), x_sl, (), num_bins=2,
+                       want_twise=True)
+    out.loss.backward()
+    m = O.sequence_mask(x_sl.numpy(), max_len=T)
+    ref_rows = (g["lp64"].reshape(Bn, T) * m).sum(1)
+    assert_sums_close(out.log_prob.cpu().numpy(), ref_rows, "GMM row sums")
+    assert_sums_close(out.loss.item(), -ref_rows.sum() / float(x_sl.sum()), "GMM loss")
+    assert (r.grad.cpu().numpy()[~m] == 0).all()
+
+
+def test_gaussian_ll_and_mc_kl(B):
+    g = load_golden("gaussian_ll")
+    for e, eps in (("0", 0.0), ("1", 1e-2)):
+        mu, sd = cu(g["mu_q"]).requires_grad_(True), cu(g["sd_q"]).requires_grad_(True)
+        lp = B.gaussian_ll(cu(g["y"]), mu, sd, epsilon=eps, reduce_dim=None)
+        (lp * cu(g["gout"])).sum().backward()
+        assert_values_close(lp.detach().cpu().numpy(), g[f"lp64_{e}"], "gaussian_ll")
+        ref = g[f"g_mu64_{e}"]
+        np.testing.assert_allclose(mu.grad.cpu().numpy(), ref, rtol=RTOL, atol=1e-7 * np.abs(ref).max())
+        if eps == 0:
+            ref = g["g_sd64_0"]
+            np.testing.assert_allclose(sd.grad.cpu().numpy(), ref, rtol=RTOL, atol=1e-7 * np.abs(ref).max())
+        else:
+            assert sd.grad is None or (sd.grad == 0).all()          # detached by the reference's no_grad clamp
+    # reduce_dim = -1 sums the last axis like the reference (log_likelihoods.py:39)
+    lp_sum = B.gaussian_ll(cu(g["y"]), cu(g["mu_q"]), cu(g["sd_q"]), epsilon=0)
+    np.testing.assert_allclose(lp_sum.cpu().numpy(), g["lp64_0"].sum(-1), rtol=1e-5)
+    ins = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+    kl = B.kl_divergence_gaussian_mc(*ins, cu(g["y"]))
+    (kl * cu(g["gout"])).sum().backward()
+    assert_values_close(kl.detach().cpu().numpy(), g["klmc64"], "MC KL", atol=2e-6)
+    for t, n in zip(ins, ("mu_q", "sd_q", "mu_p", "sd_p")):
+        ref = g[f"klmc_g_{n}64"]
+        np.testing.assert_allclose(t.grad.cpu().numpy(), ref, rtol=RTOL, atol=1e-7 * np.abs(ref).max(), err_msg=n)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT, load_golden
-from parity import assert_grads_close, assert_values_close
+from parity import assert_grads_close, assert_values_close, gmm_row_factor
 
 SRC = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
 OUT_DIR = os.path.join(ROOT, "tests", "hostsim", "_build")
@@ -17,12 +17,17 @@ LIB = os.path.join(OUT_DIR, "libhostsim.so")
 FP = ctypes.POINTER(ctypes.c_float)
 
 
-@pytest.fixture(scope="module")
-def sim():
+@pytest.fixture(scope="module", params=["libm", "mufu"])
+def sim(request):
+    """libm: exact transcendentals.  mufu: ex2 / lg2 / rcp results degraded to the error class of the MUFU approximations
+    (2^-22 relative, 2^-22 absolute for lg2 near 0; blvm_math.cuh BLVM_HOSTSIM_MUFU_BITS) so that a closed form that only
+    passes with libm's last ulps fails here rather than on the GPU."""
     os.makedirs(OUT_DIR, exist_ok=True)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I",
-                    os.path.join(ROOT, "benchmarking-lvms_b200", "csrc"), "-o", LIB, SRC], check=True)
-    return ctypes.CDLL(LIB)
+    lib = LIB if request.param == "libm" else LIB.replace(".so", "_mufu.so")
+    extra = [] if request.param == "libm" else ["-DBLVM_HOSTSIM_MUFU_BITS=2"]
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", *extra, "-I",
+                    os.path.join(ROOT, "benchmarking-lvms_b200", "csrc"), "-o", lib, SRC], check=True)
+    return ctypes.CDLL(lib)
 
 
 def P(a):
@@ -126,3 +131,54 @@ def test_kl_closed_forms(sim):
             ref = g[f"g_{nme}64_{i}"]
             np.testing.assert_allclose(o[~tie], ref[~tie], rtol=1e-5, atol=1e-7 * np.abs(ref).max(), err_msg=nme)
     assert (outs[0][0, 0, :4] == 0).all()  # q == p gives exactly 0
+
+
+@pytest.mark.parametrize("K", [1, 5, 10, 20, 7])
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_gmm_closed_forms(sim, K, force_generic):
+    """Gaussian mixture from the packed Linear output (softplus + epsilon inside, chain rule folded in) and from
+    (logits, mu, sd) against the reference's fp64 run."""
+    from oracle import blvm_oracle as O
+    g = load_golden(f"gmm_K{K}")
+    y = np.ascontiguousarray(g["y"][:, 0], np.float32)
+    raw = np.ascontiguousarray(g["raw"], np.float32)
+    gout = np.ascontiguousarray(g["gout"], np.float32)
+    N = raw.shape[0]
+    lp = np.empty(N, np.float32)
+    gr = np.empty_like(raw)
+    sim.hostsim_gmm(P(y), P(raw), P(gout), ctypes.c_int64(N), K, ctypes.c_float(float(g["beta"])), ctypes.c_float(float(g["sd_add"])),
+                    ctypes.c_float(0.0), 1, force_generic, P(lp), P(gr))
+    assert_values_close(lp, g["lp64"], "GMM log-prob (from raw)")
+    assert_grads_close(gr, g["graw64"], K, np.abs(g["gout"]), "GMM grads (from raw)",
+                       row_factor=gmm_row_factor(g["y"], g["raw"], K, float(g["beta"]), float(g["sd_add"])))
+    # the oracle's closed form agrees with the reference's autograd too
+    L, G = O.gmm_value_and_grad(g["y"].astype(np.float64), g["raw"].astype(np.float64), K, 1, float(g["beta"]), float(g["sd_add"]),
+                                g["gout"].astype(np.float64))
+    np.testing.assert_allclose(L, g["lp64"], rtol=1e-12)
+    assert np.abs(G - g["graw64"]).max() <= 1e-9 * np.abs(g["graw64"]).max()
+    # "sd given" variant: pack [logits | mu | sd] with the reference's own fp64 sd
+    packed = np.ascontiguousarray(np.concatenate([g["raw"][:, :2 * K], g["sd64"][:, 0].astype(np.float32)], -1), np.float32)
+    sim.hostsim_gmm(P(y), P(packed), P(gout), ctypes.c_int64(N), K, ctypes.c_float(1.0), ctypes.c_float(0.0), ctypes.c_float(0.0),
+                    0, force_generic, P(lp), P(gr))
+    assert_values_close(lp, g["lp64"], "GMM log-prob (sd given)", rtol=2e-5)   # sd itself was rounded to fp32
+
+
+def test_gaussian_ll_closed_forms(sim):
+    from oracle import blvm_oracle as O
+    g = load_golden("gaussian_ll")
+    y, mu, sd, gout = (np.ascontiguousarray(g[k], np.float32).reshape(-1) for k in ("y", "mu_q", "sd_q", "gout"))
+    n = y.size
+    for e, eps in (("0", 0.0), ("1", 1e-2)):
+        lp, gm, gs = (np.empty(n, np.float32) for _ in range(3))
+        sim.hostsim_gauss(P(y), P(mu), P(sd), P(gout), ctypes.c_int64(n), ctypes.c_float(eps), P(lp), P(gm), P(gs))
+        assert_values_close(lp, g[f"lp64_{e}"].reshape(-1), "gaussian_ll")
+        np.testing.assert_allclose(gm, g[f"g_mu64_{e}"].reshape(-1), rtol=1e-5, atol=1e-7 * np.abs(g[f"g_mu64_{e}"]).max())
+        np.testing.assert_allclose(gs, g[f"g_sd64_{e}"].reshape(-1), rtol=1e-5, atol=1e-7 * np.abs(g[f"g_sd64_0"]).max())
+        ol, om, os_ = O.gaussian_ll_value_and_grad(g["y"].astype(np.float64), g["mu_q"].astype(np.float64), g["sd_q"].astype(np.float64),
+                                                   eps, g["gout"].astype(np.float64))
+        np.testing.assert_allclose(ol, g[f"lp64_{e}"], rtol=1e-12)
+        np.testing.assert_allclose(om, g[f"g_mu64_{e}"], rtol=1e-10)
+        np.testing.assert_allclose(os_, g[f"g_sd64_{e}"], rtol=1e-10, atol=1e-300)
+    assert (g["g_sd64_1"] == 0).all()          # the reference's no_grad clamp detaches sd (kept)
+    kl = O.kl_divergence_gaussian_mc(*[g[k].astype(np.float64) for k in ("mu_q", "sd_q", "mu_p", "sd_p", "y")])
+    np.testing.assert_allclose(kl, g["klmc64"], rtol=1e-12)
