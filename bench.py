@@ -43,6 +43,10 @@ def parse():
                     help="the K-step timed region is repeated back to back until this much time has passed (so that "
                          "nvidia-smi can observe clocks under load); the median repeat is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reference-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only.  cpu (the contract arm): the C port of the reference path on the host cores.  "
+                         "cuda (informational): the reference's own op chain as eager PyTorch + autograd on this GPU "
+                         "(oracle/torch_eager.py, bit-identical to the reference's fp32 run) -- what a blvm experiment runs today")
     ap.add_argument("--B", type=int, default=256, help="utterances per GPU")
     ap.add_argument("--T", type=int, default=16000, help="samples per utterance (config 5 sweep: 16000..128000)")
     ap.add_argument("--K", type=int, default=10, help="mixture components (config 5 sweep: 1/10/30)")
@@ -138,6 +142,51 @@ def run_reference_arm(a):
                 "its path (pinned against the reference's golden vectors) on all host threads",
     }
     print(json.dumps(line))
+
+
+def run_reference_eager_cuda(a):
+    """The reference's op chain (eager PyTorch kernels + autograd) on cuda:0, device-resident inputs, CUDA events."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from oracle import torch_eager as TE
+    dev = torch.device("cuda", 0)
+    y_np, raw_np, kl_np, x_sl_np = synth_numpy(a.B, a.T, a.K, 1234, a.ragged)
+    x_sl = torch.from_numpy(x_sl_np)
+    y = torch.from_numpy(y_np).to(dev)
+    raw = torch.from_numpy(raw_np).to(dev).requires_grad_(True)
+    kl = [torch.from_numpy(t).to(dev).requires_grad_(True) for t in kl_np]
+
+    def step():
+        raw.grad = None
+        for t in kl:
+            t.grad = None
+        loss, _, _, _ = TE.elbo_step(y, raw, x_sl, [(*kl, STRIDE, FREE_NATS)], BETA, a.K, NUM_BINS, torch.float32)
+        loss.backward()
+        return loss
+
+    steps, warmup = max(1, min(a.steps, 50)), max(3, min(a.warmup, 10))
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n = float(x_sl.sum())
+    print(json.dumps({
+        "impl": "reference", "reference_device": "cuda", "metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1), "loss": float(loss.detach()),
+        "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9, "gpu_launches": 0,
+        "note": "informational: the reference's op chain as eager PyTorch + autograd on the same B200 (oracle/torch_eager.py, "
+                "pinned bit-identical to the reference's fp32 run on CPU); float32 masks (CW-VAE/STCN/WaveNet style), the "
+                "range assert's host sync included like in the reference",
+    }))
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -450,7 +499,9 @@ def run_gpu_arm(a):
 
 def main():
     a = parse()
-    if a.impl == "reference":
+    if a.impl == "reference" and a.reference_device == "cuda":
+        run_reference_eager_cuda(a)
+    elif a.impl == "reference":
         run_reference_arm(a)
     else:
         run_gpu_arm(a)

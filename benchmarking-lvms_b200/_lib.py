@@ -28,6 +28,7 @@ SIGNATURES = {
     "blvm_dl_chunks": (_i64, [_i64]),
     "blvm_kl_chunks": (_i64, [_i64]),
     "blvm_dmol_has_fast_path": (_i32, [_i32, _i32]),
+    "blvm_set_stream_mode": (_i32, [_i32]),
     "blvm_dmol_fwd": (_i32, [_p, _p, _i32, _p, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p]),
     "blvm_dmol_fwd_grad": (_i32, [_p, _p, _i32, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _i32, _f32, _i32, _p, _p, _p, _p, _p]),
     "blvm_gmm_chunks": (_i64, [_i64, _i32, _i32]),

@@ -5,10 +5,12 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "host_common.h"
 
 #include "dmol_kernels.cuh"
+#include "dmol_stream_kernel.cuh"
 #include "kl_kernels.cuh"
 #include "misc_kernels.cuh"
 #include "sample_kernels.cuh"
@@ -43,10 +45,75 @@ int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
   return check_launch("dmol_tile_kernel");
 }
 
+// ---- persistent pipelined variant (dmol_stream_kernel.cuh) ------------------------------------------------------------
+#ifndef BLVM_STREAM_STAGES
+#define BLVM_STREAM_STAGES 2
+#define BLVM_STREAM_LOOKAHEAD 1
+#endif
+#ifndef BLVM_STREAM_TPB
+#define BLVM_STREAM_TPB 128
+#endif
+#ifndef BLVM_STREAM_MAX_K
+#define BLVM_STREAM_MAX_K 5      // K above this keeps the one-tile-per-CTA kernel (already at the HBM roofline)
+#endif
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// 0 = tile kernel only, 1 = stream kernel where eligible (default), read once (A/B runs set it before the first call)
+int g_stream_mode = -1;
+int stream_mode() {
+  if (g_stream_mode < 0) {
+    const char* e = getenv("BLVM_B200_STREAM");
+    g_stream_mode = e ? (atoi(e) != 0) : 1;
+  }
+  return g_stream_mode;
+}
+
+template <typename TP>
+bool stream_eligible(const DmolArgs& A, int K) {
+  const int64_t row_bytes = A.T * 3 * K * static_cast<int64_t>(sizeof(TP));
+  return A.T % 4 == 0 && row_bytes % 16 == 0 && aligned(A.raw, 16) && aligned(A.y, 16) && (!A.graw || aligned(A.graw, 16));
+}
+
+template <int K, bool GRAD, int UMODE, typename TP, int LIK = kLikDmol>
+int launch_stream(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
+  constexpr int TPB = (128 * DmolSpt<K>::value) % BLVM_STREAM_TPB == 0 ? BLVM_STREAM_TPB : 128;
+  constexpr int S = BLVM_STREAM_STAGES, LA = BLVM_STREAM_LOOKAHEAD;
+  constexpr size_t smem = StreamLayout<K, TPB, TP>::bytes(S);
+  auto kern = dmol_stream_kernel<K, TPB, S, LA, GRAD, UMODE, TP, LIK>;
+  static int resident = 0;  // CTAs per SM; per instantiation, benign race
+  if (resident == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem);
+    if (e != cudaSuccess || occ < 1) return fail(BLVM_ERR_CUDA, "occupancy query (smem=%zu): %s", smem, cudaGetErrorString(e));
+    resident = occ;
+  }
+  const int64_t slots = static_cast<int64_t>(sm_count()) * resident;
+  const unsigned grid = static_cast<unsigned>(tiles < slots ? tiles : slots);
+  kern<<<grid, TPB, smem, st>>>(A, tiles);
+  return check_launch("dmol_stream_kernel");
+}
+
 // u = h / s <= h * exp(-log_epsilon) for every element: if that bound is tiny (16-bit bins with the -7 clamp: 0.0167)
 // the kernel specialisation without the large-u code is exact to O(u^4) ~ 1e-7 (blvm_math.cuh).
 template <int K, bool GRAD, typename TP>
 int launch_tile_dtype(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
+  if constexpr (K <= BLVM_STREAM_MAX_K) {
+    if (stream_mode() && stream_eligible<TP>(A, K)) {
+      if (blvm_host::u_is_tiny(A.C)) return launch_stream<K, GRAD, kUTiny, TP>(A, tiles, st);
+      return launch_stream<K, GRAD, kUGeneral, TP>(A, tiles, st);
+    }
+  }
   if (blvm_host::u_is_tiny(A.C)) return launch_tile_mode<K, GRAD, kUTiny, TP>(A, tiles, st);
   return launch_tile_mode<K, GRAD, kUGeneral, TP>(A, tiles, st);
 }
@@ -197,6 +264,11 @@ int64_t blvm_dmol_chunks(int64_t T, int K, int D) {
   return (T + ts - 1) / ts;
 }
 int64_t blvm_dl_chunks(int64_t T) { return (T + kTile * kDlSpt - 1) / (kTile * kDlSpt); }
+int blvm_set_stream_mode(int mode) {
+  const int prev = stream_mode();
+  g_stream_mode = mode < 0 ? -1 : (mode != 0);
+  return prev;
+}
 int blvm_dmol_has_fast_path(int K, int D) { return dmol_has_register_kernel(K, D) ? 1 : 0; }
 int64_t blvm_kl_chunks(int64_t row_elems) { return (row_elems + kKlChunk - 1) / kKlChunk; }
 

@@ -62,6 +62,11 @@ int64_t blvm_dl_chunks(int64_t T);
 /* 1 if (K, D) has a register-resident TMA kernel (D == 1 and K in {1,2,3,4,5,6,8,10,12,16,20,30}); other shapes run the
  * generic fp32 kernel. */
 int blvm_dmol_has_fast_path(int K, int D);
+/* Kernel selection knob for A/B measurements and tests (process-wide, not thread-safe against concurrent launches):
+ * 1 = small-K shapes whose tile slabs are 16-byte aligned run the persistent pipelined kernel (dmol_stream_kernel),
+ * 0 = always one tile per CTA (dmol_tile_kernel), -1 = default (env BLVM_B200_STREAM, else 1).  Returns the previous
+ * mode.  Both kernels produce bit-identical outputs. */
+int blvm_set_stream_mode(int mode);
 int64_t blvm_kl_chunks(int64_t row_elems);
 
 /*
