@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--T", type=int, default=16000, help="samples per utterance (config 5 sweep: 16000..128000)")
     ap.add_argument("--K", type=int, default=10, help="mixture components (config 5 sweep: 1/10/30)")
     ap.add_argument("--ragged", action="store_true", help="x_sl ~ T*U(0.5,1) instead of full length")
+    ap.add_argument("--workload", default="config5", choices=sorted(WORKLOADS),
+                    help="config5 (default, the configuration the metric is quoted on; --B/--T/--K apply) or the likelihood/KL/ELBO "
+                         "tail of BASELINE configs 2-4 at their full shapes (informational: parity-test cases, not bench lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
@@ -61,19 +64,48 @@ def parse():
     return ap.parse_args()
 
 
+# latent levels = [(overall stride, width)]; free nats of level l scale with stride_l / stride_0 (clockwork_vae.py:151)
+WORKLOADS = {
+    "config5": dict(name="config5: standalone DMoL+KL ELBO", levels=[(STRIDE, ZDIM)]),
+    "config2": dict(name="config2: WaveNet tail (DMoL only)", B=32, T=16000, K=10, levels=[]),
+    "config3": dict(name="config3: SRNN tail", B=64, T=32000, K=10, levels=[(64, 64)]),
+    "config3z256": dict(name="config3: SRNN tail, z 256 (benchmarks.txt)", B=64, T=32000, K=10, levels=[(64, 256)]),
+    "config4": dict(name="config4: Clockwork-VAE 3-level tail", B=32, T=65536, K=10, levels=[(64, 128), (512, 64), (4096, 32)]),
+}
+
+
+def apply_workload(a):
+    w = WORKLOADS[a.workload]
+    for k in ("B", "T", "K"):
+        if k in w:
+            setattr(a, k, w[k])
+    a.levels = list(w["levels"])
+    return a
+
+
+def level_free_nats(a, l):
+    return FREE_NATS * a.levels[l][0] / a.levels[0][0]
+
+
 def workload_config(a, n_gpus):
-    return {
-        "workload": f"config5: standalone DMoL+KL ELBO, per GPU {a.B} utterances x {a.T} samples, DMoL K={a.K}, "
-                    f"num_bins={NUM_BINS}, 1 latent layer stride {STRIDE} width {ZDIM}, beta {BETA}, free_nats {FREE_NATS}",
+    lv = ", ".join(f"stride {s} width {z}" for s, z in a.levels) or "none"
+    kl_bytes = sum(32 * a.B * (a.T // s) * z for s, z in a.levels)
+    total = a.B * a.T * 4 * (2 + 6 * a.K) + kl_bytes
+    cfg = {
+        "workload": f"{WORKLOADS[a.workload]['name']}, per GPU {a.B} utterances x {a.T} samples, DMoL K={a.K}, "
+                    f"num_bins={NUM_BINS}, latent layers: {lv}, beta {BETA}, free_nats {FREE_NATS}",
         "utterances_per_gpu": a.B, "samples_per_utterance": a.T, "num_mix": a.K, "num_bins": NUM_BINS,
-        "latent_stride": STRIDE, "latent_width": ZDIM, "ragged": bool(a.ragged),
+        "latent_levels": [list(x) for x in a.levels], "ragged": bool(a.ragged),
         "global_samples_per_step": a.B * a.T * n_gpus, "parallelism": f"dp{n_gpus} (utterance sharding)",
-        "l2": "inputs+outputs ~%.2f GB per step per GPU, larger than the 126 MB L2 (no flush needed)"
-              % ((a.B * a.T * 4 * (2 + 6 * a.K) + 32 * a.B * (a.T // STRIDE) * ZDIM) / 1e9),
+        "l2": ("inputs+outputs ~%.2f GB per step per GPU, larger than the 126 MB L2 (no flush needed)" % (total / 1e9)) if total > 2.5e8
+              else ("inputs+outputs ~%.0f MB per step per GPU: NOT larger than L2, informational only" % (total / 1e6)),
     }
+    if a.workload == "config5":   # keys of the earlier rounds' lines
+        cfg.update(latent_stride=STRIDE, latent_width=ZDIM)
+    return cfg
 
 
-def synth_numpy(B, T, K, seed, ragged):
+def synth_numpy(B, T, K, seed, ragged, levels=((STRIDE, ZDIM),)):
     """Synthetic inputs: y on the rescaled 16-bit grid, raw ~ N(0,1) with locs near y and log-scales
     *2-4 (straddles the -7 clamp and the cdf_delta threshold), KL inputs mu ~ N(0,1), sd = softplus(N(0,1)) + 1e-6."""
     import numpy as np
@@ -82,14 +114,16 @@ def synth_numpy(B, T, K, seed, ragged):
     raw = rng.standard_normal((B, T, 3 * K), dtype=np.float32)
     raw[..., K:2 * K] = y[..., None] + 0.1 * raw[..., K:2 * K]
     raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
-    Tz = T // STRIDE
-    kl = [rng.standard_normal((B, Tz, ZDIM), dtype=np.float32) for _ in range(4)]
-    for i in (1, 3):
-        kl[i] = (np.log1p(np.exp(kl[i])) + 1e-6).astype(np.float32)
+    kls = []
+    for stride, zdim in levels:
+        kl = [rng.standard_normal((B, T // stride, zdim), dtype=np.float32) for _ in range(4)]
+        for i in (1, 3):
+            kl[i] = (np.log1p(np.exp(kl[i])) + 1e-6).astype(np.float32)
+        kls.append(kl)
     x_sl = np.full(B, T, np.int64)
     if ragged:
         x_sl = (T * rng.uniform(0.5, 1.0, B)).astype(np.int64)
-    return y, raw, kl, x_sl
+    return y, raw, kls, x_sl
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -101,16 +135,20 @@ def cpu_port_throughput(a, steps, warmup, target_step_s=1.5):
     cores = C.use_all_cores()
     # calibrate on a few utterances, then size the sample so that one step takes ~target_step_s
     rows0 = max(1, min(a.B, cores))
-    y, raw, kl, x_sl = synth_numpy(rows0, a.T, a.K, 99, a.ragged)
-    lv = [dict(mu_q=kl[0], sd_q=kl[1], mu_p=kl[2], sd_p=kl[3], stride=STRIDE, free_nats=FREE_NATS)]
+    def lvls(kls):
+        return [dict(mu_q=kl[0], sd_q=kl[1], mu_p=kl[2], sd_p=kl[3], stride=a.levels[l][0], free_nats=level_free_nats(a, l))
+                for l, kl in enumerate(kls)]
+
+    y, raw, kls, x_sl = synth_numpy(rows0, a.T, a.K, 99, a.ragged, a.levels)
+    lv = lvls(kls)
     C.elbo_step(y, raw, x_sl, lv, BETA, a.K, NUM_BINS)
     t0 = time.perf_counter()
     C.elbo_step(y, raw, x_sl, lv, BETA, a.K, NUM_BINS)
     per_row = (time.perf_counter() - t0) / rows0
     rows = int(max(rows0, min(a.B, target_step_s / max(per_row, 1e-9))))
     rows = max(cores, rows - rows % cores) if rows >= cores else rows
-    y, raw, kl, x_sl = synth_numpy(rows, a.T, a.K, 100, a.ragged)
-    lv = [dict(mu_q=kl[0], sd_q=kl[1], mu_p=kl[2], sd_p=kl[3], stride=STRIDE, free_nats=FREE_NATS)]
+    y, raw, kls, x_sl = synth_numpy(rows, a.T, a.K, 100, a.ragged, a.levels)
+    lv = lvls(kls)
     for _ in range(warmup):
         C.elbo_step(y, raw, x_sl, lv, BETA, a.K, NUM_BINS)
     ts = []
@@ -151,17 +189,19 @@ def run_reference_eager_cuda(a):
     import torch
     from oracle import torch_eager as TE
     dev = torch.device("cuda", 0)
-    y_np, raw_np, kl_np, x_sl_np = synth_numpy(a.B, a.T, a.K, 1234, a.ragged)
+    y_np, raw_np, kl_np, x_sl_np = synth_numpy(a.B, a.T, a.K, 1234, a.ragged, a.levels)
     x_sl = torch.from_numpy(x_sl_np)
     y = torch.from_numpy(y_np).to(dev)
     raw = torch.from_numpy(raw_np).to(dev).requires_grad_(True)
-    kl = [torch.from_numpy(t).to(dev).requires_grad_(True) for t in kl_np]
+    kls = [[torch.from_numpy(t).to(dev).requires_grad_(True) for t in kl] for kl in kl_np]
 
     def step():
         raw.grad = None
-        for t in kl:
-            t.grad = None
-        loss, _, _, _ = TE.elbo_step(y, raw, x_sl, [(*kl, STRIDE, FREE_NATS)], BETA, a.K, NUM_BINS, torch.float32)
+        for kl in kls:
+            for t in kl:
+                t.grad = None
+        lv = [(*kl, a.levels[l][0], level_free_nats(a, l)) for l, kl in enumerate(kls)]
+        loss, _, _, _ = TE.elbo_step(y, raw, x_sl, lv, BETA, a.K, NUM_BINS, torch.float32)
         loss.backward()
         return loss
 
@@ -261,21 +301,21 @@ def run_gpu_arm(a):
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     B, T, K = a.B, a.T, a.K
-    Tz = T // STRIDE
 
     # ---- synthetic inputs: pinned host copies (e2e arm) and device-resident copies (value arm) -----------------------
-    y_np, raw_np, kl_np, x_sl_np = synth_numpy(B, T, K, 1234 + rank, a.ragged)
+    y_np, raw_np, kl_np, x_sl_np = synth_numpy(B, T, K, 1234 + rank, a.ragged, a.levels)
     x_sl = torch.from_numpy(x_sl_np)
     host = dict(y=torch.from_numpy(y_np).pin_memory(), raw=torch.from_numpy(raw_np).pin_memory(),
-                kl=[torch.from_numpy(t).pin_memory() for t in kl_np])
+                kl=[[torch.from_numpy(t).pin_memory() for t in kl] for kl in kl_np])
     y_d = host["y"].to(dev)
     raw_d = host["raw"].to(dev).requires_grad_(True)
-    kl_d = [t.to(dev).requires_grad_(True) for t in host["kl"]]
+    kl_d = [[t.to(dev).requires_grad_(True) for t in kl] for kl in host["kl"]]
     n_valid = float(x_sl.sum())
     denom = n_valid  # per-rank normaliser; the global loss is recombined from the all-reduced sums
     params = blvm_b200.DMoLParams(raw_d, K, 1, -7.0)
     x_dev = x_sl.to(dev)            # `value` arm: every input, the lengths included, is resident in HBM
-    lens_dev = blvm_b200.level_lengths(x_dev, STRIDE)
+    lens_dev = [blvm_b200.level_lengths(x_dev, s) for s, _ in a.levels]
+    fnats = [level_free_nats(a, l) for l in range(len(a.levels))]
 
     pending = []
     ex, gsums = None, None
@@ -299,9 +339,11 @@ def run_gpu_arm(a):
     def compute_step():
         """One step of the path through the public API: forward (values + gradients) and backward."""
         raw_d.grad = None
-        for t in kl_d:
-            t.grad = None
-        out = blvm_b200.fused_elbo(y_d, params, x_sl, [blvm_b200.KLLevel(*kl_d, lens=lens_dev)], BETA, FREE_NATS,
+        for kl in kl_d:
+            for t in kl:
+                t.grad = None
+        levels = [blvm_b200.KLLevel(*kl, lens=lens_dev[l], free_nats=fnats[l]) for l, kl in enumerate(kl_d)]
+        out = blvm_b200.fused_elbo(y_d, params, x_sl, levels, BETA, FREE_NATS,
                                    num_bins=NUM_BINS, denom=denom, x_sl_device=x_dev, exchange=ex)
         out.loss.backward()
         # with `exchange=ex` the finalize kernel itself publishes this step's sums to every rank over NVLink peer memory
@@ -381,7 +423,7 @@ def run_gpu_arm(a):
             pending.pop().wait()
         e1.record()
         sync_all()
-        launches = ops.launch_count() if mode == "eager" else 4 * a.steps
+        launches = ops.launch_count() if mode == "eager" else (2 + len(a.levels)) * a.steps
         region_ms.append(e0.elapsed_time(e1))
         done = torch.tensor([1.0 if (time.perf_counter() - t_begin >= a.min_seconds or len(region_ms) >= 200) else 0.0], device=dev)
         if world > 1:
@@ -415,14 +457,15 @@ def run_gpu_arm(a):
     # ---- e2e: the public API from pinned host buffers, H2D + D2H inside the timed region -----------------------------
     e2e = None
     if not a.no_e2e:
-        h2d = sum(t.numel() * t.element_size() for t in [host["y"], host["raw"], *host["kl"]]) + x_sl.numel() * 8
+        h2d = sum(t.numel() * t.element_size() for t in [host["y"], host["raw"], *[t for kl in host["kl"] for t in kl]]) + x_sl.numel() * 8
         d2h = 8 * 8 + 4 * B * 8
 
         def step_e2e():
             y = host["y"].to(dev, non_blocking=True)
             raw = host["raw"].to(dev, non_blocking=True).requires_grad_(True)
-            kl = [t.to(dev, non_blocking=True).requires_grad_(True) for t in host["kl"]]
-            out = blvm_b200.fused_elbo(y, blvm_b200.DMoLParams(raw, K, 1, -7.0), x_sl, [blvm_b200.KLLevel(*kl, stride=STRIDE)],
+            kls = [[t.to(dev, non_blocking=True).requires_grad_(True) for t in kl] for kl in host["kl"]]
+            levels = [blvm_b200.KLLevel(*kl, stride=a.levels[l][0], free_nats=fnats[l]) for l, kl in enumerate(kls)]
+            out = blvm_b200.fused_elbo(y, blvm_b200.DMoLParams(raw, K, 1, -7.0), x_sl, levels,
                                        BETA, FREE_NATS, num_bins=NUM_BINS, denom=denom)
             out.loss.backward()
             sums = out.sums
@@ -483,7 +526,7 @@ def run_gpu_arm(a):
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "mode": mode, "exchange": exchange_kind,
             "timed_region_repeats": len(region_ms), "timed_region_ms_min_max": [min(region_ms), max(region_ms)],
-            "step": "fused_elbo(...).loss.backward() through the Python API" + (" (4 kernels, replayed from CUDA graphs)" if mode == "graph" else "")
+            "step": "fused_elbo(...).loss.backward() through the Python API" + (f" ({2 + len(a.levels)} kernels: likelihood, KL per level, finalize; replayed from CUDA graphs)" if mode == "graph" else "")
                     + (("; sums exchange: " + exchange_kind) if world > 1 else ""),
         }
         if not a.no_cpu_baseline and n_gpus == 1:
@@ -498,7 +541,7 @@ def run_gpu_arm(a):
 
 
 def main():
-    a = parse()
+    a = apply_workload(parse())
     if a.impl == "reference" and a.reference_device == "cuda":
         run_reference_eager_cuda(a)
     elif a.impl == "reference":

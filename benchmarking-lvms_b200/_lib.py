@@ -37,8 +37,8 @@ SIGNATURES = {
     "blvm_dl_fwd_grad": (_i32, [_p, _p, _p, _p, _f32, _i64, _i64, _i32, _f32, _i32, _p, _p, _p, _p, _p]),
     "blvm_kl_gaussian_fwd": (_i32, [_p, _p, _p, _p, _i64, _p, _p]),
     "blvm_kl_gaussian_bwd": (_i32, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
-    "blvm_kl_elbo_fwd_grad": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "blvm_kl_reduce_fwd_grad": (_i32, [_p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _p]),
+    "blvm_kl_elbo_fwd_grad": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
+    "blvm_kl_reduce_fwd_grad": (_i32, [_p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _i32, _p]),
     "blvm_elbo_finalize": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64, _f64, _f64, _p, _p, _p, _p]),
     "blvm_elbo_finalize_publish": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64,
                                           _f64, _f64, _p, _p, _p, ctypes.POINTER(_p), _i32, _i32, _p, _p, _p, _p]),
@@ -58,6 +58,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 BLVM_DTYPE_F32, BLVM_DTYPE_F16, BLVM_DTYPE_BF16 = 0, 1, 2
 BLVM_FLAG_MASK_OUTPUT = 1
 BLVM_FLAG_SKIP_PADDED = 2
+BLVM_FLAG_OVERLAP_PREV = 4
 BLVM_MAX_KL_LEVELS = 8
 
 

@@ -57,6 +57,32 @@ int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
 #define BLVM_STREAM_MAX_K 5      // K above this keeps the one-tile-per-CTA kernel (already at the HBM roofline)
 #endif
 
+// Launch with (pdl = true) or without the programmatic-stream-serialization attribute (ptx_sm100.cuh: pdl_*).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// 1 (default) = KL / finalize launches use programmatic dependent launch where the caller allows it; env BLVM_B200_PDL=0 disables
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("BLVM_B200_PDL");
+    on = e ? (atoi(e) != 0) : 1;
+  }
+  return on != 0;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -361,15 +387,16 @@ static bool kl_vec_ok(const KlArgs& A, bool grad) {
   return vec;
 }
 
-static int launch_kl(KlArgs& A, bool grad, cudaStream_t st) {
+static int launch_kl(KlArgs& A, bool grad, cudaStream_t st, bool overlap_prev = false) {
   A.chunks = blvm_kl_chunks(A.row_elems);
   const int64_t tiles = A.B * A.chunks;
   if (tiles == 0) return BLVM_OK;
   if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
   A.vec = kl_vec_ok(A, grad) ? 1 : 0;
   const unsigned g = static_cast<unsigned>(tiles);
-  if (grad) kl_kernel<true><<<g, kKlTPB, 0, st>>>(A);
-  else kl_kernel<false><<<g, kKlTPB, 0, st>>>(A);
+  const bool pdl = overlap_prev && pdl_enabled();
+  const cudaError_t e = grad ? launch_ex(kl_kernel<true>, g, kKlTPB, 0, st, pdl, A) : launch_ex(kl_kernel<false>, g, kKlTPB, 0, st, pdl, A);
+  if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "kl_kernel: %s", cudaGetErrorString(e));
   return check_launch("kl_kernel");
 }
 
@@ -395,7 +422,7 @@ int blvm_kl_gaussian_bwd(const float* mu_q, const float* sd_q, const float* mu_p
 
 int blvm_kl_elbo_fwd_grad(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p, const int64_t* lens,
                           int64_t B, int64_t Tz, int64_t Z, double free_nats, float gscale, float* kl, float* g_mu_q,
-                          float* g_sd_q, float* g_mu_p, float* g_sd_p, double* part_kl, double* part_klfn,
+                          float* g_sd_q, float* g_mu_p, float* g_sd_p, double* part_kl, double* part_klfn, int flags,
                           blvm_stream_t stream) {
   if (B < 0 || Tz < 0 || Z < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad shape B=%lld Tz=%lld Z=%lld", (long long)B, (long long)Tz, (long long)Z);
   if (B * Tz > 0 && (!mu_q || !sd_q || !mu_p || !sd_p)) return fail(BLVM_ERR_INVALID_ARGUMENT, "null input");
@@ -408,11 +435,11 @@ int blvm_kl_elbo_fwd_grad(const float* mu_q, const float* sd_q, const float* mu_
   A.min_kl = static_cast<float>(free_nats / static_cast<double>(Z));  // python float / int, then torch.tensor(..., fp32)
   A.kl = kl; A.g_mu_q = g_mu_q; A.g_sd_q = g_sd_q; A.g_mu_p = g_mu_p; A.g_sd_p = g_sd_p;
   A.part_kl = part_kl; A.part_klfn = part_klfn; A.B = B; A.row_elems = Tz * Z; A.Z = Z;
-  return launch_kl(A, grad, static_cast<cudaStream_t>(stream));
+  return launch_kl(A, grad, static_cast<cudaStream_t>(stream), (flags & BLVM_FLAG_OVERLAP_PREV) != 0);
 }
 
 int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int64_t Tz, int64_t Z, double free_nats,
-                            float gscale, float* gkl, double* part_kl, double* part_klfn, blvm_stream_t stream) {
+                            float gscale, float* gkl, double* part_kl, double* part_klfn, int flags, blvm_stream_t stream) {
   if (B < 0 || Tz < 0 || Z < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad shape");
   if (B * Tz > 0 && !kl) return fail(BLVM_ERR_INVALID_ARGUMENT, "null kl");
   if (!part_kl || !part_klfn) return fail(BLVM_ERR_INVALID_ARGUMENT, "null partials");
@@ -424,7 +451,9 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
   const int64_t tiles = B * A.chunks;
   if (tiles == 0) return BLVM_OK;
   if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
-  kl_kernel<false><<<static_cast<unsigned>(tiles), kKlTPB, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  const bool pdl = (flags & BLVM_FLAG_OVERLAP_PREV) != 0 && pdl_enabled();
+  const cudaError_t e = launch_ex(kl_kernel<false>, static_cast<unsigned>(tiles), kKlTPB, 0, static_cast<cudaStream_t>(stream), pdl, A);
+  if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "kl_kernel (materialised KL): %s", cudaGetErrorString(e));
   return check_launch("kl_kernel (materialised KL)");
 }
 
@@ -442,7 +471,10 @@ static int finalize_impl(const double* logp_part, int64_t logp_chunks, const dou
     A.kl_part[l] = kl_part_host[l]; A.klfn_part[l] = klfn_part_host[l]; A.kl_chunks[l] = kl_chunks_host[l];
   }
   const unsigned blocks = static_cast<unsigned>(B > 0 ? (B + kFinWarps - 1) / kFinWarps : 1);
-  elbo_finalize_kernel<<<blocks, kFinTPB, 0, static_cast<cudaStream_t>(stream)>>>(A, sync_counter, X);
+  // always a programmatic dependent: the kernel waits for its predecessor before its first read, so this is safe after
+  // any kernel, and after a blvm kernel (which releases its dependents early) the CTAs are already resident when it ends
+  const cudaError_t e = launch_ex(elbo_finalize_kernel, blocks, kFinTPB, 0, static_cast<cudaStream_t>(stream), pdl_enabled(), A, sync_counter, X);
+  if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "elbo_finalize_kernel: %s", cudaGetErrorString(e));
   return check_launch("elbo_finalize_kernel");
 }
 
@@ -538,8 +570,9 @@ int blvm_scale_inplace_multi(void* const* bufs_host, const int64_t* ns_host, con
     if (A.dtype[i] < 0 || A.dtype[i] > 2) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad dtype for buffer %d", i);
     nmax = ns_host[i] > nmax ? ns_host[i] : nmax;
   }
-  const int64_t want = (nmax + 1023) / 1024;
-  dim3 grid(static_cast<unsigned>(want < 148 * 4 ? (want > 0 ? want : 1) : 148 * 4), static_cast<unsigned>(count));
+  const int64_t want = (nmax + 1023) / 1024;   // a CTA iteration covers 256 threads x 4 elements
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  const unsigned grid = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
   scale_inplace_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   return check_launch("scale_inplace_multi_kernel");
 }

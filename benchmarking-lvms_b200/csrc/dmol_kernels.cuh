@@ -285,6 +285,7 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
 template <int K, int TPB, bool GRAD, int UMODE, typename TP, int LIK = kLikDmol>
 __global__ void __launch_bounds__(TPB, DmolMinBlocks<K>::value) dmol_tile_kernel(const DmolArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
+  ptx::pdl_launch_dependents();   // a KL / finalize launch of the same step may fill this grid's tail (they wait for us to finish)
   const bool pending = dmol_tile_body<K, TPB, GRAD, UMODE, TP, LIK>(A, blockIdx.x, smem);
   if (pending && threadIdx.x == 0) ptx::bulk_wait_read0();  // smem must outlive the bulk store's read
 }
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(TPB, DmolMinBlocks<K>::value) dmol_tile_kernel
 template <int TPB, bool GRAD>
 __global__ void __launch_bounds__(TPB) dmol_generic_kernel(const DmolArgs A) {
   __shared__ double scratch[TPB / 32];
+  ptx::pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int64_t tile_id = blockIdx.x;
   const int64_t b = tile_id / A.chunks;
@@ -344,6 +346,7 @@ constexpr int kDlSpt = 8;
 template <int TPB, bool GRAD>
 __global__ void __launch_bounds__(TPB) dl_kernel(const DmolArgs A) {
   __shared__ double scratch[TPB / 32];
+  ptx::pdl_launch_dependents();
   constexpr int TILE = TPB * kDlSpt;
   const int tid = threadIdx.x;
   const int64_t tile_id = blockIdx.x;

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(TPB) dmol_stream_kernel(const DmolArgs A, cons
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t first = blockIdx.x, stride = gridDim.x;
+  ptx::pdl_launch_dependents();   // persistent grid: every CTA is resident, dependents may queue behind it right away
   if (first >= n_tiles) return;
   const int64_t count = (n_tiles - first + stride - 1) / stride;   // tiles of this CTA
   const uint64_t pol = ptx::policy_evict_first();

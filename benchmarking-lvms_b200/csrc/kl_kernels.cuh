@@ -139,7 +139,12 @@ __device__ __forceinline__ void kl_tile_body(const KlArgs& A, const int64_t tile
 template <bool GRAD>
 __global__ void __launch_bounds__(kKlTPB) kl_kernel(const KlArgs A) {
   __shared__ double scratch[2 * (kKlTPB / 32)];
+  ptx::pdl_launch_dependents();
   kl_tile_body<kKlTPB, GRAD>(A, blockIdx.x, scratch);
+  // Launched with BLVM_FLAG_OVERLAP_PREV this grid runs next to the DMoL (or previous KL level's) grid of the same step,
+  // none of whose outputs it reads.  Waiting for that grid HERE, before any CTA of this one retires, makes completion
+  // transitive: when this grid is complete so is everything before it, which is what the finalize kernel's own wait relies on.
+  ptx::pdl_wait();
 }
 
 // ---- finalize: per-tile partials -> per-utterance sums -> loss / ELBO / bits-per-dim --------------------------------
@@ -241,23 +246,48 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// lanes stride over the chunks of one utterance (coalesced), fixed-order butterfly: deterministic
-__device__ __forceinline__ double warp_row_sum(const double* __restrict__ p, int64_t n, int lane) {
+// Lane-partial sum of one utterance's chunk partials, lanes strided over the chunks (coalesced).  The first SLOTS loads are
+// issued unconditionally up front (predicated, no dependent add in between) so that the loads of ALL arrays of the
+// utterance are in flight together: the kernel is a chain of L2 latencies, not of bytes.  Fixed order: deterministic.
+template <int SLOTS>
+__device__ __forceinline__ void lane_first_loads(const double* __restrict__ p, int64_t n, int lane, double (&v)[SLOTS]) {
+#pragma unroll
+  for (int u = 0; u < SLOTS; ++u) {
+    const int64_t c = lane + 32 * u;
+    v[u] = (p != nullptr && c < n) ? __ldcg(p + c) : 0.0;   // written by other CTAs: read through L2
+  }
+}
+template <int SLOTS>
+__device__ __forceinline__ double lane_finish(const double* __restrict__ p, int64_t n, int lane, const double (&v)[SLOTS]) {
   double s = 0.0;
-  for (int64_t c = lane; c < n; c += 32) s += __ldcg(p + c);   // written by other CTAs: read through L2
-  return warp_sum_f64(s);
+#pragma unroll
+  for (int u = 0; u < SLOTS; ++u) s += v[u];
+  if (p != nullptr)
+    for (int64_t c = lane + 32 * SLOTS; c < n; c += 32) s += __ldcg(p + c);
+  return s;
 }
 
 // Reduce the per-tile partials of utterance b (called by ONE warp; lane 0 writes the row entries).
 __device__ __forceinline__ void finalize_row(const FinalizeArgs& A, int64_t b, int lane) {
-  const double logp = A.logp_part ? warp_row_sum(A.logp_part + b * A.logp_chunks, A.logp_chunks, lane) : 0.0;
+  double v_logp[4], v_kl[kMaxLevels][1], v_fn[kMaxLevels][1];
+  lane_first_loads<4>(A.logp_part ? A.logp_part + b * A.logp_chunks : nullptr, A.logp_chunks, lane, v_logp);
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) {
+    const bool on = l < A.n_levels;
+    lane_first_loads<1>(on ? A.kl_part[l] + b * A.kl_chunks[l] : nullptr, on ? A.kl_chunks[l] : 0, lane, v_kl[l]);
+    lane_first_loads<1>(on ? A.klfn_part[l] + b * A.kl_chunks[l] : nullptr, on ? A.kl_chunks[l] : 0, lane, v_fn[l]);
+  }
+  const double logp = warp_sum_f64(lane_finish<4>(A.logp_part ? A.logp_part + b * A.logp_chunks : nullptr, A.logp_chunks, lane, v_logp));
   double kl = 0.0, fn = 0.0;
-  for (int l = 0; l < A.n_levels; ++l) {
-    const double kl_l = warp_row_sum(A.kl_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane);
-    const double fn_l = warp_row_sum(A.klfn_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane);
-    if (lane == 0) A.rows[(4 + l) * A.B + b] = kl_l;
-    kl += kl_l;   // sum over levels (clockwork_vae.py:155, stcn.py:290)
-    fn += fn_l;
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) {
+    if (l < A.n_levels) {
+      const double kl_l = warp_sum_f64(lane_finish<1>(A.kl_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane, v_kl[l]));
+      const double fn_l = warp_sum_f64(lane_finish<1>(A.klfn_part[l] + b * A.kl_chunks[l], A.kl_chunks[l], lane, v_fn[l]));
+      if (lane == 0) A.rows[(4 + l) * A.B + b] = kl_l;
+      kl += kl_l;   // sum over levels (clockwork_vae.py:155, stcn.py:290)
+      fn += fn_l;
+    }
   }
   if (lane == 0) {
     A.rows[0 * A.B + b] = logp;
@@ -283,12 +313,23 @@ __device__ __forceinline__ void finalize_scalars(const FinalizeArgs& A, const Ex
     t_nan_logp += (logp == logp) ? logp : 0.0;           // nansum (wavenet.py:145)
     t_len += static_cast<double>(A.x_sl[r]);
   }
-  const double s_logp = block_sum_f64<NW>(t_logp, scratch + 0 * NW);
-  const double s_kl = block_sum_f64<NW>(t_kl, scratch + 1 * NW);
-  const double s_fn = block_sum_f64<NW>(t_fn, scratch + 2 * NW);
-  const double s_obj = block_sum_f64<NW>(t_obj, scratch + 3 * NW);
-  const double s_nan = block_sum_f64<NW>(t_nan_logp, scratch + 4 * NW);
-  const double s_len = block_sum_f64<NW>(t_len, scratch + 5 * NW);
+  // six sums, one barrier: warp butterflies (independent chains), one shared-memory hop, thread 0 adds the warps in order
+  double t6[6] = {t_logp, t_kl, t_fn, t_obj, t_nan_logp, t_len};
+#pragma unroll
+  for (int q = 0; q < 6; ++q) t6[q] = warp_sum_f64(t6[q]);
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) scratch[q * NW + (tid >> 5)] = t6[q];
+  }
+  __syncthreads();
+  double s6[6] = {0, 0, 0, 0, 0, 0};
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s6[q] += scratch[q * NW + w];
+  }
+  const double s_logp = s6[0], s_kl = s6[1], s_fn = s6[2], s_obj = s6[3], s_nan = s6[4], s_len = s6[5];
   if (tid == 0) {
     const double dn = A.denom > 0.0 ? A.denom : s_len;
     A.scalars[0] = -s_obj / dn;                          // loss (vrnn.py:277), consistent with the gradients' 1/denom
@@ -336,6 +377,7 @@ static __global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const Fin
   __shared__ bool is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = static_cast<int64_t>(blockIdx.x) * kFinWarps + warp;
+  ptx::pdl_wait();   // launched as a programmatic dependent: the CTAs are resident before the partial sums are final
   if (b < A.B) finalize_row(A, b, lane);
   __threadfence();
   __syncthreads();

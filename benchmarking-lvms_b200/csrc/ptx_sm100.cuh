@@ -57,6 +57,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // wait until the smem source of all committed bulk stores has been read (safe to reuse / exit)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization attribute
+// may start once every CTA of its predecessor has executed launch_dependents (or exited); it must execute wait before
+// it touches anything the predecessor produces (wait returns when the predecessor grid has completed and flushed).
+// Both are no-ops when the launch carries no programmatic dependency.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // streaming global accesses that do not pollute L1
 __device__ __forceinline__ float ldg_stream(const float* p) {
   float v;

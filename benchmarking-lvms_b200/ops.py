@@ -378,6 +378,35 @@ class ELBOSpec:
     exchange: object = None        # distributed.SumsExchange: publish the sums to all ranks from the finalize kernel
 
 
+_unit_grads = {}
+
+
+def _unit_grad(device: torch.device) -> torch.Tensor:
+    """A persistent fp64 scalar 1.0 per device: the implicit gradient of `loss.backward()`."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    t = _unit_grads.get(key)
+    if t is None:
+        t = torch.ones((), dtype=torch.float64, device=device)
+        _unit_grads[key] = t
+    return t
+
+
+class FusedLoss(torch.Tensor):
+    """The scalar loss returned by the fused ELBO op.  An ordinary tensor in every respect except that a plain
+    `loss.backward()` hands autograd a persistent device-resident 1.0 as the root gradient (instead of letting it
+    allocate and fill a fresh `ones_like`), which `_FusedELBO.backward` recognises: the gradients written by the forward
+    pass are already d loss / d input, so neither the fill kernel nor the rescale launch runs.  Any other use
+    (`scaler.scale(loss).backward()`, `(loss + reg).backward()`, an explicit `gradient=`) goes through the generic
+    device-side rescale.  Results of arithmetic on it are plain tensors."""
+
+    __torch_function__ = torch._C._disabled_torch_function_impl
+
+    def backward(self, gradient=None, retain_graph=None, create_graph=False, inputs=None):
+        if gradient is None and self.is_cuda and self.dtype == torch.float64 and self.dim() == 0:
+            gradient = _unit_grad(self.device)
+        return torch.Tensor.backward(self, gradient, retain_graph, create_graph, inputs)
+
+
 class _FusedELBO(torch.autograd.Function):
     """inputs: spec, y (B,T[,D]), x_sl_dev (B) int64, raw (B,T,P), then the KL tensors of every level, flattened.
     outputs: loss () fp64 [differentiable], scalars (8) fp64, rows (4+L, B) fp64, log_prob_twise (B,T) or empty.
@@ -459,7 +488,10 @@ class _FusedELBO(torch.autograd.Function):
             kl_ptrs, klfn_ptrs, kl_chunks = [], [], []
             i = 0
             gscale = spec.beta / spec.denom
-            for lv, (Tz, Z, chunks) in zip(spec.levels, shapes):
+            for li, (lv, (Tz, Z, chunks)) in enumerate(zip(spec.levels, shapes)):
+                # the launch just before this one is this step's likelihood / previous KL level, which produces none of
+                # this level's inputs: the KL grid may fill that grid's tail (programmatic dependent launch)
+                kflags = _lib.BLVM_FLAG_OVERLAP_PREV if (has_lik or li > 0) else 0
                 ts = kl_tensors[i:i + lv.n_tensors]
                 i += lv.n_tensors
                 pk = base + 8 * off
@@ -469,13 +501,13 @@ class _FusedELBO(torch.autograd.Function):
                     g4 = [torch.empty_like(ts[0]) for _ in range(4)] if spec.need_grad else [None] * 4
                     rc = lib.blvm_kl_elbo_fwd_grad(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
                                                    _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale, None,
-                                                   _ptr(g4[0]), _ptr(g4[1]), _ptr(g4[2]), _ptr(g4[3]), pk, pf, stream)
+                                                   _ptr(g4[0]), _ptr(g4[1]), _ptr(g4[2]), _ptr(g4[3]), pk, pf, kflags, stream)
                     check(rc, "blvm_kl_elbo_fwd_grad")
                     grads += g4
                 else:
                     gk = torch.empty_like(ts[0]) if spec.need_grad else None
                     rc = lib.blvm_kl_reduce_fwd_grad(ts[0].data_ptr(), _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale,
-                                                     _ptr(gk), pk, pf, stream)
+                                                     _ptr(gk), pk, pf, kflags, stream)
                     check(rc, "blvm_kl_reduce_fwd_grad")
                     grads.append(gk)
                 _count()
@@ -520,6 +552,9 @@ class _FusedELBO(torch.autograd.Function):
         g = g_loss if (g_loss.dtype == torch.float64 and g_loss.is_contiguous()) else g_loss.to(torch.float64).contiguous()
         grads = list(ctx.grads)
         bufs = [b for b in grads if b is not None]
+        unit = _unit_grads.get(g.device.index)
+        if unit is not None and g.data_ptr() == unit.data_ptr():
+            bufs = []                  # FusedLoss.backward(): the root gradient is the constant 1, nothing to rescale
         if bufs:
             n = len(bufs)
             with _on_device(g.device):
@@ -540,7 +575,8 @@ class _FusedELBO(torch.autograd.Function):
 
 
 def fused_elbo_apply(spec: ELBOSpec, y, x_sl_dev, raw, kl_tensors: Sequence[torch.Tensor]):
-    return _FusedELBO.apply(spec, y, x_sl_dev, raw, *kl_tensors)
+    loss, scalars, rows, twise = _FusedELBO.apply(spec, y, x_sl_dev, raw, *kl_tensors)
+    return loss.as_subclass(FusedLoss), scalars, rows, twise
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -37,6 +37,11 @@ enum {
 enum {
   BLVM_FLAG_MASK_OUTPUT = 1, /* per-sample log-prob output is multiplied by the sequence mask (vrnn.py:268) */
   BLVM_FLAG_SKIP_PADDED = 2, /* tiles entirely inside the padding are not read; their outputs are exact zeros */
+  BLVM_FLAG_OVERLAP_PREV = 4, /* KL launches only.  The caller guarantees that the kernel launched IMMEDIATELY BEFORE on this
+                                 stream is a blvm DMoL / DL / GMM / KL launch of the same step and produces none of this
+                                 call's inputs: this launch may then start while that kernel is still draining
+                                 (programmatic dependent launch) and does not complete before it has.  Ordering with respect
+                                 to everything earlier on the stream is unchanged. */
 };
 
 /* element type of the likelihood parameters `raw` (and of their gradient): the AMP Linear output can be consumed as is */
@@ -148,15 +153,16 @@ int blvm_kl_gaussian_bwd(const float* mu_q, const float* sd_q, const float* mu_p
  *   g_*         (B, Tz, Z) nullable together: d(gscale * sum_masked max(kl, free_nats/Z)) / d inputs,
  *               torch.maximum's 1/2-1/2 rule at exact ties
  *   part_kl, part_klfn (B, blvm_kl_chunks(Tz*Z)) fp64: masked per-tile sums of kl and of max(kl, free_nats/Z)
+ *   flags       0 or BLVM_FLAG_OVERLAP_PREV
  */
 int blvm_kl_elbo_fwd_grad(const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p,
                           const int64_t* lens, int64_t B, int64_t Tz, int64_t Z, double free_nats, float gscale,
                           float* kl, float* g_mu_q, float* g_sd_q, float* g_mu_p, float* g_sd_p, double* part_kl,
-                          double* part_klfn, blvm_stream_t stream);
+                          double* part_klfn, int flags, blvm_stream_t stream);
 
 /* Same reduction when the caller already holds the elementwise KL (compute_elbo's `kld_twise` argument). gkl nullable. */
 int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int64_t Tz, int64_t Z, double free_nats,
-                            float gscale, float* gkl, double* part_kl, double* part_klfn, blvm_stream_t stream);
+                            float gscale, float* gkl, double* part_kl, double* part_klfn, int flags, blvm_stream_t stream);
 
 /*
  * Partials -> per-utterance log p(x|z), KL, free-nats KL, ELBO -> loss and bits-per-dim.

@@ -689,7 +689,7 @@ def test_no_out_of_bounds_writes(T, K, B):
     pf = arena2[off:off + 2 * Bn * kc].view(torch.float64)
     lens = torch.tensor([Tz, 5, 0], device=dev)
     rc = lib.blvm_kl_elbo_fwd_grad(*[t.data_ptr() for t in ins], lens.data_ptr(), Bn, Tz, Z, 0.5, 1e-3, None,
-                                   *[o.data_ptr() for o in outs], pk.data_ptr(), pf.data_ptr(), ops._stream())
+                                   *[o.data_ptr() for o in outs], pk.data_ptr(), pf.data_ptr(), 0, ops._stream())
     assert rc == 0
     torch.cuda.synchronize()
     guard_mask = torch.ones_like(arena2, dtype=torch.bool)
@@ -820,3 +820,76 @@ def test_stream_kernel_bit_identical_to_tile_kernel(K, dtype, Bn, T, B):
     # sanity against the oracle on one utterance (the stream path itself is what the golden tests exercise for K <= 5)
     lp = res[(1, 1, False)][0]
     assert torch.isfinite(lp).all() and (lp[-1, 5:] == 0).all() and (res[(1, 1, False)][1][-1, 5:] == 0).all()
+
+
+def test_plain_backward_skips_fill_and_rescale(B):
+    """`loss.backward()` on the fused op's loss hands autograd a persistent device-side 1.0: no rescale launch; a real
+    upstream factor (GradScaler-style) still goes through the device-side rescale and gives factor x the same grads."""
+    from blvm_b200 import ops
+    g = load_golden("elbo_srnn_a")
+    K, nb = int(g["K"]), int(g["num_bins"])
+
+    def run(factor):
+        raw = cu(g["raw"]).requires_grad_(True)
+        kl = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+        out = B.fused_elbo(cu(g["y"]), B.DMoLParams(raw, K, 1, -7.0), torch.tensor(g["x_sl"]), [B.KLLevel(*kl, stride=int(g["stride"]))],
+                           float(g["beta"]), float(g["free_nats"]), num_bins=nb)
+        assert type(out.loss).__name__ == "FusedLoss" and type(out.loss * 2) is torch.Tensor
+        ops.reset_launch_count()
+        if factor is None:
+            out.loss.backward()
+        else:
+            (out.loss * factor).backward()
+        n = ops.launch_count()
+        return n, raw.grad.clone(), [t.grad.clone() for t in kl], float(out.loss.detach())
+
+    n0, graw0, gkl0, loss0 = run(None)
+    n1, graw1, gkl1, _ = run(1.0)
+    n2, graw2, gkl2, _ = run(1024.0)
+    assert n0 == 0 and n1 == 1 and n2 == 1            # launches of OUR kernels inside backward
+    assert torch.equal(graw0, graw1) and all(torch.equal(a, b) for a, b in zip(gkl0, gkl1))
+    assert torch.equal(graw0 * 1024.0, graw2) and all(torch.equal(a * 1024.0, b) for a, b in zip(gkl0, gkl2))   # power of two: exact
+    np.testing.assert_allclose(loss0, float(g["loss64"]), rtol=1e-6)
+    scale = np.abs(g["graw64"]).max()
+    np.testing.assert_allclose(graw0.cpu().numpy(), g["graw64"], rtol=1e-4, atol=1e-6 * scale)
+
+
+def test_overlapped_launches_are_race_free(B, O):
+    """The KL levels are launched as programmatic dependents of the likelihood kernel (they start while it drains and the
+    finalize kernel waits for all of them): 40 repetitions of a 3-level step whose DMoL grid spans several waves must be
+    bit-identical, and equal to the oracle."""
+    gen = torch.Generator().manual_seed(77)
+    Bn, T, K, nb = 24, 24576, 10, 65536
+    strides, Zs = (64, 512, 4096), (32, 16, 8)
+    y = (torch.randint(0, nb, (Bn, T), generator=gen).float() / (nb - 1) * 2 - 1)
+    raw = torch.randn(Bn, T, 3 * K, generator=gen)
+    raw[..., K:2 * K] = y.unsqueeze(-1) + 0.1 * raw[..., K:2 * K]
+    raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+    x_sl = torch.randint(T // 2, T + 1, (Bn,), generator=gen)
+    kls = []
+    for s, Z in zip(strides, Zs):
+        t = [torch.randn(Bn, T // s, Z, generator=gen) for _ in range(4)]
+        t[1], t[3] = torch.nn.functional.softplus(t[1]) + 1e-3, torch.nn.functional.softplus(t[3]) + 1e-3
+        kls.append(t)
+    yd, rawd = y.cuda(), raw.cuda().requires_grad_(True)
+    klsd = [[t.cuda().requires_grad_(True) for t in kl] for kl in kls]
+    first = None
+    for it in range(40):
+        rawd.grad = None
+        for kl in klsd:
+            for t in kl:
+                t.grad = None
+        out = B.fused_elbo(yd, B.DMoLParams(rawd, K, 1, -7.0), x_sl, [B.KLLevel(*kl, stride=s, free_nats=0.25 * s / strides[0])
+                                                                      for kl, s in zip(klsd, strides)], 0.7, 0.25, num_bins=nb)
+        out.loss.backward()
+        cur = [out.sums.clone(), out.log_prob.clone(), out.kl.clone(), out.kl_fn.clone(), rawd.grad.clone()] + [t.grad.clone() for kl in klsd for t in kl]
+        if first is None:
+            first = cur
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(first, cur)), f"repetition {it} differs from the first"
+    ref = O.fused_elbo_value_and_grad(y[:4].numpy(), raw[:4].numpy(), x_sl[:4].numpy(),
+                                      [dict(mu_q=kl[0][:4].numpy(), sd_q=kl[1][:4].numpy(), mu_p=kl[2][:4].numpy(), sd_p=kl[3][:4].numpy(),
+                                            stride=s, free_nats=0.25 * s / strides[0]) for kl, s in zip(kls, strides)], 0.7, K, nb)
+    assert_sums_close(first[1][:4].cpu().numpy(), ref["logp"], "log p rows")
+    assert_sums_close(first[2][:4].cpu().numpy(), ref["kl"], "KL rows")
+    assert_sums_close(first[3][:4].cpu().numpy(), ref["kl_fn"], "free-nats KL rows")
