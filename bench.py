@@ -542,6 +542,12 @@ def run_gpu_arm(a):
 
 def main():
     a = apply_workload(parse())
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 on their own (NCCL prints its version banner
+    # there) are pointed at stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if a.impl == "reference" and a.reference_device == "cuda":
         run_reference_eager_cuda(a)
     elif a.impl == "reference":
