@@ -13,23 +13,28 @@ from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "benchmarking-lvms_b200")
 VAR_DIR = os.path.join(PKG, "lib", "variants")
-# tag: (stages, lookahead, tpb)
-VARIANTS = {"s3l1": (3, 1, 128), "s2l1": (2, 1, 128), "s4l2": (4, 2, 128), "s3l2": (3, 2, 128), "s3l1t256": (3, 1, 256), "s4l2t256": (4, 2, 256)}
+# tag: (stages, lookahead, tpb[, samples per thread for K <= 2, for K <= 5])
+VARIANTS = {"s3l1": (3, 1, 128), "s2l1": (2, 1, 128), "s4l2": (4, 2, 128), "s3l2": (3, 2, 128), "s3l1t256": (3, 1, 256), "s4l2t256": (4, 2, 256),
+            "s2l1_spt84": (2, 1, 128, 8, 4), "s2l1_spt42": (2, 1, 128, 4, 2), "s2l1_spt44": (2, 1, 128, 4, 4), "s2l1_spt82": (2, 1, 128, 8, 2),
+            "s3l1_spt42": (3, 1, 128, 4, 2), "s2l1_spt21": (2, 1, 128, 2, 1)}
 
 
 def build():
     os.makedirs(VAR_DIR, exist_ok=True)
 
     def one(tag):
-        s, la, tpb = VARIANTS[tag]
+        s, la, tpb = VARIANTS[tag][:3]
+        spt = VARIANTS[tag][3:]
         out = os.path.join(VAR_DIR, f"libblvm_b200_{tag}.so")
         cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
                f"-DBLVM_STREAM_STAGES={s}", f"-DBLVM_STREAM_LOOKAHEAD={la}", f"-DBLVM_STREAM_TPB={tpb}", "-DBLVM_STREAM_MAX_K=10",
+               *([f"-DBLVM_SPT_2={spt[0]}", f"-DBLVM_SPT_5={spt[1]}", "-DBLVM_SPT_8=2", "-DBLVM_SPT_12=1"] if spt else []),
                "-o", out, os.path.join(PKG, "csrc", "blvm_b200.cu")]
         subprocess.run(cmd, check=True)
         return out
 
-    tags = [t for t in VARIANTS if not os.path.exists(os.path.join(VAR_DIR, f"libblvm_b200_{t}.so")) or "--force" in sys.argv]
+    want = [t for t in sys.argv[2:] if t in VARIANTS] or list(VARIANTS)
+    tags = [t for t in want if not os.path.exists(os.path.join(VAR_DIR, f"libblvm_b200_{t}.so")) or "--force" in sys.argv]
     with ThreadPoolExecutor(max_workers=6) as pool:
         for o in pool.map(one, tags):
             print("built", o)
@@ -80,6 +85,7 @@ def run(Ks, Ts, tags):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", choices=["build", "run"])
+    ap.add_argument("build_tags", nargs="*")
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--Ks", type=int, nargs="+", default=[1, 2, 5, 10])
     ap.add_argument("--Ts", type=int, nargs="+", default=[16000, 64000])
