@@ -65,6 +65,9 @@ def main():
         byt = N * (8 + 3 * K * esz)
         print(f"K={K:2d} {dtn:8s} dmol fwd only: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
               f"{byt / med / 1e6:7.0f} GB/s algorithmic")
+        med, best = timeit(lambda: ops.dmol_sample_mode(raw, K, 1, -7.0))
+        print(f"K={K:2d} {dtn:8s} sample+mode  : {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
+              f"{N * (3 * K * esz + 12) / med / 1e6:7.0f} GB/s if every parameter byte were read")
         del raw, graw
     # single discretized logistic (DiscretizedLogisticDense): packed (B, T, 2)
     y = torch.randint(0, nb, (B, T), device=dev).float() / (nb - 1) * 2 - 1
