@@ -182,6 +182,20 @@ bool dmol_has_register_kernel(int K, int D) {
   }
 }
 
+template <int K, typename TP>
+int launch_sample_tile(const SampleArgs& A, int64_t tiles, cudaStream_t st) {
+  constexpr size_t smem = ((size_t(kTile) * DmolSpt<K>::value * 3 * K * sizeof(TP) + 15) / 16) * 16 + 16;
+  auto kern = dmol_sample_mode_tile_kernel<K, TP>;
+  static bool configured = false;
+  if (!configured) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
+  return check_launch("dmol_sample_mode_tile_kernel");
+}
+
 template <bool GRAD>
 int dispatch_dmol(const DmolArgs& A, int raw_dtype, cudaStream_t st) {
   const int64_t tiles = A.B * A.chunks;
@@ -531,13 +545,33 @@ int blvm_dmol_sample_mode(const void* raw, int raw_dtype, int64_t N, int K, int 
   if (N < 0 || K < 1 || D < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad shape N=%lld K=%d D=%d", (long long)N, K, D);
   if (N > 0 && !raw) return fail(BLVM_ERR_INVALID_ARGUMENT, "null raw");
   if (N == 0) return BLVM_OK;
-  const int64_t blocks = (N + 255) / 256;
-  if (blocks > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many samples");
   SampleArgs A{};
   A.raw = raw; A.N = N; A.K = K; A.D = D; A.log_eps = log_epsilon; A.seed = seed; A.offset = offset;
   A.sample = sample; A.mode = mode; A.mode_index = mode_index;
-  const unsigned g = static_cast<unsigned>(blocks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // register-kernel shapes whose slabs are 16-byte aligned: TMA-staged tiles; both kernels draw identical samples
+  const int64_t esz = raw_dtype == BLVM_DTYPE_F32 ? 4 : 2;
+  if (D == 1 && dmol_has_register_kernel(K, D) && aligned(raw, 16) && (N * 3 * K * esz) % 16 == 0) {
+    const int64_t tile = dmol_tile_samples(K, D);
+    const int64_t tiles = (N + tile - 1) / tile;
+    if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many samples");
+    switch (K) {
+#define BLVM_CASE(KK)                                                                                              \
+  case KK:                                                                                                         \
+    switch (raw_dtype) {                                                                                           \
+      case BLVM_DTYPE_F32: return launch_sample_tile<KK, float>(A, tiles, st);                                     \
+      case BLVM_DTYPE_F16: return launch_sample_tile<KK, __half>(A, tiles, st);                                    \
+      case BLVM_DTYPE_BF16: return launch_sample_tile<KK, __nv_bfloat16>(A, tiles, st);                            \
+      default: return fail(BLVM_ERR_INVALID_ARGUMENT, "raw_dtype=%d", raw_dtype);                                  \
+    }
+      BLVM_FOR_EACH_K(BLVM_CASE)
+#undef BLVM_CASE
+      default: break;
+    }
+  }
+  const int64_t blocks = (N + 255) / 256;
+  if (blocks > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many samples");
+  const unsigned g = static_cast<unsigned>(blocks);
   switch (raw_dtype) {
     case BLVM_DTYPE_F32: dmol_sample_mode_kernel<float><<<g, 256, 0, st>>>(A); break;
     case BLVM_DTYPE_F16: dmol_sample_mode_kernel<__half><<<g, 256, 0, st>>>(A); break;

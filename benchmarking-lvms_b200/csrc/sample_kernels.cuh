@@ -1,11 +1,20 @@
 // Fused sample() + mode() of the discretized logistic mixture: one read of the packed parameters
-// produces the Gumbel-max mixture sample and the mode, instead of the reference's ~12 eager kernels
-//   rsample_discretized_logistic_mixture  blvm/utils/variational.py:309-349  (uniform -> gumbel -> argmax -> gather ->
-//                                          logistic inverse CDF -> clamp)
+// produces the mixture sample and the mode, instead of the reference's ~12 eager kernels
+//   rsample_discretized_logistic_mixture  blvm/utils/variational.py:309-349  (mixture indicator -> gather -> logistic
+//                                          inverse CDF -> clamp)
 //   DiscretizedLogisticMixtureDense.mode   blvm/modules/distributions.py:363-368 (argmax of the logits -> gather loc)
-// Random numbers: Philox4x32-10 keyed by (seed), counter = (sample index, draw block, offset): reproducible for a given
-// seed/offset and independent of the launch geometry.  The stream differs from torch's generator, so parity with the
-// reference is distributional (tests/test_gpu_parity.py: component frequencies, CDF, clamp, mode exactness).
+// The reference draws the indicator by Gumbel-max (K uniforms, 2K logs per sample); the same categorical distribution
+// softmax(logits) is drawn here by inverse CDF from ONE uniform (K exps, a running sum), so a sample costs one
+// Philox4x32-10 call instead of four at K = 10 — the kernel was issue-bound on the generator.
+// Random numbers: Philox4x32-10 keyed by (seed), counter = (sample index, dimension block, offset): reproducible for a
+// given seed/offset, independent of the launch geometry and of which of the two kernels below runs.  The stream differs
+// from torch's generator, so parity with the reference is distributional (tests/test_gpu_parity.py: component
+// frequencies, CDF, clamp, mode exactness).
+//
+// dmol_sample_mode_tile_kernel<K, TP>: register-kernel shapes with 16-byte aligned slabs — the tile's parameter slab comes
+// in with one TMA bulk copy like in dmol_tile_kernel (every byte of the rows is fetched from HBM anyway: the logits and
+// the gathered components touch almost every 32-byte sector), threads read logits and the two gathered components from
+// shared memory.  dmol_sample_mode_kernel<TP>: any K, D, alignment, straight from global memory.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -13,6 +22,8 @@
 #include <stdint.h>
 
 #include "blvm_math.cuh"
+#include "dmol_kernels.cuh"
+#include "ptx_sm100.cuh"
 
 namespace blvm {
 
@@ -56,51 +67,135 @@ struct SampleArgs {
   int32_t* mode_index;  // (N) nullable: argmax of the logits (for the backward of mode())
 };
 
+struct SampleRng {
+  uint32_t k0, k1, c0, c1, o0;
+  __device__ __forceinline__ SampleRng(const SampleArgs& A, int64_t n)
+      : k0(static_cast<uint32_t>(A.seed)), k1(static_cast<uint32_t>(A.seed >> 32)), c0(static_cast<uint32_t>(n)),
+        c1(static_cast<uint32_t>(static_cast<uint64_t>(n) >> 32)), o0(static_cast<uint32_t>(A.offset)) {}
+  __device__ __forceinline__ Philox4 block(uint32_t i) const { return philox4x32_10(c0, c1, i, o0, k0, k1); }
+};
+
+// Categorical draw by inverse CDF over softmax(logits) + first-max argmax.  `get(k)` returns logit k as float.  Two
+// evaluation orders must not differ between the kernels: max first, then e_k = ex2((l_k - max) log2 e) summed in index order.
+template <typename Get>
+__device__ __forceinline__ void pick_components(int K, float u, Get get, int& pick, int& best_m) {
+  float vm = -INFINITY;
+  best_m = 0;
+  for (int k = 0; k < K; ++k) {
+    const float l = get(k);
+    if (l > vm) { vm = l; best_m = k; }
+  }
+  float total = 0.f;
+  for (int k = 0; k < K; ++k) total += fast_ex2((get(k) - vm) * kLog2e);
+  const float t = u * total;          // u in [0, 1): t < total, so some prefix sum exceeds it (up to rounding: last component)
+  float cum = 0.f;
+  pick = K - 1;
+  bool found = false;
+  for (int k = 0; k < K; ++k) {
+    cum += fast_ex2((get(k) - vm) * kLog2e);
+    if (!found && cum > t) { pick = k; found = true; }
+  }
+}
+
+// logistic inverse CDF on the chosen component, u ~ U(1e-8, 1 - 1e-8), clamp to [-1, 1]  (variational.py:282-306)
+__device__ __forceinline__ float logistic_sample(float loc, float ls, float log_eps, uint32_t bits) {
+  ls = (ls < log_eps) ? log_eps : ls;
+  const float u = u01_to(bits, 1e-8f, 1.0f - 1e-8f);
+  const float x = loc + __expf(ls) * (__logf(u) - __logf(1.0f - u));
+  return fminf(fmaxf(x, -1.0f), 1.0f);
+}
+
+// word j of the per-sample random stream: word 0 draws the mixture indicator, word 1 + d the logistic of dimension d
+__device__ __forceinline__ uint32_t rng_word(const SampleRng& R, const Philox4& first, int j) {
+  if (j < 4) return j == 0 ? first.x : (j == 1 ? first.y : (j == 2 ? first.z : first.w));
+  const Philox4 b = R.block(static_cast<uint32_t>(j >> 2));
+  const int r = j & 3;
+  return r == 0 ? b.x : (r == 1 ? b.y : (r == 2 ? b.z : b.w));
+}
+
 template <typename TP>
 __global__ void __launch_bounds__(256) dmol_sample_mode_kernel(const SampleArgs A) {
   const int64_t n = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (n >= A.N) return;
   const int K = A.K, D = A.D, P = K * (2 * D + 1);
   const TP* p = static_cast<const TP*>(A.raw) + n * P;
-  // mixture indicator: Gumbel-max with u ~ U(1e-5, 1 - 1e-5)  (variational.py:338-339); mode: plain argmax (first max)
-  int best_g = 0, best_m = 0;
-  float vg = -INFINITY, vm = -INFINITY;
-  const uint32_t k0 = static_cast<uint32_t>(A.seed), k1 = static_cast<uint32_t>(A.seed >> 32);
-  const uint32_t c0 = static_cast<uint32_t>(n), c1 = static_cast<uint32_t>(static_cast<uint64_t>(n) >> 32);
-  const uint32_t o0 = static_cast<uint32_t>(A.offset);
-  for (int kb = 0; kb < K; kb += 4) {
-    const Philox4 rnd = philox4x32_10(c0, c1, static_cast<uint32_t>(kb >> 2), o0, k0, k1);
-    const uint32_t bits[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = kb + j;
-      if (k < K) {
-        const float logit = param_to_float<TP>(p[k]);
-        const float u = u01_to(bits[j], 1e-5f, 1.0f - 1e-5f);
-        const float gumbel = -__logf(-__logf(u));
-        const float s = logit + gumbel;
-        if (s > vg) { vg = s; best_g = k; }
-        if (logit > vm) { vm = logit; best_m = k; }
-      }
-    }
-  }
+  const SampleRng R(A, n);
+  const Philox4 first = R.block(0);
+  int pick, best_m;
+  pick_components(K, static_cast<float>(first.x >> 8) * (1.0f / 16777216.0f), [&](int k) { return param_to_float<TP>(p[k]); }, pick, best_m);
   if (A.mode_index) A.mode_index[n] = best_m;
-  // logistic inverse CDF on the chosen component, u ~ U(1e-8, 1 - 1e-8), clamp to [-1, 1]  (variational.py:282-306)
-  const Philox4 rnd = philox4x32_10(c0, c1, 0x40000000u, o0, k0, k1);
-  const uint32_t bits[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
   for (int d = 0; d < D; ++d) {
     const TP* pd = p + K + d * 2 * K;
     if (A.mode) A.mode[n * D + d] = param_to_float<TP>(pd[best_m]);
-    if (A.sample) {
-      const float loc = param_to_float<TP>(pd[best_g]);
-      float ls = param_to_float<TP>(pd[K + best_g]);
-      ls = (ls < A.log_eps) ? A.log_eps : ls;
-      uint32_t b = bits[d & 3];
-      if (d >= 4) b = philox4x32_10(c0, c1, 0x40000000u + static_cast<uint32_t>(d >> 2), o0, k0, k1).x;
-      const float u = u01_to(b, 1e-8f, 1.0f - 1e-8f);
-      const float x = loc + __expf(ls) * (__logf(u) - __logf(1.0f - u));
-      A.sample[n * D + d] = fminf(fmaxf(x, -1.0f), 1.0f);
+    if (A.sample)
+      A.sample[n * D + d] = logistic_sample(param_to_float<TP>(pd[pick]), param_to_float<TP>(pd[K + pick]), A.log_eps, rng_word(R, first, 1 + d));
+  }
+}
+
+// D == 1, compile-time K: one tile of 128 * DmolSpt<K> samples per CTA, slab staged by TMA (see the header comment).
+template <int K, typename TP>
+__global__ void __launch_bounds__(128) dmol_sample_mode_tile_kernel(const SampleArgs A) {
+  constexpr int P = 3 * K, TPB = 128, SPT = DmolSpt<K>::value, TILE = TPB * SPT;
+  constexpr size_t kTileBytes = ((size_t(TILE) * P * sizeof(TP) + 15) / 16) * 16;
+  extern __shared__ __align__(128) unsigned char smem[];
+  TP* tile = reinterpret_cast<TP*>(smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kTileBytes);
+  const int tid = threadIdx.x;
+  const int64_t s0 = static_cast<int64_t>(blockIdx.x) * TILE;
+  const int n = static_cast<int>(min(static_cast<int64_t>(TILE), A.N - s0));
+  if (tid == 0) {
+    const uint32_t bytes = static_cast<uint32_t>(n) * P * sizeof(TP);   // 16-byte multiple: checked on the host
+    ptx::mbar_init(bar, 1);
+    ptx::fence_mbar_init();
+    ptx::mbar_arrive_expect_tx(bar, bytes);
+    ptx::bulk_g2s(tile, static_cast<const TP*>(A.raw) + s0 * P, bytes, bar, ptx::policy_evict_first());
+  }
+  __syncthreads();
+  ptx::mbar_wait(bar, 0);
+#pragma unroll
+  for (int j = 0; j < SPT; ++j) {
+    const int i = j * TPB + tid;
+    if (i >= n) break;
+    const int64_t s = s0 + i;
+    const TP* row = tile + i * P;
+    float logit[K];
+    if constexpr (sizeof(TP) == 4 && K % 2 == 0) {   // 64-bit shared loads: conflict-free for odd 3K/2 (dmol_kernels.cuh)
+#pragma unroll
+      for (int k = 0; k < K / 2; ++k) {
+        const float2 v = reinterpret_cast<const float2*>(row)[k];
+        logit[2 * k] = v.x;
+        logit[2 * k + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) logit[k] = param_to_float<TP>(row[k]);
     }
+    const SampleRng R(A, s);
+    const Philox4 first = R.block(0);
+    // same arithmetic, same order as pick_components (results must not depend on which kernel runs)
+    float vm = -INFINITY;
+    int best_m = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (logit[k] > vm) { vm = logit[k]; best_m = k; }
+    float e[K], total = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      e[k] = fast_ex2((logit[k] - vm) * kLog2e);
+      total += e[k];
+    }
+    const float t = (static_cast<float>(first.x >> 8) * (1.0f / 16777216.0f)) * total;
+    float cum = 0.f;
+    int pick = K - 1;
+    bool found = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      cum += e[k];
+      if (!found && cum > t) { pick = k; found = true; }
+    }
+    if (A.mode_index) A.mode_index[s] = best_m;
+    if (A.mode) A.mode[s] = param_to_float<TP>(row[K + best_m]);
+    if (A.sample) A.sample[s] = logistic_sample(param_to_float<TP>(row[K + pick]), param_to_float<TP>(row[2 * K + pick]), A.log_eps, first.y);
   }
 }
 

@@ -893,3 +893,48 @@ def test_overlapped_launches_are_race_free(B, O):
     assert_sums_close(first[1][:4].cpu().numpy(), ref["logp"], "log p rows")
     assert_sums_close(first[2][:4].cpu().numpy(), ref["kl"], "KL rows")
     assert_sums_close(first[3][:4].cpu().numpy(), ref["kl_fn"], "free-nats KL rows")
+
+
+@pytest.mark.parametrize("K", [1, 4, 5, 10, 30])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_sample_mode_tile_kernel_matches_direct_kernel(K, dtype, B):
+    """The TMA-staged sample/mode kernel (aligned slabs) and the direct kernel (here forced by a 4-byte-offset view) draw
+    the SAME samples for a given (seed, offset), and the categorical draw follows softmax(logits) when the logits vary
+    per sample."""
+    from blvm_b200 import ops
+    lib = B._lib.lib
+    gen = torch.Generator().manual_seed(900 + K)
+    N = 128 * 64 + 48                                   # 16-byte multiple of bytes for every K; last tile is partial
+    raw = torch.randn(N, 3 * K, generator=gen)
+    raw[:, K:2 * K] = torch.linspace(-0.8, 0.8, K) if K > 1 else 0.0   # well separated components (>= 60 scales apart)
+    raw[:, 2 * K:] = -8.0                                              # clamped to -7 inside: scale 9e-4
+    raw = raw.to(dtype).cuda()
+    esz = raw.element_size()
+    buf = torch.empty(raw.numel() + 16 // esz, dtype=dtype, device="cuda")
+    off = 4 // esz if esz == 4 else 2                   # 4-byte offset: not 16-byte aligned -> direct kernel
+    shifted = buf[off:off + raw.numel()].view(N, 3 * K)
+    shifted.copy_(raw)
+    assert raw.data_ptr() % 16 == 0 and shifted.data_ptr() % 16 != 0
+    outs = []
+    for t in (raw, shifted):
+        smp = torch.empty(N, 1, device="cuda")
+        mode = torch.empty(N, 1, device="cuda")
+        idx = torch.empty(N, dtype=torch.int32, device="cuda")
+        rc = lib.blvm_dmol_sample_mode(t.data_ptr(), ops._DTYPE_CODE[dtype], N, K, 1, -7.0, 1234567, 42, smp.data_ptr(), mode.data_ptr(),
+                                       idx.data_ptr(), ops._stream())
+        assert rc == 0
+        torch.cuda.synchronize()
+        outs.append((smp, mode, idx))
+    for a, b, name in zip(outs[0], outs[1], ("sample", "mode", "mode index")):
+        assert torch.equal(a, b), f"{name}: tile kernel and direct kernel disagree"
+    logits = raw[:, :K].float()
+    assert torch.equal(torch.gather(logits, 1, outs[0][2].long().unsqueeze(1))[:, 0], logits.max(-1).values)   # an argmax (ties: bf16)
+    assert torch.equal(outs[0][1][:, 0], torch.gather(raw[:, K:2 * K].float(), 1, outs[0][2].long().unsqueeze(1))[:, 0])
+    assert float(outs[0][0].abs().max()) <= 1.0
+    if K >= 4:
+        # chosen component ~ softmax(logits): the mean log-probability of the drawn components matches its expectation
+        comp = (outs[0][0] - raw[:, K:2 * K].float()).abs().argmin(-1)
+        lsm = torch.log_softmax(logits.double(), -1)
+        got = torch.gather(lsm, 1, comp.unsqueeze(1)).mean().item()
+        want = (lsm.exp() * lsm).sum(-1).mean().item()
+        assert abs(got - want) < 0.05, (got, want)      # N = 8240 draws: the standard error is ~0.015
