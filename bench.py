@@ -43,10 +43,11 @@ def parse():
                     help="the K-step timed region is repeated back to back until this much time has passed (so that "
                          "nvidia-smi can observe clocks under load); the median repeat is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reference-device", default="cpu", choices=["cpu", "cuda"],
+    ap.add_argument("--reference-device", default="cpu", choices=["cpu", "cpu-torch", "cuda"],
                     help="--impl reference only.  cpu (the contract arm): the C port of the reference path on the host cores.  "
-                         "cuda (informational): the reference's own op chain as eager PyTorch + autograd on this GPU "
-                         "(oracle/torch_eager.py, bit-identical to the reference's fp32 run) -- what a blvm experiment runs today")
+                         "cuda / cpu-torch (informational): the reference's own op chain as eager PyTorch + autograd on this GPU / on "
+                         "the host threads (oracle/torch_eager.py, bit-identical to the reference's fp32 run) -- what a blvm "
+                         "experiment runs today")
     ap.add_argument("--B", type=int, default=256, help="utterances per GPU")
     ap.add_argument("--T", type=int, default=16000, help="samples per utterance (config 5 sweep: 16000..128000)")
     ap.add_argument("--K", type=int, default=10, help="mixture components (config 5 sweep: 1/10/30)")
@@ -182,14 +183,19 @@ def run_reference_arm(a):
     print(json.dumps(line))
 
 
-def run_reference_eager_cuda(a):
-    """The reference's op chain (eager PyTorch kernels + autograd) on cuda:0, device-resident inputs, CUDA events."""
+def run_reference_eager_torch(a, on_cuda):
+    """The reference's op chain (eager PyTorch kernels + autograd) on cuda:0 (device-resident inputs, CUDA events) or on the
+    host threads (a bounded sample of the utterances, wall clock)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch
     from oracle import torch_eager as TE
-    dev = torch.device("cuda", 0)
-    y_np, raw_np, kl_np, x_sl_np = synth_numpy(a.B, a.T, a.K, 1234, a.ragged, a.levels)
+    dev = torch.device("cuda", 0) if on_cuda else torch.device("cpu")
+    rows = a.B
+    if not on_cuda:
+        torch.set_num_threads(os.cpu_count() or 1)
+        rows = max(1, min(a.B, int(16 * 16000 * 10 / (a.T * max(a.K, 1)))))     # ~0.5-1 s per step on 16 cores
+    y_np, raw_np, kl_np, x_sl_np = synth_numpy(rows, a.T, a.K, 1234, a.ragged, a.levels)
     x_sl = torch.from_numpy(x_sl_np)
     y = torch.from_numpy(y_np).to(dev)
     raw = torch.from_numpy(raw_np).to(dev).requires_grad_(True)
@@ -205,27 +211,42 @@ def run_reference_eager_cuda(a):
         loss.backward()
         return loss
 
-    steps, warmup = max(1, min(a.steps, 50)), max(3, min(a.warmup, 10))
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    torch.cuda.reset_peak_memory_stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
     n = float(x_sl.sum())
+    if on_cuda:
+        steps, warmup = max(1, min(a.steps, 50)), max(3, min(a.warmup, 10))
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        extra = {"peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9}
+        where = "on the same B200"
+    else:
+        steps, warmup = max(1, min(a.steps, 10)), max(1, min(a.warmup, 2))
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = step()
+        ms = (time.perf_counter() - t0) / steps * 1e3
+        extra = {"cpu_baseline": {"value": n / (ms * 1e-3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                  "sample": f"{rows} of {a.B} utterances x {a.T} samples (same generator), fp32, eager PyTorch ops + autograd "
+                                            f"(oracle/torch_eager.py), {steps} timed steps after {warmup} warm-up"}}
+        where = f"on {torch.get_num_threads()} host threads"
     print(json.dumps({
-        "impl": "reference", "reference_device": "cuda", "metric": METRIC, "value": n / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
-        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1), "loss": float(loss.detach()),
-        "peak_memory_gb": torch.cuda.max_memory_allocated() / 1e9, "gpu_launches": 0,
-        "note": "informational: the reference's op chain as eager PyTorch + autograd on the same B200 (oracle/torch_eager.py, "
-                "pinned bit-identical to the reference's fp32 run on CPU); float32 masks (CW-VAE/STCN/WaveNet style), the "
-                "range assert's host sync included like in the reference",
+        "impl": "reference", "reference_device": "cuda" if on_cuda else "cpu-torch", "metric": METRIC, "value": n / (ms * 1e-3),
+        "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, 1), "loss": float(loss.detach()),
+        "gpu_launches": 0, **extra,
+        "note": f"informational: the reference's op chain as eager PyTorch + autograd {where} (oracle/torch_eager.py, pinned "
+                "bit-identical to the reference's fp32 run on CPU); float32 masks (CW-VAE/STCN/WaveNet style), the range "
+                "assert's host sync included like in the reference",
     }))
 
 
@@ -548,8 +569,8 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_stdout, "w")
-    if a.impl == "reference" and a.reference_device == "cuda":
-        run_reference_eager_cuda(a)
+    if a.impl == "reference" and a.reference_device != "cpu":
+        run_reference_eager_torch(a, a.reference_device == "cuda")
     elif a.impl == "reference":
         run_reference_arm(a)
     else:
