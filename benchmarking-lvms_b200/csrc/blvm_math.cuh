@@ -216,6 +216,105 @@ BLVM_HD void dl_mid(float y, float mu, float raw_ls, const DmolConsts& C, float&
   }
 }
 
+// ---- two components per instruction: packed fp32x2 arithmetic (sm_100a FFMA2) -------------------------------------------
+// Blackwell's FMA pipe executes fma/mul/add on a PAIR of fp32 values held in an aligned register pair in one instruction
+// (PTX fma.rn.f32x2 -> SASS FFMA2).  The kernels are bound by issue slots, not by FMA-pipe lanes (ncu: issue-active 72 %,
+// fma pipe 35 %), so evaluating components k and k+1 of a sample together removes about a fifth of all instructions; the
+// MUFU evaluations, compares and selects stay scalar.  Each lane of a packed op rounds exactly like the scalar op, so the
+// host build below (plain fmaf / * / +) computes the same values.
+#ifndef BLVM_PACKED_FP32
+#define BLVM_PACKED_FP32 1
+#endif
+struct F2 {
+  float x, y;
+};
+BLVM_HD F2 f2(float a, float b) { return F2{a, b}; }
+BLVM_HD F2 f2(float a) { return F2{a, a}; }
+#if defined(__CUDA_ARCH__) && BLVM_PACKED_FP32
+__device__ __forceinline__ unsigned long long f2_pack(F2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ F2 f2_unpack(unsigned long long v) {
+  F2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(r);
+}
+#else
+BLVM_HD F2 fma2(F2 a, F2 b, F2 c) { return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+BLVM_HD F2 mul2(F2 a, F2 b) { return F2{a.x * b.x, a.y * b.y}; }
+BLVM_HD F2 add2(F2 a, F2 b) { return F2{a.x + b.x, a.y + b.y}; }
+#endif
+BLVM_HD F2 abs2(F2 a) { return F2{fabsf(a.x), fabsf(a.y)}; }
+BLVM_HD F2 ex2_2(F2 a) { return F2{fast_ex2(a.x), fast_ex2(a.y)}; }
+BLVM_HD F2 lg2_2(F2 a) { return F2{fast_lg2(a.x), fast_lg2(a.y)}; }
+BLVM_HD F2 rcp_2(F2 a) { return F2{fast_rcp(a.x), fast_rcp(a.y)}; }
+
+// dl_mid<GRAD, kUTiny> for components k and k+1 of one sample (same formulas, same order of operations per lane; negations
+// are folded into constants because packed operands carry no sign modifiers).
+template <bool GRAD>
+BLVM_HD void dl_mid_pair_tiny(float y, F2 mu, F2 raw_ls, const DmolConsts& C, F2& lp, F2& dmu, F2& dls) {
+  const bool below_x = raw_ls.x < C.log_eps, below_y = raw_ls.y < C.log_eps;
+  const F2 ls = f2(below_x ? C.log_eps : raw_ls.x, below_y ? C.log_eps : raw_ls.y);   // clamp(min): NaN propagates like torch
+  // inv = exp(-ls), compensated (accurate_exp): -ls log2(e) = p_hi + p_lo, exp = 2^p_hi (1 + ln2 p_lo)
+  constexpr float kLog2eLo = 1.925963033500011e-08f;
+  const F2 p_hi = mul2(ls, f2(-kLog2e));
+  const F2 p_lo = fma2(ls, f2(-kLog2eLo), fma2(ls, f2(-kLog2e), mul2(p_hi, f2(-1.f))));
+  const F2 e0 = ex2_2(p_hi);
+#if BLVM_COMPENSATED_EXP
+  const F2 inv = fma2(e0, mul2(p_lo, f2(kLn2)), e0);
+#else
+  const F2 inv = e0;
+#endif
+  const F2 m = mul2(inv, fma2(mu, f2(-1.f), f2(y)));              // mid_in                     :202,219
+  const F2 u = mul2(inv, f2(C.h));
+  const F2 am = abs2(m);
+  const F2 E = ex2_2(mul2(am, f2(-kLog2e)));
+  const F2 p1 = add2(E, f2(1.f));
+  const F2 r = rcp_2(p1);
+  const F2 common = fma2(lg2_2(p1), f2(-2.f * kLn2), fma2(am, f2(-1.f), mul2(ls, f2(-1.f))));   // m - ls - 2 softplus(m)  :220
+  const F2 lp_fb = add2(common, f2(-C.log_half_bins));            // second arm of :221-223
+  F2 th = f2(0.f);
+  if (GRAD) {
+    const F2 hx = mul2(am, f2(0.5f)), hx2 = mul2(hx, hx);
+    const F2 th_series = mul2(hx, fma2(hx2, fma2(hx2, f2(2.0f / 15.0f), f2(-1.0f / 3.0f)), f2(1.0f)));
+    const F2 th_exact = mul2(fma2(E, f2(-1.f), f2(1.f)), r);      // (1 - E) / (1 + E) = tanh(|m| / 2)
+    th = f2(am.x < 0.25f ? th_series.x : th_exact.x, am.y < 0.25f ? th_series.y : th_exact.y);
+  }
+  const F2 u2 = mul2(u, u);
+  const F2 ner2 = mul2(mul2(E, r), mul2(r, f2(-1.f)));            // -E / (1+E)^2
+  const F2 neps = mul2(ner2, u2);                                 // -E w / (1+E)^2,  w = u^2 + O(u^4)
+  const F2 lp_d = add2(common, add2(fma2(u2, f2(1.0f / 6.0f), f2(C.log_two_h)), neps));   // log cdf_delta, first arm of :221-223
+  const bool big_x = lp_d.x > C.log_delta_thresh, big_y = lp_d.y > C.log_delta_thresh;   // cdf_delta > 1e-5
+  lp = f2(big_x ? lp_d.x : lp_fb.x, big_y ? lp_d.y : lp_fb.y);
+  if (GRAD) {
+    const F2 th_d = fma2(neps, th, th);                           // th / (1 + eps)
+    const F2 udu = fma2(u2, fma2(ner2, f2(2.0f), f2(1.0f / 3.0f)), f2(1.0f));            // u coth(u) - u cdf_delta
+    const F2 th_sel = f2(big_x ? th_d.x : th.x, big_y ? th_d.y : th.y);
+    const F2 it = mul2(inv, th_sel);
+    dmu = f2(copysignf(it.x, m.x), copysignf(it.y, m.y));         // -inv * d lp/d m
+    dls = fma2(am, th_sel, f2(big_x ? -udu.x : -1.0f, big_y ? -udu.y : -1.0f));          // -(m d/dm + u d/du)  resp.  -m d/dm - 1
+    if (below_x) dls.x = 0.f;   // clamp(min=eps) blocks the gradient strictly below eps, passes at equality
+    if (below_y) dls.y = 0.f;
+  }
+}
+
 // y in the first / last bin (clipped samples): log sigmoid(a) resp. log(1 - sigmoid(b))   :213,216,226-227
 template <bool GRAD>
 BLVM_HD void dl_edge(float y, int edge, float mu, float raw_ls, const DmolConsts& C, float& lp, float& dmu, float& dls) {
@@ -372,8 +471,23 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
       }
     }
   } else if (edge == kEdgeNone) {   // hoisted out of the component loop: the hot loop below has no edge test
+    constexpr int KP = (UMODE == kUTiny && K >= 2) ? (K / 2) * 2 : 0;   // components evaluated two at a time (packed fp32x2)
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < KP; k += 2) {
+      F2 lp, dmu = f2(0.f), dls = f2(0.f);
+      dl_mid_pair_tiny<GRAD>(y, f2(r[K + k], r[K + k + 1]), f2(r[2 * K + k], r[2 * K + k + 1]), C, lp, dmu, dls);
+      const F2 vv = add2(lp, f2(r[k], r[k + 1]));
+      v[k] = vv.x;
+      v[k + 1] = vv.y;
+      if (GRAD) {
+        r[K + k] = dmu.x;
+        r[K + k + 1] = dmu.y;
+        r[2 * K + k] = dls.x;
+        r[2 * K + k + 1] = dls.y;
+      }
+    }
+#pragma unroll
+    for (int k = KP; k < K; ++k) {
       float lp, dmu = 0.f, dls = 0.f;
       dl_mid<GRAD, UMODE>(y, r[K + k], r[2 * K + k], C, lp, dmu, dls);
       v[k] = (K == 1) ? lp : lp + r[k];
@@ -413,22 +527,50 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
   }
   float s1 = 0.f, s2 = 0.f;
   const float nm1 = -m1 * kLog2e, nm2 = -m2 * kLog2e;
+  if constexpr (K % 2 == 0) {   // two components per packed instruction (even / odd partial sums, added at the end)
+    F2 s1p = f2(0.f), s2p = f2(0.f);
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    v[k] = fast_ex2(fmaf(v[k], kLog2e, nm1));   // exp(v_k - max), one FFMA per argument
-    r[k] = fast_ex2(fmaf(r[k], kLog2e, nm2));
-    s1 += v[k];
-    s2 += r[k];
+    for (int k = 0; k < K; k += 2) {
+      const F2 ev = ex2_2(fma2(f2(v[k], v[k + 1]), f2(kLog2e), f2(nm1)));   // exp(v_k - max)
+      const F2 er = ex2_2(fma2(f2(r[k], r[k + 1]), f2(kLog2e), f2(nm2)));
+      v[k] = ev.x; v[k + 1] = ev.y;
+      r[k] = er.x; r[k + 1] = er.y;
+      s1p = add2(s1p, ev);
+      s2p = add2(s2p, er);
+    }
+    s1 = s1p.x + s1p.y;
+    s2 = s2p.x + s2p.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      v[k] = fast_ex2(fmaf(v[k], kLog2e, nm1));   // exp(v_k - max), one FFMA per argument
+      r[k] = fast_ex2(fmaf(r[k], kLog2e, nm2));
+      s1 += v[k];
+      s2 += r[k];
+    }
   }
   const float L = (m1 - m2) + kLn2 * (fast_lg2(s1) - fast_lg2(s2));
   if (GRAD) {
     const float g1 = g * fast_rcp(s1), g2 = g * fast_rcp(s2);
+    if constexpr (K % 2 == 0) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float gr = g1 * v[k];            // g * responsibility_k
-      r[k] = gr - g2 * r[k];                 // g * (resp_k - softmax_k)
-      r[K + k] *= gr;
-      r[2 * K + k] *= gr;
+      for (int k = 0; k < K; k += 2) {
+        const F2 gr = mul2(f2(g1), f2(v[k], v[k + 1]));                     // g * responsibility_k
+        const F2 gl = fma2(f2(r[k], r[k + 1]), f2(-g2), gr);                // g * (resp_k - softmax_k)
+        const F2 gm = mul2(f2(r[K + k], r[K + k + 1]), gr);
+        const F2 gs = mul2(f2(r[2 * K + k], r[2 * K + k + 1]), gr);
+        r[k] = gl.x; r[k + 1] = gl.y;
+        r[K + k] = gm.x; r[K + k + 1] = gm.y;
+        r[2 * K + k] = gs.x; r[2 * K + k + 1] = gs.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float gr = g1 * v[k];            // g * responsibility_k
+        r[k] = gr - g2 * r[k];                 // g * (resp_k - softmax_k)
+        r[K + k] *= gr;
+        r[2 * K + k] *= gr;
+      }
     }
   }
   return L;

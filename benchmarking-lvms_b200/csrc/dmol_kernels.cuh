@@ -167,9 +167,14 @@ template <int K>
 struct DmolSpt {
   static constexpr int value = K <= 1 ? BLVM_SPT_1 : K <= 2 ? BLVM_SPT_2 : (K <= 5 ? BLVM_SPT_5 : (K <= 8 ? BLVM_SPT_8 : (K <= 12 ? BLVM_SPT_12 : 1)));
 };
-template <int K>
+#ifndef BLVM_MINB_MIDK
+#define BLVM_MINB_MIDK 8  // 8 < K <= 12, gradient kernels: 64 registers (8 CTAs/SM; the packed-fp32 evaluation would otherwise take
+                          // 79 and K = 10 fwd+grad drops from 156 to 162 us).  The forward-only kernels are left uncapped:
+                          // K = 10 fwd 98.7 us capped, 86.3 us (6.07 TB/s) uncapped.
+#endif
+template <int K, bool GRAD = true>
 struct DmolMinBlocks {
-  static constexpr int value = K > 12 ? BLVM_MINB_BIGK : 0;   // 0 = no constraint
+  static constexpr int value = K > 12 ? BLVM_MINB_BIGK : ((K > 8 && GRAD) ? BLVM_MINB_MIDK : 0);   // 0 = no constraint
 };
 
 template <int K, int TPB, typename TP>
@@ -286,7 +291,7 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
 }
 
 template <int K, int TPB, bool GRAD, int UMODE, typename TP, int LIK = kLikDmol>
-__global__ void __launch_bounds__(TPB, DmolMinBlocks<K>::value) dmol_tile_kernel(const DmolArgs A) {
+__global__ void __launch_bounds__(TPB, DmolMinBlocks<K, GRAD>::value) dmol_tile_kernel(const DmolArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   ptx::pdl_launch_dependents();   // a KL / finalize launch of the same step may fill this grid's tail (they wait for us to finish)
   const bool pending = dmol_tile_body<K, TPB, GRAD, UMODE, TP, LIK>(A, blockIdx.x, smem);
