@@ -211,12 +211,17 @@ def cwvae_compute_elbo(self, y, seq_mask, level_masks, x_sl, parameters, kld_lay
 
 
 def stcn_compute_loss(self, y, x_sl, parameters, mu_p, sd_p, mu_q, sd_q, z, free_nats: float, beta: float):
-    """Drop-in for STCN.compute_loss (blvm/models/stcn/stcn.py:256-297), top-down (analytic KL) variant: every latent
-    level goes through the fully fused KL kernel.  mask -> free nats -> mask (:286-289) equals max(kl, fn/Z) on valid
-    steps and 0 on padded ones, which is what the kernel computes."""
-    if not self.top_down:
-        raise NotImplementedError("bottom-up STCN uses the Monte-Carlo KL (variational.py:73-83), outside this path")
-    levels = [KLLevel(mu_q[l], sd_q[l], mu_p[l], sd_p[l], stride=self.n_stack_frames) for l in range(self.n_latents)]
+    """Drop-in for STCN.compute_loss (blvm/models/stcn/stcn.py:256-297).  Top-down (analytic KL, :286): every latent level
+    goes through the fully fused KL kernel.  Bottom-up (:288): the level's KL is the Monte-Carlo estimate
+    log q(z) - log p(z) (variational.py:73-83, two Gaussian log-density kernels) handed to the fused op as a materialised
+    KL.  mask -> free nats -> mask (:286-289) equals max(kl, fn/Z) on valid steps and 0 on padded ones, which is what
+    the kernel computes (also for negative MC estimates)."""
+    if self.top_down:
+        levels = [KLLevel(mu_q[l], sd_q[l], mu_p[l], sd_p[l], stride=self.n_stack_frames) for l in range(self.n_latents)]
+    else:
+        from .variational import kl_divergence_gaussian_mc
+        levels = [KLLevel(kld=kl_divergence_gaussian_mc(mu_q[l], sd_q[l], mu_p[l], sd_p[l], z[l]), stride=self.n_stack_frames)
+                  for l in range(self.n_latents)]
     r = fused_elbo(y, parameters, x_sl, levels, beta, free_nats, num_bins=self.likelihood_module.num_bins)
     f = torch.float32
     return r.loss.to(f), r.elbo.to(f), r.log_prob.to(f), r.kl.to(f), [k.to(f) for k in r.kl_levels]

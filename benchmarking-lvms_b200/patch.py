@@ -58,14 +58,7 @@ def patch_blvm():
     _rebind_method(cwvae.CWVAE, "compute_elbo", elbo.cwvae_compute_elbo)
     _rebind_method(wavenet.WaveNet, "compute_loss", elbo.wavenet_compute_loss)
 
-    ref_stcn_loss = stcn.STCN.__dict__["compute_loss"]
-
-    def stcn_compute_loss(self, *args, **kwargs):
-        if not self.top_down:  # Monte-Carlo KL variant is outside the path: keep the reference's code for it
-            return ref_stcn_loss(self, *args, **kwargs)
-        return elbo.stcn_compute_loss(self, *args, **kwargs)
-
-    _rebind_method(stcn.STCN, "compute_loss", stcn_compute_loss)
+    _rebind_method(stcn.STCN, "compute_loss", elbo.stcn_compute_loss)   # top-down (analytic KL) and bottom-up (MC KL)
     return [f"{getattr(o, '__name__', o)}.{a}" for o, a, _ in _saved[before:]]
 
 

@@ -365,14 +365,18 @@ def elbo_cwvae(y, raw, kld_layerwise, x_sl, overall_strides, beta=1, free_nats=0
     return loss, elbo, log_prob, kld, kld_l
 
 
-def elbo_stcn(y, raw, kl_inputs, x_sl, n_stack_frames, beta, free_nats, K=10, num_bins=65536):
-    """blvm/models/stcn/stcn.py:256-297 (top_down=True). kl_inputs = [(mu_q, sd_q, mu_p, sd_p)] per latent level."""
+def elbo_stcn(y, raw, kl_inputs, x_sl, n_stack_frames, beta, free_nats, K=10, num_bins=65536, z=None):
+    """blvm/models/stcn/stcn.py:256-297. kl_inputs = [(mu_q, sd_q, mu_p, sd_p)] per latent level; `z` (list, one per
+    level) selects the bottom-up variant: Monte-Carlo KL log q(z) - log p(z) (:288) instead of the analytic KL (:286)."""
     x_sl = np.asarray(x_sl)
     log_prob_twise = _dmol_lp_bt(y, raw, K, num_bins)                 # :278
     seq_mask = sequence_mask(x_sl)                                    # :280
     log_prob = (log_prob_twise * seq_mask).sum(1)                     # :281
     z_mask = seq_mask[:, ::n_stack_frames][..., None]                 # :284
-    klds = [kl_divergence_gaussian(*ins) * z_mask for ins in kl_inputs]               # :286
+    if z is None:
+        klds = [kl_divergence_gaussian(*ins) * z_mask for ins in kl_inputs]           # :286
+    else:
+        klds = [kl_divergence_gaussian_mc(*ins, z[l]) * z_mask for l, ins in enumerate(kl_inputs)]   # :288
     klds_fn = [discount_free_nats(k, free_nats, -1) * z_mask for k in klds]           # :289 (mask, fn, mask)
     kld = np.concatenate(klds, -1).sum((1, 2))                        # :290
     kld_fn = np.concatenate(klds_fn, -1).sum((1, 2))                  # :291

@@ -428,8 +428,47 @@ def make_gmm():
             out[f"klmc_g_{nme}{tag}"] = t.grad.numpy()
     save("gaussian_ll", **out)
 
+def make_stcn_bottom_up():
+    """STCN with top_down=False (stcn.py:286-288): the KL of every level is the Monte-Carlo estimate log q(z) - log p(z)
+    (variational.py:73-83), which can be negative; mask -> free nats -> mask as in the analytic variant."""
+    K, nb = 10, 65536
+    beta, free_nats = 0.5, 0.0625
+    gen = torch.Generator().manual_seed(4250)
+    B, T, S = 3, 64, 1
+    Zs = [8, 4]
+    x_sl = torch.tensor([64, 33, 5])
+    y, raw = _dmol_inputs(gen, B, T, K, nb)
+    kl_ins = [_kl_inputs(gen, B, T // S, z) for z in Zs]
+    zs = [ins[0] + ins[1] * torch.randn(ins[0].shape, generator=gen) for ins in kl_ins]       # z ~ q
+    out = dict(y=_np(y), raw=_np(raw), x_sl=x_sl.numpy(), n_stack_frames=S, beta=beta, free_nats=free_nats, K=K,
+               num_bins=nb, n_latents=len(Zs))
+    for l, ins in enumerate(kl_ins):
+        out.update({f"{n}_{l}": _np(t) for n, t in zip(("mu_q", "sd_q", "mu_p", "sd_p"), ins)})
+        out[f"z_{l}"] = _np(zs[l])
+    for tag, dt in (("32", torch.float32), ("64", torch.float64)):
+        r = raw.to(dt).clone().requires_grad_(True)
+        lv = [[t.to(dt).clone().requires_grad_(True) for t in ins] for ins in kl_ins]
+        self = SimpleNamespace(likelihood_module=_likelihood(K, nb), n_stack_frames=S, top_down=False, n_latents=len(Zs))
+        mu_q, sd_q, mu_p, sd_p = ([ins[i] for ins in lv] for i in range(4))
+        zz = [z.to(dt).clone().requires_grad_(True) for z in zs]       # in the model z = rsample(q) carries gradient
+        loss, elbo, logp, kld, klds = ref_stcn.STCN.compute_loss(
+            self, y.to(dt).unsqueeze(-1), x_sl, _params_from_raw(r, K), mu_p, sd_p, mu_q, sd_q, zz, free_nats, beta)
+        loss.backward()
+        for l in range(len(Zs)):
+            out[f"g_z_{l}_{tag}"] = _np(zz[l].grad)
+        out.update({f"loss{tag}": _np(loss), f"elbo{tag}": _np(elbo), f"logp{tag}": _np(logp), f"kl{tag}": _np(kld),
+                    f"graw{tag}": _np(r.grad), f"dtype{tag}": str(elbo.dtype)})
+        for l in range(len(Zs)):
+            out[f"kl_l{l}_{tag}"] = _np(klds[l])
+            for nme, t in zip(("mu_q", "sd_q", "mu_p", "sd_p"), lv[l]):
+                out[f"g_{nme}_{l}_{tag}"] = _np(t.grad)
+    save("elbo_stcn_bottom_up", **out)
+
 
 if __name__ == "__main__":
+    if "--stcn-bu-only" in sys.argv:
+        make_stcn_bottom_up()
+        sys.exit(0)
     if "--gmm-only" in sys.argv:
         make_gmm()
         sys.exit(0)
@@ -439,3 +478,4 @@ if __name__ == "__main__":
     make_elbo_models()
     make_quantize()
     make_gmm()
+    make_stcn_bottom_up()

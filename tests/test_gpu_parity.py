@@ -276,6 +276,33 @@ def test_stcn_compute_loss(B):
     _check_dmol_grads_fused(raw.grad.cpu().numpy(), g, K)
 
 
+def test_stcn_compute_loss_bottom_up(B):
+    """top_down=False (stcn.py:288): Monte-Carlo KL through the Gaussian log-density kernels + the fused reduction."""
+    g = load_golden("elbo_stcn_bottom_up")
+    K, nb, n = int(g["K"]), int(g["num_bins"]), int(g["n_latents"])
+    self = SimpleNamespace(likelihood_module=B.DiscretizedLogisticMixtureDense(3 * K, 1, K, nb),
+                           n_stack_frames=int(g["n_stack_frames"]), top_down=False, n_latents=n)
+    raw = cu(g["raw"]).requires_grad_(True)
+    lv = [[cu(g[f"{nm}_{l}"]).requires_grad_(True) for nm in ("mu_q", "sd_q", "mu_p", "sd_p")] for l in range(n)]
+    mu_q, sd_q, mu_p, sd_p = ([ins[i] for ins in lv] for i in range(4))
+    z = [cu(g[f"z_{l}"]).requires_grad_(True) for l in range(n)]     # z = rsample(q) carries gradient in the model
+    loss, elbo, logp, kld, klds = B.stcn_compute_loss(self, cu(g["y"]).unsqueeze(-1), torch.as_tensor(g["x_sl"]),
+                                                      B.DMoLParams(raw, K, 1, -7.0), mu_p, sd_p, mu_q, sd_q, z,
+                                                      float(g["free_nats"]), float(g["beta"]))
+    loss.backward()
+    assert elbo.dtype == torch.float32
+    np.testing.assert_allclose(loss.item(), g["loss64"], rtol=2e-6)
+    np.testing.assert_allclose(elbo.detach().cpu().numpy(), g["elbo64"], rtol=2e-6)
+    np.testing.assert_allclose(kld.detach().cpu().numpy(), g["kl64"], rtol=1e-5, atol=1e-5)
+    for l in range(n):
+        ref_kl = g[f"kl_l{l}_64"]                        # a sum of signed MC terms: absolute floor from its own scale
+        np.testing.assert_allclose(klds[l].detach().cpu().numpy(), ref_kl, rtol=1e-5, atol=1e-6 * np.abs(ref_kl).max() + 1e-5)
+        for t, nm in zip(lv[l] + [z[l]], ("mu_q", "sd_q", "mu_p", "sd_p", "z")):
+            ref = g[f"g_{nm}_{l}_64"]
+            np.testing.assert_allclose(t.grad.cpu().numpy(), ref, rtol=RTOL, atol=RTOL * 1e-2 * np.abs(ref).max())
+    _check_dmol_grads_fused(raw.grad.cpu().numpy(), g, K)
+
+
 def test_wavenet_compute_loss(B):
     g = load_golden("elbo_wavenet")
     K, nb = int(g["K"]), int(g["num_bins"])
