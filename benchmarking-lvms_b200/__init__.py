@@ -12,6 +12,7 @@ or, with the reference tree importable, `blvm_b200.patch_blvm()` and run `experi
 The CUDA library is mandatory: importing this package without `lib/libblvm_b200.so` raises (no CPU fallback).
 """
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is not built)
+from .amp import register_grad_scaler
 from .distributed import SumsExchange, all_reduce_sums, combine_sums, global_denominator, shard_rows
 from .distributions import (ConditionalDistribution, DiagonalGaussianMixtureDense, DiscretizedLogisticDense,
                             DiscretizedLogisticMixtureDense, DLParams, DMoLParams, GMMParams)

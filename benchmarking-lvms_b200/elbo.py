@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Union
 
 import torch
 
-from . import ops
+from . import amp, ops
 from .distributions import DLParams, DMoLParams, GMMParams
 from .operations import level_lengths, sequence_mask
 
@@ -75,6 +75,7 @@ def fused_elbo(
     want_twise: bool = False,
     skip_padded: bool = False,
     x_sl_device: Optional[torch.Tensor] = None,
+    grad_scaler=None,
     exchange=None,
 ):
     """ELBO of a batch in one pass.
@@ -95,6 +96,10 @@ def fused_elbo(
             `value * 0`; only differs from the reference if padded parameters are non-finite).
         x_sl_device: the same lengths already on the device (B) int64; with `denom` given the call then does no
             host<->device traffic at all and can be captured in a CUDA graph.
+        grad_scaler: the `torch.amp.GradScaler` the caller will use for `scaler.scale(loss).backward()`.  Only matters for
+            fp16 parameters: with a known scaler their gradient is written in the forward pass, pre-multiplied by the
+            scaler's device-side scale (one pass instead of value + recompute, see amp.py).  Default: the single enabled
+            scaler registered through `register_grad_scaler` / observed after `patch_blvm()`, if any.
         exchange: a `blvm_b200.SumsExchange`: the finalize kernel then also publishes this rank's sums to every rank
             over NVLink peer memory (`exchange.consume()` returns the global sums).
 
@@ -165,9 +170,14 @@ def fused_elbo(
         flat += ts
 
     need_grad = torch.is_grad_enabled() and ((raw is not None and raw.requires_grad) or any(t.requires_grad for t in flat))
+    loss_scale = None
+    if need_grad and likelihood == "dmol" and raw.dtype == torch.float16:
+        scaler = grad_scaler if grad_scaler is not None else amp.active_grad_scaler(raw.device)
+        if scaler is not None and getattr(scaler, "_enabled", True) and getattr(scaler, "_scale", None) is not None:
+            loss_scale = amp.scale_tensor_f64(scaler)
     spec = ops.ELBOSpec(K=K, D=D, num_bins=int(num_bins), log_epsilon=float(log_eps), beta=float(beta), denom=total,
                         levels=specs, want_twise=want_twise, skip_padded=skip_padded, need_grad=need_grad,
-                        likelihood=likelihood, exchange=exchange, gmm=gmm)
+                        likelihood=likelihood, exchange=exchange, gmm=gmm, loss_scale=loss_scale)
     loss, sums, rows, twise = ops.fused_elbo_apply(spec, y, x_sl_dev, raw, flat)
     return SimpleNamespace(loss=loss, log_prob=rows[0], kl=rows[1], kl_fn=rows[2], elbo=rows[3],
                            kl_levels=[rows[4 + l] for l in range(len(specs))], sums=sums,

@@ -376,6 +376,7 @@ class ELBOSpec:
     likelihood: str = "dmol"       # "dmol" | "dl" | "gmm" | "none"
     gmm: tuple = (1.0, 0.0)        # (softplus beta, sd epsilon) of the Gaussian-mixture sd activation
     exchange: object = None        # distributed.SumsExchange: publish the sums to all ranks from the finalize kernel
+    loss_scale: Optional[torch.Tensor] = None   # fp64 device scalar (a GradScaler's scale): fp16 gradients in ONE pass, pre-scaled
 
 
 _unit_grads = {}
@@ -454,7 +455,8 @@ class _FusedELBO(torch.autograd.Function):
                 # fp16 parameters (AMP with a GradScaler): gradients of magnitude ~1/sum(x_sl) would underflow in fp16
                 # before the loss scale is applied, so the gradient is produced in backward (second launch, with the
                 # upstream grad_output read from the device); fp32 / bf16 parameters get it in this pass.
-                deferred = spec.need_grad and raw.dtype == torch.float16
+                prescaled = spec.need_grad and raw.dtype == torch.float16 and spec.loss_scale is not None
+                deferred = spec.need_grad and raw.dtype == torch.float16 and not prescaled
                 graw = torch.empty_like(raw) if (spec.need_grad and not deferred) else None
                 gscale = -1.0 / spec.denom
                 lp_ptr = twise.data_ptr() if spec.want_twise else None
@@ -465,7 +467,10 @@ class _FusedELBO(torch.autograd.Function):
                         rc = lib.blvm_dmol_fwd(y.data_ptr(), raw.data_ptr(), dt, x_sl_dev.data_ptr(), B, T, spec.K, spec.D,
                                                spec.num_bins, spec.log_epsilon, flags, lp_ptr, logp_ptr, err.data_ptr(), stream)
                     else:
-                        rc = lib.blvm_dmol_fwd_grad(y.data_ptr(), raw.data_ptr(), dt, x_sl_dev.data_ptr(), None, gscale, None,
+                        # known loss scale (amp.py): the kernel multiplies it in from the device, the fp16 gradient is
+                        # written pre-scaled in this pass and backward multiplies by grad_output / scale (== 1)
+                        rc = lib.blvm_dmol_fwd_grad(y.data_ptr(), raw.data_ptr(), dt, x_sl_dev.data_ptr(), None, gscale,
+                                                    spec.loss_scale.data_ptr() if prescaled else None,
                                                     B, T, spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags, lp_ptr,
                                                     graw.data_ptr(), logp_ptr, err.data_ptr(), stream)
                     if deferred:
@@ -536,6 +541,7 @@ class _FusedELBO(torch.autograd.Function):
         if not hasattr(ctx, "deferred"):
             ctx.deferred = None
         ctx.grads = grads
+        ctx.prescale = spec.loss_scale if (has_lik and spec.need_grad and raw.dtype == torch.float16 and spec.loss_scale is not None) else None
         ctx.consumed = False
         ctx.mark_non_differentiable(scalars, rows, twise)
         _maybe_strict(dev)
@@ -551,19 +557,30 @@ class _FusedELBO(torch.autograd.Function):
             return (None, None, None) + tuple(None for _ in ctx.grads)
         g = g_loss if (g_loss.dtype == torch.float64 and g_loss.is_contiguous()) else g_loss.to(torch.float64).contiguous()
         grads = list(ctx.grads)
-        bufs = [b for b in grads if b is not None]
         unit = _unit_grads.get(g.device.index)
-        if unit is not None and g.data_ptr() == unit.data_ptr():
-            bufs = []                  # FusedLoss.backward(): the root gradient is the constant 1, nothing to rescale
-        if bufs:
+        is_unit = unit is not None and g.data_ptr() == unit.data_ptr()   # FusedLoss.backward(): the root gradient is the constant 1
+
+        def rescale(bufs, factor):
             n = len(bufs)
             with _on_device(g.device):
                 rc = lib.blvm_scale_inplace_multi((ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs]),
                                                   (ctypes.c_int64 * n)(*[b.numel() for b in bufs]),
-                                                  (ctypes.c_int * n)(*[_DTYPE_CODE[b.dtype] for b in bufs]), n, g.data_ptr(),
+                                                  (ctypes.c_int * n)(*[_DTYPE_CODE[b.dtype] for b in bufs]), n, factor.data_ptr(),
                                                   _stream())
                 check(rc, "blvm_scale_inplace_multi")
             _count()
+
+        if ctx.prescale is not None and grads[0] is not None:
+            # the likelihood gradient already carries the loss scale S: multiply by grad_output / S, which is exactly 1 for
+            # scaler.scale(loss).backward() (the launch then exits at once); everything else gets the plain grad_output
+            rescale([grads[0]], g / ctx.prescale)
+            rest = [b for b in grads[1:] if b is not None]
+            if rest and not is_unit:
+                rescale(rest, g)
+        else:
+            bufs = [b for b in grads if b is not None]
+            if bufs and not is_unit:
+                rescale(bufs, g)
         if ctx.deferred is not None:   # fp16 parameters: value+gradient launch now, scaled by the device-side grad_output
             y, raw, x_sl_dev = ctx.saved_tensors
             B, T, K, D, num_bins, log_eps, flags, gscale = ctx.deferred

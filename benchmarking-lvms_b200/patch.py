@@ -4,7 +4,7 @@ stcn.py:28-29, clockwork_vae.py:27-28), so every `blvm.*` module's globals are r
 import sys
 from types import ModuleType
 
-from . import distributions, elbo, log_likelihoods, variational
+from . import amp, distributions, elbo, log_likelihoods, variational
 
 __all__ = ["patch_blvm", "unpatch_blvm"]
 
@@ -59,10 +59,14 @@ def patch_blvm():
     _rebind_method(wavenet.WaveNet, "compute_loss", elbo.wavenet_compute_loss)
 
     _rebind_method(stcn.STCN, "compute_loss", elbo.stcn_compute_loss)   # top-down (analytic KL) and bottom-up (MC KL)
+    # `--use_amp True` (fp16 autocast + GradScaler, the reference's benchmark default): learn about the script's scaler so
+    # that fp16 gradients are produced in one pass with its device-side scale (amp.py)
+    amp.observe_grad_scalers()
     return [f"{getattr(o, '__name__', o)}.{a}" for o, a, _ in _saved[before:]]
 
 
 def unpatch_blvm():
+    amp.stop_observing()
     while _saved:
         owner, attr, original = _saved.pop()
         setattr(owner, attr, original)

@@ -968,3 +968,45 @@ def test_sample_mode_tile_kernel_matches_direct_kernel(K, dtype, B):
         got = torch.gather(lsm, 1, comp.unsqueeze(1)).mean().item()
         want = (lsm.exp() * lsm).sum(-1).mean().item()
         assert abs(got - want) < 0.05, (got, want)      # N = 8240 draws: the standard error is ~0.015
+
+
+def test_fp16_single_pass_with_known_grad_scaler(B):
+    """`--use_amp True` (fp16 autocast + GradScaler): with the scaler known, the fp16 likelihood gradient is written in the
+    forward pass pre-multiplied by the scaler's device-side scale, and `scaler.scale(loss).backward()` only launches the
+    early-exit rescale; results are bit-identical to the deferred two-pass path, also for a second, different upstream
+    factor, and the KL gradients still receive the plain upstream gradient."""
+    from blvm_b200 import amp, ops
+    g = load_golden("elbo_srnn_a")
+    K, nb = int(g["K"]), int(g["num_bins"])
+    scaler = torch.amp.GradScaler("cuda", init_scale=4096.0)
+    scaler.scale(torch.zeros(1, device="cuda"))          # the scale tensor is created lazily by the first scale() call
+    assert scaler._scale is not None
+
+    def run(use_scaler, extra=1.0):
+        raw = cu(g["raw"]).to(torch.float16).requires_grad_(True)
+        kl = [cu(g[n]).requires_grad_(True) for n in ("mu_q", "sd_q", "mu_p", "sd_p")]
+        ops.reset_launch_count()
+        out = B.fused_elbo(cu(g["y"]), B.DMoLParams(raw, K, 1, -7.0), torch.tensor(g["x_sl"]), [B.KLLevel(*kl, stride=int(g["stride"]))],
+                           float(g["beta"]), float(g["free_nats"]), num_bins=nb, denom=3.0e5, grad_scaler=scaler if use_scaler else None)
+        n_fwd = ops.launch_count()
+        (scaler.scale(out.loss) * extra).backward()
+        return n_fwd, ops.launch_count() - n_fwd, raw.grad.clone(), [t.grad.clone() for t in kl], float(out.loss.detach())
+
+    assert amp.active_grad_scaler(torch.device("cuda", torch.cuda.current_device())) is None   # nothing registered: explicit only
+    fa, ba, graw_a, gkl_a, loss_a = run(True)
+    fb, bb, graw_b, gkl_b, loss_b = run(False)
+    assert (fa, fb) == (3, 3) and ba == 2 and bb == 2     # a: 2 rescale launches (1 early exit); b: KL rescale + gradient kernel
+    assert loss_a == loss_b
+    assert graw_a.dtype == torch.float16 and torch.equal(graw_a, graw_b)
+    assert all(torch.equal(x, y) for x, y in zip(gkl_a, gkl_b))
+    assert (graw_a != 0).float().mean().item() > 0.2 and torch.isfinite(graw_a).all()   # the padding is zero, the rest survives fp16
+    _, _, graw_c, gkl_c, _ = run(True, extra=0.5)         # upstream gradient != scale: the generic device-side ratio
+    _, _, graw_d, gkl_d, _ = run(False, extra=0.5)
+    np.testing.assert_allclose(graw_c.float().cpu().numpy(), graw_d.float().cpu().numpy(), rtol=2e-3, atol=1e-7)
+    assert all(torch.equal(x, y) for x, y in zip(gkl_c, gkl_d))
+    # registered scalers are picked up without the argument
+    amp.register_grad_scaler(scaler)
+    try:
+        assert amp.active_grad_scaler(torch.device("cuda", torch.cuda.current_device())) is scaler
+    finally:
+        amp._scalers.discard(scaler)
