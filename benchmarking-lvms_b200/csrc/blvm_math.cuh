@@ -266,10 +266,12 @@ BLVM_HD F2 ex2_2(F2 a) { return F2{fast_ex2(a.x), fast_ex2(a.y)}; }
 BLVM_HD F2 lg2_2(F2 a) { return F2{fast_lg2(a.x), fast_lg2(a.y)}; }
 BLVM_HD F2 rcp_2(F2 a) { return F2{fast_rcp(a.x), fast_rcp(a.y)}; }
 
-// dl_mid<GRAD, kUTiny> for components k and k+1 of one sample (same formulas, same order of operations per lane; negations
-// are folded into constants because packed operands carry no sign modifiers).
+// dl_mid<GRAD, kUTiny> for two (sample, component) pairs at once: components k and k+1 of one sample (y.x == y.y), or the
+// single component of two samples when K == 1.  Same formulas as dl_mid, one fixed order of operations per lane (negations
+// are folded into constants because packed operands carry no sign modifiers); in kUTiny mode EVERY mid-bin evaluation
+// goes through this function (a leftover component duplicates its lane), so a value never depends on what it was paired with.
 template <bool GRAD>
-BLVM_HD void dl_mid_pair_tiny(float y, F2 mu, F2 raw_ls, const DmolConsts& C, F2& lp, F2& dmu, F2& dls) {
+BLVM_HD void dl_mid_pair_tiny(F2 y, F2 mu, F2 raw_ls, const DmolConsts& C, F2& lp, F2& dmu, F2& dls) {
   const bool below_x = raw_ls.x < C.log_eps, below_y = raw_ls.y < C.log_eps;
   const F2 ls = f2(below_x ? C.log_eps : raw_ls.x, below_y ? C.log_eps : raw_ls.y);   // clamp(min): NaN propagates like torch
   // inv = exp(-ls), compensated (accurate_exp): -ls log2(e) = p_hi + p_lo, exp = 2^p_hi (1 + ln2 p_lo)
@@ -282,7 +284,7 @@ BLVM_HD void dl_mid_pair_tiny(float y, F2 mu, F2 raw_ls, const DmolConsts& C, F2
 #else
   const F2 inv = e0;
 #endif
-  const F2 m = mul2(inv, fma2(mu, f2(-1.f), f2(y)));              // mid_in                     :202,219
+  const F2 m = mul2(inv, fma2(mu, f2(-1.f), y));                  // mid_in                     :202,219
   const F2 u = mul2(inv, f2(C.h));
   const F2 am = abs2(m);
   const F2 E = ex2_2(mul2(am, f2(-kLog2e)));
@@ -471,11 +473,11 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
       }
     }
   } else if (edge == kEdgeNone) {   // hoisted out of the component loop: the hot loop below has no edge test
-    constexpr int KP = (UMODE == kUTiny && K >= 2) ? (K / 2) * 2 : 0;   // components evaluated two at a time (packed fp32x2)
+    constexpr int KP = (UMODE == kUTiny) ? (K / 2) * 2 : 0;   // components evaluated two at a time (packed fp32x2)
 #pragma unroll
     for (int k = 0; k < KP; k += 2) {
       F2 lp, dmu = f2(0.f), dls = f2(0.f);
-      dl_mid_pair_tiny<GRAD>(y, f2(r[K + k], r[K + k + 1]), f2(r[2 * K + k], r[2 * K + k + 1]), C, lp, dmu, dls);
+      dl_mid_pair_tiny<GRAD>(f2(y), f2(r[K + k], r[K + k + 1]), f2(r[2 * K + k], r[2 * K + k + 1]), C, lp, dmu, dls);
       const F2 vv = add2(lp, f2(r[k], r[k + 1]));
       v[k] = vv.x;
       v[k + 1] = vv.y;
@@ -489,7 +491,13 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
 #pragma unroll
     for (int k = KP; k < K; ++k) {
       float lp, dmu = 0.f, dls = 0.f;
-      dl_mid<GRAD, UMODE>(y, r[K + k], r[2 * K + k], C, lp, dmu, dls);
+      if constexpr (UMODE == kUTiny) {   // leftover component (odd K): the pair function with its lane duplicated
+        F2 lp2, dmu2 = f2(0.f), dls2 = f2(0.f);
+        dl_mid_pair_tiny<GRAD>(f2(y), f2(r[K + k]), f2(r[2 * K + k]), C, lp2, dmu2, dls2);
+        lp = lp2.x; dmu = dmu2.x; dls = dls2.x;
+      } else {
+        dl_mid<GRAD, UMODE>(y, r[K + k], r[2 * K + k], C, lp, dmu, dls);
+      }
       v[k] = (K == 1) ? lp : lp + r[k];
       if (GRAD) {
         r[K + k] = dmu;
@@ -574,6 +582,31 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     }
   }
   return L;
+}
+
+// K == 1 (a single discretized logistic with a dead logit column), 16-bit-audio mode: two SAMPLES of one thread evaluated
+// together with packed instructions.  Either sample in an edge bin sends both through dmol_sample (rare: clipped audio).
+// Bit-identical to calling dmol_sample<1, GRAD, kUTiny> on each sample.
+template <bool GRAD>
+BLVM_HD void dmol_k1_two_samples(float ya, float yb, float (&ra)[3], float (&rb)[3], float ga, float gb, const DmolConsts& C,
+                                 float& La, float& Lb) {
+  if (dmol_edge(ya, C) == kEdgeNone && dmol_edge(yb, C) == kEdgeNone) {
+    F2 lp, dmu = f2(0.f), dls = f2(0.f);
+    dl_mid_pair_tiny<GRAD>(f2(ya, yb), f2(ra[1], rb[1]), f2(ra[2], rb[2]), C, lp, dmu, dls);
+    const float za = ra[0] - ra[0], zb = rb[0] - rb[0];   // 0, or NaN for a non-finite logit (log_softmax of one logit)
+    La = lp.x + za;
+    Lb = lp.y + zb;
+    if (GRAD) {
+      const F2 g2 = f2(ga, gb);
+      const F2 gm = mul2(dmu, g2), gs = mul2(dls, g2);
+      ra[0] = ga * za; rb[0] = gb * zb;
+      ra[1] = gm.x; rb[1] = gm.y;
+      ra[2] = gs.x; rb[2] = gs.y;
+    }
+  } else {
+    La = dmol_sample<1, GRAD, kUTiny>(ya, ra, ga, C);
+    Lb = dmol_sample<1, GRAD, kUTiny>(yb, rb, gb, C);
+  }
 }
 
 // Generic (runtime K, D >= 1) sample, two passes with recomputation; `p` is the sample's K(2D+1) parameters laid

@@ -124,31 +124,76 @@ __global__ void __launch_bounds__(TPB) dmol_stream_kernel(const DmolArgs A, cons
     ptx::mbar_wait(full + st, parity);
 
     double acc = 0.0;
+    // Interior tiles (full, fully valid, no per-sample upstream gradient) are the overwhelming majority: they run without
+    // the per-sample bound / mask / skip tests, and the range check of y is folded into one flag per thread.
+    const bool interior = !t.skip && t.n == TILE && t.nvalid == TILE && A.gout == nullptr;
+    if (interior) {
+      bool bad = false;
+      if constexpr (K == 1 && UMODE == kUTiny && LIK == kLikDmol && SPT % 2 == 0) {
+        // one component: two SAMPLES per packed instruction (bit-identical to the per-sample evaluation)
 #pragma unroll
-    for (int j = 0; j < SPT; ++j) {
-      const int i = j * TPB + tid;
-      if (i < t.n) {
-        float Lv = 0.f;
-        float r[P];
-        TP* row = tile + i * P;
-        if (!t.skip) {
-          const float yv = ytile[i];
-          if (LIK == kLikDmol && !(yv <= 1.0f && yv >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
-          float g = 0.f;
+        for (int j = 0; j < SPT; j += 2) {
+          const int ia = j * TPB + tid, ib = ia + TPB;
+          const float ya = ytile[ia], yb = ytile[ib];
+          bad |= !(ya <= 1.0f && ya >= -1.0f) | !(yb <= 1.0f && yb >= -1.0f);
+          float ra[P], rb[P], La, Lb;
+          RowIO<TP, P>::load(tile + ia * P, ra);
+          RowIO<TP, P>::load(tile + ib * P, rb);
+          dmol_k1_two_samples<GRAD>(ya, yb, ra, rb, gs, gs, A.C, La, Lb);
           if (GRAD) {
-            g = (i < t.nvalid) ? gs : 0.f;
-            if (A.gout) g *= ptx::ldg_stream(A.gout + t.s0 + i);
+            RowIO<TP, P>::store(tile + ia * P, ra);
+            RowIO<TP, P>::store(tile + ib * P, rb);
           }
-          RowIO<TP, P>::load(row, r);
-          Lv = dmol_sample<K, GRAD, UMODE, LIK>(yv, r, g, A.C);
-        } else {
-#pragma unroll
-          for (int q = 0; q < P; ++q) r[q] = 0.f;
+          if (A.lp) {
+            A.lp[t.s0 + ia] = La;
+            A.lp[t.s0 + ib] = Lb;
+          }
+          acc += static_cast<double>(La);
+          acc += static_cast<double>(Lb);
         }
-        if (GRAD) RowIO<TP, P>::store(row, r);
-        const float Lm = (i < t.nvalid) ? Lv : Lv * 0.0f;   // log_prob * mask (NaN/inf propagate like `* 0`), vrnn.py:268
-        if (A.lp) A.lp[t.s0 + i] = (A.flags & kFlagMaskOutput) ? Lm : Lv;
-        acc += static_cast<double>(Lm);
+      } else {
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+          const int i = j * TPB + tid;
+          const float yv = ytile[i];
+          bad |= !(yv <= 1.0f && yv >= -1.0f);
+          float r[P];
+          TP* row = tile + i * P;
+          RowIO<TP, P>::load(row, r);
+          const float Lv = dmol_sample<K, GRAD, UMODE, LIK>(yv, r, gs, A.C);
+          if (GRAD) RowIO<TP, P>::store(row, r);
+          if (A.lp) A.lp[t.s0 + i] = Lv;
+          acc += static_cast<double>(Lv);
+        }
+      }
+      if (LIK == kLikDmol && bad && A.err_flag) atomicOr(A.err_flag, 1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) {
+        const int i = j * TPB + tid;
+        if (i < t.n) {
+          float Lv = 0.f;
+          float r[P];
+          TP* row = tile + i * P;
+          if (!t.skip) {
+            const float yv = ytile[i];
+            if (LIK == kLikDmol && !(yv <= 1.0f && yv >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
+            float g = 0.f;
+            if (GRAD) {
+              g = (i < t.nvalid) ? gs : 0.f;
+              if (A.gout) g *= ptx::ldg_stream(A.gout + t.s0 + i);
+            }
+            RowIO<TP, P>::load(row, r);
+            Lv = dmol_sample<K, GRAD, UMODE, LIK>(yv, r, g, A.C);
+          } else {
+#pragma unroll
+            for (int q = 0; q < P; ++q) r[q] = 0.f;
+          }
+          if (GRAD) RowIO<TP, P>::store(row, r);
+          const float Lm = (i < t.nvalid) ? Lv : Lv * 0.0f;   // log_prob * mask (NaN/inf propagate like `* 0`), vrnn.py:268
+          if (A.lp) A.lp[t.s0 + i] = (A.flags & kFlagMaskOutput) ? Lm : Lv;
+          acc += static_cast<double>(Lm);
+        }
       }
     }
 
