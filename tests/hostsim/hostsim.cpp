@@ -124,3 +124,17 @@ extern "C" void hostsim_gauss(const float* y, const float* mu, const float* sd, 
     g_sd[i] = g * dsd;
   }
 }
+
+// K == 1, 16-bit mode: samples n and n + N/2 evaluated together (two samples per packed instruction, blvm_math.cuh:
+// dmol_k1_two_samples) — must equal the per-sample evaluation bit for bit.
+extern "C" void hostsim_k1_pairs(const float* y, const float* raw, const float* gout, int64_t N, int num_bins, float log_eps,
+                                 float* lp, float* graw) {
+  const DmolConsts C = make_consts(num_bins, log_eps);
+  const int64_t H = N / 2;
+  for (int64_t n = 0; n < H; ++n) {
+    float ra[3], rb[3];
+    for (int i = 0; i < 3; ++i) { ra[i] = raw[n * 3 + i]; rb[i] = raw[(n + H) * 3 + i]; }
+    dmol_k1_two_samples<true>(y[n], y[n + H], ra, rb, gout ? gout[n] : 1.f, gout ? gout[n + H] : 1.f, C, lp[n], lp[n + H]);
+    for (int i = 0; i < 3; ++i) { graw[n * 3 + i] = ra[i]; graw[(n + H) * 3 + i] = rb[i]; }
+  }
+}

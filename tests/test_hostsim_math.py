@@ -58,6 +58,21 @@ def test_dmol_closed_forms(sim, case, force_generic):
     assert_grads_close(gr, g["graw64"], int(g["K"]), np.abs(g["gout"]), "grads")
 
 
+def test_k1_two_samples_per_instruction_bit_identical(sim):
+    """K = 1 in 16-bit mode pairs two samples per packed fp32x2 instruction inside the persistent kernel; the pairing
+    (including pairs that contain an edge-bin sample, which fall back) must not change a single bit."""
+    g = load_golden("dmol_K1_nb65536")
+    lp_ref, gr_ref = run_dmol(sim, g)
+    y = np.ascontiguousarray(g["y"], np.float32)
+    raw = np.ascontiguousarray(g["raw"], np.float32)
+    gout = np.ascontiguousarray(g["gout"], np.float32)
+    N = raw.shape[0] - raw.shape[0] % 2
+    lp = np.empty(N, np.float32)
+    gr = np.empty((N, 3), np.float32)
+    sim.hostsim_k1_pairs(P(y), P(raw), P(gout), ctypes.c_int64(N), 65536, ctypes.c_float(-7.0), P(lp), P(gr))
+    assert np.array_equal(lp, lp_ref[:N]) and np.array_equal(gr, gr_ref[:N])
+
+
 def test_dmol_non_power_of_two_bins(sim):
     """num_bins = 255: the y-edge thresholds are not exact in fp32, so the predicates follow the reference's fp32
     compare (rows where the fp64 run decides differently are compared with its fp32 run), and one forced row sits on
