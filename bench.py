@@ -385,9 +385,10 @@ def run_gpu_arm(a):
     mode = a.mode
     runner = step_eager
     if mode in ("auto", "graph"):
-        # Capture the compute part of the step (fused_elbo + backward: 4 kernels) in two CUDA graphs with separate
+        # Capture the compute part of the step (fused_elbo + backward: likelihood, one KL kernel per level, finalize) in two CUDA graphs with separate
         # output workspaces and replay them alternately; the exchange stays an eager NCCL call on the previous replay's
-        # sums.  Removes ~190 us/step of Python + launch overhead (the GPU work is ~200 us/step).
+        # sums.  Takes Python and launch overhead off the critical path (eager launches are now as fast at this size: the
+        # host side of a step is shorter than its ~190 us of GPU work; graphs matter for the small model-shaped workloads).
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
