@@ -21,6 +21,13 @@ _i32 = ctypes.c_int
 _f32 = ctypes.c_float
 _f64 = ctypes.c_double
 
+class KLLevelStruct(ctypes.Structure):
+    """blvm_kl_level_t (include/blvm_b200.h)."""
+    _fields_ = [("mu_q", _p), ("sd_q", _p), ("mu_p", _p), ("sd_p", _p), ("kl", _p), ("lens", _p), ("Tz", _i64), ("Z", _i64),
+                ("free_nats", _f64), ("g_mu_q", _p), ("g_sd_q", _p), ("g_mu_p", _p), ("g_sd_p", _p), ("g_kl", _p),
+                ("part_kl", _p), ("part_klfn", _p)]
+
+
 SIGNATURES = {
     "blvm_version": (_i32, []),
     "blvm_last_error_string": (ctypes.c_char_p, []),
@@ -39,6 +46,7 @@ SIGNATURES = {
     "blvm_kl_gaussian_bwd": (_i32, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "blvm_kl_elbo_fwd_grad": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "blvm_kl_reduce_fwd_grad": (_i32, [_p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _i32, _p]),
+    "blvm_kl_elbo_levels_fwd_grad": (_i32, [ctypes.POINTER(KLLevelStruct), _i32, _i64, _f32, _i32, _p]),
     "blvm_elbo_finalize": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64, _f64, _f64, _p, _p, _p, _p]),
     "blvm_elbo_finalize_publish": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64,
                                           _f64, _f64, _p, _p, _p, ctypes.POINTER(_p), _i32, _i32, _p, _p, _p, _p]),

@@ -471,6 +471,54 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
   return check_launch("kl_kernel (materialised KL)");
 }
 
+int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, int flags,
+                                 blvm_stream_t stream) {
+  if (n_levels < 1 || n_levels > kMaxLevels) return fail(BLVM_ERR_INVALID_ARGUMENT, "n_levels=%d out of [1, %d]", n_levels, kMaxLevels);
+  if (!levels_host || B < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "null levels / negative B");
+  KlMultiArgs M{};
+  M.n_levels = n_levels;
+  bool any_grad = false;
+  int64_t total = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const blvm_kl_level_t& L = levels_host[l];
+    if (L.Tz < 0 || L.Z < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: bad shape Tz=%lld Z=%lld", l, (long long)L.Tz, (long long)L.Z);
+    if (!L.part_kl || !L.part_klfn) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: null partials", l);
+    KlArgs& A = M.level[l];
+    A.lens = L.lens; A.gscale = gscale; A.fn_enabled = (L.free_nats != 0.0) ? 1 : 0;
+    A.min_kl = static_cast<float>(L.free_nats / static_cast<double>(L.Z));
+    A.part_kl = L.part_kl; A.part_klfn = L.part_klfn; A.B = B; A.row_elems = L.Tz * L.Z; A.Z = L.Z;
+    A.chunks = blvm_kl_chunks(A.row_elems);
+    bool grad = false;
+    if (L.kl) {
+      if (L.mu_q || L.sd_q || L.mu_p || L.sd_p) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: give the four parameter tensors or kl, not both", l);
+      A.kl_in = L.kl; A.gkl = L.g_kl;
+    } else {
+      if (B * L.Tz > 0 && (!L.mu_q || !L.sd_q || !L.mu_p || !L.sd_p)) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: null input", l);
+      grad = L.g_mu_q != nullptr;
+      if (grad && (!L.g_sd_q || !L.g_mu_p || !L.g_sd_p)) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: gradient outputs must be given together", l);
+      A.mu_q = L.mu_q; A.sd_q = L.sd_q; A.mu_p = L.mu_p; A.sd_p = L.sd_p;
+      A.g_mu_q = L.g_mu_q; A.g_sd_q = L.g_sd_q; A.g_mu_p = L.g_mu_p; A.g_sd_p = L.g_sd_p;
+      A.vec = kl_vec_ok(A, grad) ? 1 : 0;
+    }
+    any_grad = any_grad || grad;
+    M.tile_begin[l] = total;
+    total += B * A.chunks;
+  }
+  M.tile_begin[n_levels] = total;
+  if (total == 0) return BLVM_OK;
+  if (total > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
+  // a parameter level without gradient outputs inside a launch that computes gradients for another one would write through
+  // null pointers: require consistency
+  for (int l = 0; l < n_levels; ++l)
+    if (!M.level[l].kl_in && any_grad && !M.level[l].g_mu_q) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: gradient outputs missing", l);
+  const bool pdl = (flags & BLVM_FLAG_OVERLAP_PREV) != 0 && pdl_enabled();
+  const unsigned g = static_cast<unsigned>(total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = any_grad ? launch_ex(kl_multi_kernel<true>, g, kKlTPB, 0, st, pdl, M) : launch_ex(kl_multi_kernel<false>, g, kKlTPB, 0, st, pdl, M);
+  if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "kl_multi_kernel: %s", cudaGetErrorString(e));
+  return check_launch("kl_multi_kernel");
+}
+
 static int finalize_impl(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
                          const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
                          const int64_t* x_sl, int64_t B, double beta, double denom, double* rows, double* scalars,

@@ -147,8 +147,26 @@ __global__ void __launch_bounds__(kKlTPB) kl_kernel(const KlArgs A) {
   ptx::pdl_wait();
 }
 
-// ---- finalize: per-tile partials -> per-utterance sums -> loss / ELBO / bits-per-dim --------------------------------
+// All latent levels of a hierarchical model (Clockwork-VAE: 3, STCN: up to 5) in ONE launch: the grid is the concatenation of
+// the levels' tile ranges, a CTA finds its level by a scan over at most 8 prefix sums.  Same tile body, same partial-sum
+// layout as one kl_kernel launch per level (bit-identical), 2 + 1 instead of 2 + L launches per step.
 constexpr int kMaxLevels = 8;
+struct KlMultiArgs {
+  KlArgs level[kMaxLevels];
+  int64_t tile_begin[kMaxLevels + 1];
+  int n_levels;
+};
+template <bool GRAD>
+__global__ void __launch_bounds__(kKlTPB) kl_multi_kernel(const __grid_constant__ KlMultiArgs M) {
+  __shared__ double scratch[2 * (kKlTPB / 32)];
+  ptx::pdl_launch_dependents();
+  int l = 0;
+  while (l + 1 < M.n_levels && static_cast<int64_t>(blockIdx.x) >= M.tile_begin[l + 1]) ++l;
+  kl_tile_body<kKlTPB, GRAD>(M.level[l], static_cast<int64_t>(blockIdx.x) - M.tile_begin[l], scratch);
+  ptx::pdl_wait();   // see kl_kernel
+}
+
+// ---- finalize: per-tile partials -> per-utterance sums -> loss / ELBO / bits-per-dim --------------------------------
 struct FinalizeArgs {
   const double* logp_part;          // (B, logp_chunks), nullable (=> log p = 0)
   int64_t logp_chunks;

@@ -493,6 +493,7 @@ class _FusedELBO(torch.autograd.Function):
             kl_ptrs, klfn_ptrs, kl_chunks = [], [], []
             i = 0
             gscale = spec.beta / spec.denom
+            multi = (_lib.KLLevelStruct * L)() if L >= 2 else None   # hierarchies: all levels in one launch
             for li, (lv, (Tz, Z, chunks)) in enumerate(zip(spec.levels, shapes)):
                 # the launch just before this one is this step's likelihood / previous KL level, which produces none of
                 # this level's inputs: the KL grid may fill that grid's tail (programmatic dependent launch)
@@ -504,21 +505,35 @@ class _FusedELBO(torch.autograd.Function):
                 off += 2 * B * chunks
                 if lv.kind == "inputs":
                     g4 = [torch.empty_like(ts[0]) for _ in range(4)] if spec.need_grad else [None] * 4
-                    rc = lib.blvm_kl_elbo_fwd_grad(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
-                                                   _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale, None,
-                                                   _ptr(g4[0]), _ptr(g4[1]), _ptr(g4[2]), _ptr(g4[3]), pk, pf, kflags, stream)
-                    check(rc, "blvm_kl_elbo_fwd_grad")
+                    if multi is None:
+                        rc = lib.blvm_kl_elbo_fwd_grad(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
+                                                       _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale, None,
+                                                       _ptr(g4[0]), _ptr(g4[1]), _ptr(g4[2]), _ptr(g4[3]), pk, pf, kflags, stream)
+                        check(rc, "blvm_kl_elbo_fwd_grad")
+                    else:
+                        multi[li] = _lib.KLLevelStruct(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(), None,
+                                                       _ptr(lv.lens), Tz, Z, lv.free_nats, _ptr(g4[0]), _ptr(g4[1]), _ptr(g4[2]),
+                                                       _ptr(g4[3]), None, pk, pf)
                     grads += g4
                 else:
                     gk = torch.empty_like(ts[0]) if spec.need_grad else None
-                    rc = lib.blvm_kl_reduce_fwd_grad(ts[0].data_ptr(), _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale,
-                                                     _ptr(gk), pk, pf, kflags, stream)
-                    check(rc, "blvm_kl_reduce_fwd_grad")
+                    if multi is None:
+                        rc = lib.blvm_kl_reduce_fwd_grad(ts[0].data_ptr(), _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale,
+                                                         _ptr(gk), pk, pf, kflags, stream)
+                        check(rc, "blvm_kl_reduce_fwd_grad")
+                    else:
+                        multi[li] = _lib.KLLevelStruct(None, None, None, None, ts[0].data_ptr(), _ptr(lv.lens), Tz, Z, lv.free_nats,
+                                                       None, None, None, None, _ptr(gk), pk, pf)
                     grads.append(gk)
-                _count()
+                if multi is None:
+                    _count()
                 kl_ptrs.append(pk)
                 klfn_ptrs.append(pf)
                 kl_chunks.append(chunks)
+            if multi is not None:
+                rc = lib.blvm_kl_elbo_levels_fwd_grad(multi, L, B, gscale, _lib.BLVM_FLAG_OVERLAP_PREV if has_lik else 0, stream)
+                check(rc, "blvm_kl_elbo_levels_fwd_grad")
+                _count()
 
             PtrArr = ctypes.c_void_p * max(L, 1)
             I64Arr = ctypes.c_int64 * max(L, 1)

@@ -165,6 +165,25 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
                             float gscale, float* gkl, double* part_kl, double* part_klfn, int flags, blvm_stream_t stream);
 
 /*
+ * All latent levels of a step in ONE launch (Clockwork-VAE: 3 levels, clockwork_vae.py:147-155; STCN: n_latents levels,
+ * stcn.py:284-292).  Per level either the four Gaussian parameter tensors (fully fused, like blvm_kl_elbo_fwd_grad) or the
+ * materialised elementwise KL (like blvm_kl_reduce_fwd_grad); outputs, partial-sum layout and values are identical to one
+ * call per level.  `levels_host` is a HOST array of n_levels (<= BLVM_MAX_KL_LEVELS) descriptors holding device pointers.
+ */
+typedef struct blvm_kl_level {
+  const float *mu_q, *sd_q, *mu_p, *sd_p; /* (B, Tz, Z) each; all NULL when `kl` is given */
+  const float* kl;                        /* (B, Tz, Z) materialised elementwise KL, or NULL */
+  const int64_t* lens;                    /* (B) valid latent steps, nullable */
+  int64_t Tz, Z;
+  double free_nats;                       /* budget per latent step of this level; 0 disables */
+  float *g_mu_q, *g_sd_q, *g_mu_p, *g_sd_p; /* gradients out, nullable together (with the four inputs) */
+  float* g_kl;                            /* d/d kl out, nullable (with `kl`) */
+  double *part_kl, *part_klfn;            /* (B, blvm_kl_chunks(Tz*Z)) fp64 */
+} blvm_kl_level_t;
+int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, int flags,
+                                 blvm_stream_t stream);
+
+/*
  * Partials -> per-utterance log p(x|z), KL, free-nats KL, ELBO -> loss and bits-per-dim.
  * Replaces vrnn.py:269-277 / srnn.py:149-158 / clockwork_vae.py:155-159 / stcn.py:290-297 / wavenet.py:143-145 and
  * the BitsPerDimMetric arithmetic (blvm/evaluation/metrics.py:443-468).
