@@ -461,6 +461,24 @@ template <int K, bool GRAD, int UMODE = kUGeneral, int LIK = kLikDmol>
 BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts& C) {
   const int edge = (LIK == kLikDmol) ? dmol_edge(y, C) : kEdgeNone;
   float v[K];
+  // Logits centred on their maximum FIRST (like log_softmax in the reference, log_likelihoods.py:230): the dominant
+  // component's weight is then exactly 0 and large |logits| (~100) cost no absolute precision in a log-prob that is
+  // itself close to 0 (wide bins).  log p = logsumexp_k(lp_k + w_k) - log sum_k exp(w_k),  w_k = logit_k - max logit.
+  if constexpr (K > 1) {
+    float m2 = r[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) m2 = fmaxf(m2, r[k]);
+    if constexpr (K % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < K; k += 2) {
+        const F2 w = add2(f2(r[k], r[k + 1]), f2(-m2));
+        r[k] = w.x; r[k + 1] = w.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) r[k] = r[k] - m2;
+    }
+  }
   if (LIK != kLikDmol) {   // Gaussian mixture: same layout and mixture algebra, different component density
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -527,20 +545,17 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     }
     return L1;
   }
-  float m1 = v[0], m2 = r[0];
+  float m1 = v[0];
 #pragma unroll
-  for (int k = 1; k < K; ++k) {
-    m1 = fmaxf(m1, v[k]);
-    m2 = fmaxf(m2, r[k]);
-  }
+  for (int k = 1; k < K; ++k) m1 = fmaxf(m1, v[k]);
   float s1 = 0.f, s2 = 0.f;
-  const float nm1 = -m1 * kLog2e, nm2 = -m2 * kLog2e;
+  const float nm1 = -m1 * kLog2e;
   if constexpr (K % 2 == 0) {   // two components per packed instruction (even / odd partial sums, added at the end)
     F2 s1p = f2(0.f), s2p = f2(0.f);
 #pragma unroll
     for (int k = 0; k < K; k += 2) {
       const F2 ev = ex2_2(fma2(f2(v[k], v[k + 1]), f2(kLog2e), f2(nm1)));   // exp(v_k - max)
-      const F2 er = ex2_2(fma2(f2(r[k], r[k + 1]), f2(kLog2e), f2(nm2)));
+      const F2 er = ex2_2(mul2(f2(r[k], r[k + 1]), f2(kLog2e)));             // exp(w_k)
       v[k] = ev.x; v[k + 1] = ev.y;
       r[k] = er.x; r[k + 1] = er.y;
       s1p = add2(s1p, ev);
@@ -552,12 +567,12 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       v[k] = fast_ex2(fmaf(v[k], kLog2e, nm1));   // exp(v_k - max), one FFMA per argument
-      r[k] = fast_ex2(fmaf(r[k], kLog2e, nm2));
+      r[k] = fast_ex2(r[k] * kLog2e);
       s1 += v[k];
       s2 += r[k];
     }
   }
-  const float L = (m1 - m2) + kLn2 * (fast_lg2(s1) - fast_lg2(s2));
+  const float L = m1 + kLn2 * (fast_lg2(s1) - fast_lg2(s2));
   if (GRAD) {
     const float g1 = g * fast_rcp(s1), g2 = g * fast_rcp(s2);
     if constexpr (K % 2 == 0) {
@@ -624,6 +639,7 @@ template <bool GRAD>
 BLVM_HD float dmol_sample_generic(const float* yv, const float* p, int K, int D, float g, const DmolConsts& C, float* o,
                                   int lik = kLikDmol) {
   float m1 = -INFINITY, m2 = -INFINITY;
+  for (int k = 0; k < K; ++k) m2 = fmaxf(m2, p[k]);   // logits centred on their maximum first (see dmol_sample)
   for (int k = 0; k < K; ++k) {
     float lpk = 0.f;
     for (int d = 0; d < D; ++d) {
@@ -631,9 +647,8 @@ BLVM_HD float dmol_sample_generic(const float* yv, const float* p, int K, int D,
       any_component<false>(lik, yv[d], p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, a, b);
       lpk += lp;
     }
-    const float vk = lpk + p[k];
+    const float vk = lpk + (p[k] - m2);
     m1 = fmaxf(m1, vk);
-    m2 = fmaxf(m2, p[k]);
     if (vk != vk) m1 = vk;  // NaN propagates
   }
   float s1 = 0.f, s2 = 0.f;
@@ -644,10 +659,10 @@ BLVM_HD float dmol_sample_generic(const float* yv, const float* p, int K, int D,
       any_component<false>(lik, yv[d], p[K + d * 2 * K + k], p[K + d * 2 * K + K + k], C, lp, a, b);
       lpk += lp;
     }
-    s1 += fast_ex2((lpk + p[k] - m1) * kLog2e);
+    s1 += fast_ex2((lpk + (p[k] - m2) - m1) * kLog2e);
     s2 += fast_ex2((p[k] - m2) * kLog2e);
   }
-  const float L = (m1 - m2) + kLn2 * (fast_lg2(s1) - fast_lg2(s2));
+  const float L = m1 + kLn2 * (fast_lg2(s1) - fast_lg2(s2));
   if (GRAD) {
     const float g1 = g * fast_rcp(s1), g2 = g * fast_rcp(s2);
     for (int k = 0; k < K; ++k) {
@@ -659,7 +674,7 @@ BLVM_HD float dmol_sample_generic(const float* yv, const float* p, int K, int D,
         o[K + d * 2 * K + k] = dmu;
         o[K + d * 2 * K + K + k] = dls;
       }
-      const float gr = g1 * fast_ex2((lpk + p[k] - m1) * kLog2e);
+      const float gr = g1 * fast_ex2((lpk + (p[k] - m2) - m1) * kLog2e);
       o[k] = gr - g2 * fast_ex2((p[k] - m2) * kLog2e);
       for (int d = 0; d < D; ++d) {
         o[K + d * 2 * K + k] *= gr;

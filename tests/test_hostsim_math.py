@@ -197,3 +197,32 @@ def test_gaussian_ll_closed_forms(sim):
     assert (g["g_sd64_1"] == 0).all()          # the reference's no_grad clamp detaches sd (kept)
     kl = O.kl_divergence_gaussian_mc(*[g[k].astype(np.float64) for k in ("mu_q", "sd_q", "mu_p", "sd_p", "y")])
     np.testing.assert_allclose(kl, g["klmc64"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("nb", [65536, 256])
+@pytest.mark.parametrize("K", [2, 5, 10, 30])
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_dmol_extreme_regimes_against_fp64_oracle(sim, nb, K, force_generic):
+    """Beyond the goldens: logits up to +-100, locations 1e-4 .. 3 away from the target in either direction, log-scales
+    from -12 (clamped) to +4, edge-bin targets — the regimes where a closed form could overflow, cancel or lose the
+    absolute precision of a log-prob close to 0.  The fp32 device math stays within the parity tolerances of the
+    reference run in fp64 (the reference's own fp32 run is off by up to 80x that tolerance there)."""
+    from oracle import blvm_oracle as O
+    rng = np.random.default_rng(1000 + K + nb)
+    N = 2000
+    y = (rng.integers(0, nb, N) / (nb - 1) * 2 - 1).astype(np.float32)
+    y[:40] = rng.choice(np.array([-1.0, 1.0, 2 / nb - 1, 1 - 2 / nb], np.float32), 40)
+    raw = np.empty((N, 3 * K), np.float32)
+    raw[:, :K] = rng.normal(0, 1, (N, K)) * rng.choice([1, 10, 40], (N, 1))
+    raw[:, K:2 * K] = y[:, None] + rng.normal(0, 1, (N, K)) * rng.choice([1e-4, 1e-2, 0.3, 3.0], (N, K))
+    raw[:, 2 * K:] = rng.uniform(-12, 4, (N, K))
+    gout = rng.normal(0, 1, N).astype(np.float32)
+    lp = np.empty(N, np.float32)
+    gr = np.empty_like(raw)
+    sim.hostsim_dmol(P(y), P(raw), P(gout), ctypes.c_int64(N), K, 1, nb, ctypes.c_float(-7.0), force_generic, P(lp), P(gr))
+    assert np.isfinite(lp).all() and np.isfinite(gr).all()
+    L, G = O.dmol_value_and_grad(y.astype(np.float64), raw.astype(np.float64), K, 1, nb, -7.0, gout.astype(np.float64))
+    _, delta = O.dmol_branches(y.astype(np.float64).reshape(N, 1), raw.astype(np.float64), K, 1, nb, -7.0)   # (N, 1, K)
+    ok = ~(np.abs(delta / 1e-5 - 1) < 2e-4).any(axis=(1, 2))     # knife-edge rows: the reference's two arms differ there
+    assert_values_close(lp[ok], L[ok], "log-prob (extreme regimes)")
+    assert_grads_close(gr[ok], G[ok], K, np.abs(gout[ok]), "grads (extreme regimes)")
