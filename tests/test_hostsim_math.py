@@ -226,3 +226,26 @@ def test_dmol_extreme_regimes_against_fp64_oracle(sim, nb, K, force_generic):
     ok = ~(np.abs(delta / 1e-5 - 1) < 2e-4).any(axis=(1, 2))     # knife-edge rows: the reference's two arms differ there
     assert_values_close(lp[ok], L[ok], "log-prob (extreme regimes)")
     assert_grads_close(gr[ok], G[ok], K, np.abs(gout[ok]), "grads (extreme regimes)")
+
+
+def test_kl_extreme_regimes_against_fp64_oracle(sim):
+    """Standard deviations from e^-12 to e^5, ratios sd_q/sd_p from 1 +- 1e-6 to e^+-5, mean gaps from 0 to 30: the KL stays
+    within the parity tolerance of the fp64 reference and every gradient within 1e-6 of the magnitude of its (possibly
+    cancelling) terms."""
+    from oracle import blvm_oracle as O
+    rng = np.random.default_rng(3)
+    n = 100000
+    mu_q = (rng.normal(0, 1, n) * rng.choice([1e-3, 1, 30], n)).astype(np.float32)
+    mu_p = (mu_q + rng.normal(0, 1, n) * rng.choice([0, 1e-6, 1e-3, 1, 30], n)).astype(np.float32)
+    sd_q = np.exp(rng.uniform(-12, 5, n)).astype(np.float32)
+    sd_p = (sd_q * np.exp(rng.normal(0, 1, n) * rng.choice([0, 1e-6, 1e-3, 1, 5], n))).astype(np.float32)
+    outs = [np.empty(n, np.float32) for _ in range(6)]
+    sim.hostsim_kl(P(mu_q), P(sd_q), P(mu_p), P(sd_p), None, ctypes.c_int64(n), ctypes.c_float(0.0), 0, *[P(o) for o in outs])
+    assert all(np.isfinite(o).all() for o in outs)
+    q, sq, p, sp = (a.astype(np.float64) for a in (mu_q, sd_q, mu_p, sd_p))
+    kl, _, grads = O.kl_value_and_grad(q, sq, p, sp, free_nats=0.0, gout=None)
+    assert_values_close(outs[0], kl, "KL (extreme regimes)")
+    d2 = (q - p) ** 2
+    scales = (np.abs(q - p) / sp ** 2, 1 / sq + sq / sp ** 2, np.abs(q - p) / sp ** 2, 1 / sp + (sq ** 2 + d2) / sp ** 3)
+    for o, g, sc, nm in zip(outs[2:], grads, scales, ("mu_q", "sd_q", "mu_p", "sd_p")):
+        assert (np.abs(o - g) <= 1e-6 * sc + 1e-30).all(), nm
