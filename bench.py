@@ -553,7 +553,7 @@ def run_gpu_arm(a):
         }
         if not a.no_cpu_baseline and n_gpus == 1:
             try:
-                line["cpu_baseline"], _ = cpu_port_throughput(a, steps=5, warmup=1)
+                line["cpu_baseline"], _ = cpu_port_throughput(a, steps=40, warmup=2, target_step_s=0.4)   # ~15-20 s of CPU work
             except Exception as ex:  # the checker must never take the measurement down
                 line["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line))
