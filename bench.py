@@ -473,8 +473,29 @@ def run_gpu_arm(a):
     k1.record()
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / n_kern
-    clocks = sampler.stop() if rank == 0 else None
     del graw, part
+    # context for the roofline: the same device's copy bandwidth measured the same way (back-to-back launches for ~1 s, i.e.
+    # under the same power cap as the kernel loop above), next to the burst figure of MEASURED_PEAKS.json
+    sustained_copy = None
+    if rank == 0:
+        try:
+            src = torch.empty(1 << 28, dtype=torch.float32, device=dev)     # 1 GiB, read + written: 2 GiB per copy
+            dst = torch.empty_like(src)
+            for _ in range(3):
+                dst.copy_(src)
+            torch.cuda.synchronize()
+            n_copy = 600
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(n_copy):
+                dst.copy_(src)
+            c1.record()
+            torch.cuda.synchronize()
+            sustained_copy = 2 * src.numel() * 4 * n_copy / (c0.elapsed_time(c1) * 1e-3) / 1e9
+            del src, dst
+        except Exception:
+            sustained_copy = None
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the public API from pinned host buffers, H2D + D2H inside the timed region -----------------------------
     e2e = None
@@ -545,7 +566,9 @@ def run_gpu_arm(a):
             "roofline": {"bound": "hbm", "kernel": f"dmol_tile_kernel<K={K},128,grad>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": kern_ms * 1e3,
-                         "frac_of_nominal_8TBs": achieved / 8000.0},
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "sustained_copy_gbs": sustained_copy,
+                         "frac_of_sustained_copy": (achieved / sustained_copy) if sustained_copy else None},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "mode": mode, "exchange": exchange_kind,
             "timed_region_repeats": len(region_ms), "timed_region_ms_min_max": [min(region_ms), max(region_ms)],
             "step": "fused_elbo(...).loss.backward() through the Python API" + (f" ({2 + min(len(a.levels), 1)} kernels: likelihood, KL of all levels, finalize; replayed from CUDA graphs)" if mode == "graph" else "")
