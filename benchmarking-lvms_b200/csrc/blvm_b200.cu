@@ -9,8 +9,7 @@
 
 #include "host_common.h"
 
-#include "dmol_kernels.cuh"
-#include "dmol_stream_kernel.cuh"
+#include "dmol_dispatch.cuh"
 #include "kl_kernels.cuh"
 #include "misc_kernels.cuh"
 #include "sample_kernels.cuh"
@@ -23,57 +22,26 @@ static_assert(BLVM_MAX_KL_LEVELS == kMaxLevels, "level cap");
 static_assert(BLVM_MAX_SCALE_BUFFERS == kMaxScaleBuffers, "scale buffer cap");
 static_assert(BLVM_FLAG_MASK_OUTPUT == kFlagMaskOutput && BLVM_FLAG_SKIP_PADDED == kFlagSkipPadded, "flags");
 
+namespace blvm_host {   // instantiated in blvm_dmol_f32.cu / _f16.cu / _bf16.cu
+extern template int dmol_dispatch_tp<float>(const blvm::DmolArgs&, bool, int64_t, cudaStream_t);
+extern template int dmol_dispatch_tp<__half>(const blvm::DmolArgs&, bool, int64_t, cudaStream_t);
+extern template int dmol_dispatch_tp<__nv_bfloat16>(const blvm::DmolArgs&, bool, int64_t, cudaStream_t);
+extern template int sample_dispatch_tp<float>(const blvm::SampleArgs&, int64_t, cudaStream_t);
+extern template int sample_dispatch_tp<__half>(const blvm::SampleArgs&, int64_t, cudaStream_t);
+extern template int sample_dispatch_tp<__nv_bfloat16>(const blvm::SampleArgs&, int64_t, cudaStream_t);
+}  // namespace blvm_host
+
 namespace {
 
-constexpr int kTile = BLVM_DMOL_TILE;
+using blvm_host::kTile;
 using blvm_host::aligned;
 using blvm_host::check_launch;
 using blvm_host::fail;
 using blvm_host::make_consts;
 
-template <int K, bool GRAD, int UMODE, typename TP>
-int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
-  constexpr size_t smem = dmol_tile_smem_bytes<K, kTile, TP>();
-  auto kern = dmol_tile_kernel<K, kTile, GRAD, UMODE, TP>;
-  static bool configured = false;  // per instantiation; benign race (idempotent attribute)
-  if (!configured) {
-    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
-  kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
-  return check_launch("dmol_tile_kernel");
-}
-
-// ---- persistent pipelined variant (dmol_stream_kernel.cuh) ------------------------------------------------------------
-#ifndef BLVM_STREAM_STAGES
-#define BLVM_STREAM_STAGES 2
-#define BLVM_STREAM_LOOKAHEAD 1
-#endif
-#ifndef BLVM_STREAM_TPB
-#define BLVM_STREAM_TPB 128
-#endif
-#ifndef BLVM_STREAM_MAX_K
-#define BLVM_STREAM_MAX_K 5      // K above this keeps the one-tile-per-CTA kernel (already at the HBM roofline)
-#endif
-
-// Launch with (pdl = true) or without the programmatic-stream-serialization attribute (ptx_sm100.cuh: pdl_*).
-template <typename... KArgs, typename... Args>
-cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
-
 // 1 (default) = KL / finalize launches use programmatic dependent launch where the caller allows it; env BLVM_B200_PDL=0 disables
+}  // namespace
+namespace blvm_host {
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -102,59 +70,15 @@ int stream_mode() {
   }
   return g_stream_mode;
 }
-
-template <typename TP>
-bool stream_eligible(const DmolArgs& A, int K) {
-  const int64_t row_bytes = A.T * 3 * K * static_cast<int64_t>(sizeof(TP));
-  return A.T % 4 == 0 && row_bytes % 16 == 0 && aligned(A.raw, 16) && aligned(A.y, 16) && (!A.graw || aligned(A.graw, 16));
-}
-
-template <int K, bool GRAD, int UMODE, typename TP, int LIK = kLikDmol>
-int launch_stream(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
-  constexpr int TPB = (128 * DmolSpt<K>::value) % BLVM_STREAM_TPB == 0 ? BLVM_STREAM_TPB : 128;
-  constexpr int S = BLVM_STREAM_STAGES, LA = BLVM_STREAM_LOOKAHEAD;
-  constexpr size_t smem = StreamLayout<K, TPB, TP>::bytes(S);
-  auto kern = dmol_stream_kernel<K, TPB, S, LA, GRAD, UMODE, TP, LIK>;
-  static int resident = 0;  // CTAs per SM; per instantiation, benign race
-  if (resident == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem);
-    if (e != cudaSuccess || occ < 1) return fail(BLVM_ERR_CUDA, "occupancy query (smem=%zu): %s", smem, cudaGetErrorString(e));
-    resident = occ;
-  }
-  const int64_t slots = static_cast<int64_t>(sm_count()) * resident;
-  const unsigned grid = static_cast<unsigned>(tiles < slots ? tiles : slots);
-  kern<<<grid, TPB, smem, st>>>(A, tiles);
-  return check_launch("dmol_stream_kernel");
-}
-
-// u = h / s <= h * exp(-log_epsilon) for every element: if that bound is tiny (16-bit bins with the -7 clamp: 0.0167)
-// the kernel specialisation without the large-u code is exact to O(u^4) ~ 1e-7 (blvm_math.cuh).
-template <int K, bool GRAD, typename TP>
-int launch_tile_dtype(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
-  if constexpr (K <= BLVM_STREAM_MAX_K) {
-    if (stream_mode() && stream_eligible<TP>(A, K)) {
-      if (blvm_host::u_is_tiny(A.C)) return launch_stream<K, GRAD, kUTiny, TP>(A, tiles, st);
-      return launch_stream<K, GRAD, kUGeneral, TP>(A, tiles, st);
-    }
-  }
-  if (blvm_host::u_is_tiny(A.C)) return launch_tile_mode<K, GRAD, kUTiny, TP>(A, tiles, st);
-  return launch_tile_mode<K, GRAD, kUGeneral, TP>(A, tiles, st);
-}
-
-template <int K, bool GRAD>
-int launch_tile(const DmolArgs& A, int raw_dtype, int64_t tiles, cudaStream_t st) {
-  switch (raw_dtype) {
-    case BLVM_DTYPE_F32: return launch_tile_dtype<K, GRAD, float>(A, tiles, st);
-    case BLVM_DTYPE_F16: return launch_tile_dtype<K, GRAD, __half>(A, tiles, st);
-    case BLVM_DTYPE_BF16: return launch_tile_dtype<K, GRAD, __nv_bfloat16>(A, tiles, st);
-    default: return fail(BLVM_ERR_INVALID_ARGUMENT, "raw_dtype=%d", raw_dtype);
-  }
-}
-
-#define BLVM_FOR_EACH_K(X) X(1) X(2) X(3) X(4) X(5) X(6) X(8) X(10) X(12) X(16) X(20) X(30)
+}  // namespace blvm_host
+namespace {
+using blvm_host::dmol_dispatch_tp;
+using blvm_host::g_stream_mode;
+using blvm_host::launch_ex;
+using blvm_host::pdl_enabled;
+using blvm_host::sample_dispatch_tp;
+using blvm_host::sm_count;
+using blvm_host::stream_mode;
 
 // samples per partial sum: the register kernel's tile (128 * samples-per-thread, a function of K) or 128 (generic / DL)
 int64_t dmol_tile_samples(int K, int D) {
@@ -182,34 +106,17 @@ bool dmol_has_register_kernel(int K, int D) {
   }
 }
 
-template <int K, typename TP>
-int launch_sample_tile(const SampleArgs& A, int64_t tiles, cudaStream_t st) {
-  constexpr size_t smem = ((size_t(kTile) * DmolSpt<K>::value * 3 * K * sizeof(TP) + 15) / 16) * 16 + 16;
-  auto kern = dmol_sample_mode_tile_kernel<K, TP>;
-  static bool configured = false;
-  if (!configured) {
-    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
-  kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
-  return check_launch("dmol_sample_mode_tile_kernel");
-}
-
 template <bool GRAD>
 int dispatch_dmol(const DmolArgs& A, int raw_dtype, cudaStream_t st) {
   const int64_t tiles = A.B * A.chunks;
   if (tiles == 0) return BLVM_OK;
   if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)tiles);
-  if (A.D == 1) {
-    switch (A.K) {
-#define BLVM_CASE(KK) \
-  case KK:            \
-    return launch_tile<KK, GRAD>(A, raw_dtype, tiles, st);
-      BLVM_FOR_EACH_K(BLVM_CASE)
-#undef BLVM_CASE
-      default:
-        break;
+  if (dmol_has_register_kernel(A.K, A.D)) {
+    switch (raw_dtype) {
+      case BLVM_DTYPE_F32: return dmol_dispatch_tp<float>(A, GRAD, tiles, st);
+      case BLVM_DTYPE_F16: return dmol_dispatch_tp<__half>(A, GRAD, tiles, st);
+      case BLVM_DTYPE_BF16: return dmol_dispatch_tp<__nv_bfloat16>(A, GRAD, tiles, st);
+      default: return fail(BLVM_ERR_INVALID_ARGUMENT, "raw_dtype=%d", raw_dtype);
     }
   }
   if (raw_dtype != BLVM_DTYPE_F32)
@@ -603,18 +510,11 @@ int blvm_dmol_sample_mode(const void* raw, int raw_dtype, int64_t N, int K, int 
     const int64_t tile = dmol_tile_samples(K, D);
     const int64_t tiles = (N + tile - 1) / tile;
     if (tiles > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many samples");
-    switch (K) {
-#define BLVM_CASE(KK)                                                                                              \
-  case KK:                                                                                                         \
-    switch (raw_dtype) {                                                                                           \
-      case BLVM_DTYPE_F32: return launch_sample_tile<KK, float>(A, tiles, st);                                     \
-      case BLVM_DTYPE_F16: return launch_sample_tile<KK, __half>(A, tiles, st);                                    \
-      case BLVM_DTYPE_BF16: return launch_sample_tile<KK, __nv_bfloat16>(A, tiles, st);                            \
-      default: return fail(BLVM_ERR_INVALID_ARGUMENT, "raw_dtype=%d", raw_dtype);                                  \
-    }
-      BLVM_FOR_EACH_K(BLVM_CASE)
-#undef BLVM_CASE
-      default: break;
+    switch (raw_dtype) {
+      case BLVM_DTYPE_F32: return sample_dispatch_tp<float>(A, tiles, st);
+      case BLVM_DTYPE_F16: return sample_dispatch_tp<__half>(A, tiles, st);
+      case BLVM_DTYPE_BF16: return sample_dispatch_tp<__nv_bfloat16>(A, tiles, st);
+      default: return fail(BLVM_ERR_INVALID_ARGUMENT, "raw_dtype=%d", raw_dtype);
     }
   }
   const int64_t blocks = (N + 255) / 256;
