@@ -29,7 +29,7 @@ def build():
         cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
                f"-DBLVM_STREAM_STAGES={s}", f"-DBLVM_STREAM_LOOKAHEAD={la}", f"-DBLVM_STREAM_TPB={tpb}", "-DBLVM_STREAM_MAX_K=10",
                *([f"-DBLVM_SPT_1={spt[0]}", f"-DBLVM_SPT_2={spt[0]}", f"-DBLVM_SPT_5={spt[1]}", "-DBLVM_SPT_8=2", "-DBLVM_SPT_12=1"] if spt else []),
-               "-o", out, os.path.join(PKG, "csrc", "blvm_b200.cu")]
+               "-o", out] + [os.path.join(PKG, "csrc", f) for f in ("blvm_b200.cu", "blvm_dmol_f32.cu", "blvm_dmol_f16.cu", "blvm_dmol_bf16.cu")]
         subprocess.run(cmd, check=True)
         return out
 
