@@ -318,6 +318,8 @@ def run_gpu_arm(a):
         raise SystemExit("bench.py --impl ours needs a GPU (blvm_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # before any pinned allocation: keep this rank (and, by first touch, its host buffers) on the GPU's NUMA node
+    numa_node = blvm_b200.bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
@@ -569,7 +571,7 @@ def run_gpu_arm(a):
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "sustained_copy_gbs": sustained_copy,
                          "frac_of_sustained_copy": (achieved / sustained_copy) if sustained_copy else None},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "mode": mode, "exchange": exchange_kind,
+            "e2e": e2e, "numa_node_rank0": numa_node, "gpu_launches": launches, "clocks": clocks, "mode": mode, "exchange": exchange_kind,
             "timed_region_repeats": len(region_ms), "timed_region_ms_min_max": [min(region_ms), max(region_ms)],
             "step": "fused_elbo(...).loss.backward() through the Python API" + (f" ({2 + min(len(a.levels), 1)} kernels: likelihood, KL of all levels, finalize; replayed from CUDA graphs)" if mode == "graph" else "")
                     + (("; sums exchange: " + exchange_kind) if world > 1 else ""),

@@ -13,7 +13,7 @@ The CUDA library is mandatory: importing this package without `lib/libblvm_b200.
 """
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is not built)
 from .amp import register_grad_scaler
-from .distributed import SumsExchange, all_reduce_sums, combine_sums, global_denominator, shard_rows
+from .distributed import SumsExchange, all_reduce_sums, bind_to_gpu_numa_node, combine_sums, global_denominator, shard_rows
 from .distributions import (ConditionalDistribution, DiagonalGaussianMixtureDense, DiscretizedLogisticDense,
                             DiscretizedLogisticMixtureDense, DLParams, DMoLParams, GMMParams)
 from .elbo import (KLLevel, cwvae_compute_elbo, fused_elbo, pack_dmol_params, srnn_compute_elbo, stcn_compute_loss,

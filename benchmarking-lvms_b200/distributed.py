@@ -6,7 +6,44 @@ from typing import Optional, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_rows", "global_denominator", "all_reduce_sums", "combine_sums", "SumsExchange"]
+__all__ = ["shard_rows", "global_denominator", "all_reduce_sums", "combine_sums", "SumsExchange", "bind_to_gpu_numa_node"]
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """One process per GPU: run this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE allocating pinned host
+    buffers (first touch places them on that node).  Otherwise about half the ranks of an 8-GPU box stage their
+    host->device copies through the socket interconnect, which caps the aggregate H2D rate well below 8 PCIe links.
+    Best effort: returns the node number, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        if all(hasattr(props, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[device_index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else device_index
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else str(bus)).lower()
+            if len(bus.split(":")[0]) == 8:        # NVML prints an 8-digit domain, sysfs uses 4
+                bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
 
 
 def shard_rows(n_rows: int, rank: int, world_size: int):
