@@ -31,9 +31,13 @@ struct KlArgs {
   int vec;               // 1: 128-bit accesses are legal for every pointer and row (set by the host)
 };
 
-constexpr int kKlTPB = 256;
+#ifndef BLVM_KL_TPB
+#define BLVM_KL_TPB 128   // 8 elements per thread: per-thread overhead (index arithmetic, fp64 block sums) amortised over twice the work
+#endif
+constexpr int kKlTPB = BLVM_KL_TPB;
 constexpr int kKlVec = 4;
-constexpr int kKlChunk = kKlTPB * kKlVec;  // elements per CTA
+constexpr int kKlChunk = 1024;             // elements per CTA = per partial sum (BLVM_KL_TILE)
+static_assert(kKlChunk % (kKlTPB * kKlVec) == 0, "a CTA covers its chunk with whole 128-bit vectors per thread");
 
 // s_kl / s_fn accumulate the (at most 4) elements of one thread in fp32 — KL terms are non-negative, so the 4-term fp32
 // sum is good to ~1e-7 relative — and are widened to fp64 once per thread for the block reduction (fp32->fp64
@@ -60,8 +64,11 @@ template <int TPB, bool GRAD>
 __device__ __forceinline__ void kl_tile_body(const KlArgs& A, const int64_t tile_id, double* scratch) {
   constexpr int EPT = kKlChunk / TPB;                    // elements per thread (4 at 256 threads, 8 at 128)
   const int tid = threadIdx.x;
-  const int64_t b = tile_id / A.chunks;
-  const int64_t c = tile_id - b * A.chunks;
+  // 32-bit division: the host rejects launches with more than 2^31 - 1 tiles, and a 64-bit divide costs ~100 instructions
+  // per thread — a quarter of this kernel's issue slots when a thread only owns 4 elements
+  const unsigned tile32 = static_cast<unsigned>(tile_id), chunks32 = static_cast<unsigned>(A.chunks);
+  const int64_t b = tile32 / chunks32;
+  const int64_t c = tile32 - static_cast<unsigned>(b) * chunks32;
   const int64_t e0 = c * kKlChunk;                       // first element of this chunk within the row
   const int64_t max_steps = A.row_elems / A.Z;
   int64_t len = A.lens ? A.lens[b] : max_steps;
