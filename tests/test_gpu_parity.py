@@ -1010,3 +1010,73 @@ def test_fp16_single_pass_with_known_grad_scaler(B):
         assert amp.active_grad_scaler(torch.device("cuda", torch.cuda.current_device())) is scaler
     finally:
         amp._scalers.discard(scaler)
+
+
+def test_cuda_graph_replay_matches_eager(B):
+    """bench.py times the step replayed from a CUDA graph (programmatic dependent launches are captured as graph edges):
+    the replay must compute exactly what the eager call computes, also after the inputs have been rewritten in place."""
+    gen = torch.Generator().manual_seed(31)
+    Bn, T, K, nb = 16, 8192, 10, 65536
+    strides, Zs = (64, 512), (32, 16)
+
+    def inputs(seed):
+        g = torch.Generator().manual_seed(seed)
+        y = (torch.randint(0, nb, (Bn, T), generator=g).float() / (nb - 1) * 2 - 1)
+        raw = torch.randn(Bn, T, 3 * K, generator=g)
+        raw[..., K:2 * K] = y.unsqueeze(-1) + 0.1 * raw[..., K:2 * K]
+        raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+        kls = []
+        for s, Z in zip(strides, Zs):
+            t = [torch.randn(Bn, T // s, Z, generator=g) for _ in range(4)]
+            t[1], t[3] = torch.nn.functional.softplus(t[1]) + 1e-3, torch.nn.functional.softplus(t[3]) + 1e-3
+            kls.append(t)
+        return y, raw, kls
+
+    x_sl = torch.randint(T // 2, T + 1, (Bn,), generator=gen)
+    x_dev = x_sl.cuda()
+    lens = [B.level_lengths(x_dev, s) for s in strides]
+    denom = float(x_sl.sum())
+    y0, raw0, kls0 = inputs(1)
+    y_d, raw_d = y0.cuda(), raw0.cuda().requires_grad_(True)
+    kl_d = [[t.cuda().requires_grad_(True) for t in kl] for kl in kls0]
+
+    def step():
+        raw_d.grad = None
+        for kl in kl_d:
+            for t in kl:
+                t.grad = None
+        out = B.fused_elbo(y_d, B.DMoLParams(raw_d, K, 1, -7.0), x_sl, [B.KLLevel(*kl, lens=ln) for kl, ln in zip(kl_d, lens)],
+                           0.5, 0.0625, num_bins=nb, denom=denom, x_sl_device=x_dev)
+        out.loss.backward()
+        return out.sums, out.log_prob, raw_d.grad, [t.grad for kl in kl_d for t in kl]
+
+    def snapshot(res):
+        sums, logp, graw, gkl = res
+        return [sums.clone(), logp.clone(), graw.clone()] + [g.clone() for g in gkl]
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static = step()
+    for seed in (1, 2, 3):
+        y1, raw1, kls1 = inputs(seed)
+        with torch.no_grad():
+            y_d.copy_(y1)
+            raw_d.copy_(raw1)
+            for kl, new in zip(kl_d, kls1):
+                for t, n in zip(kl, new):
+                    t.copy_(n)
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        replayed = snapshot(static)
+        eager = snapshot(step())
+        torch.cuda.synchronize()
+        for a, b, name in zip(replayed, eager, ["sums", "log_prob", "graw"] + [f"gkl{i}" for i in range(8)]):
+            assert torch.equal(a, b), f"seed {seed}: {name} differs between graph replay and the eager call"
