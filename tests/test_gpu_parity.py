@@ -665,7 +665,7 @@ def test_fused_sample_and_mode(B):
     assert xs16.dtype == torch.float32 and float(xs16.abs().max()) <= 1.0
 
 
-@pytest.mark.parametrize("T,K", [(127, 10), (1000, 1), (333, 5), (130, 30), (64, 7)])
+@pytest.mark.parametrize("T,K", [(127, 10), (1000, 1), (333, 5), (130, 30), (64, 7), (2052, 1), (4096, 2), (1540, 5), (2048, 3)])
 def test_no_out_of_bounds_writes(T, K, B):
     """compute-sanitizer is closed on this pool, so out-of-bounds writes are checked with canaries: every output of the
     DMoL / KL kernels lives inside one arena with poisoned guard bands on both sides (tail tiles, unaligned slabs,
