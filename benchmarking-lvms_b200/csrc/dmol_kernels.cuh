@@ -167,6 +167,10 @@ template <int K>
 struct DmolSpt {
   static constexpr int value = K <= 1 ? BLVM_SPT_1 : K <= 2 ? BLVM_SPT_2 : (K <= 5 ? BLVM_SPT_5 : (K <= 8 ? BLVM_SPT_8 : (K <= 12 ? BLVM_SPT_12 : 1)));
 };
+#ifndef BLVM_MINB_K20
+#define BLVM_MINB_K20 5   // 16 < K <= 20: 96 registers, 5 CTAs/SM (K = 20: 311.7 -> 299.6 us, 6.67 TB/s)
+#define BLVM_MINB_K16 6   // 12 < K <= 16: 80 registers, 6 CTAs/SM (K = 16: 324 -> 285 us; its 192-byte rows are 4-way bank conflicted)
+#endif
 #ifndef BLVM_MINB_MIDK
 #define BLVM_MINB_MIDK 8  // 8 < K <= 12, gradient kernels: 64 registers (8 CTAs/SM; the packed-fp32 evaluation would otherwise take
                           // 79 and K = 10 fwd+grad drops from 156 to 162 us).  The forward-only kernels are left uncapped:
@@ -174,7 +178,7 @@ struct DmolSpt {
 #endif
 template <int K, bool GRAD = true>
 struct DmolMinBlocks {
-  static constexpr int value = K > 12 ? BLVM_MINB_BIGK : ((K > 8 && GRAD) ? BLVM_MINB_MIDK : 0);   // 0 = no constraint
+  static constexpr int value = K > 20 ? BLVM_MINB_BIGK : (K > 16 ? BLVM_MINB_K20 : (K > 12 ? BLVM_MINB_K16 : ((K > 8 && GRAD) ? BLVM_MINB_MIDK : 0)));   // 0 = no constraint
 };
 
 template <int K, int TPB, typename TP>
@@ -227,46 +231,72 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
   }
 
   // sample j of this thread is tile-local index j*TPB + tid: coalesced y / log-prob accesses, conflict-free smem rows
-  float yv[SPT], g[SPT];
   float gs = A.gscale;
   if (GRAD && A.gscale_dev) gs *= static_cast<float>(*A.gscale_dev);
-#pragma unroll
-  for (int j = 0; j < SPT; ++j) {
-    const int i = j * TPB + tid;
-    yv[j] = 0.f;
-    g[j] = 0.f;
-    if (i < n) {
-      yv[j] = ptx::ldg_stream(A.y + s0 + i);
-      if (LIK == kLikDmol && !(yv[j] <= 1.0f && yv[j] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
-      if (GRAD) {
-        g[j] = (i < nvalid) ? gs : 0.f;
-        if (A.gout) g[j] *= ptx::ldg_stream(A.gout + s0 + i);
-      }
-    }
-  }
-  __syncthreads();  // mbarrier init / plain loads visible to everyone
-  if (!skip && bulk_in) ptx::mbar_wait(bar, 0);
-
   double acc = 0.0;
+  // Interior tiles (full, fully valid, no per-sample upstream gradient) are almost all tiles: no per-sample bound / mask /
+  // skip tests, the y-range check folded into one flag per thread.  Same arithmetic, bit-identical results.
+  // (K > 12 runs at the 128-register cap: a second copy of the sample body costs more in spills than the tests it saves)
+  const bool interior = (K <= 12) && !skip && n == TILE && nvalid == TILE && A.gout == nullptr;
+  if (interior) {
+    float yv[SPT];
 #pragma unroll
-  for (int j = 0; j < SPT; ++j) {
-    const int i = j * TPB + tid;
-    if (i < n) {
-      float L = 0.f;
+    for (int j = 0; j < SPT; ++j) yv[j] = ptx::ldg_stream(A.y + s0 + j * TPB + tid);   // in flight while the slab lands
+    __syncthreads();  // mbarrier init / plain loads visible to everyone
+    if (bulk_in) ptx::mbar_wait(bar, 0);
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const int i = j * TPB + tid;
+      bad |= !(yv[j] <= 1.0f && yv[j] >= -1.0f);
       float r[P];
       TP* row = tile + i * P;
-      if (!skip) {
-        RowIO<TP, P>::load(row, r);
-        L = dmol_sample<K, GRAD, UMODE, LIK>(yv[j], r, g[j], A.C);
-      } else {
-#pragma unroll
-        for (int q = 0; q < P; ++q) r[q] = 0.f;
-      }
+      RowIO<TP, P>::load(row, r);
+      const float L = dmol_sample<K, GRAD, UMODE, LIK>(yv[j], r, gs, A.C);
       if (GRAD) RowIO<TP, P>::store(row, r);
-      // reference semantics: log_prob * mask (NaN/inf in the padding propagate like `* 0`), vrnn.py:268
-      const float Lm = (i < nvalid) ? L : L * 0.0f;
-      if (A.lp) A.lp[s0 + i] = (A.flags & kFlagMaskOutput) ? Lm : L;
-      acc += static_cast<double>(Lm);
+      if (A.lp) A.lp[s0 + i] = L;
+      acc += static_cast<double>(L);
+    }
+    if (LIK == kLikDmol && bad && A.err_flag) atomicOr(A.err_flag, 1);
+  } else {
+    float yv[SPT], g[SPT];
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const int i = j * TPB + tid;
+      yv[j] = 0.f;
+      g[j] = 0.f;
+      if (i < n) {
+        yv[j] = ptx::ldg_stream(A.y + s0 + i);
+        if (LIK == kLikDmol && !(yv[j] <= 1.0f && yv[j] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
+        if (GRAD) {
+          g[j] = (i < nvalid) ? gs : 0.f;
+          if (A.gout) g[j] *= ptx::ldg_stream(A.gout + s0 + i);
+        }
+      }
+    }
+    __syncthreads();  // mbarrier init / plain loads visible to everyone
+    if (!skip && bulk_in) ptx::mbar_wait(bar, 0);
+
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const int i = j * TPB + tid;
+      if (i < n) {
+        float L = 0.f;
+        float r[P];
+        TP* row = tile + i * P;
+        if (!skip) {
+          RowIO<TP, P>::load(row, r);
+          L = dmol_sample<K, GRAD, UMODE, LIK>(yv[j], r, g[j], A.C);
+        } else {
+#pragma unroll
+          for (int q = 0; q < P; ++q) r[q] = 0.f;
+        }
+        if (GRAD) RowIO<TP, P>::store(row, r);
+        // reference semantics: log_prob * mask (NaN/inf in the padding propagate like `* 0`), vrnn.py:268
+        const float Lm = (i < nvalid) ? L : L * 0.0f;
+        if (A.lp) A.lp[s0 + i] = (A.flags & kFlagMaskOutput) ? Lm : L;
+        acc += static_cast<double>(Lm);
+      }
     }
   }
 
