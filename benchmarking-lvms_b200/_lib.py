@@ -25,7 +25,7 @@ class KLLevelStruct(ctypes.Structure):
     """blvm_kl_level_t (include/blvm_b200.h)."""
     _fields_ = [("mu_q", _p), ("sd_q", _p), ("mu_p", _p), ("sd_p", _p), ("kl", _p), ("lens", _p), ("Tz", _i64), ("Z", _i64),
                 ("free_nats", _f64), ("g_mu_q", _p), ("g_sd_q", _p), ("g_mu_p", _p), ("g_sd_p", _p), ("g_kl", _p),
-                ("part_kl", _p), ("part_klfn", _p)]
+                ("part_kl", _p), ("part_klfn", _p), ("z", _p), ("g_z", _p)]
 
 
 SIGNATURES = {

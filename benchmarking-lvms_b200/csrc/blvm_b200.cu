@@ -405,6 +405,7 @@ int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_level
       if (grad && (!L.g_sd_q || !L.g_mu_p || !L.g_sd_p)) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: gradient outputs must be given together", l);
       A.mu_q = L.mu_q; A.sd_q = L.sd_q; A.mu_p = L.mu_p; A.sd_p = L.sd_p;
       A.g_mu_q = L.g_mu_q; A.g_sd_q = L.g_sd_q; A.g_mu_p = L.g_mu_p; A.g_sd_p = L.g_sd_p;
+      A.z = L.z; A.g_z = L.z ? L.g_z : nullptr;
       A.vec = kl_vec_ok(A, grad) ? 1 : 0;
     }
     any_grad = any_grad || grad;

@@ -410,6 +410,21 @@ BLVM_HD void gauss_component(float y, float mu, float p, const DmolConsts& C, fl
 struct KlTerms {
   float kl, z, rho_m1, rho_p1, inv_sp, q;  // q = (rho-1)(rho+1) + z^2
 };
+// log(rho), rho = sd_q/sd_p, as 2 atanh(s), s = (sd_q - sd_p)/(sd_q + sd_p): exact near rho = 1, where the KL's
+// q/2 - log(rho) cancels; odd series to s^11 for |s| < 0.2 (truncation 3e-10 relative), MUFU.LG2 of the quotient elsewhere
+// (|log rho| > 0.4).  d = sd_q - sd_p, ssum = sd_q + sd_p, inv_sp = 1/sd_p are passed in (the callers have them).
+BLVM_HD float log_sd_ratio(float sd_q, float sd_p, float d, float ssum, float inv_sp) {
+  const float s = d * rcp_nr(ssum), s2 = s * s;
+  float p = 1.0f / 11.0f;
+  p = fmaf(p, s2, 1.0f / 9.0f);
+  p = fmaf(p, s2, 1.0f / 7.0f);
+  p = fmaf(p, s2, 1.0f / 5.0f);
+  p = fmaf(p, s2, 1.0f / 3.0f);
+  p = fmaf(p, s2, 1.0f);
+  const float log_series = 2.0f * s * p, log_mufu = kLn2 * fast_lg2(sd_q * inv_sp);   // both evaluated: a select, no branch
+  (void)sd_p;
+  return (fabsf(s) < 0.2f) ? log_series : log_mufu;
+}
 BLVM_HD KlTerms kl_gaussian_terms(float mu_q, float sd_q, float mu_p, float sd_p) {
   KlTerms t;
   t.inv_sp = rcp_nr(sd_p);
@@ -418,18 +433,7 @@ BLVM_HD KlTerms kl_gaussian_terms(float mu_q, float sd_q, float mu_p, float sd_p
   t.rho_m1 = d * t.inv_sp;
   t.rho_p1 = ssum * t.inv_sp;
   t.q = fmaf(t.rho_m1, t.rho_p1, t.z * t.z);
-  // log(rho) = 2 atanh(s), s = (sd_q - sd_p)/(sd_q + sd_p): exact near rho = 1, where kl = q/2 - log(rho) cancels;
-  // odd series to s^11 for |s| < 0.2 (truncation 3e-10 relative), MUFU.LG2 of the quotient elsewhere (|log rho| > 0.4).
-  const float s = d * rcp_nr(ssum), s2 = s * s;
-  float p = 1.0f / 11.0f;
-  p = fmaf(p, s2, 1.0f / 9.0f);
-  p = fmaf(p, s2, 1.0f / 7.0f);
-  p = fmaf(p, s2, 1.0f / 5.0f);
-  p = fmaf(p, s2, 1.0f / 3.0f);
-  p = fmaf(p, s2, 1.0f);
-  const float log_series = 2.0f * s * p, log_mufu = kLn2 * fast_lg2(sd_q * t.inv_sp);   // both evaluated: a select, no branch
-  const float log_rho = (fabsf(s) < 0.2f) ? log_series : log_mufu;
-  t.kl = 0.5f * t.q - log_rho;
+  t.kl = 0.5f * t.q - log_sd_ratio(sd_q, sd_p, d, ssum, t.inv_sp);
   return t;
 }
 // d kl / d (mu_q, sd_q, mu_p, sd_p), each multiplied by g.
@@ -439,6 +443,30 @@ BLVM_HD void kl_gaussian_grads(const KlTerms& t, float sd_q, float g, float& g_m
   g_mu_p = -g_mu_q;
   g_sd_q = g * (t.rho_m1 * t.rho_p1) * rcp_nr(sd_q);  // -1/sd_q + sd_q/sd_p^2
   g_sd_p = -g * t.q * t.inv_sp;                       // 1/sd_p - (sd_q^2 + d^2)/sd_p^3
+}
+// Monte-Carlo KL of one latent element (variational.py:73-83, bottom-up STCN stcn.py:288): log q(z) - log p(z) with both
+// Gaussian log-densities of log_likelihoods.py:17-39 (epsilon = 0); the 0.5 log(2 pi) terms cancel.
+//   kl = 0.5 (ap - aq)(ap + aq) - log(sd_q/sd_p),   aq = (z - mu_q)/sd_q,  ap = (z - mu_p)/sd_p
+struct KlMcTerms {
+  float kl, aq, ap, inv_sq, inv_sp;
+};
+BLVM_HD KlMcTerms kl_mc_terms(float z, float mu_q, float sd_q, float mu_p, float sd_p) {
+  KlMcTerms t;
+  t.inv_sq = rcp_nr(sd_q);
+  t.inv_sp = rcp_nr(sd_p);
+  t.aq = (z - mu_q) * t.inv_sq;
+  t.ap = (z - mu_p) * t.inv_sp;
+  t.kl = 0.5f * (t.ap - t.aq) * (t.ap + t.aq) - log_sd_ratio(sd_q, sd_p, sd_q - sd_p, sd_q + sd_p, t.inv_sp);
+  return t;
+}
+// d kl / d (mu_q, sd_q, mu_p, sd_p, z), each multiplied by g
+BLVM_HD void kl_mc_grads(const KlMcTerms& t, float g, float& g_mu_q, float& g_sd_q, float& g_mu_p, float& g_sd_p, float& g_z) {
+  const float a = g * t.aq * t.inv_sq, b = g * t.ap * t.inv_sp;
+  g_mu_q = a;                                          // d/d mu_q of -aq^2/2
+  g_mu_p = -b;
+  g_sd_q = g * fmaf(t.aq, t.aq, -1.0f) * t.inv_sq;     // (aq^2 - 1)/sd_q
+  g_sd_p = g * fmaf(-t.ap, t.ap, 1.0f) * t.inv_sp;     // (1 - ap^2)/sd_p
+  g_z = b - a;
 }
 // torch.maximum(kl, c) gradient routing: 1 above, 1/2 at the exact tie, 0 below.
 BLVM_HD float free_nats_gate(float kl, float c, bool enabled) {

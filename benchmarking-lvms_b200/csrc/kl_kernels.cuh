@@ -29,6 +29,8 @@ struct KlArgs {
   const float* kl_in;    // non-null: the level's KL is already materialised (compute_elbo's `kld_twise`); reduce it
   float* gkl;            // with kl_in: d/d kl out (nullable)
   int vec;               // 1: 128-bit accesses are legal for every pointer and row (set by the host)
+  const float* z;        // non-null: Monte-Carlo KL log q(z) - log p(z) at the given sample (bottom-up STCN) instead of the analytic KL
+  float* g_z;            // with z and the other gradients: d/d z out (nullable)
 };
 
 #ifndef BLVM_KL_TPB
@@ -89,6 +91,28 @@ __device__ __forceinline__ void kl_tile_body(const KlArgs& A, const int64_t tile
         s_kl += valid ? kl : kl * 0.0f;
         s_fn += valid ? klfn : klfn * 0.0f;
         if (A.gkl) A.gkl[i] = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
+      }
+    }
+  } else if (A.z) {                                      // Monte-Carlo KL at the sample z (signed terms; not a hot path)
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const int64_t e = e0 + static_cast<int64_t>(j) * TPB + tid;
+      if (e < A.row_elems) {
+        const int64_t i = base + e;
+        const bool valid = e < nvalid_row;
+        const KlMcTerms t = kl_mc_terms(A.z[i], A.mu_q[i], A.sd_q[i], A.mu_p[i], A.sd_p[i]);
+        const float kl = t.kl;
+        const float klfn = (A.fn_enabled && kl < A.min_kl) ? A.min_kl : kl;
+        s_kl += valid ? kl : kl * 0.0f;
+        s_fn += valid ? klfn : klfn * 0.0f;
+        if (A.kl) A.kl[i] = kl;
+        if (GRAD) {
+          float g = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
+          if (A.gout) g *= A.gout[i];
+          float gz;
+          kl_mc_grads(t, g, A.g_mu_q[i], A.g_sd_q[i], A.g_mu_p[i], A.g_sd_p[i], gz);
+          if (A.g_z) A.g_z[i] = gz;
+        }
       }
     }
   } else if (A.vec) {

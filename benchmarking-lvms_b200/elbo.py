@@ -24,20 +24,25 @@ class KLLevel:
     """One latent layer's contribution to the ELBO.
 
     Either the four Gaussian parameter tensors `(mu_q, sd_q, mu_p, sd_p)`, each (B, Tz, Z) — KL, free nats, mask, sums
-    and gradients then run in one kernel — or an already materialised elementwise `kld` (B, Tz, Z) as the reference's
+    and gradients then run in one kernel (with `z=` the level's KL is the Monte-Carlo estimate log q(z) - log p(z) of
+    bottom-up STCN, same kernel) — or an already materialised elementwise `kld` (B, Tz, Z) as the reference's
     compute_elbo receives it.  `stride` = temporal stride of the layer relative to the waveform (valid steps =
     ceil(x_sl / stride)); alternatively explicit `lens` (B).  `free_nats` overrides the op-level budget for this level
     (Clockwork-VAE scales it per level, clockwork_vae.py:151).
     """
 
-    def __init__(self, mu_q=None, sd_q=None, mu_p=None, sd_p=None, *, kld=None, stride: Optional[int] = None,
+    def __init__(self, mu_q=None, sd_q=None, mu_p=None, sd_p=None, *, kld=None, z=None, stride: Optional[int] = None,
                  lens: Optional[torch.Tensor] = None, free_nats: Optional[float] = None):
         if kld is None and any(t is None for t in (mu_q, sd_q, mu_p, sd_p)):
             raise ValueError("KLLevel needs either (mu_q, sd_q, mu_p, sd_p) or kld=")
         if stride is None and lens is None:
             raise ValueError("KLLevel needs stride= or lens=")
-        self.tensors = [kld] if kld is not None else [mu_q, sd_q, mu_p, sd_p]
-        self.kind = "kld" if kld is not None else "inputs"
+        if kld is not None:
+            self.tensors, self.kind = [kld], "kld"
+        elif z is not None:   # Monte-Carlo KL log q(z) - log p(z) at the sample z (bottom-up STCN, variational.py:73-83)
+            self.tensors, self.kind = [mu_q, sd_q, mu_p, sd_p, z], "mc"
+        else:
+            self.tensors, self.kind = [mu_q, sd_q, mu_p, sd_p], "inputs"
         self.stride, self.lens, self.free_nats = stride, lens, free_nats
 
 
@@ -157,7 +162,7 @@ def fused_elbo(
     specs, flat = [], []
     for lv in kl_levels:
         ts = lv.tensors
-        if len(ts) == 4 and not (ts[0].shape == ts[1].shape == ts[2].shape == ts[3].shape):
+        if len(ts) >= 4 and not all(t.shape == ts[0].shape for t in ts):
             ts = torch.broadcast_tensors(*ts)
         ts = [_f32c(t) for t in ts]
         if ts[0].dim() != 3 or ts[0].shape[0] != B:
@@ -223,15 +228,13 @@ def cwvae_compute_elbo(self, y, seq_mask, level_masks, x_sl, parameters, kld_lay
 def stcn_compute_loss(self, y, x_sl, parameters, mu_p, sd_p, mu_q, sd_q, z, free_nats: float, beta: float):
     """Drop-in for STCN.compute_loss (blvm/models/stcn/stcn.py:256-297).  Top-down (analytic KL, :286): every latent level
     goes through the fully fused KL kernel.  Bottom-up (:288): the level's KL is the Monte-Carlo estimate
-    log q(z) - log p(z) (variational.py:73-83, two Gaussian log-density kernels) handed to the fused op as a materialised
-    KL.  mask -> free nats -> mask (:286-289) equals max(kl, fn/Z) on valid steps and 0 on padded ones, which is what
+    log q(z) - log p(z) (variational.py:73-83), evaluated by the same kernel from the four parameter tensors and the sample z
+    (value, mask, free nats, sums and all five gradients in one pass).  mask -> free nats -> mask (:286-289) equals max(kl, fn/Z) on valid steps and 0 on padded ones, which is what
     the kernel computes (also for negative MC estimates)."""
     if self.top_down:
         levels = [KLLevel(mu_q[l], sd_q[l], mu_p[l], sd_p[l], stride=self.n_stack_frames) for l in range(self.n_latents)]
     else:
-        from .variational import kl_divergence_gaussian_mc
-        levels = [KLLevel(kld=kl_divergence_gaussian_mc(mu_q[l], sd_q[l], mu_p[l], sd_p[l], z[l]), stride=self.n_stack_frames)
-                  for l in range(self.n_latents)]
+        levels = [KLLevel(mu_q[l], sd_q[l], mu_p[l], sd_p[l], z=z[l], stride=self.n_stack_frames) for l in range(self.n_latents)]
     r = fused_elbo(y, parameters, x_sl, levels, beta, free_nats, num_bins=self.likelihood_module.num_bins)
     f = torch.float32
     return r.loss.to(f), r.elbo.to(f), r.log_prob.to(f), r.kl.to(f), [k.to(f) for k in r.kl_levels]

@@ -355,7 +355,7 @@ def kl_gaussian(mu_q, sd_q, mu_p, sd_p):
 # ----------------------------------------------------------------------------------------------------------------------
 @dataclass
 class KLLevelSpec:
-    kind: str                      # "inputs" (mu_q, sd_q, mu_p, sd_p given: fully fused) or "kld" (elementwise KL given)
+    kind: str                      # "inputs" (mu_q, sd_q, mu_p, sd_p: fully fused), "mc" (+ z: Monte-Carlo KL, fully fused) or "kld" (elementwise KL given)
     free_nats: float               # budget per latent step for this level (already scaled, clockwork_vae.py:151)
     lens: Optional[torch.Tensor]   # (B) int64 on device: valid latent steps, None = all
     n_tensors: int = 4
@@ -493,7 +493,8 @@ class _FusedELBO(torch.autograd.Function):
             kl_ptrs, klfn_ptrs, kl_chunks = [], [], []
             i = 0
             gscale = spec.beta / spec.denom
-            multi = (_lib.KLLevelStruct * L)() if L >= 2 else None   # hierarchies: all levels in one launch
+            # hierarchies (and Monte-Carlo levels, which only the level-array entry point takes): all levels in one launch
+            multi = (_lib.KLLevelStruct * L)() if (L >= 2 or any(lv.kind == "mc" for lv in spec.levels)) else None
             for li, (lv, (Tz, Z, chunks)) in enumerate(zip(spec.levels, shapes)):
                 # the launch just before this one is this step's likelihood / previous KL level, which produces none of
                 # this level's inputs: the KL grid may fill that grid's tail (programmatic dependent launch)
@@ -503,7 +504,13 @@ class _FusedELBO(torch.autograd.Function):
                 pk = base + 8 * off
                 pf = pk + 8 * B * chunks
                 off += 2 * B * chunks
-                if lv.kind == "inputs":
+                if lv.kind == "mc":
+                    g5 = [torch.empty_like(ts[0]) for _ in range(5)] if spec.need_grad else [None] * 5
+                    multi[li] = _lib.KLLevelStruct(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(), None,
+                                                   _ptr(lv.lens), Tz, Z, lv.free_nats, _ptr(g5[0]), _ptr(g5[1]), _ptr(g5[2]),
+                                                   _ptr(g5[3]), None, pk, pf, ts[4].data_ptr(), _ptr(g5[4]))
+                    grads += g5
+                elif lv.kind == "inputs":
                     g4 = [torch.empty_like(ts[0]) for _ in range(4)] if spec.need_grad else [None] * 4
                     if multi is None:
                         rc = lib.blvm_kl_elbo_fwd_grad(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
@@ -513,7 +520,7 @@ class _FusedELBO(torch.autograd.Function):
                     else:
                         multi[li] = _lib.KLLevelStruct(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(), None,
                                                        _ptr(lv.lens), Tz, Z, lv.free_nats, _ptr(g4[0]), _ptr(g4[1]), _ptr(g4[2]),
-                                                       _ptr(g4[3]), None, pk, pf)
+                                                       _ptr(g4[3]), None, pk, pf, None, None)
                     grads += g4
                 else:
                     gk = torch.empty_like(ts[0]) if spec.need_grad else None
@@ -523,7 +530,7 @@ class _FusedELBO(torch.autograd.Function):
                         check(rc, "blvm_kl_reduce_fwd_grad")
                     else:
                         multi[li] = _lib.KLLevelStruct(None, None, None, None, ts[0].data_ptr(), _ptr(lv.lens), Tz, Z, lv.free_nats,
-                                                       None, None, None, None, _ptr(gk), pk, pf)
+                                                       None, None, None, None, _ptr(gk), pk, pf, None, None)
                     grads.append(gk)
                 if multi is None:
                     _count()

@@ -179,6 +179,10 @@ typedef struct blvm_kl_level {
   float *g_mu_q, *g_sd_q, *g_mu_p, *g_sd_p; /* gradients out, nullable together (with the four inputs) */
   float* g_kl;                            /* d/d kl out, nullable (with `kl`) */
   double *part_kl, *part_klfn;            /* (B, blvm_kl_chunks(Tz*Z)) fp64 */
+  const float* z;                         /* nullable (B, Tz, Z): with the four parameter tensors, the level's KL is the Monte-Carlo
+                                             estimate log q(z) - log p(z) (blvm/utils/variational.py:73-83, bottom-up STCN
+                                             stcn.py:288) instead of the analytic KL */
+  float* g_z;                             /* nullable: d/d z out (with z and the four gradient outputs) */
 } blvm_kl_level_t;
 int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, int flags,
                                  blvm_stream_t stream);

@@ -138,3 +138,14 @@ extern "C" void hostsim_k1_pairs(const float* y, const float* raw, const float* 
     for (int i = 0; i < 3; ++i) { graw[n * 3 + i] = ra[i]; graw[(n + H) * 3 + i] = rb[i]; }
   }
 }
+
+// Monte-Carlo KL log q(z) - log p(z) of one latent element and its five gradients (blvm_math.cuh: kl_mc_terms / kl_mc_grads)
+extern "C" void hostsim_kl_mc(const float* z, const float* mu_q, const float* sd_q, const float* mu_p, const float* sd_p,
+                              const float* gout, int64_t n, float* kl, float* g_mu_q, float* g_sd_q, float* g_mu_p, float* g_sd_p,
+                              float* g_z) {
+  for (int64_t i = 0; i < n; ++i) {
+    const KlMcTerms t = kl_mc_terms(z[i], mu_q[i], sd_q[i], mu_p[i], sd_p[i]);
+    kl[i] = t.kl;
+    kl_mc_grads(t, gout ? gout[i] : 1.f, g_mu_q[i], g_sd_q[i], g_mu_p[i], g_sd_p[i], g_z[i]);
+  }
+}

@@ -249,3 +249,27 @@ def test_kl_extreme_regimes_against_fp64_oracle(sim):
     scales = (np.abs(q - p) / sp ** 2, 1 / sq + sq / sp ** 2, np.abs(q - p) / sp ** 2, 1 / sp + (sq ** 2 + d2) / sp ** 3)
     for o, g, sc, nm in zip(outs[2:], grads, scales, ("mu_q", "sd_q", "mu_p", "sd_p")):
         assert (np.abs(o - g) <= 1e-6 * sc + 1e-30).all(), nm
+
+
+def test_kl_mc_closed_forms(sim):
+    """Monte-Carlo KL log q(z) - log p(z) (variational.py:73-83) and its gradients against the reference's fp64 run."""
+    g = load_golden("gaussian_ll")
+    z, mu_q, sd_q, mu_p, sd_p, gout = (np.ascontiguousarray(g[k], np.float32).reshape(-1) for k in ("y", "mu_q", "sd_q", "mu_p", "sd_p", "gout"))
+    n = z.size
+    outs = [np.empty(n, np.float32) for _ in range(6)]
+    sim.hostsim_kl_mc(P(z), P(mu_q), P(sd_q), P(mu_p), P(sd_p), P(gout), ctypes.c_int64(n), *[P(o) for o in outs])
+    ref = g["klmc64"].reshape(-1)
+    # a difference of two log-densities: the error is bounded relative to the size of its terms (the golden contains
+    # sd_q = 1e-3 rows with |kl| ~ 1e6), 1e-6 of them
+    aq, ap = (z - mu_q) / sd_q, (z - mu_p) / sd_p
+    scale = 0.5 * aq.astype(np.float64) ** 2 + 0.5 * ap.astype(np.float64) ** 2 + np.abs(np.log(sd_q.astype(np.float64) / sd_p))
+    assert (np.abs(outs[0] - ref) <= 1e-6 * scale + 1e-7).all()
+    for o, nm in zip(outs[1:5], ("mu_q", "sd_q", "mu_p", "sd_p")):
+        r = g[f"klmc_g_{nm}64"].reshape(-1)
+        np.testing.assert_allclose(o, r, rtol=1e-5, atol=1e-7 * np.abs(r).max(), err_msg=nm)
+    # d/dz is not in the golden: finite differences of the fp64 oracle
+    from oracle import blvm_oracle as O
+    z64, q, sq, p, sp = (a.astype(np.float64) for a in (z, mu_q, sd_q, mu_p, sd_p))
+    h = 1e-6
+    fd = (O.kl_divergence_gaussian_mc(q, sq, p, sp, z64 + h) - O.kl_divergence_gaussian_mc(q, sq, p, sp, z64 - h)) / (2 * h) * gout
+    np.testing.assert_allclose(outs[5], fd, rtol=2e-4, atol=1e-5 * np.abs(fd).max())
