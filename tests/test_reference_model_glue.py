@@ -53,7 +53,8 @@ def install_fakes(monkeypatch, B, O):
         for lv in spec.levels:
             ts = [t.detach().double().numpy() for t in kl_tensors[i:i + lv.n_tensors]]
             i += lv.n_tensors
-            kl = O.kl_divergence_gaussian(*ts) if lv.kind == "inputs" else ts[0]
+            kl = (O.kl_divergence_gaussian(*ts) if lv.kind == "inputs" else
+                  O.kl_divergence_gaussian_mc(*ts) if lv.kind == "mc" else ts[0])
             m = O.sequence_mask(lv.lens.numpy(), max_len=kl.shape[1])[..., None].astype(np.float64)
             kl_rows.append((kl * m).sum((1, 2)))
             fn_rows.append((O.discount_free_nats(kl, lv.free_nats, -1) * m).sum((1, 2)))
@@ -92,6 +93,8 @@ def build(M, name):
         return M.CWVAEAudio(z_size=[8, 4], h_size=[16, 16], strides=[16, 4], num_level_layers=2, stride_per_layer=4, likelihood="DMoL", num_bins=2 ** 16)
     if name == "stcn":
         return M.STCN(likelihood="DMoL", n_layers=2, latent_size=[8, 4], res_channels=16)
+    if name == "stcn_bottom_up":   # Monte-Carlo KL at the sampled z (stcn.py:288)
+        return M.STCN(likelihood="DMoL", n_layers=2, latent_size=[8, 4], res_channels=16, top_down=False)
     if name == "wavenet":
         return M.WaveNet(likelihood=lik(x_dim=16, y_dim=1, num_mix=10, num_bins=2 ** 16), n_layers=2, n_stacks=1, res_channels=16)
     if name == "lstm":
@@ -99,7 +102,7 @@ def build(M, name):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["vrnn", "srnn", "cwvae", "stcn", "wavenet", "lstm"])
+@pytest.mark.parametrize("name", ["vrnn", "srnn", "cwvae", "stcn", "stcn_bottom_up", "wavenet", "lstm"])
 def test_patched_model_matches_reference_model(name, env, monkeypatch):
     M, B, O = env
     T = 1600 if name != "cwvae" else 1024
