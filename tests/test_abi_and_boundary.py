@@ -137,3 +137,29 @@ def test_patch_blvm_rebinds_reference_names():
         B.unpatch_blvm()
     vrnn = sys.modules["blvm.models.vrnn"]
     assert vrnn.VRNN.compute_elbo is not B.vrnn_compute_elbo
+
+
+def test_grad_scaler_observation_and_numa_binding_are_safe_without_a_gpu():
+    """amp.observe_grad_scalers() registers scalers constructed afterwards and restores GradScaler.__init__ when stopped; a
+    disabled scaler (or one whose scale tensor does not exist yet) is never 'active'; the NUMA helper is a no-op when the
+    topology cannot be read."""
+    import torch
+    import blvm_b200
+    from blvm_b200 import amp
+    orig_init = torch.amp.GradScaler.__init__
+    amp.observe_grad_scalers()
+    try:
+        assert torch.amp.GradScaler.__init__ is not orig_init
+        s = torch.amp.GradScaler("cuda", enabled=False)
+        assert s in amp._scalers
+        assert amp.active_grad_scaler(torch.device("cuda", 0)) is None
+    finally:
+        amp.stop_observing()
+    assert torch.amp.GradScaler.__init__ is orig_init
+    s2 = torch.amp.GradScaler("cuda", enabled=False)
+    assert s2 not in amp._scalers
+    assert blvm_b200.register_grad_scaler(s2) is s2 and s2 in amp._scalers
+    amp._scalers.discard(s2)
+    amp._scalers.discard(s)
+    if not torch.cuda.is_available():
+        assert blvm_b200.bind_to_gpu_numa_node(0) is None
