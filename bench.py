@@ -7,7 +7,10 @@
 Workload = BASELINE.json configs[4] ("standalone DMoL+KL ELBO kernel sweep", the configuration the metric
 "DMoL+KL ELBO fwd+bwd at 1/2/4/8 B200; % HBM roofline" is quoted on) at its first grid point: per GPU 256 utterances x
 16000 samples, DMoL K=10, 16-bit bins, one latent layer of stride 64 / width 64 (SRNN-like), beta 0.5, free nats 1/16.
-Weak scaling: every rank owns its own 256 utterances; the only collective is the all-reduce of the scalar sums.
+Weak scaling: every rank owns its own 256 utterances; the only exchange is that of the scalar sums (fused into the
+finalize kernel over NVLink peer memory, or an NCCL all-reduce).  `--workload config2|config3|config3z256|config4` run the
+same step at the shapes of BASELINE configs 2-4 (informational); `--impl reference --reference-device cuda|cpu-torch`
+time the reference's own op chain as eager PyTorch on this GPU / on the host threads (informational).
 
 One JSON line on stdout (rank 0).  `value` times K steps with inputs resident in HBM (CUDA events, max over ranks);
 `e2e` times the same step through the public API from pinned HOST buffers (H2D of every input + D2H of the result
