@@ -28,6 +28,17 @@ class KLLevelStruct(ctypes.Structure):
                 ("part_kl", _p), ("part_klfn", _p), ("z", _p), ("g_z", _p)]
 
 
+class ElboStepStruct(ctypes.Structure):
+    """blvm_elbo_step_t (include/blvm_b200.h)."""
+    _fields_ = [("likelihood", _i32), ("raw_dtype", _i32), ("K", _i32), ("D", _i32), ("num_bins", _i32), ("flags", _i32),
+                ("n_levels", _i32), ("rank", _i32), ("world", _i32), ("log_epsilon", _f32), ("B", _i64), ("T", _i64),
+                ("y", _p), ("raw", _p), ("x_sl", _p), ("lp_twise", _p), ("graw", _p), ("loss_scale", _p),
+                ("gmm_softplus_beta", _f64), ("gmm_sd_add", _f64), ("beta", _f64), ("denom", _f64),
+                ("levels", KLLevelStruct * 8), ("workspace", _p), ("sync_counter", _p), ("err_flag", _p),
+                ("peer_bases_host", ctypes.POINTER(_p)), ("exchange_counters", _p), ("prev_global_sums", _p),
+                ("exchange_err", _p)]
+
+
 SIGNATURES = {
     "blvm_version": (_i32, []),
     "blvm_last_error_string": (ctypes.c_char_p, []),
@@ -51,6 +62,9 @@ SIGNATURES = {
     "blvm_elbo_finalize_publish": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64,
                                           _f64, _f64, _p, _p, _p, ctypes.POINTER(_p), _i32, _i32, _p, _p, _p, _p]),
     "blvm_exchange_buffer_bytes": (_i64, []),
+    "blvm_elbo_step_workspace_doubles": (_i64, [ctypes.POINTER(ElboStepStruct)]),
+    "blvm_elbo_step": (_i32, [ctypes.POINTER(ElboStepStruct), _p]),
+    "blvm_row_gate_inplace": (_i32, [_p, _i32, _i64, _i64, _p, _p]),
     "blvm_exchange_consume": (_i32, [_p, _i32, _p, _i32, _f64, _p, _p, _p]),
     "blvm_quantize": (_i32, [_p, _i64, _p, _i64, _p, _p]),
     "blvm_dmol_sample_mode": (_i32, [_p, _i32, _i64, _i32, _i32, _f32, ctypes.c_uint64, ctypes.c_uint64, _p, _p, _p, _p]),
@@ -67,7 +81,10 @@ BLVM_DTYPE_F32, BLVM_DTYPE_F16, BLVM_DTYPE_BF16 = 0, 1, 2
 BLVM_FLAG_MASK_OUTPUT = 1
 BLVM_FLAG_SKIP_PADDED = 2
 BLVM_FLAG_OVERLAP_PREV = 4
+BLVM_FLAG_NANSUM_LOSS = 8
+BLVM_LIK_NONE, BLVM_LIK_DMOL, BLVM_LIK_DL, BLVM_LIK_GMM = 0, 1, 2, 3
 BLVM_MAX_KL_LEVELS = 8
+BLVM_KL_TILE = 1024
 
 
 class BlvmError(RuntimeError):

@@ -32,8 +32,15 @@ def active_grad_scaler(device: torch.device):
     scaler or a scale that has not been created yet all fall back to the deferred-gradient path)."""
     found = None
     for s in list(_scalers):
+        if not getattr(s, "_enabled", False):
+            continue
         scale = getattr(s, "_scale", None)
-        if not getattr(s, "_enabled", False) or scale is None or scale.device != device:
+        if scale is None and hasattr(s, "_lazy_init_scale_growth_tracker"):
+            # the scale tensor is created by the first `scaler.scale(loss)`, i.e. AFTER the first forward pass; create it now
+            # exactly as that call would (same init value, same device) so that the very first step is single-pass too
+            s._lazy_init_scale_growth_tracker(device)
+            scale = s._scale
+        if scale is None or scale.device != device:
             continue
         if found is not None:
             return None

@@ -21,6 +21,8 @@ static_assert(BLVM_KL_TILE == kKlChunk, "tile constant mirrors the KL kernel");
 static_assert(BLVM_MAX_KL_LEVELS == kMaxLevels, "level cap");
 static_assert(BLVM_MAX_SCALE_BUFFERS == kMaxScaleBuffers, "scale buffer cap");
 static_assert(BLVM_FLAG_MASK_OUTPUT == kFlagMaskOutput && BLVM_FLAG_SKIP_PADDED == kFlagSkipPadded, "flags");
+using blvm_host::kMaxDevices;
+using blvm_host::current_device;
 
 namespace blvm_host {   // instantiated in blvm_dmol_f32.cu / _f16.cu / _bf16.cu
 extern template int dmol_dispatch_tp<float>(const blvm::DmolArgs&, bool, int64_t, cudaStream_t);
@@ -52,13 +54,24 @@ bool pdl_enabled() {
 }
 
 int sm_count() {
-  static int n = 0;
+  static int n_dev[kMaxDevices] = {};
+  const int dev = current_device();
+  int& n = n_dev[dev];
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+// utterances up to which ONE CTA finalizes the whole step (elbo_finalize_small_kernel); env BLVM_B200_FIN_SMALL_B overrides
+int finalize_small_max_b() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BLVM_B200_FIN_SMALL_B");
+    v = e ? atoi(e) : 64;
+    if (v < 0) v = 0;
+  }
+  return v;
 }
 
 // 0 = tile kernel only, 1 = stream kernel where eligible (default), read once (A/B runs set it before the first call)
@@ -133,11 +146,12 @@ template <int K, bool GRAD, int LIK>
 int launch_gmm_tile(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
   constexpr size_t smem = dmol_tile_smem_bytes<K, kTile, float>();
   auto kern = dmol_tile_kernel<K, kTile, GRAD, kUGeneral, float, LIK>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[blvm_host::kMaxDevices] = {};
+  const int dev = blvm_host::current_device();
+  if (!configured[dev]) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-    configured = true;
+    configured[dev] = true;
   }
   kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
   return check_launch("dmol_tile_kernel<gmm>");
@@ -430,12 +444,12 @@ int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_level
 static int finalize_impl(const double* logp_part, int64_t logp_chunks, const double* const* kl_part_host,
                          const double* const* klfn_part_host, const int64_t* kl_chunks_host, int n_levels,
                          const int64_t* x_sl, int64_t B, double beta, double denom, double* rows, double* scalars,
-                         unsigned int* sync_counter, const ExchangeArgs& X, blvm_stream_t stream) {
+                         unsigned int* sync_counter, const ExchangeArgs& X, blvm_stream_t stream, int nansum_loss = 0) {
   if (n_levels < 0 || n_levels > kMaxLevels) return fail(BLVM_ERR_INVALID_ARGUMENT, "n_levels=%d out of [0, %d]", n_levels, kMaxLevels);
   if (B < 0 || !x_sl || !rows || !scalars || !sync_counter) return fail(BLVM_ERR_INVALID_ARGUMENT, "null x_sl/rows/scalars/sync_counter");
   FinalizeArgs A{};
   A.logp_part = logp_part; A.logp_chunks = logp_chunks; A.n_levels = n_levels; A.x_sl = x_sl; A.B = B; A.beta = beta;
-  A.denom = denom; A.rows = rows; A.scalars = scalars;
+  A.denom = denom; A.rows = rows; A.scalars = scalars; A.nansum_loss = nansum_loss;
   for (int l = 0; l < n_levels; ++l) {
     if (!kl_part_host[l] || !klfn_part_host[l]) return fail(BLVM_ERR_INVALID_ARGUMENT, "null KL partials at level %d", l);
     A.kl_part[l] = kl_part_host[l]; A.klfn_part[l] = klfn_part_host[l]; A.kl_chunks[l] = kl_chunks_host[l];
@@ -443,6 +457,11 @@ static int finalize_impl(const double* logp_part, int64_t logp_chunks, const dou
   const unsigned blocks = static_cast<unsigned>(B > 0 ? (B + kFinWarps - 1) / kFinWarps : 1);
   // always a programmatic dependent: the kernel waits for its predecessor before its first read, so this is safe after
   // any kernel, and after a blvm kernel (which releases its dependents early) the CTAs are already resident when it ends
+  if (B <= blvm_host::finalize_small_max_b()) {   // a handful of utterances: one CTA, no inter-CTA hand-off
+    const cudaError_t e = launch_ex(elbo_finalize_small_kernel, 1u, kFinSmallTPB, 0, static_cast<cudaStream_t>(stream), pdl_enabled(), A, X);
+    if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "elbo_finalize_small_kernel: %s", cudaGetErrorString(e));
+    return check_launch("elbo_finalize_small_kernel");
+  }
   const cudaError_t e = launch_ex(elbo_finalize_kernel, blocks, kFinTPB, 0, static_cast<cudaStream_t>(stream), pdl_enabled(), A, sync_counter, X);
   if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "elbo_finalize_kernel: %s", cudaGetErrorString(e));
   return check_launch("elbo_finalize_kernel");
@@ -476,6 +495,122 @@ int blvm_elbo_finalize_publish(const double* logp_part, int64_t logp_chunks, con
 }
 
 int64_t blvm_exchange_buffer_bytes(void) { return static_cast<int64_t>(kExBufferBytes); }
+
+// ---- the whole step from one call -----------------------------------------------------------------------------------
+static int64_t step_logp_chunks(const blvm_elbo_step_t& S) {
+  switch (S.likelihood) {
+    case BLVM_LIK_DMOL: return blvm_dmol_chunks(S.T, S.K, S.D);
+    case BLVM_LIK_DL: return blvm_dl_chunks(S.T);
+    case BLVM_LIK_GMM: return blvm_gmm_chunks(S.T, S.K, S.D);
+    default: return 0;
+  }
+}
+
+int64_t blvm_elbo_step_workspace_doubles(const blvm_elbo_step_t* S) {
+  if (!S || S->n_levels < 0 || S->n_levels > kMaxLevels || S->B < 0) return -1;
+  int64_t n = 8 + (4 + static_cast<int64_t>(S->n_levels)) * S->B + S->B * step_logp_chunks(*S);
+  for (int l = 0; l < S->n_levels; ++l) n += 2 * S->B * blvm_kl_chunks(S->levels[l].Tz * S->levels[l].Z);
+  return n;
+}
+
+int blvm_elbo_step(const blvm_elbo_step_t* desc, blvm_stream_t stream) {
+  if (!desc) return fail(BLVM_ERR_INVALID_ARGUMENT, "null descriptor");
+  const blvm_elbo_step_t& S = *desc;
+  const int L = S.n_levels;
+  if (L < 0 || L > kMaxLevels) return fail(BLVM_ERR_INVALID_ARGUMENT, "n_levels=%d out of [0, %d]", L, kMaxLevels);
+  if (S.B < 0 || !S.workspace || !S.x_sl || !S.sync_counter) return fail(BLVM_ERR_INVALID_ARGUMENT, "null workspace / x_sl / sync_counter or negative B");
+  if (S.likelihood < BLVM_LIK_NONE || S.likelihood > BLVM_LIK_GMM) return fail(BLVM_ERR_INVALID_ARGUMENT, "likelihood=%d", S.likelihood);
+  const bool has_lik = S.likelihood != BLVM_LIK_NONE;
+  const bool lik_grad = has_lik && S.graw != nullptr;
+  bool kl_grad = false;
+  for (int l = 0; l < L; ++l) kl_grad = kl_grad || S.levels[l].g_mu_q != nullptr || S.levels[l].g_kl != nullptr;
+  const double dn = S.denom;
+  if ((lik_grad || kl_grad) && !(dn > 0.0)) return fail(BLVM_ERR_INVALID_ARGUMENT, "denom=%g must be > 0 when gradients are requested", dn);
+  double* scalars = S.workspace;
+  double* rows = S.workspace + 8;
+  double* part = rows + (4 + static_cast<int64_t>(L)) * S.B;
+  const int64_t logp_chunks = step_logp_chunks(S);
+  double* logp_part = has_lik ? part : nullptr;
+  part += S.B * logp_chunks;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  if (has_lik) {
+    const int kflags = S.flags & (BLVM_FLAG_MASK_OUTPUT | BLVM_FLAG_SKIP_PADDED);
+    const float gscale = lik_grad ? static_cast<float>(-1.0 / dn) : 0.f;
+    int rc;
+    if (S.likelihood == BLVM_LIK_DMOL) {
+      rc = lik_grad ? blvm_dmol_fwd_grad(S.y, S.raw, S.raw_dtype, S.x_sl, nullptr, gscale, S.loss_scale, S.B, S.T, S.K, S.D, S.num_bins,
+                                     S.log_epsilon, kflags, S.lp_twise, S.graw, logp_part, S.err_flag, stream)
+                : blvm_dmol_fwd(S.y, S.raw, S.raw_dtype, S.x_sl, S.B, S.T, S.K, S.D, S.num_bins, S.log_epsilon, kflags, S.lp_twise,
+                                logp_part, S.err_flag, stream);
+    } else if (S.likelihood == BLVM_LIK_GMM) {
+      if (S.raw_dtype != BLVM_DTYPE_F32) return fail(BLVM_ERR_UNSUPPORTED, "Gaussian-mixture parameters must be fp32");
+      rc = blvm_gmm_fwd_grad(S.y, static_cast<const float*>(S.raw), S.x_sl, nullptr, gscale, nullptr, S.B, S.T, S.K, S.D, 1,
+                             S.gmm_softplus_beta, S.gmm_sd_add, 0.0, kflags, S.lp_twise, static_cast<float*>(S.graw), logp_part, stream);
+    } else {
+      if (S.raw_dtype != BLVM_DTYPE_F32) return fail(BLVM_ERR_UNSUPPORTED, "discretized-logistic parameters must be fp32");
+      rc = blvm_dl_fwd_grad(S.y, static_cast<const float*>(S.raw), S.x_sl, nullptr, gscale, S.B, S.T, S.num_bins, S.log_epsilon, kflags,
+                            S.lp_twise, static_cast<float*>(S.graw), logp_part, S.err_flag, stream);
+    }
+    if (rc) return rc;
+  }
+
+  const double* kl_part[kMaxLevels];
+  const double* klfn_part[kMaxLevels];
+  int64_t kl_chunks[kMaxLevels];
+  if (L > 0) {
+    blvm_kl_level_t lv[kMaxLevels];
+    for (int l = 0; l < L; ++l) {
+      lv[l] = S.levels[l];
+      kl_chunks[l] = blvm_kl_chunks(lv[l].Tz * lv[l].Z);
+      lv[l].part_kl = part;
+      lv[l].part_klfn = part + S.B * kl_chunks[l];
+      kl_part[l] = lv[l].part_kl;
+      klfn_part[l] = lv[l].part_klfn;
+      part += 2 * S.B * kl_chunks[l];
+    }
+    // the launch just before is this step's likelihood kernel, which produces none of the KL inputs: overlap its tail
+    const int rc = blvm_kl_elbo_levels_fwd_grad(lv, L, S.B, kl_grad ? static_cast<float>(S.beta / dn) : 0.f, has_lik ? BLVM_FLAG_OVERLAP_PREV : 0, stream);
+    if (rc) return rc;
+  }
+
+  ExchangeArgs X{};
+  if (S.world > 0) {
+    if (S.world > kExMaxWorld || S.rank < 0 || S.rank >= S.world) return fail(BLVM_ERR_INVALID_ARGUMENT, "rank=%d world=%d (max %d)", S.rank, S.world, kExMaxWorld);
+    if (!S.peer_bases_host || !S.exchange_counters) return fail(BLVM_ERR_INVALID_ARGUMENT, "null exchange buffers");
+    X.rank = S.rank; X.world = S.world; X.counters = S.exchange_counters; X.global_out = S.prev_global_sums; X.err = S.exchange_err;
+    for (int p = 0; p < S.world; ++p) {
+      if (!S.peer_bases_host[p]) return fail(BLVM_ERR_INVALID_ARGUMENT, "null peer buffer %d", p);
+      X.peer_base[p] = static_cast<double*>(S.peer_bases_host[p]);
+    }
+  }
+  const int nansum = (S.flags & BLVM_FLAG_NANSUM_LOSS) ? 1 : 0;
+  if (int rc = finalize_impl(logp_part, logp_chunks, kl_part, klfn_part, kl_chunks, L, S.x_sl, S.B, S.beta, dn, rows, scalars,
+                             S.sync_counter, X, stream, nansum))
+    return rc;
+  if (nansum && lik_grad) {
+    const int P = S.likelihood == BLVM_LIK_DL ? 2 : S.K * (2 * S.D + 1);
+    return blvm_row_gate_inplace(S.graw, S.raw_dtype, S.B, S.T * P, rows /* row 0 = log p per utterance */, stream);
+  }
+  (void)st;
+  return BLVM_OK;
+}
+
+int blvm_row_gate_inplace(void* buf, int dtype, int64_t B, int64_t row_elems, const double* row_values, blvm_stream_t stream) {
+  if (B < 0 || row_elems < 0 || (B * row_elems > 0 && (!buf || !row_values))) return fail(BLVM_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (B * row_elems == 0) return BLVM_OK;
+  const int64_t chunks = (row_elems + kRowGateChunk - 1) / kRowGateChunk;
+  if (B * chunks > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
+  const unsigned g = static_cast<unsigned>(B * chunks), c = static_cast<unsigned>(chunks);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case BLVM_DTYPE_F32: row_gate_kernel<float><<<g, 256, 0, st>>>(static_cast<float*>(buf), row_elems, c, row_values); break;
+    case BLVM_DTYPE_F16: row_gate_kernel<__half><<<g, 256, 0, st>>>(static_cast<__half*>(buf), row_elems, c, row_values); break;
+    case BLVM_DTYPE_BF16: row_gate_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(static_cast<__nv_bfloat16*>(buf), row_elems, c, row_values); break;
+    default: return fail(BLVM_ERR_INVALID_ARGUMENT, "dtype=%d", dtype);
+  }
+  return check_launch("row_gate_kernel");
+}
 
 int blvm_exchange_consume(void* local_base, int world, unsigned long long* exchange_counters, int lag, double beta,
                           double* out_sums, int* err_flag, blvm_stream_t stream) {

@@ -26,11 +26,12 @@ template <int K, bool GRAD, int UMODE, typename TP>
 int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
   constexpr size_t smem = dmol_tile_smem_bytes<K, kTile, TP>();
   auto kern = dmol_tile_kernel<K, kTile, GRAD, UMODE, TP>;
-  static bool configured = false;  // per instantiation; benign race (idempotent attribute)
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};  // per instantiation and device; benign race (idempotent attribute)
+  const int dev = current_device();
+  if (!configured[dev]) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-    configured = true;
+    configured[dev] = true;
   }
   kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
   return check_launch("dmol_tile_kernel");
@@ -77,7 +78,8 @@ int launch_stream(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
   constexpr int S = BLVM_STREAM_STAGES, LA = BLVM_STREAM_LOOKAHEAD;
   constexpr size_t smem = StreamLayout<K, TPB, TP>::bytes(S);
   auto kern = dmol_stream_kernel<K, TPB, S, LA, GRAD, UMODE, TP, LIK>;
-  static int resident = 0;  // CTAs per SM; per instantiation, benign race
+  static int resident_dev[kMaxDevices] = {};  // CTAs per SM; per instantiation and device, benign race
+  int& resident = resident_dev[current_device()];
   if (resident == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
@@ -112,11 +114,12 @@ template <int K, typename TP>
 int launch_sample_tile(const SampleArgs& A, int64_t tiles, cudaStream_t st) {
   constexpr size_t smem = ((size_t(kTile) * DmolSpt<K>::value * 3 * K * sizeof(TP) + 15) / 16) * 16 + 16;
   auto kern = dmol_sample_mode_tile_kernel<K, TP>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
-    configured = true;
+    configured[dev] = true;
   }
   kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
   return check_launch("dmol_sample_mode_tile_kernel");

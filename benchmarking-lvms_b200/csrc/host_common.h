@@ -13,6 +13,15 @@ int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
 const char* last_error();
 
+// Per-device launch state (function attributes, occupancy, SM count) is cached per CUDA device: one process may drive
+// several GPUs (the Python layer accepts tensors on a non-current device).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // fp32 constants rounded from double exactly like torch rounds a Python scalar that meets an fp32 tensor.

@@ -211,6 +211,7 @@ struct FinalizeArgs {
   double denom;                     // normaliser of the loss; <= 0 means sum(x_sl) (data-parallel callers pass global/world)
   double* rows;                     // (4 + n_levels, B): logp, kl, kl_fn, elbo, kl_level_l...
   double* scalars;                  // (8): loss, sum logp, sum kl, sum kl_fn, sum elbo, sum x_sl, bpd, nan-safe loss
+  int nansum_loss;                  // 1: scalars[0] is the nansum loss as well (WaveNet.compute_loss, wavenet.py:145)
 };
 
 constexpr int kFinTPB = 256;
@@ -381,7 +382,7 @@ __device__ __forceinline__ void finalize_scalars(const FinalizeArgs& A, const Ex
   const double s_logp = s6[0], s_kl = s6[1], s_fn = s6[2], s_obj = s6[3], s_nan = s6[4], s_len = s6[5];
   if (tid == 0) {
     const double dn = A.denom > 0.0 ? A.denom : s_len;
-    A.scalars[0] = -s_obj / dn;                          // loss (vrnn.py:277), consistent with the gradients' 1/denom
+    A.scalars[0] = A.nansum_loss ? -s_nan / dn : -s_obj / dn;   // loss (vrnn.py:277 / wavenet.py:145), consistent with the gradients' 1/denom
     A.scalars[1] = s_logp;
     A.scalars[2] = s_kl;
     A.scalars[3] = s_fn;
@@ -436,6 +437,20 @@ static __global__ void __launch_bounds__(kFinTPB) elbo_finalize_kernel(const Fin
   __threadfence();
   if (tid == 0) *counter = 0u;                           // ready for the next launch on this stream
   finalize_scalars<kFinTPB>(A, X, scratch);
+}
+
+// Small batches (model-shaped steps: B = 32 / 64 utterances): ONE CTA of 32 warps reduces every utterance (warp w takes rows
+// w, w + 32, ...) and then the scalars.  No inter-CTA hand-off (fence + atomic + second load phase through L2), which is
+// the longest link of the multi-CTA kernel's latency chain when there are only a handful of rows.  Same per-row and
+// per-scalar summation orders: bit-identical outputs.
+constexpr int kFinSmallTPB = 1024;
+static __global__ void __launch_bounds__(kFinSmallTPB) elbo_finalize_small_kernel(const FinalizeArgs A, const ExchangeArgs X) {
+  __shared__ double scratch[6 * (kFinSmallTPB / 32)];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ptx::pdl_wait();
+  for (int64_t b = warp; b < A.B; b += kFinSmallTPB / 32) finalize_row(A, b, lane);
+  __syncthreads();                                       // the rows (global memory, written by lane 0 of each warp) are visible CTA-wide
+  finalize_scalars<kFinSmallTPB>(A, X, scratch);
 }
 
 // Consume one published step: wait until all W ranks' slots of step `seq = published - lag` have landed in the LOCAL

@@ -54,6 +54,22 @@ __global__ void __launch_bounds__(256) gaussian_ll_kernel(const float* __restric
   }
 }
 
+// Rows of buf (B, row_elems) whose row_values[b] is NaN are multiplied by 0 (finite entries become 0, NaN stays NaN: what
+// `0 * local derivative` gives in the reference when nansum's backward hands a NaN utterance a zero gradient,
+// wavenet.py:145).  One CTA per kRowGateChunk elements of a row; CTAs of finite rows leave after reading one double.
+constexpr int kRowGateChunk = 8192;
+template <typename T>
+__global__ void __launch_bounds__(256) row_gate_kernel(T* __restrict__ buf, int64_t row_elems, unsigned chunks,
+                                                       const double* __restrict__ row_values) {
+  const unsigned b = blockIdx.x / chunks, c = blockIdx.x - b * chunks;
+  const double v = row_values[b];
+  if (v == v) return;
+  T* row = buf + static_cast<int64_t>(b) * row_elems;
+  const int64_t e0 = static_cast<int64_t>(c) * kRowGateChunk;
+  const int64_t e1 = e0 + kRowGateChunk < row_elems ? e0 + kRowGateChunk : row_elems;
+  for (int64_t i = e0 + threadIdx.x; i < e1; i += 256) row[i] = static_cast<T>(static_cast<float>(row[i]) * 0.0f);
+}
+
 constexpr int kMaxScaleBuffers = 36;
 struct ScaleMultiArgs {
   void* buf[kMaxScaleBuffers];

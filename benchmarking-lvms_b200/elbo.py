@@ -14,7 +14,10 @@ import torch
 
 from . import amp, ops
 from .distributions import DLParams, DMoLParams, GMMParams
+from .log_likelihoods import _packed_source
+from .metrics import tag_sum
 from .operations import level_lengths, sequence_mask
+from .variational import LazyKL
 
 __all__ = ["KLLevel", "fused_elbo", "vrnn_compute_elbo", "srnn_compute_elbo", "cwvae_compute_elbo", "stcn_compute_loss",
            "wavenet_compute_loss", "pack_dmol_params"]
@@ -53,8 +56,8 @@ def pack_dmol_params(parameters) -> "DMoLParams":
     if isinstance(parameters, DMoLParams):
         return parameters
     logit_probs, locs, log_scales = parameters[0], parameters[1], parameters[2]
-    src = getattr(log_scales, "_blvm_packed", None)
-    if src is not None and getattr(logit_probs, "_blvm_packed", (None,))[0] is src[0]:
+    src = _packed_source(logit_probs, locs, log_scales)   # all three must be views of the same Linear output
+    if src is not None:
         return DMoLParams(*src)
     K, D = logit_probs.size(-1), locs.size(-2)
     raw = torch.cat([logit_probs, torch.cat([locs, log_scales], dim=-1).flatten(-2)], dim=-1)
@@ -82,6 +85,7 @@ def fused_elbo(
     x_sl_device: Optional[torch.Tensor] = None,
     grad_scaler=None,
     exchange=None,
+    nansum: bool = False,
 ):
     """ELBO of a batch in one pass.
 
@@ -107,6 +111,9 @@ def fused_elbo(
             scaler registered through `register_grad_scaler` / observed after `patch_blvm()`, if any.
         exchange: a `blvm_b200.SumsExchange`: the finalize kernel then also publishes this rank's sums to every rank
             over NVLink peer memory (`exchange.consume()` returns the global sums).
+        nansum: WaveNet's reduction (wavenet.py:145): `loss = -nansum_b(log_prob_b) / sum(x_sl)`; utterances whose
+            log-prob is NaN contribute nothing to the loss and receive a zero upstream gradient (their likelihood
+            gradient rows are multiplied by 0 on the device, no host sync), the finite ones are unaffected.
 
     Returns a namespace with fp64 tensors: loss (), elbo, log_prob, kl, kl_fn (B,), kl_levels [(B,)],
     sums (8,) = [loss, sum log_prob, sum kl, sum kl_fn, sum elbo, sum x_sl, bits-per-dim, nansum-loss] and
@@ -182,7 +189,7 @@ def fused_elbo(
             loss_scale = amp.scale_tensor_f64(scaler)
     spec = ops.ELBOSpec(K=K, D=D, num_bins=int(num_bins), log_epsilon=float(log_eps), beta=float(beta), denom=total,
                         levels=specs, want_twise=want_twise, skip_padded=skip_padded, need_grad=need_grad,
-                        likelihood=likelihood, exchange=exchange, gmm=gmm, loss_scale=loss_scale)
+                        likelihood=likelihood, exchange=exchange, gmm=gmm, loss_scale=loss_scale, nansum=bool(nansum))
     loss, sums, rows, twise = ops.fused_elbo_apply(spec, y, x_sl_dev, raw, flat)
     return SimpleNamespace(loss=loss, log_prob=rows[0], kl=rows[1], kl_fn=rows[2], elbo=rows[3],
                            kl_levels=[rows[4 + l] for l in range(len(specs))], sums=sums,
@@ -192,12 +199,25 @@ def fused_elbo(
 # ----------------------------------------------------------------------------------------------------------------------
 # drop-in reducers (bound as methods by patch_blvm; `self` only needs the attributes the reference methods read)
 # ----------------------------------------------------------------------------------------------------------------------
+def _kl_level(kld, **kw) -> KLLevel:
+    """A latent level from what the model hands to compute_elbo: the drop-in `kl_divergence_gaussian` returns a LazyKL;
+    while nobody has read it, its four parameter tensors go to the fully fused KL kernel (one launch for all levels,
+    32 B/element).  A real (or already read) elementwise KL tensor takes the materialised-KL path."""
+    if isinstance(kld, LazyKL):
+        inputs = kld.kl_inputs
+        if inputs is not None:
+            return KLLevel(*inputs, **kw)
+        kld = kld.materialize()
+    return KLLevel(kld=kld, **kw)
+
+
 def _vrnn_like(self, y, parameters, kld_twise, x_sl, stride, beta, free_nats, return_fn_kl):
-    r = fused_elbo(y, parameters, x_sl, [KLLevel(kld=kld_twise, stride=stride)], beta, free_nats,
+    r = fused_elbo(y, parameters, x_sl, [_kl_level(kld_twise, stride=stride)], beta, free_nats,
                    num_bins=self.likelihood.num_bins)
     seq_mask = sequence_mask(x_sl, dtype=torch.float64, device=y.device)   # vrnn.py:266: dtype=float => float64
-    kld = r.kl_fn if return_fn_kl else r.kl
-    return r.loss, r.elbo, r.log_prob, kld, seq_mask                      # all float64 like the reference
+    kld = tag_sum(r.kl_fn, r.sums, 3) if return_fn_kl else tag_sum(r.kl, r.sums, 2)
+    # the sums over utterances already exist on the device (finalize kernel): lazily built Metric objects use them
+    return tag_sum(r.loss, r.sums, 0), tag_sum(r.elbo, r.sums, 4), tag_sum(r.log_prob, r.sums, 1), kld, seq_mask   # all float64 like the reference
 
 
 def vrnn_compute_elbo(self, y, parameters, kld_twise, x_sl, stride: int, beta: float = 1, free_nats: float = 0):
@@ -211,6 +231,14 @@ def srnn_compute_elbo(self, y, parameters, kld_twise, x_sl, stride: int, beta: f
     return _vrnn_like(self, y, parameters, kld_twise, x_sl, stride, beta, free_nats, False)
 
 
+def _f32_outputs(r):
+    """(loss, elbo, log_prob, kl, [kl per level]) in float32 (CW-VAE / STCN return types), each tagged with the device-side
+    sum over utterances the finalize kernel already produced."""
+    f = torch.float32
+    return (tag_sum(r.loss.to(f), r.sums, 0), tag_sum(r.elbo.to(f), r.sums, 4), tag_sum(r.log_prob.to(f), r.sums, 1),
+            tag_sum(r.kl.to(f), r.sums, 2), [k.to(f) for k in r.kl_levels])
+
+
 def cwvae_compute_elbo(self, y, seq_mask, level_masks, x_sl, parameters, kld_layerwise: List[torch.Tensor],
                        beta: float = 1, free_nats: float = 0):
     """Drop-in for CWVAE.compute_elbo (blvm/models/clockwork_vae/clockwork_vae.py:132-161): float32 outputs,
@@ -219,10 +247,9 @@ def cwvae_compute_elbo(self, y, seq_mask, level_masks, x_sl, parameters, kld_lay
     levels = []
     for l in range(self.num_levels):
         fn = free_nats * self.overall_strides[l] / self.overall_strides[0]
-        levels.append(KLLevel(kld=kld_layerwise[l], lens=level_masks[l].sum(1), free_nats=fn))
+        levels.append(_kl_level(kld_layerwise[l], lens=level_masks[l].sum(1), free_nats=fn))
     r = fused_elbo(y, parameters, x_sl, levels, beta, free_nats, num_bins=self.likelihood.num_bins)
-    f = torch.float32
-    return r.loss.to(f), r.elbo.to(f), r.log_prob.to(f), r.kl.to(f), [k.to(f) for k in r.kl_levels]
+    return _f32_outputs(r)
 
 
 def stcn_compute_loss(self, y, x_sl, parameters, mu_p, sd_p, mu_q, sd_q, z, free_nats: float, beta: float):
@@ -236,15 +263,12 @@ def stcn_compute_loss(self, y, x_sl, parameters, mu_p, sd_p, mu_q, sd_q, z, free
     else:
         levels = [KLLevel(mu_q[l], sd_q[l], mu_p[l], sd_p[l], z=z[l], stride=self.n_stack_frames) for l in range(self.n_latents)]
     r = fused_elbo(y, parameters, x_sl, levels, beta, free_nats, num_bins=self.likelihood_module.num_bins)
-    f = torch.float32
-    return r.loss.to(f), r.elbo.to(f), r.log_prob.to(f), r.kl.to(f), [k.to(f) for k in r.kl_levels]
+    return _f32_outputs(r)
 
 
 def wavenet_compute_loss(self, y, x_sl, parameters):
     """Drop-in for WaveNet.compute_loss (blvm/models/wavenet/wavenet.py:128-146): (loss, log_prob (B,),
     log_prob_twise (B, T)); the loss uses nansum over utterances (:145)."""
-    r = fused_elbo(y, parameters, x_sl, (), 1.0, 0.0, num_bins=self.likelihood.num_bins, want_twise=True)
+    r = fused_elbo(y, parameters, x_sl, (), 1.0, 0.0, num_bins=self.likelihood.num_bins, want_twise=True, nansum=True)
     f = torch.float32
-    # loss == nansum-loss whenever every utterance log-prob is finite; select without a sync
-    loss = torch.where(torch.isnan(r.loss.detach()), r.sums[7], r.loss)
-    return loss.to(f), r.log_prob.to(f), r.log_prob_twise
+    return tag_sum(r.loss.to(f), r.sums, 0), tag_sum(r.log_prob.to(f), r.sums, 1), r.log_prob_twise

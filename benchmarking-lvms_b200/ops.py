@@ -375,11 +375,26 @@ class ELBOSpec:
     need_grad: bool = True
     likelihood: str = "dmol"       # "dmol" | "dl" | "gmm" | "none"
     gmm: tuple = (1.0, 0.0)        # (softplus beta, sd epsilon) of the Gaussian-mixture sd activation
+    nansum: bool = False           # WaveNet.compute_loss: loss = -nansum(logp)/sum(x_sl), NaN utterances get a zero gradient
     exchange: object = None        # distributed.SumsExchange: publish the sums to all ranks from the finalize kernel
     loss_scale: Optional[torch.Tensor] = None   # fp64 device scalar (a GradScaler's scale): fp16 gradients in ONE pass, pre-scaled
 
 
 _unit_grads = {}
+_LIK_CODE = {"none": _lib.BLVM_LIK_NONE, "dmol": _lib.BLVM_LIK_DMOL, "dl": _lib.BLVM_LIK_DL, "gmm": _lib.BLVM_LIK_GMM}
+_chunk_cache = {}
+
+
+def _logp_chunks(likelihood: str, T: int, K: int, D: int) -> int:
+    """Partial sums per utterance of the likelihood kernel (a function of the tile size the library picks for K)."""
+    key = (likelihood, T, K, D)
+    n = _chunk_cache.get(key)
+    if n is None:
+        n = int({"dmol": lambda: lib.blvm_dmol_chunks(T, K, D), "dl": lambda: lib.blvm_dl_chunks(T),
+                 "gmm": lambda: lib.blvm_gmm_chunks(T, K, D)}[likelihood]())
+        if len(_chunk_cache) < 4096:
+            _chunk_cache[key] = n
+    return n
 
 
 def _unit_grad(device: torch.device) -> torch.Tensor:
@@ -413,7 +428,8 @@ class _FusedELBO(torch.autograd.Function):
     outputs: loss () fp64 [differentiable], scalars (8) fp64, rows (4+L, B) fp64, log_prob_twise (B,T) or empty.
 
     Host-side cost matters here (a step is ~200 us of GPU time): one fp64 workspace allocation holds the outputs and
-    all per-tile partial sums, and the step is 3 + L launches (DMoL, one per KL level, finalize); backward is one."""
+    all per-tile partial sums, and the step is ONE call into the library (`blvm_elbo_step`: likelihood, the KL of all
+    levels in one launch, finalize = 3 launches); backward launches nothing on a plain `loss.backward()`."""
 
     @staticmethod
     def forward(ctx, spec: ELBOSpec, y, x_sl_dev, raw, *kl_tensors):
@@ -424,146 +440,85 @@ class _FusedELBO(torch.autograd.Function):
         assert L <= _lib.BLVM_MAX_KL_LEVELS, f"at most {_lib.BLVM_MAX_KL_LEVELS} KL levels"
         has_lik = spec.likelihood != "none"
         T = raw.shape[1] if has_lik else 0
-        logp_chunks = 0
-        if has_lik:
-            logp_chunks = int({"dmol": lambda: lib.blvm_dmol_chunks(T, spec.K, spec.D), "dl": lambda: lib.blvm_dl_chunks(T),
-                               "gmm": lambda: lib.blvm_gmm_chunks(T, spec.K, spec.D)}[spec.likelihood]())
-        shapes = []
-        i = 0
-        for lv in spec.levels:
-            Bz, Tz, Z = kl_tensors[i].shape
-            assert Bz == B, f"KL level batch {Bz} != {B}"
-            shapes.append((Tz, Z, int(lib.blvm_kl_chunks(Tz * Z))))
-            i += lv.n_tensors
-        n_out = 8 + (4 + L) * B
-        n_ws = n_out + B * logp_chunks + sum(2 * B * c for _, _, c in shapes)
-        ws = torch.empty(n_ws, dtype=torch.float64, device=dev)   # outputs + partial sums, one allocation
-        base = ws.data_ptr()
-        scalars = ws[:8]
-        rows = ws[8:n_out].view(4 + L, B)
-        off = n_out
+        st = _lib.ElboStepStruct()
+        st.likelihood = _LIK_CODE[spec.likelihood]
+        st.K, st.D, st.num_bins, st.log_epsilon = spec.K, spec.D, spec.num_bins, spec.log_epsilon
+        st.B, st.T, st.n_levels = B, T, L
+        st.beta, st.denom = spec.beta, spec.denom
+        st.x_sl = x_sl_dev.data_ptr()
+        n_ws = 8 + (4 + L) * B
         grads: List[Optional[torch.Tensor]] = []
         twise = torch.empty(B, T, dtype=torch.float32, device=dev) if (has_lik and spec.want_twise) else torch.empty(0, device=dev)
+        prescaled = deferred = False
+        if has_lik:
+            n_ws += B * _logp_chunks(spec.likelihood, T, spec.K, spec.D)
+            # fp16 parameters (AMP with a GradScaler): gradients of magnitude ~1/sum(x_sl) would underflow in fp16 before
+            # the loss scale is applied.  With a known scaler (amp.py) the kernel multiplies its device-side scale in and
+            # writes the fp16 gradient pre-scaled in this pass; otherwise the gradient is produced in backward (second
+            # launch, with the upstream grad_output read from the device).  fp32 / bf16 parameters get it in this pass.
+            prescaled = spec.need_grad and raw.dtype == torch.float16 and spec.loss_scale is not None
+            deferred = spec.need_grad and raw.dtype == torch.float16 and not prescaled
+            graw = torch.empty_like(raw) if (spec.need_grad and not deferred) else None
+            st.raw_dtype = _DTYPE_CODE[raw.dtype]
+            st.flags = (BLVM_FLAG_MASK_OUTPUT | (BLVM_FLAG_SKIP_PADDED if spec.skip_padded else 0)
+                        | (_lib.BLVM_FLAG_NANSUM_LOSS if spec.nansum else 0))
+            st.y, st.raw = y.data_ptr(), raw.data_ptr()
+            st.lp_twise = twise.data_ptr() if spec.want_twise else None
+            st.graw = _ptr(graw)
+            st.loss_scale = spec.loss_scale.data_ptr() if prescaled else None
+            st.gmm_softplus_beta, st.gmm_sd_add = spec.gmm
+            st.err_flag = _err_flag(dev).data_ptr()
+            if deferred:
+                ctx.save_for_backward(y, raw, x_sl_dev)
+                ctx.deferred = (B, T, spec.K, spec.D, spec.num_bins, spec.log_epsilon, st.flags & 3, -1.0 / spec.denom)
+            grads.append(graw)
+        else:
+            grads.append(None)
 
+        i = 0
+        for li, lv in enumerate(spec.levels):
+            ts = kl_tensors[i:i + lv.n_tensors]
+            i += lv.n_tensors
+            Bz, Tz, Z = ts[0].shape
+            assert Bz == B, f"KL level batch {Bz} != {B}"
+            n_ws += 2 * B * (-(-(Tz * Z) // _lib.BLVM_KL_TILE))
+            d = st.levels[li]
+            d.lens, d.Tz, d.Z, d.free_nats = _ptr(lv.lens), Tz, Z, lv.free_nats
+            if lv.kind == "kld":
+                gk = torch.empty_like(ts[0]) if spec.need_grad else None
+                d.kl, d.g_kl = ts[0].data_ptr(), _ptr(gk)
+                grads.append(gk)
+                continue
+            n_g = 5 if lv.kind == "mc" else 4
+            g = [torch.empty_like(ts[0]) for _ in range(n_g)] if spec.need_grad else [None] * n_g
+            d.mu_q, d.sd_q, d.mu_p, d.sd_p = ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr()
+            d.g_mu_q, d.g_sd_q, d.g_mu_p, d.g_sd_p = _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3])
+            if lv.kind == "mc":
+                d.z, d.g_z = ts[4].data_ptr(), _ptr(g[4])
+            grads += g
+
+        ws = torch.empty(n_ws, dtype=torch.float64, device=dev)   # outputs + partial sums, one allocation
+        scalars = ws[:8]
+        rows = ws[8:8 + (4 + L) * B].view(4 + L, B)
+        st.workspace = ws.data_ptr()
+        ex = spec.exchange
+        if ex is not None:   # finalize + all-gather of the sums over NVLink peer memory, one kernel
+            st.rank, st.world = ex.rank, ex.world
+            st.peer_bases_host = (ctypes.c_void_p * ex.world)(*ex.peer_ptrs)
+            st.exchange_counters, st.prev_global_sums, st.exchange_err = ex.counters.data_ptr(), ex.global_sums.data_ptr(), ex.err.data_ptr()
         with _on_device(dev):
-            stream = _stream(dev.index)
-            logp_ptr = None
-            if has_lik:
-                flags = BLVM_FLAG_MASK_OUTPUT | (BLVM_FLAG_SKIP_PADDED if spec.skip_padded else 0)
-                logp_ptr = base + 8 * off
-                off += B * logp_chunks
-                # fp16 parameters (AMP with a GradScaler): gradients of magnitude ~1/sum(x_sl) would underflow in fp16
-                # before the loss scale is applied, so the gradient is produced in backward (second launch, with the
-                # upstream grad_output read from the device); fp32 / bf16 parameters get it in this pass.
-                prescaled = spec.need_grad and raw.dtype == torch.float16 and spec.loss_scale is not None
-                deferred = spec.need_grad and raw.dtype == torch.float16 and not prescaled
-                graw = torch.empty_like(raw) if (spec.need_grad and not deferred) else None
-                gscale = -1.0 / spec.denom
-                lp_ptr = twise.data_ptr() if spec.want_twise else None
-                err = _err_flag(dev)
-                if spec.likelihood == "dmol":
-                    dt = _DTYPE_CODE[raw.dtype]
-                    if graw is None:
-                        rc = lib.blvm_dmol_fwd(y.data_ptr(), raw.data_ptr(), dt, x_sl_dev.data_ptr(), B, T, spec.K, spec.D,
-                                               spec.num_bins, spec.log_epsilon, flags, lp_ptr, logp_ptr, err.data_ptr(), stream)
-                    else:
-                        # known loss scale (amp.py): the kernel multiplies it in from the device, the fp16 gradient is
-                        # written pre-scaled in this pass and backward multiplies by grad_output / scale (== 1)
-                        rc = lib.blvm_dmol_fwd_grad(y.data_ptr(), raw.data_ptr(), dt, x_sl_dev.data_ptr(), None, gscale,
-                                                    spec.loss_scale.data_ptr() if prescaled else None,
-                                                    B, T, spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags, lp_ptr,
-                                                    graw.data_ptr(), logp_ptr, err.data_ptr(), stream)
-                    if deferred:
-                        ctx.save_for_backward(y, raw, x_sl_dev)
-                        ctx.deferred = (B, T, spec.K, spec.D, spec.num_bins, spec.log_epsilon, flags, gscale)
-                elif spec.likelihood == "gmm":
-                    rc = lib.blvm_gmm_fwd_grad(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), None, gscale, None, B, T,
-                                               spec.K, spec.D, 1, spec.gmm[0], spec.gmm[1], 0.0, flags, lp_ptr, _ptr(graw),
-                                               logp_ptr, stream)
-                else:
-                    rc = lib.blvm_dl_fwd_grad(y.data_ptr(), raw.data_ptr(), x_sl_dev.data_ptr(), None, gscale, B, T,
-                                              spec.num_bins, spec.log_epsilon, flags, lp_ptr, _ptr(graw), logp_ptr,
-                                              err.data_ptr(), stream)
-                check(rc, "blvm DMoL/DL kernel")
-                _count()
-                grads.append(graw)
-            else:
-                grads.append(None)
-
-            kl_ptrs, klfn_ptrs, kl_chunks = [], [], []
-            i = 0
-            gscale = spec.beta / spec.denom
-            # hierarchies (and Monte-Carlo levels, which only the level-array entry point takes): all levels in one launch
-            multi = (_lib.KLLevelStruct * L)() if (L >= 2 or any(lv.kind == "mc" for lv in spec.levels)) else None
-            for li, (lv, (Tz, Z, chunks)) in enumerate(zip(spec.levels, shapes)):
-                # the launch just before this one is this step's likelihood / previous KL level, which produces none of
-                # this level's inputs: the KL grid may fill that grid's tail (programmatic dependent launch)
-                kflags = _lib.BLVM_FLAG_OVERLAP_PREV if (has_lik or li > 0) else 0
-                ts = kl_tensors[i:i + lv.n_tensors]
-                i += lv.n_tensors
-                pk = base + 8 * off
-                pf = pk + 8 * B * chunks
-                off += 2 * B * chunks
-                if lv.kind == "mc":
-                    g5 = [torch.empty_like(ts[0]) for _ in range(5)] if spec.need_grad else [None] * 5
-                    multi[li] = _lib.KLLevelStruct(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(), None,
-                                                   _ptr(lv.lens), Tz, Z, lv.free_nats, _ptr(g5[0]), _ptr(g5[1]), _ptr(g5[2]),
-                                                   _ptr(g5[3]), None, pk, pf, ts[4].data_ptr(), _ptr(g5[4]))
-                    grads += g5
-                elif lv.kind == "inputs":
-                    g4 = [torch.empty_like(ts[0]) for _ in range(4)] if spec.need_grad else [None] * 4
-                    if multi is None:
-                        rc = lib.blvm_kl_elbo_fwd_grad(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(),
-                                                       _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale, None,
-                                                       _ptr(g4[0]), _ptr(g4[1]), _ptr(g4[2]), _ptr(g4[3]), pk, pf, kflags, stream)
-                        check(rc, "blvm_kl_elbo_fwd_grad")
-                    else:
-                        multi[li] = _lib.KLLevelStruct(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr(), None,
-                                                       _ptr(lv.lens), Tz, Z, lv.free_nats, _ptr(g4[0]), _ptr(g4[1]), _ptr(g4[2]),
-                                                       _ptr(g4[3]), None, pk, pf, None, None)
-                    grads += g4
-                else:
-                    gk = torch.empty_like(ts[0]) if spec.need_grad else None
-                    if multi is None:
-                        rc = lib.blvm_kl_reduce_fwd_grad(ts[0].data_ptr(), _ptr(lv.lens), B, Tz, Z, lv.free_nats, gscale,
-                                                         _ptr(gk), pk, pf, kflags, stream)
-                        check(rc, "blvm_kl_reduce_fwd_grad")
-                    else:
-                        multi[li] = _lib.KLLevelStruct(None, None, None, None, ts[0].data_ptr(), _ptr(lv.lens), Tz, Z, lv.free_nats,
-                                                       None, None, None, None, _ptr(gk), pk, pf, None, None)
-                    grads.append(gk)
-                if multi is None:
-                    _count()
-                kl_ptrs.append(pk)
-                klfn_ptrs.append(pf)
-                kl_chunks.append(chunks)
-            if multi is not None:
-                rc = lib.blvm_kl_elbo_levels_fwd_grad(multi, L, B, gscale, _lib.BLVM_FLAG_OVERLAP_PREV if has_lik else 0, stream)
-                check(rc, "blvm_kl_elbo_levels_fwd_grad")
-                _count()
-
-            PtrArr = ctypes.c_void_p * max(L, 1)
-            I64Arr = ctypes.c_int64 * max(L, 1)
-            ex = spec.exchange
-            if ex is None:
-                rc = lib.blvm_elbo_finalize(logp_ptr, logp_chunks, PtrArr(*kl_ptrs), PtrArr(*klfn_ptrs), I64Arr(*kl_chunks), L,
-                                            x_sl_dev.data_ptr(), B, spec.beta, spec.denom, rows.data_ptr(), scalars.data_ptr(),
-                                            _sync_counter(dev).data_ptr(), stream)
-            else:   # finalize + all-gather of the sums over NVLink peer memory, one kernel
-                rc = lib.blvm_elbo_finalize_publish(logp_ptr, logp_chunks, PtrArr(*kl_ptrs), PtrArr(*klfn_ptrs),
-                                                    I64Arr(*kl_chunks), L, x_sl_dev.data_ptr(), B, spec.beta, spec.denom,
-                                                    rows.data_ptr(), scalars.data_ptr(), _sync_counter(dev).data_ptr(),
-                                                    (ctypes.c_void_p * ex.world)(*ex.peer_ptrs), ex.rank, ex.world,
-                                                    ex.counters.data_ptr(), ex.global_sums.data_ptr(), ex.err.data_ptr(), stream)
-            check(rc, "blvm_elbo_finalize")
-            _count()
+            st.sync_counter = _sync_counter(dev).data_ptr()
+            # ONE call: likelihood kernel, the KL of all levels (one launch, overlapping the likelihood grid's tail),
+            # finalize (a programmatic dependent) and, for WaveNet's nansum, the NaN-row gate
+            check(lib.blvm_elbo_step(ctypes.byref(st), _stream(dev.index)), "blvm_elbo_step")
+        _count((1 if has_lik else 0) + (1 if L else 0) + 1 + (1 if (spec.nansum and has_lik and grads[0] is not None) else 0))
 
         loss = scalars[:1].view(())
         ctx.set_materialize_grads(False)   # no zero-filled grads for the detached outputs
-        if not hasattr(ctx, "deferred"):
+        if not deferred:
             ctx.deferred = None
         ctx.grads = grads
-        ctx.prescale = spec.loss_scale if (has_lik and spec.need_grad and raw.dtype == torch.float16 and spec.loss_scale is not None) else None
+        ctx.prescale = spec.loss_scale if prescaled else None
         ctx.consumed = False
         ctx.mark_non_differentiable(scalars, rows, twise)
         _maybe_strict(dev)
@@ -624,6 +579,12 @@ def fused_elbo_apply(spec: ELBOSpec, y, x_sl_dev, raw, kl_tensors: Sequence[torc
 def _next_rng(device: torch.device):
     """Philox key / offset taken from (and advanced on) torch's CUDA generator of the device, the way torch's own
     kernels consume it: `torch.manual_seed(s)` makes the sample stream reproducible."""
+    if torch.cuda.is_current_stream_capturing():
+        # seed and offset are launch ARGUMENTS here: a captured launch would replay the same samples forever and bypass
+        # torch's graph-safe generator protocol.  Keep sample()/mode() outside captured regions (the ELBO step itself is
+        # capturable: it draws nothing).
+        raise RuntimeError("blvm_b200: sample()/mode() cannot be captured in a CUDA graph (the Philox offset is a host-side "
+                           "launch argument); call them outside the captured region")
     gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
     seed = int(gen.initial_seed()) & 0xFFFFFFFFFFFFFFFF
     offset = int(gen.get_offset())

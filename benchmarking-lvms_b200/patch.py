@@ -4,7 +4,7 @@ stcn.py:28-29, clockwork_vae.py:27-28), so every `blvm.*` module's globals are r
 import sys
 from types import ModuleType
 
-from . import amp, distributions, elbo, log_likelihoods, variational
+from . import amp, distributions, elbo, log_likelihoods, metrics, variational
 
 __all__ = ["patch_blvm", "unpatch_blvm"]
 
@@ -62,11 +62,16 @@ def patch_blvm():
     # `--use_amp True` (fp16 autocast + GradScaler, the reference's benchmark default): learn about the script's scaler so
     # that fp16 gradients are produced in one pass with its device-side scale (amp.py)
     amp.observe_grad_scalers()
+    # the models' Metric objects (vrnn.py:346-355 ...) read their device values lazily: one D2H sync per step instead of
+    # one per metric (metrics.py:241-244)
+    import blvm.evaluation.metrics as ref_metrics
+    metrics.patch_metric_syncs(ref_metrics)
     return [f"{getattr(o, '__name__', o)}.{a}" for o, a, _ in _saved[before:]]
 
 
 def unpatch_blvm():
     amp.stop_observing()
+    metrics.unpatch_metric_syncs()
     while _saved:
         owner, attr, original = _saved.pop()
         setattr(owner, attr, original)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BLVM_B200_VERSION 100 /* 0.1.0 */
+#define BLVM_B200_VERSION 200 /* 0.2.0 */
 
 enum {
   BLVM_OK = 0,
@@ -42,6 +42,9 @@ enum {
                                  call's inputs: this launch may then start while that kernel is still draining
                                  (programmatic dependent launch) and does not complete before it has.  Ordering with respect
                                  to everything earlier on the stream is unchanged. */
+  BLVM_FLAG_NANSUM_LOSS = 8, /* blvm_elbo_step only: scalars[0] is WaveNet's -nansum(logp)/sum(x_sl) (wavenet.py:145) and the
+                                likelihood gradient rows of utterances whose log-prob is NaN are multiplied by 0 afterwards
+                                (what nansum's backward hands them in the reference) */
 };
 
 /* element type of the likelihood parameters `raw` (and of their gradient): the AMP Linear output can be consumed as is */
@@ -224,6 +227,51 @@ int blvm_elbo_finalize_publish(const double* logp_part, int64_t logp_chunks, con
                                unsigned long long* exchange_counters, double* prev_global_sums, int* err_flag,
                                blvm_stream_t stream);
 int64_t blvm_exchange_buffer_bytes(void);
+
+/*
+ * One step of the whole path from ONE call: likelihood (value + gradient + masked row partials), the KL of every latent
+ * level in one launch, finalize (+ the NVLink exchange when `world > 0`).  Same kernels, same partial-sum layout and
+ * bit-identical results as the separate entry points above; what it removes is host time (one FFI crossing, no
+ * per-level calls), which is what bounds the model-shaped steps (BASELINE configs 2-4: 29-115 us of GPU time).
+ * Replaces, in one go, the tail of every reference model: `likelihood.log_prob` + `kl_divergence_gaussian` +
+ * `compute_elbo` / `compute_loss` (vrnn.py:255-279, srnn.py:137-160, clockwork_vae.py:132-161, stcn.py:256-297,
+ * wavenet.py:128-146).
+ *   likelihood  BLVM_LIK_*; with BLVM_LIK_NONE the step is KL-only (log p = 0)
+ *   graw        nullable: NULL = forward only (no gradient is written anywhere: the levels' g_* must be NULL too)
+ *   loss_scale  nullable fp64 device scalar multiplied into the likelihood gradient (fp16 parameters under a GradScaler)
+ *   levels      n_levels descriptors; their part_kl / part_klfn members are IGNORED (placed in the workspace)
+ *   workspace   blvm_elbo_step_workspace_doubles(desc) fp64 values: [scalars 8 | rows (4 + n_levels) x B | partial sums];
+ *               scalars and rows are the outputs documented at blvm_elbo_finalize
+ *   world       0 = no exchange; otherwise the exchange arguments of blvm_elbo_finalize_publish
+ */
+enum { BLVM_LIK_NONE = 0, BLVM_LIK_DMOL = 1, BLVM_LIK_DL = 2, BLVM_LIK_GMM = 3 };
+typedef struct blvm_elbo_step {
+  int likelihood, raw_dtype, K, D, num_bins, flags, n_levels, rank, world;
+  float log_epsilon;
+  int64_t B, T;
+  const float* y;              /* (B, T, D) */
+  const void* raw;             /* (B, T, P) */
+  const int64_t* x_sl;         /* (B) int64, device */
+  float* lp_twise;             /* nullable (B, T): masked per-sample log-prob */
+  void* graw;                  /* nullable (B, T, P), element type raw_dtype */
+  const double* loss_scale;    /* nullable */
+  double gmm_softplus_beta, gmm_sd_add;   /* BLVM_LIK_GMM: the sd activation (distributions.py:167-170) */
+  double beta, denom;          /* denom <= 0: sum(x_sl); the gradients are scaled with -1/denom resp. beta/denom */
+  blvm_kl_level_t levels[BLVM_MAX_KL_LEVELS];
+  double* workspace;
+  unsigned int* sync_counter;  /* as for blvm_elbo_finalize */
+  int* err_flag;               /* nullable: y-range flag of the DMoL / DL kernels */
+  void* const* peer_bases_host;
+  unsigned long long* exchange_counters;
+  double* prev_global_sums;
+  int* exchange_err;
+} blvm_elbo_step_t;
+int64_t blvm_elbo_step_workspace_doubles(const blvm_elbo_step_t* desc_host);
+int blvm_elbo_step(const blvm_elbo_step_t* desc_host, blvm_stream_t stream);
+
+/* In-place: rows b of buf (B, row_elems) (element type `dtype`) whose row_values[b] (fp64) is NaN are multiplied by 0;
+ * CTAs of finite rows exit after reading one double.  The backward of nansum over utterances (wavenet.py:145). */
+int blvm_row_gate_inplace(void* buf, int dtype, int64_t B, int64_t row_elems, const double* row_values, blvm_stream_t stream);
 /*
  * Consume step `published - lag` (no-op if it does not exist or was consumed): wait for all ranks' slots in the LOCAL
  * buffer, add them in rank order -> out_sums (8) fp64 = [global loss, sum log_prob, sum kl, sum kl_fn, sum elbo,

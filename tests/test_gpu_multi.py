@@ -85,3 +85,30 @@ def test_fused_finalize_exchange_two_gpus():
         np.testing.assert_allclose(last[:7], ref[:7], rtol=1e-12)             # identical to the NCCL all-reduce path
     assert np.array_equal(got[0][2], got[1][2])                              # bit-identical on both ranks
     np.testing.assert_allclose(np.mean([x[4] for x in got]), g["loss64"], rtol=1e-6)   # mean of rank losses == global
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node")
+def test_one_process_drives_two_devices():
+    """Per-device launch state: function attributes (opt-in dynamic shared memory of the stream / tile kernels),
+    occupancy and SM count are cached per CUDA device.  One process runs the same small-K (stream kernel: > 48 KB of dynamic
+    shared memory at K = 5) and K = 30 (tile kernel: 46 KB slabs) steps on cuda:0 first and then on cuda:1; results must be
+    bit-identical and the second device must not fail with an invalid-argument launch error."""
+    import blvm_b200 as B
+    g = torch.Generator().manual_seed(11)
+    for K in (5, 4, 30, 10):
+        Bn, T, nb = 3, 4096, 65536
+        y = (torch.randint(0, nb, (Bn, T), generator=g).float() / (nb - 1) * 2 - 1)
+        raw = torch.randn(Bn, T, 3 * K, generator=g)
+        raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+        x_sl = torch.tensor([T, T - 100, T // 2])
+        outs = []
+        for d in (0, 1):
+            dev = torch.device("cuda", d)
+            r = raw.to(dev).requires_grad_(True)
+            out = B.fused_elbo(y.to(dev), B.DMoLParams(r, K, 1, -7.0), x_sl, (), num_bins=nb)
+            out.loss.backward()
+            s, m, _ = B.ops.dmol_sample_mode(r, K, 1, -7.0)
+            torch.cuda.synchronize(dev)
+            outs.append((out.loss.item(), out.log_prob.cpu(), r.grad.cpu(), m.cpu()))
+        assert outs[0][0] == outs[1][0]
+        assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])

@@ -80,6 +80,10 @@ def install_fakes(monkeypatch, B, O):
     monkeypatch.setattr(ops, "kl_gaussian", fake_kl)
     monkeypatch.setattr(ops, "fused_elbo_apply", fake_fused)
     monkeypatch.setattr(ops, "param_tensor", lambda raw, K, D: raw.float().contiguous())
+    # exercise the CUDA-only laziness on CPU: the KL handle (variational.LazyKL) and the batched metric reads
+    from blvm_b200 import metrics, variational
+    monkeypatch.setattr(variational, "_LAZY_DEVICE_TYPES", {"cuda", "cpu"})
+    monkeypatch.setattr(metrics, "_LAZY_DEVICE_TYPES", {"cuda", "cpu"})
 
 
 def build(M, name):
@@ -129,9 +133,25 @@ def test_patched_model_matches_reference_model(name, env, monkeypatch):
         ours_model.load_state_dict(state)
         lik = [m for m in ours_model.modules() if isinstance(m, B.DiscretizedLogisticMixtureDense)]
         assert len(lik) == 1
+        from blvm_b200 import metrics as bm, ops
+        calls = {"kl_eager": 0}
+        eager_kl = ops.kl_gaussian
+        monkeypatch.setattr(ops, "kl_gaussian", lambda *a: (calls.__setitem__("kl_eager", calls["kl_eager"] + 1), eager_kl(*a))[1])
+        saved0 = bm.syncs_saved
         loss, metrics, out = run(ours_model)
+        if name in ("vrnn", "srnn", "cwvae"):
+            # the models hand kl_divergence_gaussian's result straight to compute_elbo: the handle must stay unread, i.e. the
+            # level runs through the fused KL kernel and the elementwise KL is never materialised
+            assert calls["kl_eager"] == 0, "the elementwise KL was materialised on the drop-in path"
+        if name != "lstm":
+            assert bm.syncs_saved > saved0                                 # Metric objects were built lazily ...
+        values = [(m.name, m.value, getattr(m, "weight_by", None)) for m in metrics]   # ... and read here, all at once
+        values_ref = [(m.name, m.value, getattr(m, "weight_by", None)) for m in metrics_ref]
     finally:
         B.unpatch_blvm()
+    for (n1, v1, w1), (n2, v2, w2) in zip(values, values_ref):
+        assert n1 == n2 and w1 == w2, (n1, n2, w1, w2)
+        np.testing.assert_allclose(v1, v2, rtol=5e-5, err_msg=f"metric {n1}")
 
     assert loss.dtype == loss_ref.dtype, (loss.dtype, loss_ref.dtype)   # float64 for VRNN/SRNN, float32 elsewhere
     np.testing.assert_allclose(float(loss), float(loss_ref), rtol=2e-5)
