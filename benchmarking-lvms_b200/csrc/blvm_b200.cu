@@ -153,7 +153,10 @@ int launch_gmm_tile(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
     if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
     configured[dev] = true;
   }
-  kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
+  constexpr int G = DmolGroup<K, float>::value;
+  DmolArgs A2 = A;
+  A2.ctas_per_row = (A.chunks + G - 1) / G;
+  kern<<<static_cast<unsigned>(A.B * A2.ctas_per_row), kTile, smem, st>>>(A2);
   return check_launch("dmol_tile_kernel<gmm>");
 }
 
@@ -190,6 +193,7 @@ int dispatch_gmm(const DmolArgs& A, cudaStream_t st) {
 
 int validate_dmol(const float* y, const void* raw, int64_t B, int64_t T, int K, int D, int num_bins) {
   if (B < 0 || T < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "negative size B=%lld T=%lld", (long long)B, (long long)T);
+  if (T > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "T=%lld: utterances are limited to 2^31 - 1 samples", (long long)T);
   if (K < 1 || D < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "K=%d D=%d must be >= 1", K, D);
   if (num_bins < 2) return fail(BLVM_ERR_INVALID_ARGUMENT, "num_bins=%d must be >= 2", num_bins);
   if (B * T > 0 && (!y || !raw)) return fail(BLVM_ERR_INVALID_ARGUMENT, "null y/raw");

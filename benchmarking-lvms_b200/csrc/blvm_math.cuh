@@ -45,6 +45,10 @@ struct DmolConsts {
   float hi_thresh;      // 1 - 2/num_bins            log_likelihoods.py:227   y >  hi  -> upper edge bin
   float log_half_bins;  // log(num_bins/2)           log_likelihoods.py:222
   float log_eps;        // log_epsilon (-7)          distributions.py:386
+  // the same constants in log2 units for dl_mid_pair_tiny (products formed in double on the host)
+  float log_half_bins2;     // log2(num_bins/2)
+  float neg_log_ratio2;     // -log2(num_bins/(num_bins-1)) = -[log(2h) + log(nb/2)] log2(e): first arm minus second arm at u = 0
+  float log_delta_thresh2;  // log2(float(1e-5))
 };
 
 // Host build (tests/hostsim): libm stands in for the MUFU unit.  With -DBLVM_HOSTSIM_MUFU_BITS=n the result is degraded
@@ -101,7 +105,7 @@ BLVM_HD float fast_exp(float x) { return fast_ex2(x * kLog2e); }
 // exp(x) with the rounding of the scaled argument compensated: x*log2(e) = p_hi + p_lo exactly (to ~2^-48),
 // exp(x) = 2^p_hi * (1 + ln2 * p_lo).  Leaves only the MUFU.EX2 error (~2^-22.5); 3 extra FMA-pipe ops.
 #ifndef BLVM_COMPENSATED_EXP
-#define BLVM_COMPENSATED_EXP 1
+#define BLVM_COMPENSATED_EXP 2   // 2: compensated in the scalar paths (dl_mid / dl_edge), plain MUFU in dl_mid_pair_tiny; 1: everywhere; 0: nowhere
 #endif
 BLVM_HD float accurate_exp(float x) {
   constexpr float kLog2eLo = 1.925963033500011e-08f;  // log2(e) - float(log2(e))
@@ -267,53 +271,77 @@ BLVM_HD F2 lg2_2(F2 a) { return F2{fast_lg2(a.x), fast_lg2(a.y)}; }
 BLVM_HD F2 rcp_2(F2 a) { return F2{fast_rcp(a.x), fast_rcp(a.y)}; }
 
 // dl_mid<GRAD, kUTiny> for two (sample, component) pairs at once: components k and k+1 of one sample (y.x == y.y), or the
-// single component of two samples when K == 1.  Same formulas as dl_mid, one fixed order of operations per lane (negations
-// are folded into constants because packed operands carry no sign modifiers); in kUTiny mode EVERY mid-bin evaluation
-// goes through this function (a leftover component duplicates its lane), so a value never depends on what it was paired with.
+// single component of two samples when K == 1.  In kUTiny mode EVERY mid-bin evaluation goes through this function (a
+// leftover component duplicates its lane), so a value never depends on what it was paired with.
+//
+// The kernels that call this are bound by issue slots (ncu r2a, bf16 K = 10: 105 M warp instructions, issue-active 79 %,
+// DRAM 46 %), so the formulas of dl_mid are arranged for the fewest instructions:
+//  * the log-prob is carried in log2 units (lp2 = lp * log2(e)): the MUFU.EX2 arguments p = -ls log2(e) and t = -|m| log2(e)
+//    ARE the two leading terms of lp2, and the mixture's exp / log work in base 2 anyway (dmol_sample converts once);
+//  * selections are arithmetic blends with a 0 / -1 float (one FSET each, packed FMAs afterwards) instead of predicates
+//    that live across the whole evaluation: with 5-15 pairs in flight the compiler ran out of predicate registers and
+//    spilled them into a bit mask (2-3 LOP3 per predicate);
+//  * signs are folded into constants and into rn = 1/(-(1+E)) because packed operands carry no negate modifier in PTX;
+//  * exp(-ls) is the plain MUFU result: its 2^-22.5 relative error plus the argument rounding (|ls| <= 7: 3e-7) stays
+//    below 4 % of the parity tolerance in m, lp and the gradients (tools/hostsim_accuracy.py; -DBLVM_COMPENSATED_EXP=1
+//    restores the compensated evaluation).
+// Out: lp2 (log2 units); if GRAD, dmu = d lp/d loc and dls = d lp/d raw_log_scale in natural units.
+constexpr float kInvLn2Sixth = kLog2e / 6.0f;
 template <bool GRAD>
-BLVM_HD void dl_mid_pair_tiny(F2 y, F2 mu, F2 raw_ls, const DmolConsts& C, F2& lp, F2& dmu, F2& dls) {
+BLVM_HD void dl_mid_pair_tiny(F2 y, F2 mu, F2 raw_ls, const DmolConsts& C, F2& lp2, F2& dmu, F2& dls) {
   const bool below_x = raw_ls.x < C.log_eps, below_y = raw_ls.y < C.log_eps;
   const F2 ls = f2(below_x ? C.log_eps : raw_ls.x, below_y ? C.log_eps : raw_ls.y);   // clamp(min): NaN propagates like torch
-  // inv = exp(-ls), compensated (accurate_exp): -ls log2(e) = p_hi + p_lo, exp = 2^p_hi (1 + ln2 p_lo)
+  const F2 p = mul2(ls, f2(-kLog2e));                             // log2 of exp(-log_scale)     :203
+#if BLVM_COMPENSATED_EXP == 1
   constexpr float kLog2eLo = 1.925963033500011e-08f;
-  const F2 p_hi = mul2(ls, f2(-kLog2e));
-  const F2 p_lo = fma2(ls, f2(-kLog2eLo), fma2(ls, f2(-kLog2e), mul2(p_hi, f2(-1.f))));
-  const F2 e0 = ex2_2(p_hi);
-#if BLVM_COMPENSATED_EXP
+  const F2 p_lo = fma2(ls, f2(-kLog2eLo), fma2(ls, f2(-kLog2e), mul2(p, f2(-1.f))));
+  const F2 e0 = ex2_2(p);
   const F2 inv = fma2(e0, mul2(p_lo, f2(kLn2)), e0);
 #else
-  const F2 inv = e0;
+  const F2 inv = ex2_2(p);
 #endif
   const F2 m = mul2(inv, fma2(mu, f2(-1.f), y));                  // mid_in                     :202,219
   const F2 u = mul2(inv, f2(C.h));
   const F2 am = abs2(m);
-  const F2 E = ex2_2(mul2(am, f2(-kLog2e)));
-  const F2 p1 = add2(E, f2(1.f));
-  const F2 r = rcp_2(p1);
-  const F2 common = fma2(lg2_2(p1), f2(-2.f * kLn2), fma2(am, f2(-1.f), mul2(ls, f2(-1.f))));   // m - ls - 2 softplus(m)  :220
-  const F2 lp_fb = add2(common, f2(-C.log_half_bins));            // second arm of :221-223
-  F2 th = f2(0.f);
+  const F2 t = mul2(am, f2(-kLog2e));
+  const F2 E = ex2_2(t);                                          // exp(-|m|)
+  const F2 p1n = fma2(E, f2(-1.f), f2(-1.f));                     // -(1 + E)
+  const F2 rn = rcp_2(p1n);                                       // -1/(1+E)
+  const F2 l = f2(fast_lg2(-p1n.x), fast_lg2(-p1n.y));            // log2(1+E)   (the negation is an operand modifier)
+  const F2 common2 = fma2(l, f2(-2.f), add2(t, p));               // [m - ls - 2 softplus(m)] log2(e)   :220
+  const F2 lp_fb2 = add2(common2, f2(-C.log_half_bins2));         // second arm of :221-223
+  const F2 u2 = mul2(u, u);
+  const F2 Ern = mul2(E, rn);                                     // -E / (1+E)
+  const F2 er2 = mul2(Ern, rn);                                   // E / (1+E)^2
+  const F2 eps = mul2(er2, u2);                                   // E w / (1+E)^2,  w = u^2 + O(u^4)
+  // first arm minus second arm, negated:  -[log(2h) + log(nb/2) + u^2/6 - eps] log2(e)
+  const F2 ndlt2 = fma2(eps, f2(kLog2e), fma2(u2, f2(-kInvLn2Sixth), f2(C.neg_log_ratio2)));
+  const F2 lp_d2 = fma2(ndlt2, f2(-1.f), lp_fb2);                 // log2 cdf_delta, first arm of :221-223
+  const float thr2 = C.log_delta_thresh2;
+#if defined(__CUDA_ARCH__)
+  // -[cdf_delta > 1e-5] as one select of a bit pattern per lane (the compiler otherwise selects an integer and converts it)
+  const F2 nsel = f2(__int_as_float(lp_d2.x > thr2 ? 0xBF800000 : 0), __int_as_float(lp_d2.y > thr2 ? 0xBF800000 : 0));
+#else
+  const F2 nsel = f2(lp_d2.x > thr2 ? -1.f : 0.f, lp_d2.y > thr2 ? -1.f : 0.f);   // -[cdf_delta > 1e-5]
+#endif
+  lp2 = fma2(nsel, ndlt2, lp_fb2);
   if (GRAD) {
+    // tanh(|m|/2) = (1-E)/(1+E); odd series below 1/4 so that the bin-centre gradient does not cancel
     const F2 hx = mul2(am, f2(0.5f)), hx2 = mul2(hx, hx);
     const F2 th_series = mul2(hx, fma2(hx2, fma2(hx2, f2(2.0f / 15.0f), f2(-1.0f / 3.0f)), f2(1.0f)));
-    const F2 th_exact = mul2(fma2(E, f2(-1.f), f2(1.f)), r);      // (1 - E) / (1 + E) = tanh(|m| / 2)
-    th = f2(am.x < 0.25f ? th_series.x : th_exact.x, am.y < 0.25f ? th_series.y : th_exact.y);
-  }
-  const F2 u2 = mul2(u, u);
-  const F2 ner2 = mul2(mul2(E, r), mul2(r, f2(-1.f)));            // -E / (1+E)^2
-  const F2 neps = mul2(ner2, u2);                                 // -E w / (1+E)^2,  w = u^2 + O(u^4)
-  const F2 lp_d = add2(common, add2(fma2(u2, f2(1.0f / 6.0f), f2(C.log_two_h)), neps));   // log cdf_delta, first arm of :221-223
-  const bool big_x = lp_d.x > C.log_delta_thresh, big_y = lp_d.y > C.log_delta_thresh;   // cdf_delta > 1e-5
-  lp = f2(big_x ? lp_d.x : lp_fb.x, big_y ? lp_d.y : lp_fb.y);
-  if (GRAD) {
-    const F2 th_d = fma2(neps, th, th);                           // th / (1 + eps)
-    const F2 udu = fma2(u2, fma2(ner2, f2(2.0f), f2(1.0f / 3.0f)), f2(1.0f));            // u coth(u) - u cdf_delta
-    const F2 th_sel = f2(big_x ? th_d.x : th.x, big_y ? th_d.y : th.y);
+    const F2 th_exact = fma2(Ern, f2(2.f), f2(1.f));              // 1 - 2E/(1+E) = (1-E)/(1+E)
+    const F2 th = f2(am.x < 0.25f ? th_series.x : th_exact.x, am.y < 0.25f ? th_series.y : th_exact.y);
+    const F2 th_sel = fma2(mul2(nsel, eps), th, th);              // th / (1 + eps) on the first arm, th on the second
+    const F2 c = fma2(mul2(nsel, u2), fma2(er2, f2(-2.0f), f2(1.0f / 3.0f)), f2(-1.0f));   // -(u coth(u) - u cdf_delta)  resp.  -1
+    // clamp(min=eps) blocks the gradient strictly below eps, passes at equality (own compares: the `below` predicates die early)
+#if defined(__CUDA_ARCH__)
+    const F2 gate = f2(__int_as_float(raw_ls.x >= C.log_eps ? 0x3F800000 : 0), __int_as_float(raw_ls.y >= C.log_eps ? 0x3F800000 : 0));
+#else
+    const F2 gate = f2(raw_ls.x >= C.log_eps ? 1.f : 0.f, raw_ls.y >= C.log_eps ? 1.f : 0.f);
+#endif
     const F2 it = mul2(inv, th_sel);
     dmu = f2(copysignf(it.x, m.x), copysignf(it.y, m.y));         // -inv * d lp/d m
-    dls = fma2(am, th_sel, f2(big_x ? -udu.x : -1.0f, big_y ? -udu.y : -1.0f));          // -(m d/dm + u d/du)  resp.  -m d/dm - 1
-    if (below_x) dls.x = 0.f;   // clamp(min=eps) blocks the gradient strictly below eps, passes at equality
-    if (below_y) dls.y = 0.f;
+    dls = mul2(fma2(am, th_sel, c), gate);                        // -(m d/dm + u d/du)  resp.  -m d/dm - 1
   }
 }
 
@@ -488,23 +516,25 @@ enum : int { kLikDmol = 0, kLikGmmRaw = 1, kLikGmmSd = 2 };
 template <int K, bool GRAD, int UMODE = kUGeneral, int LIK = kLikDmol>
 BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts& C) {
   const int edge = (LIK == kLikDmol) ? dmol_edge(y, C) : kEdgeNone;
-  float v[K];
-  // Logits centred on their maximum FIRST (like log_softmax in the reference, log_likelihoods.py:230): the dominant
-  // component's weight is then exactly 0 and large |logits| (~100) cost no absolute precision in a log-prob that is
-  // itself close to 0 (wide bins).  log p = logsumexp_k(lp_k + w_k) - log sum_k exp(w_k),  w_k = logit_k - max logit.
+  float v[K];   // lp_k + log_softmax numerator, in LOG2 units (the exp / log of the mixture algebra are MUFU.EX2 / LG2)
+  // Logits centred on their maximum FIRST (like log_softmax in the reference, log_likelihoods.py:230) and scaled to log2
+  // units in the same FMA: w_k = (logit_k - max logit) log2(e).  The rounding of max*log2(e) is a shift common to all
+  // components, which cancels in logsumexp_k(lp_k + w_k) - logsumexp_k(w_k): large |logits| (~100) cost no absolute
+  // precision in a log-prob that is itself close to 0 (wide bins).
   if constexpr (K > 1) {
     float m2 = r[0];
 #pragma unroll
     for (int k = 1; k < K; ++k) m2 = fmaxf(m2, r[k]);
+    const float nm2 = -m2 * kLog2e;
     if constexpr (K % 2 == 0) {
 #pragma unroll
       for (int k = 0; k < K; k += 2) {
-        const F2 w = add2(f2(r[k], r[k + 1]), f2(-m2));
+        const F2 w = fma2(f2(r[k], r[k + 1]), f2(kLog2e), f2(nm2));
         r[k] = w.x; r[k + 1] = w.y;
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < K; ++k) r[k] = r[k] - m2;
+      for (int k = 0; k < K; ++k) r[k] = fmaf(r[k], kLog2e, nm2);
     }
   }
   if (LIK != kLikDmol) {   // Gaussian mixture: same layout and mixture algebra, different component density
@@ -512,7 +542,7 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     for (int k = 0; k < K; ++k) {
       float lp, dmu = 0.f, dp = 0.f;
       gauss_component<GRAD, LIK == kLikGmmRaw>(y, r[K + k], r[2 * K + k], C, lp, dmu, dp);
-      v[k] = (K == 1) ? lp : lp + r[k];
+      v[k] = (K == 1) ? lp * kLog2e : fmaf(lp, kLog2e, r[k]);
       if (GRAD) {
         r[K + k] = dmu;
         r[2 * K + k] = dp;
@@ -522,9 +552,9 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     constexpr int KP = (UMODE == kUTiny) ? (K / 2) * 2 : 0;   // components evaluated two at a time (packed fp32x2)
 #pragma unroll
     for (int k = 0; k < KP; k += 2) {
-      F2 lp, dmu = f2(0.f), dls = f2(0.f);
-      dl_mid_pair_tiny<GRAD>(f2(y), f2(r[K + k], r[K + k + 1]), f2(r[2 * K + k], r[2 * K + k + 1]), C, lp, dmu, dls);
-      const F2 vv = add2(lp, f2(r[k], r[k + 1]));
+      F2 lp2, dmu = f2(0.f), dls = f2(0.f);
+      dl_mid_pair_tiny<GRAD>(f2(y), f2(r[K + k], r[K + k + 1]), f2(r[2 * K + k], r[2 * K + k + 1]), C, lp2, dmu, dls);
+      const F2 vv = add2(lp2, f2(r[k], r[k + 1]));
       v[k] = vv.x;
       v[k + 1] = vv.y;
       if (GRAD) {
@@ -536,15 +566,17 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     }
 #pragma unroll
     for (int k = KP; k < K; ++k) {
-      float lp, dmu = 0.f, dls = 0.f;
+      float lp2, dmu = 0.f, dls = 0.f;
       if constexpr (UMODE == kUTiny) {   // leftover component (odd K): the pair function with its lane duplicated
-        F2 lp2, dmu2 = f2(0.f), dls2 = f2(0.f);
-        dl_mid_pair_tiny<GRAD>(f2(y), f2(r[K + k]), f2(r[2 * K + k]), C, lp2, dmu2, dls2);
-        lp = lp2.x; dmu = dmu2.x; dls = dls2.x;
+        F2 l2, dmu2 = f2(0.f), dls2 = f2(0.f);
+        dl_mid_pair_tiny<GRAD>(f2(y), f2(r[K + k]), f2(r[2 * K + k]), C, l2, dmu2, dls2);
+        lp2 = l2.x; dmu = dmu2.x; dls = dls2.x;
       } else {
+        float lp;
         dl_mid<GRAD, UMODE>(y, r[K + k], r[2 * K + k], C, lp, dmu, dls);
+        lp2 = lp * kLog2e;
       }
-      v[k] = (K == 1) ? lp : lp + r[k];
+      v[k] = (K == 1) ? lp2 : lp2 + r[k];
       if (GRAD) {
         r[K + k] = dmu;
         r[2 * K + k] = dls;
@@ -555,7 +587,7 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     for (int k = 0; k < K; ++k) {  // (unrolled too: r[] must stay in registers)
       float lp, dmu = 0.f, dls = 0.f;
       dl_edge<GRAD>(y, edge, r[K + k], r[2 * K + k], C, lp, dmu, dls);
-      v[k] = (K == 1) ? lp : lp + r[k];
+      v[k] = (K == 1) ? lp * kLog2e : fmaf(lp, kLog2e, r[k]);
       if (GRAD) {
         r[K + k] = dmu;
         r[2 * K + k] = dls;
@@ -565,7 +597,7 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
   if constexpr (K == 1) {
     // one component: log_softmax(logit) = 0, responsibility = softmax = 1, d/d logit = 0 (NaN/inf logits still propagate)
     const float z = r[0] - r[0];   // 0, or NaN for a non-finite logit
-    const float L1 = v[0] + z;
+    const float L1 = fmaf(v[0], kLn2, z);
     if (GRAD) {
       r[0] = g * z;
       r[1] *= g;
@@ -577,13 +609,12 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
 #pragma unroll
   for (int k = 1; k < K; ++k) m1 = fmaxf(m1, v[k]);
   float s1 = 0.f, s2 = 0.f;
-  const float nm1 = -m1 * kLog2e;
   if constexpr (K % 2 == 0) {   // two components per packed instruction (even / odd partial sums, added at the end)
     F2 s1p = f2(0.f), s2p = f2(0.f);
 #pragma unroll
     for (int k = 0; k < K; k += 2) {
-      const F2 ev = ex2_2(fma2(f2(v[k], v[k + 1]), f2(kLog2e), f2(nm1)));   // exp(v_k - max)
-      const F2 er = ex2_2(mul2(f2(r[k], r[k + 1]), f2(kLog2e)));             // exp(w_k)
+      const F2 ev = ex2_2(add2(f2(v[k], v[k + 1]), f2(-m1)));               // exp(v_k - max)
+      const F2 er = ex2_2(f2(r[k], r[k + 1]));                              // exp(w_k)
       v[k] = ev.x; v[k + 1] = ev.y;
       r[k] = er.x; r[k + 1] = er.y;
       s1p = add2(s1p, ev);
@@ -594,13 +625,13 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
   } else {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      v[k] = fast_ex2(fmaf(v[k], kLog2e, nm1));   // exp(v_k - max), one FFMA per argument
-      r[k] = fast_ex2(r[k] * kLog2e);
+      v[k] = fast_ex2(v[k] - m1);
+      r[k] = fast_ex2(r[k]);
       s1 += v[k];
       s2 += r[k];
     }
   }
-  const float L = m1 + kLn2 * (fast_lg2(s1) - fast_lg2(s2));
+  const float L = kLn2 * (m1 + (fast_lg2(s1) - fast_lg2(s2)));
   if (GRAD) {
     const float g1 = g * fast_rcp(s1), g2 = g * fast_rcp(s2);
     if constexpr (K % 2 == 0) {
@@ -637,8 +668,8 @@ BLVM_HD void dmol_k1_two_samples(float ya, float yb, float (&ra)[3], float (&rb)
     F2 lp, dmu = f2(0.f), dls = f2(0.f);
     dl_mid_pair_tiny<GRAD>(f2(ya, yb), f2(ra[1], rb[1]), f2(ra[2], rb[2]), C, lp, dmu, dls);
     const float za = ra[0] - ra[0], zb = rb[0] - rb[0];   // 0, or NaN for a non-finite logit (log_softmax of one logit)
-    La = lp.x + za;
-    Lb = lp.y + zb;
+    La = fmaf(lp.x, kLn2, za);   // the pair function returns log2 units
+    Lb = fmaf(lp.y, kLn2, zb);
     if (GRAD) {
       const F2 g2 = f2(ga, gb);
       const F2 gm = mul2(dmu, g2), gs = mul2(dls, g2);

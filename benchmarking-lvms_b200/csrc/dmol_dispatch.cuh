@@ -33,7 +33,11 @@ int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
     if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
     configured[dev] = true;
   }
-  kern<<<static_cast<unsigned>(tiles), kTile, smem, st>>>(A);
+  constexpr int G = DmolGroup<K, TP>::value;           // chunks per CTA (dmol_kernels.cuh)
+  DmolArgs A2 = A;
+  A2.ctas_per_row = (A.chunks + G - 1) / G;
+  (void)tiles;
+  kern<<<static_cast<unsigned>(A.B * A2.ctas_per_row), kTile, smem, st>>>(A2);
   return check_launch("dmol_tile_kernel");
 }
 

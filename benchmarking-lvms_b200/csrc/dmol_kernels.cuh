@@ -38,6 +38,7 @@ struct DmolArgs {
   double* partials;        // (B, chunks) masked per-tile sums of log-prob, nullptr = not wanted
   int* err_flag;           // set to 1 if any y is outside [-1, 1] (the reference's assert, log_likelihoods.py:195)
   int64_t B, T, chunks;
+  int64_t ctas_per_row;    // tile kernel: ceil(chunks / DmolGroup) CTAs per utterance (set by the launcher)
   int K, D;
   int flags;
   int lik;                 // kLikDmol / kLikGmmRaw / kLikGmmSd (generic kernel; the register kernels take it as a template argument)
@@ -128,9 +129,9 @@ struct RowIO<__nv_bfloat16, P> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[P]) {
     if constexpr (P % 2 == 0) {
 #pragma unroll
-      for (int i = 0; i < P / 2; ++i) {
-        const float2 v = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(p)[i]);
-        r[2 * i] = v.x; r[2 * i + 1] = v.y;
+      for (int i = 0; i < P / 2; ++i) {   // bf16 -> fp32 is a 16-bit shift: one SHL and one AND per pair
+        const uint32_t w = reinterpret_cast<const uint32_t*>(p)[i];
+        r[2 * i] = __uint_as_float(w << 16); r[2 * i + 1] = __uint_as_float(w & 0xffff0000u);
       }
     } else {
 #pragma unroll
@@ -181,9 +182,30 @@ struct DmolMinBlocks {
   static constexpr int value = K > 20 ? BLVM_MINB_BIGK : (K > 16 ? BLVM_MINB_K20 : (K > 12 ? BLVM_MINB_K16 : ((K > 8 && GRAD) ? BLVM_MINB_MIDK : 0)));   // 0 = no constraint
 };
 
+// Chunks per CTA of the tile kernel.  The partial-sum layout (one fp64 per chunk of 128 * DmolSpt<K> samples, what
+// blvm_dmol_chunks() counts) is fixed by K alone; a CTA may cover G consecutive chunks of an utterance with ONE slab, ONE
+// mbarrier / bulk load / bulk store / block reduction: it writes its sum into the first chunk's slot and zeros into the
+// others (the finalize kernel only ever adds a row's slots up).  The per-CTA fixed cost (index and bounds arithmetic,
+// barriers, the fp64 block sum: ~240 warp instructions, ncu r2a) is what makes the 16-bit kernels issue-bound at one
+// sample per thread; their slabs are half as large, so two chunks per CTA keep the shared-memory footprint of the fp32 kernel.
+#ifndef BLVM_GROUP_H16
+#define BLVM_GROUP_H16 2   // fp16 / bf16 parameters
+#endif
+#ifndef BLVM_GROUP_F32
+#define BLVM_GROUP_F32 1
+#endif
+template <int K, typename TP>
+struct DmolGroup {
+  static constexpr int want = sizeof(TP) == 2 ? BLVM_GROUP_H16 : BLVM_GROUP_F32;
+  // K <= 5 already walks 4-8 samples per thread (and normally runs the stream kernel); slabs are kept at or below 32 KB
+  // (measured r2b, bf16: K = 10 107 -> 98.8 us, K = 16 170 -> 162 us with two chunks per CTA, but K = 30 (46 KB slabs, 4 CTAs
+  // per SM either way) 320 -> 357 us: long serialised load / evaluate / store phases with too few CTAs to overlap them)
+  static constexpr int value = (K > 5 && size_t(128) * DmolSpt<K>::value * want * 3 * K * sizeof(TP) <= 32 * 1024) ? want : 1;
+};
+
 template <int K, int TPB, typename TP>
 constexpr size_t dmol_tile_smem_bytes() {
-  return ((size_t(TPB) * DmolSpt<K>::value * 3 * K * sizeof(TP) + 15) / 16) * 16 + 16 /*mbarrier*/ + (TPB / 32) * sizeof(double);
+  return ((size_t(TPB) * DmolSpt<K>::value * DmolGroup<K, TP>::value * 3 * K * sizeof(TP) + 15) / 16) * 16 + 16 /*mbarrier*/ + (TPB / 32) * sizeof(double);
 }
 
 // The body of one tile; returns true if a bulk store is still reading the tile's shared memory (the caller must execute
@@ -192,7 +214,8 @@ template <int K, int TPB, bool GRAD, int UMODE, typename TP, int LIK = kLikDmol>
 __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t tile_id, unsigned char* smem) {
   constexpr int P = 3 * K;
   constexpr int NW = TPB / 32;
-  constexpr int SPT = DmolSpt<K>::value;
+  constexpr int G = DmolGroup<K, TP>::value;            // chunks (partial-sum slots) per CTA
+  constexpr int SPT = DmolSpt<K>::value * G;
   constexpr int TILE = TPB * SPT;
   constexpr size_t kTileBytes = ((size_t(TILE) * P * sizeof(TP) + 15) / 16) * 16;
   TP* tile = reinterpret_cast<TP*>(smem);
@@ -200,14 +223,18 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
   double* scratch = reinterpret_cast<double*>(smem + kTileBytes + 16);
 
   const int tid = threadIdx.x;
-  const int64_t b = tile_id / A.chunks;
-  const int64_t c = tile_id - b * A.chunks;
-  const int64_t t0 = c * TILE;
-  const int n = static_cast<int>(min(static_cast<int64_t>(TILE), A.T - t0));  // samples of this tile
-  const int64_t s0 = b * A.T + t0;                                            // first flat sample
-  int64_t len = A.x_sl ? A.x_sl[b] : A.T;
-  len = len < 0 ? 0 : (len > A.T ? A.T : len);
-  const int nvalid = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(n), len - t0)));
+  // row-local arithmetic in 32 bits (the host rejects T >= 2^31 and more than 2^31 - 1 tiles); only the flat sample
+  // offset of the tile is 64-bit (2.95 G parameter elements at the top of config 5)
+  const unsigned tile32 = static_cast<unsigned>(tile_id), cpr = static_cast<unsigned>(A.ctas_per_row);
+  const unsigned b = tile32 / cpr;
+  const unsigned c = tile32 - b * cpr;                  // CTA index within the utterance
+  const int T32 = static_cast<int>(A.T);
+  const int t0 = static_cast<int>(c) * TILE;
+  const int n = min(TILE, T32 - t0);                    // samples of this tile
+  const int64_t s0 = static_cast<int64_t>(b) * A.T + t0;   // first flat sample
+  int64_t len64 = A.x_sl ? A.x_sl[b] : A.T;
+  const int len = static_cast<int>(len64 < 0 ? 0 : (len64 > A.T ? A.T : len64));
+  const int nvalid = max(0, min(n, len - t0));
 
   const TP* gsrc = static_cast<const TP*>(A.raw) + s0 * P;
   TP* gdst = GRAD ? static_cast<TP*>(A.graw) + s0 * P : nullptr;
@@ -315,7 +342,16 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
   }
   if (A.partials) {
     const double s = block_sum_f64<NW>(acc, scratch);
-    if (tid == 0) A.partials[tile_id] = s;
+    if (tid == 0) {
+      double* slot = A.partials + static_cast<int64_t>(b) * A.chunks + static_cast<int64_t>(c) * G;
+      slot[0] = s;
+      if constexpr (G > 1) {
+        const int64_t left = A.chunks - static_cast<int64_t>(c) * G;   // slots of this utterance from ours on
+#pragma unroll
+        for (int q = 1; q < G; ++q)
+          if (q < left) slot[q] = 0.0;
+      }
+    }
   }
   return GRAD && bulk_out;
 }

@@ -34,6 +34,10 @@ inline blvm::DmolConsts make_consts(int num_bins, float log_epsilon) {
   C.hi_thresh = static_cast<float>(1.0 - 2.0 / num_bins);
   C.log_half_bins = static_cast<float>(log(num_bins / 2.0));
   C.log_eps = log_epsilon;
+  const double log2e = 1.4426950408889634;
+  C.log_half_bins2 = static_cast<float>(log(num_bins / 2.0) * log2e);
+  C.neg_log_ratio2 = static_cast<float>(-log(static_cast<double>(num_bins) / (num_bins - 1)) * log2e);
+  C.log_delta_thresh2 = static_cast<float>(log(static_cast<double>(blvm::kDeltaThresh)) * log2e);
   return C;
 }
 

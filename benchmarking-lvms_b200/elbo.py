@@ -214,7 +214,13 @@ def _kl_level(kld, **kw) -> KLLevel:
 def _vrnn_like(self, y, parameters, kld_twise, x_sl, stride, beta, free_nats, return_fn_kl):
     r = fused_elbo(y, parameters, x_sl, [_kl_level(kld_twise, stride=stride)], beta, free_nats,
                    num_bins=self.likelihood.num_bins)
-    seq_mask = sequence_mask(x_sl, dtype=torch.float64, device=y.device)   # vrnn.py:266: dtype=float => float64
+    # vrnn.py:266: dtype=float => float64; T = max(x_sl) from the host copy, the comparison against the lengths the fused
+    # op already uploaded (no second host->device copy, no synchronisation)
+    x_sl_host = x_sl if isinstance(x_sl, torch.Tensor) else torch.as_tensor(x_sl)
+    if x_sl_host.is_cuda:
+        seq_mask = sequence_mask(x_sl_host, dtype=torch.float64, device=y.device)
+    else:
+        seq_mask = (torch.arange(int(x_sl_host.max()), device=y.device).unsqueeze(0) < r.x_sl.unsqueeze(1)).to(torch.float64)
     kld = tag_sum(r.kl_fn, r.sums, 3) if return_fn_kl else tag_sum(r.kl, r.sums, 2)
     # the sums over utterances already exist on the device (finalize kernel): lazily built Metric objects use them
     return tag_sum(r.loss, r.sums, 0), tag_sum(r.elbo, r.sums, 4), tag_sum(r.log_prob, r.sums, 1), kld, seq_mask   # all float64 like the reference

@@ -17,6 +17,10 @@ static DmolConsts make_consts(int num_bins, float log_eps) {
   C.hi_thresh = (float)(1.0 - 2.0 / num_bins);
   C.log_half_bins = (float)std::log(num_bins / 2.0);
   C.log_eps = log_eps;
+  const double log2e = 1.4426950408889634;
+  C.log_half_bins2 = (float)(std::log(num_bins / 2.0) * log2e);
+  C.neg_log_ratio2 = (float)(-std::log((double)num_bins / (num_bins - 1)) * log2e);
+  C.log_delta_thresh2 = (float)(std::log((double)kDeltaThresh) * log2e);
   return C;
 }
 

@@ -10,10 +10,13 @@ Clockwork-VAE, STCN top-down and bottom-up, WaveNet, LSTM) is built from the sta
 once unpatched (the reference's own eager op chain) and once under `blvm_b200.patch_blvm()` (the kernels), from the same
 weights, inputs and RNG state.
 
-Tolerances.  The comparison partner here is the reference's *fp32* run (there is no fp64 run of a whole model with the
-same latent samples), whose DMoL arithmetic carries `sigmoid(a) - sigmoid(b)` cancellation noise (tests/parity.py,
-DESIGN.md §4): the loss agrees to 5e-6 relative, every weight gradient to 2e-4 of its tensor scale (measured worst
-cases are printed; the kernel-level tests hold the 1e-5 / 1e-6 bars against the fp64 anchor).
+Tolerances and anchor.  A whole model cannot be rerun in fp64 with the same latent samples (the RNG stream depends on the
+dtype), so the anchor is the unpatched reference model with ONLY its likelihood function evaluated in fp64
+(`discretized_logistic_mixture_ll` called with `.double()` inputs inside the reference's own `log_prob`; body, KL and
+reduction untouched, same weights / inputs / RNG).  That removes the one large error source of the reference's fp32 run on
+16-bit audio -- the `sigmoid(a) - sigmoid(b)` cancellation (tests/parity.py), which shows up as up to 5e-3 of
+a weight-gradient tensor's scale.  Against that anchor: loss rel 2e-6, every weight gradient within 1e-4 of its tensor's
+scale, and never further away than the reference's own fp32 run is (the kernel-level tests hold the 1e-5 / 1e-6 bars).
 """
 import copy
 import importlib
@@ -33,8 +36,8 @@ sys.path.insert(0, ROOT)
 from oracle import ref_loader  # noqa: E402
 
 MODELS = ["vrnn", "srnn", "cwvae", "stcn", "stcn_bottom_up", "wavenet", "lstm"]
-LOSS_RTOL = 5e-6
-GRAD_TOL = 2e-4        # of the tensor's max |gradient|
+LOSS_RTOL = 2e-6
+GRAD_TOL = 1e-4        # of the tensor's max |gradient|
 
 
 @pytest.fixture(scope="module")
@@ -96,7 +99,26 @@ def train_step(model, x, x_sl, kwargs, use_amp, scaler_cls):
     return loss.detach(), grads, values, outputs, scaler
 
 
-def run_pair(M, name, use_amp):
+class likelihood_in_fp64:
+    """Context: the reference's DMoL log-likelihood function evaluates in fp64 (inputs upcast, result cast back)."""
+
+    def __enter__(self):
+        self.mod = importlib.import_module("blvm.modules.distributions")
+        self.orig = self.mod.discretized_logistic_mixture_ll
+        orig = self.orig
+
+        def ll64(y, logit_probs, locs, log_scales, **kw):
+            return orig(y.double(), logit_probs.double(), locs.double(), log_scales.double(), **kw).to(logit_probs.dtype)
+
+        self.mod.discretized_logistic_mixture_ll = ll64
+        return self
+
+    def __exit__(self, *exc):
+        self.mod.discretized_logistic_mixture_ll = self.orig
+        return False
+
+
+def run_pair(M, name, use_amp, anchor64=False):
     import blvm_b200 as B
     x, x_sl, kwargs = inputs(name)
     ref_model = build(M, name).cuda()
@@ -105,6 +127,9 @@ def run_pair(M, name, use_amp):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         r = train_step(ref_model, x, x_sl, kwargs, use_amp, scaler_cls)
+        if anchor64:
+            with likelihood_in_fp64():
+                r = (r, train_step(ref_model, x, x_sl, kwargs, use_amp, scaler_cls))
     del ref_model
     try:
         rebound = B.patch_blvm()
@@ -126,21 +151,26 @@ def run_pair(M, name, use_amp):
 
 @pytest.mark.parametrize("name", MODELS)
 def test_patched_training_step_matches_reference_fp32(name, ref):
-    (loss_r, grads_r, vals_r, out_r, _), (loss_o, grads_o, vals_o, out_o, _), launches = run_pair(ref, name, use_amp=False)
+    (ref32, ref64), (loss_o, grads_o, vals_o, out_o, _), launches = run_pair(ref, name, use_amp=False, anchor64=True)
+    loss_32, grads_32 = ref32[0], ref32[1]
+    loss_r, grads_r, vals_r, out_r, _ = ref64          # the anchor: reference model, likelihood function in fp64
     assert loss_o.dtype == loss_r.dtype, (loss_o.dtype, loss_r.dtype)     # float64 for VRNN/SRNN, float32 elsewhere
     rel = abs(float(loss_o) - float(loss_r)) / abs(float(loss_r))
+    rel32 = abs(float(loss_32) - float(loss_r)) / abs(float(loss_r))
     assert set(grads_o) == set(grads_r), "a parameter lost (or gained) its gradient under the patch"
-    worst, worst_name = 0.0, None
+    worst, worst_name, worst32 = 0.0, None, 0.0
     for n, g in grads_r.items():
         scale = float(g.abs().max())
         if scale == 0.0:
             assert float(grads_o[n].abs().max()) == 0.0, n
             continue
         e = float((grads_o[n] - g).abs().max()) / scale
+        worst32 = max(worst32, float((grads_32[n] - g).abs().max()) / scale)
         if e > worst:
             worst, worst_name = e, n
-    print(f"[{name}] loss ref {float(loss_r):.8f} ours {float(loss_o):.8f} rel {rel:.2e}; worst weight-grad error "
-          f"{worst:.2e} of its scale ({worst_name}); {len(grads_r)} gradient tensors; {launches} blvm launches")
+    print(f"[{name}] loss anchor {float(loss_r):.8f} ours {float(loss_o):.8f} rel {rel:.2e} (reference fp32: {rel32:.2e}); worst "
+          f"weight-grad error {worst:.2e} of its scale ({worst_name}) (reference fp32: {worst32:.2e}); {len(grads_r)} gradient "
+          f"tensors; {launches} blvm launches")
     assert rel < LOSS_RTOL
     assert worst < GRAD_TOL, (worst, worst_name)
     assert [n for n, _ in vals_o] == [n for n, _ in vals_r]              # metric list order preserved (vrnn.py:346-355)
@@ -150,7 +180,7 @@ def test_patched_training_step_matches_reference_fp32(name, ref):
         if hasattr(out_r, key):
             a, b = getattr(out_o, key), getattr(out_r, key)
             assert a.dtype == b.dtype and a.shape == b.shape, key
-            np.testing.assert_allclose(a.double().cpu().numpy(), b.double().cpu().numpy(), rtol=2e-5, err_msg=key)
+            np.testing.assert_allclose(a.detach().double().cpu().numpy(), b.detach().double().cpu().numpy(), rtol=2e-5, err_msg=key)
     assert sorted(vars(out_o)) == sorted(vars(out_r))
 
 
@@ -202,7 +232,9 @@ def test_patched_step_has_one_fused_kl_launch_and_one_metric_sync(name, ref):
                 vals = [m.value for m in metrics]
             finally:
                 torch.cuda.set_sync_debug_mode("default")
-        return sum("synchroniz" in str(i.message).lower() for i in w), vals
+        found = [(os.path.relpath(i.filename, ROOT) if i.filename.startswith(ROOT) else i.filename, i.lineno) for i in w
+                 if "synchroniz" in str(i.message).lower()]
+        return found, vals
 
     syncs_ref, _ = forward_and_read(model_ref)
     try:
@@ -220,11 +252,15 @@ def test_patched_step_has_one_fused_kl_launch_and_one_metric_sync(name, ref):
             ops.kl_gaussian = real
     finally:
         B.unpatch_blvm()
-    print(f"[{name}] host syncs per step: reference {syncs_ref}, patched {syncs}; blvm launches {launches}")
+    def ours(found):   # synchronisations caused by the path (likelihood / KL / compute_elbo / Metric objects), not by the model body
+        return [f for f in found if "benchmarking-lvms_b200" in f[0] or f[0].endswith(("evaluation/metrics.py", "utils/log_likelihoods.py", "utils/variational.py"))
+                or (f[0].endswith("utils/operations.py") and 90 <= f[1] <= 119)]      # sequence_mask (operations.py:90-119)
+    print(f"[{name}] host syncs per step: reference {len(syncs_ref)} (path: {len(ours(syncs_ref))}), patched {len(syncs)} "
+          f"(path: {len(ours(syncs))}); blvm launches {launches}\n   reference: {sorted(set(syncs_ref))}\n   patched:   {sorted(set(syncs))}")
     assert eager["n"] == 0, "the elementwise KL was materialised"
     assert launches == 4, launches          # sample+mode, likelihood, KL (all levels), finalize
-    assert syncs == 1, syncs
-    assert syncs_ref >= 5
+    assert len(ours(syncs)) == 1, syncs     # the one batched read of the metrics
+    assert len(ours(syncs_ref)) >= 5
 
 
 def test_wavenet_nansum_keeps_gradient_of_finite_rows(ref):
@@ -245,11 +281,10 @@ def test_wavenet_nansum_keeps_gradient_of_finite_rows(ref):
     x_sl = torch.tensor([T, T - 100, T // 2, 9])
 
     lik_ref = ref_dist.DiscretizedLogisticMixtureDense(x_dim=3 * K, y_dim=1, num_mix=K, num_bins=nb)
-    raw_r = raw0.cuda().requires_grad_(True)
+    raw_r = raw0.cuda().double().requires_grad_(True)      # the reference's code in fp64: the parity anchor (tests/parity.py)
     lls = raw_r[..., K:].view(Bn, T, 1, 2 * K)
     params_ref = (raw_r[..., :K], lls[..., :K], lls[..., K:].clamp(min=-7.0))          # distributions.py:383-386
-    y_ok = torch.where(torch.isnan(y), torch.zeros_like(y), y)
-    loss_r, logp_r, _ = ref_wavenet.WaveNet.compute_loss(SimpleNamespace(likelihood=lik_ref), y_ok, x_sl, params_ref)
+    loss_r, logp_r, _ = ref_wavenet.WaveNet.compute_loss(SimpleNamespace(likelihood=lik_ref), y.double(), x_sl, params_ref)
     loss_r.backward()
 
     raw_o = raw0.cuda().requires_grad_(True)
@@ -257,11 +292,13 @@ def test_wavenet_nansum_keeps_gradient_of_finite_rows(ref):
     loss_o, logp_o, _ = B.wavenet_compute_loss(SimpleNamespace(likelihood=lik), y, x_sl, B.DMoLParams(raw_o, K, 1, -7.0))
     loss_o.backward()
     assert torch.isnan(logp_r[1]) and torch.isnan(logp_o[1]) and torch.isfinite(loss_o)
-    np.testing.assert_allclose(loss_o.item(), loss_r.item(), rtol=5e-6)
-    go, gr = raw_o.grad.cpu(), raw_r.grad.cpu()
+    np.testing.assert_allclose(loss_o.item(), loss_r.item(), rtol=1e-6)
+    go, gr = raw_o.grad.double().cpu(), raw_r.grad.cpu()
     finite_rows = [0, 2, 3]
-    scale = gr[finite_rows].abs().amax(-1, keepdim=True) + 1e-30
-    assert float(((go[finite_rows] - gr[finite_rows]).abs() / scale).max()) < 1e-3     # fp32 reference: cancellation noise
+    for g0 in range(0, 3 * K, K):      # per parameter group, relative to the group's scale within the sample (tests/parity.py)
+        o, r_ = go[finite_rows][..., g0:g0 + K], gr[finite_rows][..., g0:g0 + K]
+        tol = 1e-5 * r_.abs() + 1e-5 * r_.abs().amax(-1, keepdim=True) + 1e-6 / float(x_sl.sum())
+        assert bool(((o - r_).abs() <= tol).all()), f"group {g0 // K}"
     assert float(go[finite_rows].abs().max()) > 0
     # the NaN utterance: zero gradient wherever the local derivative is finite, in both implementations
     both_finite = torch.isfinite(go[1]) & torch.isfinite(gr[1])
