@@ -64,6 +64,7 @@ SIGNATURES = {
     "blvm_exchange_buffer_bytes": (_i64, []),
     "blvm_elbo_step_workspace_doubles": (_i64, [ctypes.POINTER(ElboStepStruct)]),
     "blvm_elbo_step": (_i32, [ctypes.POINTER(ElboStepStruct), _p]),
+    "blvm_last_step_launches": (_i32, []),
     "blvm_row_gate_inplace": (_i32, [_p, _i32, _i64, _i64, _p, _p]),
     "blvm_exchange_consume": (_i32, [_p, _i32, _p, _i32, _f64, _p, _p, _p]),
     "blvm_quantize": (_i32, [_p, _i64, _p, _i64, _p, _p]),

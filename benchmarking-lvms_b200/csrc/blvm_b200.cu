@@ -396,14 +396,15 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
   return check_launch("kl_kernel (materialised KL)");
 }
 
-int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, int flags,
-                                 blvm_stream_t stream) {
+// Validate the level descriptors and lay out the concatenated tile ranges (shared by the level-array entry point and the
+// single-launch step).
+static int build_kl_multi(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, KlMultiArgs& M, bool& any_grad,
+                          int64_t& total) {
   if (n_levels < 1 || n_levels > kMaxLevels) return fail(BLVM_ERR_INVALID_ARGUMENT, "n_levels=%d out of [1, %d]", n_levels, kMaxLevels);
   if (!levels_host || B < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "null levels / negative B");
-  KlMultiArgs M{};
   M.n_levels = n_levels;
-  bool any_grad = false;
-  int64_t total = 0;
+  any_grad = false;
+  total = 0;
   for (int l = 0; l < n_levels; ++l) {
     const blvm_kl_level_t& L = levels_host[l];
     if (L.Tz < 0 || L.Z < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: bad shape Tz=%lld Z=%lld", l, (long long)L.Tz, (long long)L.Z);
@@ -431,12 +432,21 @@ int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_level
     total += B * A.chunks;
   }
   M.tile_begin[n_levels] = total;
-  if (total == 0) return BLVM_OK;
   if (total > 0x7fffffffLL) return fail(BLVM_ERR_UNSUPPORTED, "too many tiles");
   // a parameter level without gradient outputs inside a launch that computes gradients for another one would write through
   // null pointers: require consistency
   for (int l = 0; l < n_levels; ++l)
     if (!M.level[l].kl_in && any_grad && !M.level[l].g_mu_q) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: gradient outputs missing", l);
+  return BLVM_OK;
+}
+
+int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, int flags,
+                                 blvm_stream_t stream) {
+  KlMultiArgs M{};
+  bool any_grad = false;
+  int64_t total = 0;
+  if (int rc = build_kl_multi(levels_host, n_levels, B, gscale, M, any_grad, total)) return rc;
+  if (total == 0) return BLVM_OK;
   const bool pdl = (flags & BLVM_FLAG_OVERLAP_PREV) != 0 && pdl_enabled();
   const unsigned g = static_cast<unsigned>(total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -509,6 +519,9 @@ static int64_t step_logp_chunks(const blvm_elbo_step_t& S) {
     default: return 0;
   }
 }
+
+static thread_local int g_last_step_launches = 0;
+int blvm_last_step_launches(void) { return g_last_step_launches; }
 
 int64_t blvm_elbo_step_workspace_doubles(const blvm_elbo_step_t* S) {
   if (!S || S->n_levels < 0 || S->n_levels > kMaxLevels || S->B < 0) return -1;
@@ -589,6 +602,7 @@ int blvm_elbo_step(const blvm_elbo_step_t* desc, blvm_stream_t stream) {
     }
   }
   const int nansum = (S.flags & BLVM_FLAG_NANSUM_LOSS) ? 1 : 0;
+  g_last_step_launches = (has_lik ? 1 : 0) + (L > 0 ? 1 : 0) + 1 + ((nansum && lik_grad) ? 1 : 0);
   if (int rc = finalize_impl(logp_part, logp_chunks, kl_part, klfn_part, kl_chunks, L, S.x_sl, S.B, S.beta, dn, rows, scalars,
                              S.sync_counter, X, stream, nansum))
     return rc;

@@ -105,14 +105,10 @@ def _resolved(x):
     return x.resolve() if isinstance(x, _Lazy) else x
 
 
-def patch_metric_syncs(metrics_module):
-    """Rebind RunningMeanMetric.__init__ (and with it LossMetric / LLMetric / KLMetric / BitsPerDimMetric ...) of the
-    reference's `blvm.evaluation.metrics` so that device values are read lazily, all metrics of a step with one sync."""
-    if _metric_patches:
-        return
-    cls = metrics_module.RunningMeanMetric
-    base_init = metrics_module.Metric.__init__
-    orig_init = cls.__init__
+def _patch_metric_class(cls, base_init, value_attr, has_weight):
+    """Lazy constructor + lazily settling properties for one Metric class whose constructor reduces tensors on the host
+    (`values.sum().tolist()`): RunningMeanMetric (value in `running_mean`), EMAMetric (`ema`), LatestMeanMetric (`latest`)."""
+    orig_init, orig_copy = cls.__init__, cls.copy
 
     def lazy_init(self, values, name, tags=None, reduce_by=None, weight_by=None, get_best=None, log_to_console=True,
                   log_to_framework=True):
@@ -120,19 +116,28 @@ def patch_metric_syncs(metrics_module):
         numel = values.numel() if isinstance(values, torch.Tensor) else 1              # metrics.py:240
         value = _number(values, values) if isinstance(values, torch.Tensor) else values
         reduce_by = _number(reduce_by, numel)                                           # :243
-        weight_by = _number(weight_by, reduce_by)                                       # :244
+        weight_by = _number(weight_by, reduce_by) if has_weight else None               # :244
         d = self.__dict__
         if any(isinstance(v, _Lazy) for v in (value, reduce_by, weight_by)):
             d["_blvm_lazy"] = (value, reduce_by, weight_by)
         else:
-            d["weight_by"], d["running_mean"] = weight_by, value / reduce_by            # :246-247
+            if has_weight:
+                d["weight_by"] = weight_by
+            d[value_attr] = value / reduce_by                                           # :246-247
+
+    if not has_weight:   # LatestMeanMetric(values, name, tags, reduce_by, get_best, ...): no weight_by parameter
+        def lazy_init(self, values, name, tags=None, reduce_by=None, get_best=None, log_to_console=True, log_to_framework=True,  # noqa: F811
+                      _full=lazy_init):
+            _full(self, values, name, tags=tags, reduce_by=reduce_by, get_best=get_best, log_to_console=log_to_console,
+                  log_to_framework=log_to_framework)
 
     def _settle(self):
         lazy = self.__dict__.pop("_blvm_lazy", None)
         if lazy is not None:
             value, reduce_by, weight_by = (_resolved(v) for v in lazy)
-            self.__dict__.setdefault("weight_by", weight_by)
-            self.__dict__.setdefault("running_mean", value / reduce_by)
+            if has_weight:
+                self.__dict__.setdefault("weight_by", weight_by)
+            self.__dict__.setdefault(value_attr, value / reduce_by)
 
     def make_property(attr):
         def get(self):
@@ -148,20 +153,32 @@ def patch_metric_syncs(metrics_module):
         _settle(self)
         return orig_copy(self)
 
-    orig_copy = cls.copy
+    attrs = (value_attr, "weight_by") if has_weight else (value_attr,)
     cls.__init__ = lazy_init
-    cls.running_mean = make_property("running_mean")
-    cls.weight_by = make_property("weight_by")
+    for attr in attrs:
+        setattr(cls, attr, make_property(attr))
     cls.copy = lazy_copy
-    _metric_patches.append((cls, orig_init, orig_copy))
+    _metric_patches.append((cls, orig_init, attrs))
+
+
+def patch_metric_syncs(metrics_module):
+    """Rebind the constructors of the reference's `blvm.evaluation.metrics` classes that the audio models build every step --
+    RunningMeanMetric (and with it LossMetric / LLMetric / KLMetric / BitsPerDimMetric ...), EMAMetric (Clockwork-VAE,
+    clockwork_vae.py:112) and LatestMeanMetric -- so that device values are read lazily: all metrics of a step, one sync."""
+    if _metric_patches:
+        return
+    base_init = metrics_module.Metric.__init__
+    _patch_metric_class(metrics_module.RunningMeanMetric, base_init, "running_mean", True)
+    _patch_metric_class(metrics_module.EMAMetric, base_init, "ema", True)
+    _patch_metric_class(metrics_module.LatestMeanMetric, base_init, "latest", False)
 
 
 def unpatch_metric_syncs():
     while _metric_patches:
-        cls, orig_init, orig_copy = _metric_patches.pop()
+        cls, orig_init, attrs = _metric_patches.pop()
         cls.__init__ = orig_init
         if "copy" in cls.__dict__:
             del cls.copy
-        for attr in ("running_mean", "weight_by"):
+        for attr in attrs:
             if attr in cls.__dict__:
                 delattr(cls, attr)

@@ -511,7 +511,7 @@ class _FusedELBO(torch.autograd.Function):
             # ONE call: likelihood kernel, the KL of all levels (one launch, overlapping the likelihood grid's tail),
             # finalize (a programmatic dependent) and, for WaveNet's nansum, the NaN-row gate
             check(lib.blvm_elbo_step(ctypes.byref(st), _stream(dev.index)), "blvm_elbo_step")
-        _count((1 if has_lik else 0) + (1 if L else 0) + 1 + (1 if (spec.nansum and has_lik and grads[0] is not None) else 0))
+        _count(lib.blvm_last_step_launches())   # as counted by the library: likelihood, KL of all levels, finalize (+ NaN-row gate)
 
         loss = scalars[:1].view(())
         ctx.set_materialize_grads(False)   # no zero-filled grads for the detached outputs

@@ -268,6 +268,9 @@ typedef struct blvm_elbo_step {
 } blvm_elbo_step_t;
 int64_t blvm_elbo_step_workspace_doubles(const blvm_elbo_step_t* desc_host);
 int blvm_elbo_step(const blvm_elbo_step_t* desc_host, blvm_stream_t stream);
+/* Kernels the last successful blvm_elbo_step of THIS thread launched: 3 (likelihood, KL of all levels, finalize; fewer when a
+ * part is absent), + 1 for BLVM_FLAG_NANSUM_LOSS's row gate.  (What the Python layer reports as its launch count.) */
+int blvm_last_step_launches(void);
 
 /* In-place: rows b of buf (B, row_elems) (element type `dtype`) whose row_values[b] (fp64) is NaN are multiplied by 0;
  * CTAs of finite rows exit after reading one double.  The backward of nansum over utterances (wavenet.py:145). */
