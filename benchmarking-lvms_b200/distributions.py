@@ -181,8 +181,10 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
         raise NotImplementedError("Discretized mixture of logistics does not have a Distribution object (yet)")
 
     def rsample(self, params):
-        """Gumbel-max over the mixture logits, gather the chosen component, sample its logistic
-        (blvm/utils/variational.py:309-349 with the defaults eps=1e-5, hard argmax)."""
+        """Reparameterised sample: Gumbel-max over the mixture logits, gather the chosen component, sample its logistic
+        (blvm/utils/variational.py:309-349 with the defaults eps=1e-5, hard argmax).  NOT on the path (no model, experiment
+        or test of the reference calls it: they use sample(), which is the kernel above) and not a fallback for anything: a
+        composition of differentiable torch ops kept for API completeness, on whatever device the parameters live."""
         logit_probs, locs, log_scales = params[0], params[1], params[2]
         u = torch.empty_like(logit_probs).uniform_(1e-5, 1.0 - 1e-5)
         choice = torch.argmax(logit_probs - torch.log(-torch.log(u)), dim=-1, keepdim=True)   # (*, 1)
@@ -200,23 +202,31 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
             params._cache["sample_mode"] = cached
         return cached
 
+    @staticmethod
+    def _as_packed(params) -> "DMoLParams":
+        """The packed container the sample / mode kernel reads: what forward() returned, or a reference-style
+        (logit_probs, locs, log_scales) tuple packed once (its log-scales are already clamped)."""
+        if isinstance(params, DMoLParams):
+            return params
+        logit_probs, locs, log_scales = params[0], params[1], params[2]
+        K, D = logit_probs.size(-1), locs.size(-2)
+        raw = torch.cat([logit_probs, torch.cat([locs, log_scales], dim=-1).flatten(-2)], dim=-1)
+        return DMoLParams(raw, K, D, -math.inf)
+
     @torch.no_grad()
     def sample(self, params):
-        """A sample of the mixture, clamped to [-1, 1] (distributions.py:359-361, variational.py:309-349)."""
-        if isinstance(params, DMoLParams) and params.raw.is_cuda:
-            return self._fused_sample_mode(params)[0]
-        return self.rsample(params)
+        """A sample of the mixture, clamped to [-1, 1] (distributions.py:359-361, variational.py:309-349): the fused
+        sample + mode kernel.  CUDA only, like every kernel of this package (CPU tensors raise; no torch fallback)."""
+        return self._fused_sample_mode(self._as_packed(params))[0]
 
     def mode(self, params):
-        """Mean of the most probable component (distributions.py:363-368)."""
-        if isinstance(params, DMoLParams) and params.raw.is_cuda:
-            _, mode, index = self._fused_sample_mode(params)
-            if torch.is_grad_enabled() and params.raw.requires_grad:
-                return ops.mode_with_grad(params.raw, mode, index, params.K, params.D)
-            return mode if params.raw.dtype == torch.float32 else mode.to(params.raw.dtype)
-        component = params[0].argmax(-1, keepdim=True).unsqueeze(-2)
-        component = component.expand(*component.shape[:-2], params[1].size(-2), 1)
-        return torch.gather(params[1], index=component, dim=-1).squeeze(-1).contiguous()
+        """Mean of the most probable component (distributions.py:363-368), from the same kernel launch as sample();
+        differentiable w.r.t. the chosen component's location like the reference's gather."""
+        params = self._as_packed(params)
+        _, mode, index = self._fused_sample_mode(params)
+        if torch.is_grad_enabled() and params.raw.requires_grad:
+            return ops.mode_with_grad(params.raw, mode, index, params.K, params.D)
+        return mode if params.raw.dtype == torch.float32 else mode.to(params.raw.dtype)
 
     def log_prob(self, y, params, reduce_dim: int = -1):
         """Per-sample log-likelihood (*); inputs are assumed to be in [-1, 1] (distributions.py:370-379)."""

@@ -64,8 +64,11 @@ def test_module_api_surface_matches_reference():
     assert len(p) == 3 and p[0].shape == (2, 5, 10) and p[1].shape == (2, 5, 1, 10) and p[2].shape == (2, 5, 1, 10)
     assert float(p[2].min()) >= -7.0                                                 # clamp, distributions.py:386
     lp, lc, ls = p                                                                    # iterable like the tuple
-    assert m.mode(p).shape == (2, 5, 1) and m.sample(p).shape == (2, 5, 1)
-    assert float(m.sample(p).abs().max()) <= 1.0
+    assert m.rsample(p).shape == (2, 5, 1)                                            # torch-op composition, any device
+    for call in (m.mode, m.sample):                                                   # kernels: CPU tensors raise, no torch fallback
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call(p)
+    assert float(m.rsample(p).abs().max()) <= 1.0
     d = B.DiscretizedLogisticDense(x_dim=8, y_dim=1, num_bins=256)
     assert d.out_features == 2 and list(d.state_dict().keys()) == ["params.weight", "params.bias"]
     q = d(torch.randn(3, 8))

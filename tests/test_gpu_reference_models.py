@@ -104,14 +104,24 @@ class likelihood_in_fp64:
     """Context: the reference's DMoL log-likelihood and Gaussian-KL FUNCTIONS evaluate in fp64 (inputs upcast, result cast
     back to fp32) wherever the reference models call them; everything else is the unmodified fp32 model."""
 
+    def __init__(self, ulp_noise: float = 0.0):
+        # ulp_noise > 0: every per-sample log-prob is multiplied by (1 + ulp_noise * n_t), n_t ~ N(0, 1) fixed: a relative
+        # perturbation of the per-sample likelihood gradients by about one fp32 ulp -- the sensitivity probe of the test below
+        self.ulp_noise = ulp_noise
+
     def __enter__(self):
         self.saved = []
         dist = importlib.import_module("blvm.modules.distributions")
         var = importlib.import_module("blvm.utils.variational")
         ll, kl = dist.discretized_logistic_mixture_ll, var.kl_divergence_gaussian
+        ulp_noise = self.ulp_noise
 
         def ll64(y, logit_probs, locs, log_scales, **kw):
-            return ll(y.double(), logit_probs.double(), locs.double(), log_scales.double(), **kw).to(logit_probs.dtype)
+            lp = ll(y.double(), logit_probs.double(), locs.double(), log_scales.double(), **kw)
+            if ulp_noise:
+                g = torch.Generator(device=lp.device).manual_seed(77)
+                lp = lp * (1.0 + ulp_noise * torch.randn(lp.shape, generator=g, device=lp.device, dtype=lp.dtype))
+            return lp.to(logit_probs.dtype)
 
         def kl64(mu_q, sd_q, mu_p, sd_p):
             return kl(mu_q.double(), sd_q.double(), mu_p.double(), sd_p.double()).to(mu_q.dtype)
@@ -141,7 +151,11 @@ def run_pair(M, name, use_amp, anchor64=False):
         r = train_step(ref_model, x, x_sl, kwargs, use_amp, scaler_cls)
         if anchor64:
             with likelihood_in_fp64():
-                r = (r, train_step(ref_model, x, x_sl, kwargs, use_amp, scaler_cls), train_step(ref_model, x, x_sl, kwargs, use_amp, scaler_cls))
+                r64 = train_step(ref_model, x, x_sl, kwargs, use_amp, scaler_cls)
+                r64b = train_step(ref_model, x, x_sl, kwargs, use_amp, scaler_cls)
+            with likelihood_in_fp64(ulp_noise=1.2e-7):
+                r64n = train_step(ref_model, x, x_sl, kwargs, use_amp, scaler_cls)
+            r = (r, r64, r64b, r64n)
     del ref_model
     try:
         rebound = B.patch_blvm()
@@ -163,16 +177,20 @@ def run_pair(M, name, use_amp, anchor64=False):
 
 @pytest.mark.parametrize("name", MODELS)
 def test_patched_training_step_matches_reference_fp32(name, ref):
-    (ref32, ref64, ref64b), (loss_o, grads_o, vals_o, out_o, _), launches = run_pair(ref, name, use_amp=False, anchor64=True)
-    loss_32, grads_32, grads_64b = ref32[0], ref32[1], ref64b[1]
+    (ref32, ref64, ref64b, ref64n), (loss_o, grads_o, vals_o, out_o, _), launches = run_pair(ref, name, use_amp=False, anchor64=True)
+    loss_32, grads_32, grads_64b, grads_64n = ref32[0], ref32[1], ref64b[1], ref64n[1]
     loss_r, grads_r, vals_r, out_r, _ = ref64          # the anchor: reference model, likelihood function in fp64
     assert loss_o.dtype == loss_r.dtype, (loss_o.dtype, loss_r.dtype)     # float64 for VRNN/SRNN, float32 elsewhere
     rel = abs(float(loss_o) - float(loss_r)) / abs(float(loss_r))
     rel32 = abs(float(loss_32) - float(loss_r)) / abs(float(loss_r))
     assert set(grads_o) == set(grads_r), "a parameter lost (or gained) its gradient under the patch"
-    # Per tensor: our distance from the anchor, the reference fp32 run's distance from it, and the anchor's own run-to-run
-    # noise (the same anchor step executed twice: cuDNN / index-add backward kernels accumulate with atomics).  A tensor
-    # passes within GRAD_TOL of its scale, or within 3x the noise the reference shows against itself.
+    # Per tensor: our distance from the anchor, the reference fp32 run's distance from it, the anchor's own run-to-run noise
+    # (the same anchor step executed twice: cuDNN / index-add backward kernels accumulate with atomics) and its SENSITIVITY:
+    # how far the tensor moves when every per-sample log-prob of the anchor is perturbed by one fp32 ulp (1.2e-7 relative).
+    # Some models amplify that by 1e3-1e4 (an untrained Clockwork-VAE: weight gradients that are small residuals of large
+    # cancelling terms); no fp32 implementation of the likelihood can then agree with the anchor better than the probe does.
+    # A tensor passes within GRAD_TOL of its scale, or within 3x the anchor's own noise, or within 8x its one-ulp sensitivity
+    # (the kernels' per-sample values and gradients are good to 2-4 fp32 ulps, tests/parity.py).
     worst, worst_name, worst32, rows = 0.0, None, 0.0, []
     for n, g in grads_r.items():
         scale = float(g.abs().max())
@@ -182,7 +200,8 @@ def test_patched_training_step_matches_reference_fp32(name, ref):
         e = float((grads_o[n] - g).abs().max()) / scale
         e32 = float((grads_32[n] - g).abs().max()) / scale
         noise = float((grads_64b[n] - g).abs().max()) / scale
-        rows.append((e, e32, noise, n))
+        sens = float((grads_64n[n] - g).abs().max()) / scale
+        rows.append((e, e32, noise, sens, n))
         worst32 = max(worst32, e32)
         if e > worst:
             worst, worst_name = e, n
@@ -190,10 +209,10 @@ def test_patched_training_step_matches_reference_fp32(name, ref):
     print(f"\n[{name}] loss anchor {float(loss_r):.8f} ours {float(loss_o):.8f} rel {rel:.2e} (reference fp32: {rel32:.2e}); worst "
           f"weight-grad error {worst:.2e} of its scale ({worst_name}) (reference fp32: {worst32:.2e}); {len(grads_r)} gradient "
           f"tensors; {launches} blvm launches")
-    for e, e32, noise, n in rows[:4]:
-        print(f"[{name}]    {n}: ours-anchor {e:.2e}, reference fp32-anchor {e32:.2e}, anchor run-to-run {noise:.2e}")
+    for e, e32, noise, sens, n in rows[:4] + ([r for r in rows[4:] if r[0] > GRAD_TOL / 10] if os.environ.get("BLVM_TEST_VERBOSE") else []):
+        print(f"[{name}]    {n}: ours-anchor {e:.2e}, reference fp32-anchor {e32:.2e}, anchor run-to-run {noise:.2e}, one-ulp sensitivity {sens:.2e}")
     assert rel < LOSS_RTOL
-    bad = [(e, noise, n) for e, e32, noise, n in rows if e > max(GRAD_TOL, 3 * noise)]
+    bad = [(e, noise, sens, n) for e, e32, noise, sens, n in rows if e > max(GRAD_TOL, 3 * noise, 8 * sens)]
     assert not bad, bad[:3]
     assert [n for n, _ in vals_o] == [n for n, _ in vals_r]              # metric list order preserved (vrnn.py:346-355)
     for (n, a), (_, b) in zip(vals_o, vals_r):

@@ -76,6 +76,22 @@ def install_fakes(monkeypatch, B, O):
                              -(logp - kl_tot).sum() / np.log(2) / spec.denom, nan_loss], dtype=torch.float64)
         return sums[0], sums, rows, twise
 
+    def fake_sample_mode(raw, K, D, log_epsilon, want_sample=True, want_mode=True):
+        """torch stand-in for the fused sample + mode kernel (same outputs: sample, mode, mode index)."""
+        r = raw.detach().float()
+        logits = r[..., :K]
+        lls = r[..., K:].reshape(*r.shape[:-1], D, 2 * K)
+        locs, ls = lls[..., :K], lls[..., K:].clamp(min=log_epsilon)
+        idx = logits.argmax(-1)
+        g = idx[..., None, None].expand(*idx.shape, D, 1)
+        mode = torch.gather(locs, -1, g).squeeze(-1)
+        u = torch.rand_like(logits).clamp(1e-5, 1 - 1e-5)
+        pick = (logits - torch.log(-torch.log(u))).argmax(-1)[..., None, None].expand(*idx.shape, D, 1)
+        mu, s_ = torch.gather(locs, -1, pick).squeeze(-1), torch.gather(ls, -1, pick).squeeze(-1)
+        v = torch.rand_like(mu).clamp(1e-8, 1 - 1e-8)
+        return (mu + torch.exp(s_) * (torch.log(v) - torch.log(1 - v))).clamp(-1, 1), mode, idx.to(torch.int32)
+
+    monkeypatch.setattr(ops, "dmol_sample_mode", fake_sample_mode)
     monkeypatch.setattr(ops, "dmol_log_prob", fake_dmol_log_prob)
     monkeypatch.setattr(ops, "kl_gaussian", fake_kl)
     monkeypatch.setattr(ops, "fused_elbo_apply", fake_fused)
