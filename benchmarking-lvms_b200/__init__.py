@@ -15,7 +15,7 @@ from . import _lib  # noqa: F401  (fails loudly if the CUDA library is not built
 from .amp import register_grad_scaler
 from .distributed import SumsExchange, all_reduce_sums, bind_to_gpu_numa_node, combine_sums, global_denominator, shard_rows
 from .distributions import (ConditionalDistribution, DiagonalGaussianMixtureDense, DiscretizedLogisticDense,
-                            DiscretizedLogisticMixtureDense, DLParams, DMoLParams, GMMParams)
+                            DiscretizedLogisticMixtureDense, DLParams, DMoLParams, GMMParams, LinearDMoLParams)
 from .elbo import (KLLevel, cwvae_compute_elbo, fused_elbo, pack_dmol_params, srnn_compute_elbo, stcn_compute_loss,
                    vrnn_compute_elbo, wavenet_compute_loss)
 from .log_likelihoods import discretized_logistic_ll, discretized_logistic_mixture_ll, gaussian_ll, gaussian_mixture_ll

@@ -68,6 +68,11 @@ SIGNATURES = {
     "blvm_row_gate_inplace": (_i32, [_p, _i32, _i64, _i64, _p, _p]),
     "blvm_exchange_consume": (_i32, [_p, _i32, _p, _i32, _f64, _p, _p, _p]),
     "blvm_quantize": (_i32, [_p, _i64, _p, _i64, _p, _p]),
+    "blvm_linear_dmol_padded_dim": (_i32, [_i32, _i64]),
+    "blvm_linear_dmol_max_ctas": (_i64, []),
+    "blvm_linear_dmol_fwd_grad": (_i32, [_p, _p, _p, _p, _i32, _p, _f32, _p, _i64, _i64, _i64, _i32, _i32, _f32, _i32, _p, _p, _p, _i64, _p, _p, _p,
+                                         ctypes.POINTER(_i64), _p]),
+    "blvm_linear_dmol_reduce_dw": (_i32, [_p, _i64, _i64, _i32, _p, _p, _p]),
     "blvm_dmol_sample_mode": (_i32, [_p, _i32, _i64, _i32, _i32, _f32, ctypes.c_uint64, ctypes.c_uint64, _p, _p, _p, _p]),
     "blvm_scale_inplace": (_i32, [_p, _i64, _p, _p]),
     "blvm_scale_inplace_multi": (_i32, [ctypes.POINTER(_p), ctypes.POINTER(_i64), ctypes.POINTER(_i32), _i32, _p, _p]),

@@ -48,6 +48,17 @@ def active_grad_scaler(device: torch.device):
     return found
 
 
+def ensure_scale(scaler, device: torch.device) -> bool:
+    """True if `scaler` is enabled and has its device-side scale on `device`; creates the scale tensor exactly as the first
+    `scaler.scale(loss)` call would if that has not happened yet (so that the very first step is single-pass too)."""
+    if scaler is None or not getattr(scaler, "_enabled", False):
+        return False
+    if getattr(scaler, "_scale", None) is None and hasattr(scaler, "_lazy_init_scale_growth_tracker"):
+        scaler._lazy_init_scale_growth_tracker(device)
+    scale = getattr(scaler, "_scale", None)
+    return scale is not None and scale.device == device
+
+
 def scale_tensor_f64(scaler) -> torch.Tensor:
     """A private fp64 copy of the scaler's current scale (one tiny kernel; `update()` later mutates the original)."""
     return scaler._scale.detach().to(torch.float64).reshape(())

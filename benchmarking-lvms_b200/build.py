@@ -8,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libblvm_b200.so")
-SOURCES = ["blvm_b200.cu", "blvm_dmol_f32.cu", "blvm_dmol_f16.cu", "blvm_dmol_bf16.cu"]   # one object per source, compiled in parallel
-HEADERS = ["blvm_math.cuh", "ptx_sm100.cuh", "dmol_kernels.cuh", "dmol_stream_kernel.cuh", "dmol_dispatch.cuh", "kl_kernels.cuh", "misc_kernels.cuh", "sample_kernels.cuh", "host_common.h",
+SOURCES = ["blvm_b200.cu", "blvm_dmol_f32.cu", "blvm_dmol_f16.cu", "blvm_dmol_bf16.cu", "blvm_linear.cu"]   # one object per source, compiled in parallel
+HEADERS = ["blvm_math.cuh", "ptx_sm100.cuh", "dmol_kernels.cuh", "dmol_stream_kernel.cuh", "dmol_dispatch.cuh", "kl_kernels.cuh", "misc_kernels.cuh", "sample_kernels.cuh", "linear_dmol_kernel.cuh", "host_common.h",
            os.path.join("..", "..", "include", "blvm_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

@@ -15,7 +15,7 @@ import math
 
 from .log_likelihoods import discretized_logistic_ll, discretized_logistic_mixture_ll, gaussian_mixture_ll
 
-__all__ = ["ConditionalDistribution", "DiscretizedLogisticMixtureDense", "DiscretizedLogisticDense", "DMoLParams",
+__all__ = ["ConditionalDistribution", "DiscretizedLogisticMixtureDense", "DiscretizedLogisticDense", "DMoLParams", "LinearDMoLParams",
            "DLParams", "DiagonalGaussianMixtureDense", "GMMParams"]
 
 
@@ -83,6 +83,38 @@ class DMoLParams:
                 raise IndexError(i)
             self._cache[i] = self._tag(t)
         return self._cache[i]
+
+    def detach(self):
+        return DMoLParams(self.raw.detach(), self.K, self.D, self.log_epsilon)
+
+
+class LinearDMoLParams(DMoLParams):
+    """DMoLParams whose packed Linear output has NOT been computed: it carries the Linear's input and parameters instead, so
+    that `fused_elbo` can run the whole likelihood head -- `x W^T + b` on the tcgen05 tensor cores, the DMoL value and
+    gradient, and the Linear's backward -- in one kernel without the (B, T, 3K) tensor ever reaching HBM
+    (csrc/linear_dmol_kernel.cuh).  Anything else that wants the parameters (`params[i]`, `sample()`,
+    `mode()`, `log_prob()`) reads `.raw`, which evaluates the Linear once (cuBLAS) and caches it: same values as the
+    reference's `self.params(x)`, the fused path is then simply not taken."""
+
+    __slots__ = ("x", "weight", "bias", "_raw")
+
+    def __init__(self, x, weight, bias, K: int, D: int, log_epsilon: float):
+        self.x, self.weight, self.bias = x, weight, bias
+        self.K, self.D, self.log_epsilon = K, D, log_epsilon
+        self._raw = None
+        self._cache = {}
+
+    @property
+    def raw(self):
+        if self._raw is None:
+            # distributions.py:382 as autocast evaluates it: weight and bias cast to the activation dtype
+            dt = self.x.dtype
+            self._raw = torch.nn.functional.linear(self.x, self.weight.to(dt), None if self.bias is None else self.bias.to(dt))
+        return self._raw
+
+    @property
+    def materialized(self) -> bool:
+        return self._raw is not None
 
     def detach(self):
         return DMoLParams(self.raw.detach(), self.K, self.D, self.log_epsilon)
@@ -165,7 +197,8 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
     """Drop-in for blvm/modules/distributions.py:310-387: `3 * num_mix` parameters per output channel
     (mixture logit, mean, log-scale); data assumed rescaled to `num_bins` discrete values in [-1, 1]."""
 
-    def __init__(self, x_dim: int, y_dim: int, num_mix: int = 10, num_bins: int = 256, log_epsilon: float = -7.0):
+    def __init__(self, x_dim: int, y_dim: int, num_mix: int = 10, num_bins: int = 256, log_epsilon: float = -7.0,
+                 fuse_linear: bool = False):
         super().__init__()
         self.x_dim = x_dim
         self.y_dim = y_dim
@@ -174,6 +207,9 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
         self.log_epsilon = log_epsilon
         self.out_features = num_mix * (2 * y_dim + 1)
         self.params = nn.Linear(x_dim, self.out_features)
+        # opt-in (not a reference argument): under AMP, hand `fused_elbo` the Linear's input instead of its output so that the
+        # whole head runs as one tensor-core kernel (see LinearDMoLParams); everything else behaves as before
+        self.fuse_linear = fuse_linear
         self.reset_parameters()
 
     @staticmethod
@@ -236,6 +272,12 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
                                                reduce_dim=reduce_dim)
 
     def forward(self, x):
+        if self.fuse_linear and x.is_cuda and x.dim() == 3 and self.y_dim == 1:
+            # the dtype the Linear would compute in: the autocast dtype inside an autocast region, else x's own
+            dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+            if dt in (torch.float16, torch.bfloat16) and ops.linear_dmol_supported(self.num_mix, self.x_dim):
+                return LinearDMoLParams(x if x.dtype == dt else x.to(dt), self.params.weight, self.params.bias, self.num_mix,
+                                        self.y_dim, self.log_epsilon)
         return DMoLParams(self.params(x), self.num_mix, self.y_dim, self.log_epsilon)
 
 

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Union
 import torch
 
 from . import amp, ops
-from .distributions import DLParams, DMoLParams, GMMParams
+from .distributions import DLParams, DMoLParams, GMMParams, LinearDMoLParams
 from .log_likelihoods import _packed_source
 from .metrics import tag_sum
 from .operations import level_lengths, sequence_mask
@@ -120,7 +120,9 @@ def fused_elbo(
     log_prob_twise (B, T) fp32 or None.  Only `loss` is differentiable (w.r.t. the likelihood parameters and the
     tensors of every KLLevel); the others are detached.
     """
-    if parameters is not None:
+    if isinstance(parameters, LinearDMoLParams):
+        dev = parameters.x.device                       # (touching .raw would evaluate the Linear)
+    elif parameters is not None:
         dev = parameters.raw.device if hasattr(parameters, "raw") else parameters[0].device
     else:
         dev = kl_levels[0].tensors[0].device
@@ -148,7 +150,20 @@ def fused_elbo(
         lens_of = {id(lv): level_lengths(x_sl_dev, int(lv.stride)) for lv in need}
 
     likelihood, raw, K, D, log_eps, gmm = "none", None, 1, 1, -7.0, (1.0, 0.0)
-    if parameters is not None:
+    head = None   # (x, weight, bias): the likelihood head runs fused (tensor-core Linear + DMoL + Linear backward in one kernel)
+    if isinstance(parameters, LinearDMoLParams) and not parameters.materialized and not want_twise and not nansum and exchange is None \
+            and parameters.x.dim() == 3 and parameters.x.shape[0] == B:
+        p = parameters
+        fp16 = p.x.dtype == torch.float16
+        scaler = (grad_scaler if grad_scaler is not None else amp.active_grad_scaler(p.x.device)) if fp16 else None
+        # fp16 gradients need the GradScaler's factor inside the kernel (amp.py); without a known scaler the head is evaluated unfused
+        if not fp16 or not torch.is_grad_enabled() or amp.ensure_scale(scaler, p.x.device):
+            head = (p.x, p.weight, p.bias, scaler)
+            likelihood, K, D, log_eps = "linear_dmol", p.K, p.D, p.log_epsilon
+            if y.numel() != B * p.x.shape[1]:
+                raise ValueError(f"y {tuple(y.shape)} does not match the likelihood input {tuple(p.x.shape)}")
+            y = _f32c(y)
+    if parameters is not None and head is None:
         if isinstance(parameters, GMMParams):
             likelihood, raw, K, D, gmm = "gmm", parameters.raw, parameters.K, parameters.D, (parameters.beta, parameters.sd_add)
         elif isinstance(parameters, DLParams):
@@ -181,16 +196,22 @@ def fused_elbo(
         specs.append(ops.KLLevelSpec(lv.kind, float(fn or 0.0), lens, len(ts)))
         flat += ts
 
-    need_grad = torch.is_grad_enabled() and ((raw is not None and raw.requires_grad) or any(t.requires_grad for t in flat))
+    need_grad = torch.is_grad_enabled() and ((raw is not None and raw.requires_grad) or any(t.requires_grad for t in flat)
+                                             or (head is not None and any(t is not None and t.requires_grad for t in head[:3])))
     loss_scale = None
+    if head is not None and need_grad and head[3] is not None:
+        loss_scale = amp.scale_tensor_f64(head[3])
     if need_grad and likelihood == "dmol" and raw.dtype == torch.float16:
         scaler = grad_scaler if grad_scaler is not None else amp.active_grad_scaler(raw.device)
-        if scaler is not None and getattr(scaler, "_enabled", True) and getattr(scaler, "_scale", None) is not None:
+        if amp.ensure_scale(scaler, raw.device):
             loss_scale = amp.scale_tensor_f64(scaler)
     spec = ops.ELBOSpec(K=K, D=D, num_bins=int(num_bins), log_epsilon=float(log_eps), beta=float(beta), denom=total,
                         levels=specs, want_twise=want_twise, skip_padded=skip_padded, need_grad=need_grad,
                         likelihood=likelihood, exchange=exchange, gmm=gmm, loss_scale=loss_scale, nansum=bool(nansum))
-    loss, sums, rows, twise = ops.fused_elbo_apply(spec, y, x_sl_dev, raw, flat)
+    if head is not None:
+        loss, sums, rows, twise = ops.fused_linear_elbo_apply(spec, y, x_sl_dev, head[0], head[1], head[2], flat)
+    else:
+        loss, sums, rows, twise = ops.fused_elbo_apply(spec, y, x_sl_dev, raw, flat)
     return SimpleNamespace(loss=loss, log_prob=rows[0], kl=rows[1], kl_fn=rows[2], elbo=rows[3],
                            kl_levels=[rows[4 + l] for l in range(len(specs))], sums=sums,
                            log_prob_twise=twise if want_twise else None, x_sl=x_sl_dev)

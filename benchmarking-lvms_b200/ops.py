@@ -568,6 +568,160 @@ class _FusedELBO(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
+def linear_dmol_supported(K: int, x_dim: int) -> bool:
+    """Whether the fused likelihood head (Linear + DMoL + Linear backward in one tcgen05 kernel) is instantiated for this shape."""
+    return bool(lib.blvm_linear_dmol_padded_dim(int(K), int(x_dim)))
+
+
+_dw_partials = {}
+
+
+def _dw_partial_buffer(device: torch.device, dp: int):
+    """Per-(device, stream, padded x_dim) scratch for the per-CTA dW / db partials of the fused head (stream-ordered reuse)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(), dp)
+    buf = _dw_partials.get(key)
+    if buf is None:
+        buf = torch.empty(int(lib.blvm_linear_dmol_max_ctas()) * 32 * dp, dtype=torch.float32, device=device)
+        _dw_partials[key] = buf
+    return buf
+
+
+class _FusedLinearELBO(torch.autograd.Function):
+    """The fused ELBO op with the likelihood HEAD fused in: inputs spec, y (B,T), x_sl_dev, x (B,T,Din) fp16/bf16, weight (3K,Din),
+    bias (3K) (the fp32 parameters of `likelihood.params`), then the KL tensors.  One tensor-core kernel computes x W^T + b, the
+    DMoL value and gradient and dx / dW / db (csrc/linear_dmol_kernel.cuh); the KL of all levels and the finalize kernel follow
+    as in _FusedELBO.  Outputs and backward contract as _FusedELBO (gradients are produced in the forward pass)."""
+
+    @staticmethod
+    def forward(ctx, spec: ELBOSpec, y, x_sl_dev, x, weight, bias, *kl_tensors):
+        dev = x.device
+        _require_cuda(y, x_sl_dev, x, weight, bias, *kl_tensors)
+        B, T, Din = x.shape
+        L = len(spec.levels)
+        K = spec.K
+        x = x if x.is_contiguous() else x.contiguous()
+        w16 = weight.detach().to(x.dtype).contiguous()        # what autocast hands the Linear (distributions.py:382 under AMP)
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        dp = int(lib.blvm_linear_dmol_padded_dim(K, Din))
+        assert dp > 0, "unsupported shape for the fused head"
+        chunks = (T + 127) // 128
+        shapes, i = [], 0
+        for lv in spec.levels:
+            Bz, Tz, Z = kl_tensors[i].shape
+            assert Bz == B
+            shapes.append((Tz, Z, -(-(Tz * Z) // _lib.BLVM_KL_TILE)))
+            i += lv.n_tensors
+        n_out = 8 + (4 + L) * B
+        ws = torch.empty(n_out + B * chunks + sum(2 * B * c for _, _, c in shapes), dtype=torch.float64, device=dev)
+        base = ws.data_ptr()
+        scalars, rows = ws[:8], ws[8:n_out].view(4 + L, B)
+        off = n_out
+        need = spec.need_grad
+        dx = torch.empty_like(x) if need else None
+        dwp = _dw_partial_buffer(dev, dp) if need else None
+        twise = torch.empty(B, T, dtype=torch.float32, device=dev) if spec.want_twise else torch.empty(0, device=dev)
+        grads: List[Optional[torch.Tensor]] = []
+        with _on_device(dev):
+            stream = _stream(dev.index)
+            logp_ptr = base + 8 * off
+            off += B * chunks
+            used = ctypes.c_int64(0)
+            flags = BLVM_FLAG_MASK_OUTPUT
+            rc = lib.blvm_linear_dmol_fwd_grad(y.data_ptr(), x.data_ptr(), w16.data_ptr(), _ptr(b32), _DTYPE_CODE[x.dtype], x_sl_dev.data_ptr(),
+                                               -1.0 / spec.denom, spec.loss_scale.data_ptr() if spec.loss_scale is not None else None,
+                                               B, T, Din, K, spec.num_bins, spec.log_epsilon, flags, twise.data_ptr() if spec.want_twise else None,
+                                               _ptr(dx), _ptr(dwp), int(lib.blvm_linear_dmol_max_ctas()) if need else 0, logp_ptr,
+                                               _err_flag(dev).data_ptr(), None, ctypes.byref(used), stream)
+            check(rc, "blvm_linear_dmol_fwd_grad")
+            _count()
+            dW = db = None
+            if need:
+                dW = torch.empty(3 * K, Din, dtype=torch.float32, device=dev)
+                db = torch.empty(3 * K, dtype=torch.float32, device=dev)
+                check(lib.blvm_linear_dmol_reduce_dw(dwp.data_ptr(), used.value, Din, K, dW.data_ptr(), db.data_ptr(), stream), "blvm_linear_dmol_reduce_dw")
+                _count()
+            grads += [dx, dW, db if bias is not None else None]
+            kl_ptrs, klfn_ptrs, kl_chunks = [], [], []
+            if L:
+                multi = (_lib.KLLevelStruct * L)()
+                i = 0
+                for li, (lv, (Tz, Z, c)) in enumerate(zip(spec.levels, shapes)):
+                    ts = kl_tensors[i:i + lv.n_tensors]
+                    i += lv.n_tensors
+                    pk = base + 8 * off
+                    pf = pk + 8 * B * c
+                    off += 2 * B * c
+                    d = multi[li]
+                    d.lens, d.Tz, d.Z, d.free_nats, d.part_kl, d.part_klfn = _ptr(lv.lens), Tz, Z, lv.free_nats, pk, pf
+                    if lv.kind == "kld":
+                        gk = torch.empty_like(ts[0]) if need else None
+                        d.kl, d.g_kl = ts[0].data_ptr(), _ptr(gk)
+                        grads.append(gk)
+                    else:
+                        n_g = 5 if lv.kind == "mc" else 4
+                        g = [torch.empty_like(ts[0]) for _ in range(n_g)] if need else [None] * n_g
+                        d.mu_q, d.sd_q, d.mu_p, d.sd_p = ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[3].data_ptr()
+                        d.g_mu_q, d.g_sd_q, d.g_mu_p, d.g_sd_p = _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3])
+                        if lv.kind == "mc":
+                            d.z, d.g_z = ts[4].data_ptr(), _ptr(g[4])
+                        grads += g
+                    kl_ptrs.append(pk)
+                    klfn_ptrs.append(pf)
+                    kl_chunks.append(c)
+                check(lib.blvm_kl_elbo_levels_fwd_grad(multi, L, B, spec.beta / spec.denom, 0, stream), "blvm_kl_elbo_levels_fwd_grad")
+                _count()
+            PtrArr, I64Arr = ctypes.c_void_p * max(L, 1), ctypes.c_int64 * max(L, 1)
+            check(lib.blvm_elbo_finalize(logp_ptr, chunks, PtrArr(*kl_ptrs), PtrArr(*klfn_ptrs), I64Arr(*kl_chunks), L, x_sl_dev.data_ptr(), B,
+                                         spec.beta, spec.denom, rows.data_ptr(), scalars.data_ptr(), _sync_counter(dev).data_ptr(), stream),
+                  "blvm_elbo_finalize")
+            _count()
+        loss = scalars[:1].view(())
+        ctx.set_materialize_grads(False)
+        ctx.grads = grads
+        ctx.prescale = spec.loss_scale
+        ctx.consumed = False
+        ctx.mark_non_differentiable(scalars, rows, twise)
+        _maybe_strict(dev)
+        return loss, scalars, rows, twise
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        if ctx.consumed:
+            raise RuntimeError("blvm_b200 fused ELBO: backward called twice (gradients are produced in the forward pass)")
+        ctx.consumed = True
+        if g_loss is None:
+            return (None, None, None) + tuple(None for _ in ctx.grads)
+        g = g_loss if (g_loss.dtype == torch.float64 and g_loss.is_contiguous()) else g_loss.to(torch.float64).contiguous()
+        grads = list(ctx.grads)
+        unit = _unit_grads.get(g.device.index)
+        is_unit = unit is not None and g.data_ptr() == unit.data_ptr()
+
+        def rescale(bufs, factor):
+            n = len(bufs)
+            with _on_device(g.device):
+                check(lib.blvm_scale_inplace_multi((ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs]), (ctypes.c_int64 * n)(*[b.numel() for b in bufs]),
+                                                   (ctypes.c_int * n)(*[_DTYPE_CODE[b.dtype] for b in bufs]), n, factor.data_ptr(), _stream()),
+                      "blvm_scale_inplace_multi")
+            _count()
+
+        head = [b for b in grads[:3] if b is not None]
+        rest = [b for b in grads[3:] if b is not None]
+        if ctx.prescale is not None:     # the head's gradients already carry the loss scale S: multiply by grad_output / S (== 1 for scaler.scale(loss))
+            if head:
+                rescale(head, g / ctx.prescale)
+            if rest and not is_unit:
+                rescale(rest, g)
+        elif (head or rest) and not is_unit:
+            rescale(head + rest, g)
+        ctx.grads = None
+        return (None, None, None) + tuple(grads)
+
+
+def fused_linear_elbo_apply(spec: ELBOSpec, y, x_sl_dev, x, weight, bias, kl_tensors: Sequence[torch.Tensor]):
+    loss, scalars, rows, twise = _FusedLinearELBO.apply(spec, y, x_sl_dev, x, weight, bias, *kl_tensors)
+    return loss.as_subclass(FusedLoss), scalars, rows, twise
+
+
 def fused_elbo_apply(spec: ELBOSpec, y, x_sl_dev, raw, kl_tensors: Sequence[torch.Tensor]):
     loss, scalars, rows, twise = _FusedELBO.apply(spec, y, x_sl_dev, raw, *kl_tensors)
     return loss.as_subclass(FusedLoss), scalars, rows, twise

@@ -309,6 +309,29 @@ int blvm_scale_inplace(float* buf, int64_t n, const double* scale, blvm_stream_t
 int blvm_scale_inplace_multi(void* const* bufs_host, const int64_t* ns_host, const int* dtypes_host, int count,
                              const double* scale, blvm_stream_t stream);
 
+/*
+ * The likelihood HEAD in one kernel: nn.Linear(x_dim -> 3K) on the tcgen05 tensor cores (accumulator in
+ * tensor memory), DMoL value + gradient in registers, and the Linear's backward (dx, dW, db) on the tensor cores again; the
+ * (B, T, 3K) parameter tensor and its gradient never touch HBM.  Replaces DiscretizedLogisticMixtureDense.forward
+ * (blvm/modules/distributions.py:381-387: `self.params(x)`, split, clamp) + discretized_logistic_mixture_ll
+ * (blvm/utils/log_likelihoods.py:170-231) + mask / row sums (vrnn.py:266-269) + the autograd backward of all of them, for
+ * 16-bit (AMP) activations: x and W are fp16 / bf16 (W: the autocast copy of `params.weight`), accumulation is fp32.
+ *   x (B, T, Din), W (3K, Din) element type `dtype` (BLVM_DTYPE_F16 / BF16); bias (3K) fp32 nullable; y (B, T) fp32
+ *   supported: K == 10, even Din <= 79 (blvm_linear_dmol_padded_dim() != 0)
+ *   lp (B, T) nullable; partials (B, ceil(T / 128)) fp64 nullable: the layout blvm_elbo_finalize expects for K = 10
+ *   dx (B, T, Din) in `dtype` and dw_partial (dw_partial_ctas >= blvm_linear_dmol_max_ctas(), 32, padded_dim) fp32: nullable
+ *     TOGETHER (forward only).  dx = gscale * (*gscale_dev) * mask * d log p / d x; blvm_linear_dmol_reduce_dw() turns the per-CTA
+ *     partials into dW (3K, Din) and db (3K) (fixed order: bit-reproducible); *ctas_used_host (host, nullable) = CTAs launched
+ *   raw_debug (B*T, 32) fp32 nullable: the tensor-core result x W^T + b per sample (tests)
+ */
+int blvm_linear_dmol_padded_dim(int K, int64_t Din);
+int64_t blvm_linear_dmol_max_ctas(void);
+int blvm_linear_dmol_fwd_grad(const float* y, const void* x, const void* W, const float* bias, int dtype, const int64_t* x_sl,
+                              float gscale, const double* gscale_dev, int64_t B, int64_t T, int64_t Din, int K, int num_bins,
+                              float log_epsilon, int flags, float* lp, void* dx, float* dw_partial, int64_t dw_partial_ctas,
+                              double* partials, int* err_flag, float* raw_debug, int64_t* ctas_used_host, blvm_stream_t stream);
+int blvm_linear_dmol_reduce_dw(const float* dw_partial, int64_t ctas, int64_t Din, int K, float* dW, float* db, blvm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
