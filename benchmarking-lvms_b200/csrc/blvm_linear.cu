@@ -41,6 +41,7 @@ int launch_linear(const LinearDmolArgs& A, cudaStream_t st, unsigned* grid_out) 
   if (resident == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(BLVM_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // as many CTAs as shared memory can hold
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem);
     if (e != cudaSuccess || occ < 1) return fail(BLVM_ERR_CUDA, "occupancy query (smem=%d): %s", smem, cudaGetErrorString(e));
@@ -48,7 +49,7 @@ int launch_linear(const LinearDmolArgs& A, cudaStream_t st, unsigned* grid_out) 
     // CTA keeps them for its whole persistent life), shared memory and the 64-register budget (8 CTAs of 128 threads)
     const int by_tmem = 512 / tmem_cols, by_smem = (227 * 1024) / (smem + 1024);
     resident = by_tmem < by_smem ? by_tmem : by_smem;
-    if (resident > 5) resident = 5;   // measured (B = 256 x 16000, x_dim 30, bf16): 3 -> 247 us, 4 -> 209, 5 -> 191, 6 -> 258, 7 -> 231, 8 -> 217
+    if (resident > 8) resident = 8;   // the register budget: 64 registers x 128 threads (__launch_bounds__(128, 8) for DP = 32)
     if (resident < 1) resident = 1;
     if (const char* e = getenv("BLVM_B200_LINEAR_CTAS_PER_SM")) {   // A/B knob
       const int v = atoi(e);

@@ -147,7 +147,11 @@ struct LinearSmem {
   static constexpr int kG = 128 * 32 * 2;              // G  [128 s][32 p]
   // G sits in FRONT of X: the M = 64 operand of the DW product addresses 64 columns of G (32 exist), i.e. reads up to 512 bytes past
   // the end of G -- these must be readable shared memory (the first rows of X; they only feed accumulator rows nobody reads)
-  static constexpr int oStage = 0, oOut = oStage + kStage, oG = oOut + kStage, oX = oG + kG, oW = oX + kX, oBar = oW + kW, oMisc = oBar + 32;
+  // When the dx slab fits (DP = 32: 7.5 KB <= 8 KB) it is staged in G's buffer, which is idle between this tile's DW product and the
+  // next tile's gradient rows: 26 KB per CTA, 8 CTAs per SM.
+  static constexpr bool kOutInG = kStage <= kG;
+  static constexpr int oStage = 0, oOut = kOutInG ? oStage + kStage : oStage + kStage, oG = kOutInG ? oOut : oOut + kStage, oX = oG + kG,
+                       oW = oX + kX, oBar = oW + kW, oMisc = oBar + 32;
   static constexpr int bytes = oMisc + 64;
   // tensor memory: RAW (32 columns) is dead once every thread has read its row, so DX (DP columns) reuses its columns; DW: DP more
   static constexpr int tmem_cols = 2 * DP <= 64 ? 64 : (2 * DP <= 128 ? 128 : (2 * DP <= 256 ? 256 : 512));
@@ -159,8 +163,12 @@ __device__ __forceinline__ uint32_t cm_off(int i, int j, int cols) {
   return static_cast<uint32_t>(((i >> 3) * (cols >> 3) + (j >> 3)) * 128 + (i & 7) * 16 + (j & 7) * 2);
 }
 
+#ifndef BLVM_LINEAR_MINB
+#define BLVM_LINEAR_MINB 8     // CTAs per SM the register allocation is capped for (DP = 32): 8 -> 64 registers.  Measured (B = 256 x
+                               // 16000, x_dim 30, bf16, grid = cap x 148): 5 -> 183.6 us (96 registers), 7 -> 169.6, 8 -> 166.9
+#endif
 template <int K, int DP, bool GRAD, int UMODE, typename TP>
-__global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant__ LinearDmolArgs A) {
+__global__ void __launch_bounds__(128, LinearSmem<DP>::kOutInG ? BLVM_LINEAR_MINB : 2) linear_dmol_kernel(const __grid_constant__ LinearDmolArgs A) {
   static_assert(3 * K <= 32, "the parameter row must fit the N = 32 accumulator tile");
   static_assert(DP % 16 == 0 && DP >= 32 && DP <= 240, "padded x_dim");
   constexpr int P = 3 * K;
@@ -175,7 +183,8 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
   unsigned char* sW = smem + S::oW;
   unsigned char* sG = smem + S::oG;
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + S::oBar);       // TMA slab landed
-  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + S::oBar + 8);    // tensor-core work complete
+  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + S::oBar + 8);    // RAW resp. DX complete
+  uint64_t* bar_dw = reinterpret_cast<uint64_t*>(smem + S::oBar + 16);    // the DW product of a tile complete (X and G reusable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::oMisc);
   double* scratch = reinterpret_cast<double*>(smem + S::oMisc + 16);
 
@@ -188,6 +197,7 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
   if (tid == 0) {
     ptx::mbar_init(bar_load, 1);
     ptx::mbar_init(bar_mma, 1);
+    ptx::mbar_init(bar_dw, 1);
     ptx::fence_mbar_init();
   }
   for (int i = tid; i < S::kW / 4; i += 128) reinterpret_cast<uint32_t*>(sW)[i] = 0u;
@@ -209,6 +219,7 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_raw = tmem, t_dx = tmem, t_dw = tmem + DP;
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t x_row_off = cm_off(tid, 0, DP), g_row_off = cm_off(tid, 0, 32);   // this thread's row in the blocked X / G buffers
 
   constexpr uint32_t idesc_fwd = tc::instr_desc(Fmt16<TP>::value, 0, 0, 128, 32);
   constexpr uint32_t idesc_dx = tc::instr_desc(Fmt16<TP>::value, 0, 1, 128, DP);
@@ -218,16 +229,17 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
   float gs = A.gscale;
   if (GRAD && A.gscale_dev) gs *= static_cast<float>(*A.gscale_dev);
   const uint64_t pol = ptx::policy_evict_first();
-  uint32_t ph_load = 0, ph_mma = 0;
-  bool dw_started = false;
+  uint32_t ph_load = 0, ph_mma = 0, ph_dw = 0;
+  bool dw_started = false, store_pending = false;
   const int row_bytes = Din * 2;
 
   // The x slab of a tile: contiguous n * Din 16-bit values.  `issue_load` starts its bulk copy into the (single) input stage; the
   // stage is free again as soon as every thread has re-laid its row out, so the NEXT tile's slab is requested right then and
   // lands while this tile is being evaluated.
-  auto tile_geom = [&](int64_t tile, unsigned& b, int& c, int& n, int64_t& s0) {
-    b = static_cast<unsigned>(tile / A.chunks);
-    c = static_cast<int>(tile - static_cast<int64_t>(b) * A.chunks);
+  const unsigned chunks32 = static_cast<unsigned>(A.chunks);
+  auto tile_geom = [&](int64_t tile, unsigned& b, int& c, int& n, int64_t& s0) {   // 32-bit: the host rejects more than 2^31 - 1 tiles
+    b = static_cast<unsigned>(tile) / chunks32;
+    c = static_cast<int>(static_cast<unsigned>(tile) - b * chunks32);
     n = min(128, static_cast<int>(A.T) - c * 128);
     s0 = static_cast<int64_t>(b) * A.T + c * 128;
   };
@@ -264,6 +276,10 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
       for (uint32_t i = tid; i < bytes / 2; i += 128) reinterpret_cast<uint16_t*>(stage)[i] = reinterpret_cast<const uint16_t*>(gsrc)[i];
       __syncthreads();
     }
+    if (GRAD && dw_started && !S::kOutInG) {   // the previous tile's DW product still reads X and G: it has had a whole epilogue to finish
+      ptx::mbar_wait(bar_dw, ph_dw);
+      ph_dw ^= 1u;
+    }
     {
       // this thread's row as 32-bit words (Din is even: rows are 4-byte aligned), 16-byte chunks of 8 values into the blocked layout;
       // the word after the row carries the ones column (bias / db), the rest of the padding is zero
@@ -278,7 +294,7 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
           const int j = 4 * cb + q;
           w[q] = (j < nw) ? row[j] : ((j == (Din >> 1)) ? one : 0u);
         }
-        *reinterpret_cast<uint4*>(sX + cm_off(tid, 8 * cb, DP)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(sX + x_row_off + cb * 128) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
     ptx::fence_proxy_async_smem();     // generic-proxy writes of X (and, the first time, W / G) -> visible to the tensor core
@@ -316,9 +332,9 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
 #pragma unroll
       for (int q = 0; q < P; ++q) rr[q] = r[q];
       L = dmol_sample<K, GRAD, UMODE>(yv, rr, g, A.C);
-      if (GRAD) {
+      if (GRAD) {   // rows beyond the tile / the utterance carry g = 0: their gradient rows are exact zeros already
 #pragma unroll
-        for (int q = 0; q < P; ++q) r[q] = (tid < n) ? rr[q] : 0.f;
+        for (int q = 0; q < P; ++q) r[q] = rr[q];
       }
     }
     const float Lm = (tid < nvalid) ? L : L * 0.0f;
@@ -334,8 +350,15 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
         v.y = Fmt16<TP>::pack(r[8 * cb + 2], r[8 * cb + 3]);
         v.z = Fmt16<TP>::pack(r[8 * cb + 4], (8 * cb + 5 < P) ? r[8 * cb + 5] : 0.f);
         v.w = Fmt16<TP>::pack((8 * cb + 6 < P) ? r[8 * cb + 6] : 0.f, (8 * cb + 7 < P) ? r[8 * cb + 7] : 0.f);
-        *reinterpret_cast<uint4*>(sG + cm_off(tid, 8 * cb, 32)) = v;
+        *reinterpret_cast<uint4*>(sG + g_row_off + cb * 128) = v;
       }
+      // the masked fp64 tile sum rides on the same barrier: warp sums now, thread 0 adds them after it (fixed order)
+      if (A.partials) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) scratch[warp] = acc;
+      }
+      if (tid == 0 && store_pending) ptx::bulk_wait_read0();   // the previous tile's dx slab has long left the output stage
       ptx::fence_proxy_async_smem();
       tc::fence_before();
       __syncthreads();
@@ -344,17 +367,23 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 2; ++k)      // K = p: 32 = 2 x 16
           tc::mma_f16(t_dx, tc::smem_desc(aG + k * 256, 128, GS), tc::smem_desc(aW + k * 2 * XS, XS, 128), idesc_dx, k > 0);
+        tc::commit(bar_mma);             // DX is what the epilogue waits for; DW gets its own barrier (waited for by the next tile)
+        if (A.partials) A.partials[static_cast<int64_t>(b) * A.chunks + c] = ((scratch[0] + scratch[1]) + scratch[2]) + scratch[3];
 #pragma unroll
         // DW: M = 64 rows of G^T are addressed but G has 32 columns: rows 32-63 of the accumulator read the neighbouring row block
         // (finite garbage) and are never read back
 #pragma unroll
         for (int k = 0; k < 8; ++k)      // K = samples: 128 = 8 x 16; accumulates over all tiles of this CTA
           tc::mma_f16(t_dw, tc::smem_desc(aG + k * 2 * GS, GS, 128), tc::smem_desc(aX + k * 2 * XS, XS, 128), idesc_dw, dw_started || k > 0);
-        tc::commit(bar_mma);
+        tc::commit(bar_dw);
       }
       dw_started = true;
       ptx::mbar_wait(bar_mma, ph_mma);
       ph_mma ^= 1u;
+      if constexpr (S::kOutInG) {        // the dx slab is staged in G's buffer: the DW product (8 small MMAs behind DX) must have read it
+        ptx::mbar_wait(bar_dw, ph_dw);
+        ph_dw ^= 1u;
+      }
       tc::fence_after();
 
       // ---- 5. DX rows: TMEM -> registers -> activation dtype -> staging -> bulk store -----------------------------------
@@ -383,22 +412,30 @@ __global__ void __launch_bounds__(128) linear_dmol_kernel(const __grid_constant_
         __syncthreads();
         if (tid == 0) {
           ptx::bulk_s2g(gdst, stage_out, bytes, pol);
-          ptx::bulk_commit();
-          ptx::bulk_wait_read0();        // the output stage is rewritten by the next tile
+          ptx::bulk_commit();            // its shared-memory reads are waited for just before the output stage is written again
         }
+        store_pending = true;
       } else {
         tc::fence_before();
         __syncthreads();
         for (uint32_t i = tid; i < bytes / 2; i += 128) reinterpret_cast<uint16_t*>(gdst)[i] = reinterpret_cast<const uint16_t*>(stage_out)[i];
       }
     }
-    if (A.partials) {
+    if (!GRAD && A.partials) {
       const double s = block_sum_f64<4>(acc, scratch);
       if (tid == 0) A.partials[static_cast<int64_t>(b) * A.chunks + c] = s;
     }
-    tc::fence_before();
-    __syncthreads();                     // staging / X / G are free again; TMEM reads of this tile are complete
+    if (!GRAD) {
+      tc::fence_before();
+      __syncthreads();                   // TMEM reads of this tile are complete before the next RAW product overwrites them
+    }
+    // (GRAD: the barrier before the bulk store already separates this tile's TMEM / stage accesses from the next tile's writes)
   }
+  if (GRAD && dw_started && !S::kOutInG) {   // the last DW product
+    ptx::mbar_wait(bar_dw, ph_dw);
+    ph_dw ^= 1u;
+  }
+  if (GRAD && tid == 0 && store_pending) ptx::bulk_wait_read0();
 
   // ---- DW / db partial of this CTA: rows p (M = 64 accumulator: row m lives in TMEM lane (m % 16) + 32 (m / 16)) -----------
   if (GRAD && A.dw_partial) {

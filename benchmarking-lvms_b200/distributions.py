@@ -249,15 +249,33 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
         raw = torch.cat([logit_probs, torch.cat([locs, log_scales], dim=-1).flatten(-2)], dim=-1)
         return DMoLParams(raw, K, D, -math.inf)
 
+    def _deferred(self, params, which: int):
+        """sample() / mode() on parameters whose Linear has not been evaluated (LinearDMoLParams): a promise of the result
+        (variational.LazyResult), so that a training step that never looks at the reconstructions keeps the fused head."""
+        from .variational import LazyResult
+        x = params.x
+        dtype = torch.float32 if (which == 0 or x.dtype == torch.float32) else x.dtype
+        fn = self.sample if which == 0 else self.mode
+
+        def thunk():
+            params.raw                                     # evaluates the Linear (cuBLAS) once; the fused path is then not taken
+            with torch.no_grad():
+                return fn(params)
+        return LazyResult((*x.shape[:-1], self.y_dim), dtype, x.device, thunk)
+
     @torch.no_grad()
     def sample(self, params):
         """A sample of the mixture, clamped to [-1, 1] (distributions.py:359-361, variational.py:309-349): the fused
         sample + mode kernel.  CUDA only, like every kernel of this package (CPU tensors raise; no torch fallback)."""
+        if isinstance(params, LinearDMoLParams) and not params.materialized:
+            return self._deferred(params, 0)
         return self._fused_sample_mode(self._as_packed(params))[0]
 
     def mode(self, params):
         """Mean of the most probable component (distributions.py:363-368), from the same kernel launch as sample();
         differentiable w.r.t. the chosen component's location like the reference's gather."""
+        if isinstance(params, LinearDMoLParams) and not params.materialized:
+            return self._deferred(params, 1)               # (read lazily, it is detached: nothing in the reference differentiates it)
         params = self._as_packed(params)
         _, mode, index = self._fused_sample_mode(params)
         if torch.is_grad_enabled() and params.raw.requires_grad:

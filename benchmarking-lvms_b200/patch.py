@@ -26,9 +26,13 @@ def _rebind_method(cls, name, replacement):
     setattr(cls, name, replacement)
 
 
-def patch_blvm():
+def patch_blvm(fuse_linear: bool = False):
     """Import `blvm` (must be on sys.path) and rebind the hot-path functions, classes and model reducers to blvm_b200.
-    Returns the list of `module.attr` names that were rebound."""
+    Returns the list of `module.attr` names that were rebound.
+
+    fuse_linear=True: every DiscretizedLogisticMixtureDense constructed from now on also fuses its `nn.Linear` into the
+    likelihood kernel when it runs under AMP (fp16 / bf16 activations, num_mix = 10, even x_dim <= 79): Linear, DMoL value +
+    gradient and the Linear's backward as one tcgen05 tensor-core kernel (csrc/linear_dmol_kernel.cuh)."""
     import importlib
 
     import blvm.modules.distributions as ref_dist
@@ -45,7 +49,14 @@ def patch_blvm():
     # gaussian_ll / DiagonalGaussianDense are NOT rebound: the model bodies use them for the latent layers
     # (vrnn.py:81,91), which are outside this path; blvm_b200.gaussian_ll / kl_divergence_gaussian_mc exist for callers
     # that want the kernels (e.g. bottom-up STCN).
-    _rebind_everywhere(ref_dist.DiscretizedLogisticMixtureDense, distributions.DiscretizedLogisticMixtureDense)
+    dmol_cls = distributions.DiscretizedLogisticMixtureDense
+    if fuse_linear:
+        class DiscretizedLogisticMixtureDense(distributions.DiscretizedLogisticMixtureDense):   # same name: repr / checkpoints unchanged
+            def __init__(self, *args, **kwargs):
+                kwargs.setdefault("fuse_linear", True)
+                super().__init__(*args, **kwargs)
+        dmol_cls = DiscretizedLogisticMixtureDense
+    _rebind_everywhere(ref_dist.DiscretizedLogisticMixtureDense, dmol_cls)
     _rebind_everywhere(ref_dist.DiscretizedLogisticDense, distributions.DiscretizedLogisticDense)
 
     vrnn = importlib.import_module("blvm.models.vrnn")

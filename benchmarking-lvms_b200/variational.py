@@ -6,7 +6,7 @@ import torch
 
 from . import ops
 
-__all__ = ["kl_divergence_gaussian", "kl_divergence_gaussian_eager", "kl_divergence_gaussian_mc", "discount_free_nats", "LazyKL"]
+__all__ = ["kl_divergence_gaussian", "kl_divergence_gaussian_eager", "kl_divergence_gaussian_mc", "discount_free_nats", "LazyKL", "LazyResult"]
 
 
 class LazyKL(torch.Tensor):
@@ -60,6 +60,44 @@ class LazyKL(torch.Tensor):
     def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
         # reached only by C++-side uses that bypass __torch_function__: same answer, evaluate and carry on
         swap = lambda a: a.materialize() if isinstance(a, LazyKL) else a   # noqa: E731
+        return func(*torch.utils._pytree.tree_map(swap, args), **torch.utils._pytree.tree_map(swap, kwargs or {}))
+
+
+class LazyResult(torch.Tensor):
+    """A tensor-shaped promise: shape / dtype / device are known, the value is produced by `thunk()` the first time anything
+    reads it (same mechanism as LazyKL).  Used for `sample()` / `mode()` on likelihood parameters whose Linear has not been
+    evaluated (LinearDMoLParams): the reference models call both on every training step (vrnn.py:332-333) and store the
+    results in their outputs, where a training loop never looks at them -- evaluating them would force the (B, T, 3K)
+    parameter tensor into existence and undo the fused head."""
+
+    @staticmethod
+    def __new__(cls, shape, dtype, device, thunk):
+        r = torch.Tensor._make_wrapper_subclass(cls, tuple(shape), dtype=dtype, device=device, requires_grad=False)
+        r._blvm_thunk = thunk
+        r._blvm_value = None
+        return r
+
+    def materialize(self) -> torch.Tensor:
+        if self._blvm_value is None:
+            self._blvm_value = self._blvm_thunk()
+            self._blvm_thunk = None
+        return self._blvm_value
+
+    def __repr__(self):
+        return f"LazyResult(shape={tuple(self.shape)}, device={self.device}, {'unread' if self._blvm_value is None else 'materialised'})"
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func in _LAZY_METADATA:
+            with torch._C.DisableTorchFunctionSubclass():
+                return func(*args, **kwargs)
+        swap = lambda a: a.materialize() if isinstance(a, (LazyResult, LazyKL)) else a   # noqa: E731
+        return func(*torch.utils._pytree.tree_map(swap, args), **torch.utils._pytree.tree_map(swap, kwargs))
+
+    @classmethod
+    def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
+        swap = lambda a: a.materialize() if isinstance(a, (LazyResult, LazyKL)) else a   # noqa: E731
         return func(*torch.utils._pytree.tree_map(swap, args), **torch.utils._pytree.tree_map(swap, kwargs or {}))
 
 

@@ -153,8 +153,9 @@ def test_public_api_fused_head_matches_unfused_fp32_evaluation(B, dt):
     np.testing.assert_allclose(of.sums.cpu().numpy(), ou.sums.cpu().numpy(), rtol=2e-6)
     eps = 2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10   # G and dx are rounded to the activation dtype inside the fused kernel
     assert float((dxf - dxu).abs().max()) <= eps * float(dxu.abs().max())
-    assert float((dWf - dWu).abs().max()) <= 2e-3 * float(dWu.abs().max())
-    assert float((dbf - dbu).abs().max()) <= 2e-3 * float(dbu.abs().max())
+    # dW / db are formed from G rounded to the activation dtype (as an unfused AMP backward forms them); the comparison partner uses fp32 G
+    assert float((dWf - dWu).abs().max()) <= eps * float(dWu.abs().max())
+    assert float((dbf - dbu).abs().max()) <= eps * float(dbu.abs().max())
     for a, c in zip(gklf, gklu):
         assert torch.equal(a, c)                           # the KL path is untouched
 
@@ -170,7 +171,9 @@ def test_lazy_parameters_materialise_for_everything_else(B):
     with torch.autocast("cuda", dtype=torch.bfloat16):
         p, q = lik(x), plain(x)
         assert isinstance(p, B.LinearDMoLParams) and not isinstance(q, B.LinearDMoLParams)
-        assert lik.mode(p).shape == (Bn, T, 1) and p.materialized
+        m = lik.mode(p)
+        assert m.shape == (Bn, T, 1) and not p.materialized        # a promise: nothing evaluated yet
+        assert torch.equal(m + 0, plain.mode(q)) and p.materialized   # reading it evaluates the Linear (cuBLAS) and the sample/mode kernel
         assert torch.equal(p.raw, q.raw) and torch.equal(p[2], q[2]) and len(p) == 3
         out = B.fused_elbo(y, p, x_sl, (), num_bins=NB)    # materialised: the ordinary path
         ref = B.fused_elbo(y, q, x_sl, (), num_bins=NB)

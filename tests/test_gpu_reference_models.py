@@ -140,7 +140,7 @@ class likelihood_in_fp64:
         return False
 
 
-def run_pair(M, name, use_amp, anchor64=False):
+def run_pair(M, name, use_amp, anchor64=False, fuse_linear=False):
     import blvm_b200 as B
     x, x_sl, kwargs = inputs(name)
     ref_model = build(M, name).cuda()
@@ -158,7 +158,7 @@ def run_pair(M, name, use_amp, anchor64=False):
             r = (r, r64, r64b, r64n)
     del ref_model
     try:
-        rebound = B.patch_blvm()
+        rebound = B.patch_blvm(fuse_linear=fuse_linear)
         assert rebound, "patch_blvm() rebound nothing"
         model = build(M, name).cuda()
         assert set(model.state_dict()) == set(state)                      # checkpoint keys unchanged
@@ -248,6 +248,32 @@ def test_patched_amp_training_step(name, ref, monkeypatch):
     assert rel < 2e-3          # fp16 body: the two runs differ by fp16 rounding of the Linear output's consumers
     assert worst < 5e-2
     assert set(grads_o) == set(grads_r)
+
+
+@pytest.mark.parametrize("name", ["vrnn", "srnn", "stcn"])
+def test_patched_amp_step_with_the_fused_tensor_core_head(name, ref, monkeypatch):
+    """`patch_blvm(fuse_linear=True)` under `--use_amp True`: the likelihood's nn.Linear, the DMoL value + gradient and the Linear's
+    backward run as ONE tcgen05 kernel (csrc/linear_dmol_kernel.cuh); the (B, T, 3K) parameter tensor is never built because
+    `sample()` / `mode()` of the unevaluated parameters are promises nobody reads during a training step."""
+    from blvm_b200 import ops
+    from blvm_b200.variational import LazyResult
+    calls = {"head": 0}
+    real = ops.fused_linear_elbo_apply
+    monkeypatch.setattr(ops, "fused_linear_elbo_apply", lambda *a, **k: (calls.__setitem__("head", calls["head"] + 1), real(*a, **k))[1])
+    (loss_r, grads_r, vals_r, _, _), (loss_o, grads_o, vals_o, out_o, _), launches = run_pair(ref, name, use_amp=True, fuse_linear=True)
+    assert calls["head"] == 1, "the fused head was not taken"
+    rec = out_o.reconstructions
+    assert isinstance(rec, LazyResult) and rec._blvm_value is None          # promised, never evaluated by the training step
+    rel = abs(float(loss_o) - float(loss_r)) / abs(float(loss_r))
+    worst = 0.0
+    for n, g in grads_r.items():
+        scale = float(g.abs().max())
+        if scale > 0 and torch.isfinite(g).all():
+            worst = max(worst, float((grads_o[n] - g).abs().max()) / scale)
+    print(f"\n[{name} amp fused head] loss ref {float(loss_r):.6f} ours {float(loss_o):.6f} rel {rel:.2e}; worst weight-grad error {worst:.2e}; "
+          f"{launches} blvm launches")
+    assert rel < 2e-3 and worst < 5e-2 and set(grads_o) == set(grads_r)
+    assert tuple(rec.shape) == tuple(out_o.y.shape[:2]) + (1,) and float(rec.abs().max()) <= 1.0 and rec._blvm_value is not None   # reading works
 
 
 @pytest.mark.parametrize("name", ["vrnn", "srnn", "cwvae"])
