@@ -579,6 +579,71 @@ def dmol_kernel_us(dev, B, T, K, dtype, iters):
     return us, B * T * (8 + 6 * K * esz)
 
 
+def fused_head_record(dev, B, T, K, peak, iters=20):
+    """the likelihood head -- nn.Linear(30 -> 3K) + DMoL value / gradient + the Linear's backward -- as ONE
+    tcgen05 tensor-core kernel (`DiscretizedLogisticMixtureDense(fuse_linear=True)` -> fused_elbo -> backward) against the same head
+    unfused (cuBLAS Linear, the DMoL kernel on its bf16 output, autograd's two backward GEMMs), both through the public API."""
+    import torch
+
+    import blvm_b200
+    Din = 3 * K
+    g = torch.Generator(device=dev).manual_seed(11)
+    y = (torch.randint(0, NUM_BINS, (B, T), device=dev, generator=g).float() / (NUM_BINS - 1) * 2 - 1)
+    x = torch.randn(B, T, Din, device=dev, generator=g).to(torch.bfloat16).requires_grad_(True)
+    x_sl = torch.full((B,), T, dtype=torch.int64)
+    x_dev = x_sl.to(dev)
+    out = {}
+    for name, fuse in (("fused", True), ("unfused", False)):
+        lik = blvm_b200.DiscretizedLogisticMixtureDense(Din, 1, K, NUM_BINS, fuse_linear=fuse).to(dev)
+        with torch.no_grad():
+            lik.params.bias[2 * K:] -= 4.0
+
+        def step():
+            x.grad = None
+            lik.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                params = lik(x)
+            r = blvm_b200.fused_elbo(y, params, x_sl, (), num_bins=NUM_BINS, denom=float(B * T), x_sl_device=x_dev)
+            r.loss.backward()
+            return r
+
+        # replayed from a CUDA graph so that the GPU time is measured, not the Python around it (eager: see `eager_us`)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            r = step()
+        e1.record()
+        torch.cuda.synchronize()
+        eager_us = e0.elapsed_time(e1) / iters * 1e3
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            r = step()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = {"us_per_step": e0.elapsed_time(e1) / iters * 1e3, "eager_us": eager_us, "loss": float(r.loss)}
+    byts = B * T * (8 + 4 * Din)       # x and dx in bf16, y and log-prob in fp32: 128 B/sample at x_dim 30
+    us = out["fused"]["us_per_step"]
+    return {"what": f"likelihood head fwd+bwd, bf16 activations, x_dim {Din} -> 3K = {3 * K}, B={B} x T={T}: Linear + DMoL + Linear backward in one "
+                    "tcgen05 kernel (+ dW reduce + finalize) vs cuBLAS Linear + DMoL kernel + autograd GEMMs, public API, CUDA events",
+            "fused_us": us, "unfused_us": out["unfused"]["us_per_step"], "speedup": out["unfused"]["us_per_step"] / us,
+            "fused_eager_us": out["fused"]["eager_us"], "unfused_eager_us": out["unfused"]["eager_us"],
+            "note": "the two losses differ in the 3rd digit because the unfused AMP path rounds the Linear output to bf16 before the likelihood "
+                    "reads it; the fused kernel keeps the fp32 accumulators (tests/test_gpu_linear_head.py compares both with an fp32 evaluation)",
+            "algorithmic_bytes": byts, "achieved_gbs": byts / us / 1e3, "frac_of_hbm_peak": byts / us / 1e3 / peak,
+            "loss_fused": out["fused"]["loss"], "loss_unfused": out["unfused"]["loss"]}
+
+
 def run_gpu_arm(a):
     import torch
     import torch.distributed as dist
@@ -862,6 +927,12 @@ def run_gpu_arm(a):
                     torch.cuda.empty_cache()
             line["sweep"] = {"what": f"dmol fwd+grad kernel alone, B={a.B}, {a.dtype} parameters, 30 launches between CUDA events, frac = algorithmic GB/s / peak",
                              "points": sweep}
+        if n_gpus == 1 and not a.no_sweep and a.workload == "config5" and K == 10:
+            try:
+                line["fused_head"] = fused_head_record(dev, a.B, T, K, peak)
+            except Exception as err:
+                line["fused_head"] = {"error": repr(err)}
+            torch.cuda.empty_cache()
         if n_gpus == 1 and not a.no_reference_cuda:
             try:   # the "beat this" number: the reference's own eager chain on this same GPU, same shape
                 line["reference_eager_cuda"] = reference_eager_cuda(a, dev)
