@@ -751,11 +751,15 @@ def run_gpu_arm(a):
             got = ex.consume(beta=BETA, lag=0)                # ... and as the NVLink peer-store all-gather delivered them
             torch.cuda.synchronize()
             ex.check()
-            diff = (got[:7] - ref_global[:7]).abs().max()
-            flag = torch.tensor([float(diff)], device=dev, dtype=torch.float64)
+            # both add the same W fp64 values per entry, ours in rank order, NCCL in its ring / tree order: equal up to the last bits
+            # (bit-identical at W = 2 and 4 on this pool, 1e-14 relative at W = 8)
+            diff = (got[:7] - ref_global[:7]).abs()
+            rel = (diff / ref_global[:7].abs().clamp_min(1e-300)).max()
+            flag = torch.tensor([float(diff.max()), float(rel)], device=dev, dtype=torch.float64)
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-            exchange_check = {"ok": bool(flag.item() == 0.0), "max_abs_diff": float(flag.item()), "step": int(got[7].item()),
-                              "global_loss": float(got[0].item()), "what": "exchange.consume(lag=0) vs NCCL all-reduce of the same step's sums, entries 0-6, max over ranks"}
+            exchange_check = {"ok": bool(flag[1].item() <= 1e-9), "max_abs_diff": float(flag[0].item()), "max_rel_diff": float(flag[1].item()),
+                              "step": int(got[7].item()), "global_loss": float(got[0].item()),
+                              "what": "exchange.consume(lag=0) vs NCCL all-reduce of the same step's sums (fp64), entries 0-6, max over ranks; ok = rel <= 1e-9 (observed: 0 at 2 and 4 ranks, 1e-14 at 8)"}
             if not exchange_check["ok"]:
                 raise SystemExit(f"[bench] fused exchange delivered wrong sums: {exchange_check}")
         else:

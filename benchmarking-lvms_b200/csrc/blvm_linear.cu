@@ -31,9 +31,9 @@ int padded_dim(int64_t Din) {   // smallest instantiated DP with DP >= Din + 1 (
   return 0;
 }
 
-template <int DP, bool GRAD, int UMODE, typename TP>
+template <int DP, bool GRAD, int UMODE, typename TP, int DIN = 0>
 int launch_linear(const LinearDmolArgs& A, cudaStream_t st, unsigned* grid_out) {
-  auto kern = linear_dmol_kernel<kLinearK, DP, GRAD, UMODE, TP>;
+  auto kern = linear_dmol_kernel<kLinearK, DP, GRAD, UMODE, TP, DIN>;
   constexpr int smem = LinearSmem<DP>::bytes;
   constexpr int tmem_cols = LinearSmem<DP>::tmem_cols;
   static int resident_dev[kMaxDevices] = {};
@@ -68,6 +68,9 @@ int launch_linear(const LinearDmolArgs& A, cudaStream_t st, unsigned* grid_out) 
 template <int DP, typename TP>
 int dispatch_mode(const LinearDmolArgs& A, bool grad, cudaStream_t st, unsigned* grid_out) {
   const bool tiny = blvm_host::u_is_tiny(A.C);
+  if constexpr (DP == 32) {   // the reference's head: x_dim = 3 * num_mix = 30, 16-bit audio, training step
+    if (A.Din == 30 && tiny && grad) return launch_linear<DP, true, kUTiny, TP, 30>(A, st, grid_out);
+  }
   if (grad) return tiny ? launch_linear<DP, true, kUTiny, TP>(A, st, grid_out) : launch_linear<DP, true, kUGeneral, TP>(A, st, grid_out);
   return tiny ? launch_linear<DP, false, kUTiny, TP>(A, st, grid_out) : launch_linear<DP, false, kUGeneral, TP>(A, st, grid_out);
 }

@@ -163,11 +163,16 @@ __device__ __forceinline__ uint32_t cm_off(int i, int j, int cols) {
   return static_cast<uint32_t>(((i >> 3) * (cols >> 3) + (j >> 3)) * 128 + (i & 7) * 16 + (j & 7) * 2);
 }
 
+#ifndef BLVM_LINEAR_WAIT
+#define BLVM_LINEAR_WAIT(bar, ph) ptx::mbar_wait(bar, ph)
+#endif
 #ifndef BLVM_LINEAR_MINB
 #define BLVM_LINEAR_MINB 8     // CTAs per SM the register allocation is capped for (DP = 32): 8 -> 64 registers.  Measured (B = 256 x
                                // 16000, x_dim 30, bf16, grid = cap x 148): 5 -> 183.6 us (96 registers), 7 -> 169.6, 8 -> 166.9
 #endif
-template <int K, int DP, bool GRAD, int UMODE, typename TP>
+// DIN: x_dim known at compile time (30 = 3 * num_mix: every VRNN / SRNN / STCN / LSTM head of the reference, vrnn.py:464-469) so that
+// the row re-layout and the dx packing unroll without per-word predicates; 0 = read it from the arguments.
+template <int K, int DP, bool GRAD, int UMODE, typename TP, int DIN = 0>
 __global__ void __launch_bounds__(128, LinearSmem<DP>::kOutInG ? BLVM_LINEAR_MINB : 2) linear_dmol_kernel(const __grid_constant__ LinearDmolArgs A) {
   static_assert(3 * K <= 32, "the parameter row must fit the N = 32 accumulator tile");
   static_assert(DP % 16 == 0 && DP >= 32 && DP <= 240, "padded x_dim");
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(128, LinearSmem<DP>::kOutInG ? BLVM_LINEAR_MIN
   double* scratch = reinterpret_cast<double*>(smem + S::oMisc + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int Din = A.Din;
+  const int Din = DIN ? DIN : A.Din;
   const TP* Wg = static_cast<const TP*>(A.W);
 
   // ---- one-time setup: TMEM, barriers, W (+ bias column) and the constant parts of X / G in core-matrix layout ----------
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(128, LinearSmem<DP>::kOutInG ? BLVM_LINEAR_MIN
         tc::mma_f16(t_raw, tc::smem_desc(aX + k * 256, 128, XS), tc::smem_desc(aW + k * 256, 128, XS), idesc_fwd, k > 0);
       tc::commit(bar_mma);
     }
-    ptx::mbar_wait(bar_mma, ph_mma);
+    BLVM_LINEAR_WAIT(bar_mma, ph_mma);
     ph_mma ^= 1u;
     tc::fence_after();
 
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(128, LinearSmem<DP>::kOutInG ? BLVM_LINEAR_MIN
         tc::commit(bar_dw);
       }
       dw_started = true;
-      ptx::mbar_wait(bar_mma, ph_mma);
+      BLVM_LINEAR_WAIT(bar_mma, ph_mma);
       ph_mma ^= 1u;
       if constexpr (S::kOutInG) {        // the dx slab is staged in G's buffer: the DW product (8 small MMAs behind DX) must have read it
         ptx::mbar_wait(bar_dw, ph_dw);

@@ -33,6 +33,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// the same wait with a short sleep between polls: for waits that are expected to last a microsecond (tensor-core round trips), so that
+// the spinning warps do not take issue slots from the CTAs that hide the wait
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "BLVM_WAITB:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra BLVM_DONEB;\n"
+      "nanosleep.u32 40;\n"
+      "bra BLVM_WAITB;\n"
+      "BLVM_DONEB:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
