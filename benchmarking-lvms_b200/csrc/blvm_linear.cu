@@ -124,10 +124,10 @@ int blvm_linear_dmol_reduce_dw(const float* dw_partial, int64_t ctas, int64_t Di
   const int DP = K == kLinearK ? padded_dim(Din) : 0;
   if (DP == 0) return fail(BLVM_ERR_UNSUPPORTED, "unsupported K / x_dim");
   if (ctas < 0 || !dw_partial || !dW) return fail(BLVM_ERR_INVALID_ARGUMENT, "null pointer / negative count");
-  const int P = 3 * K, n = P * (static_cast<int>(Din) + 1);
+  const int P = 3 * K;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (DP == 32) linear_dmol_reduce_kernel<32><<<(n + 255) / 256, 256, 0, st>>>(dw_partial, ctas, static_cast<int>(Din), P, dW, db);
-  else linear_dmol_reduce_kernel<80><<<(n + 255) / 256, 256, 0, st>>>(dw_partial, ctas, static_cast<int>(Din), P, dW, db);
+  if (DP == 32) linear_dmol_reduce_kernel<32><<<P, 1024, 0, st>>>(dw_partial, ctas, static_cast<int>(Din), P, dW, db);
+  else linear_dmol_reduce_kernel<80><<<P, 1024, 0, st>>>(dw_partial, ctas, static_cast<int>(Din), P, dW, db);
   return check_launch("linear_dmol_reduce_kernel");
 }
 

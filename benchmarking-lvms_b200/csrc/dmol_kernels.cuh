@@ -99,54 +99,140 @@ struct RowIO<float, P> {
   }
 };
 
-template <int P>
-struct RowIO<__half, P> {
-  static __device__ __forceinline__ void load(const __half* p, float (&r)[P]) {
-    if constexpr (P % 2 == 0) {
-#pragma unroll
-      for (int i = 0; i < P / 2; ++i) {
-        const float2 v = __half22float2(reinterpret_cast<const __half2*>(p)[i]);
-        r[2 * i] = v.x; r[2 * i + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < P; ++i) r[i] = __half2float(p[i]);
-    }
+// 16-bit rows: pairs travel as 32-bit words; a row whose byte size is a multiple of 16 / 8 is moved with 128 / 64-bit accesses
+// (K = 8: three LDS.128 instead of twelve LDS.32 whose 12-word stride is 4-way bank conflicted; K = 12 / 20: LDS.64, odd strides).
+template <typename TP>
+struct Pair16;
+template <>
+struct Pair16<__half> {
+  static __device__ __forceinline__ void unpack(uint32_t w, float& a, float& b) {
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    a = v.x; b = v.y;
   }
-  static __device__ __forceinline__ void store(__half* p, const float (&r)[P]) {
-    if constexpr (P % 2 == 0) {
-#pragma unroll
-      for (int i = 0; i < P / 2; ++i) reinterpret_cast<__half2*>(p)[i] = __floats2half2_rn(r[2 * i], r[2 * i + 1]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < P; ++i) p[i] = __float2half_rn(r[i]);
-    }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+};
+template <>
+struct Pair16<__nv_bfloat16> {
+  static __device__ __forceinline__ void unpack(uint32_t w, float& a, float& b) {   // bf16 -> fp32 is a 16-bit shift: one SHL and one AND per pair
+    a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u);
+  }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
   }
 };
 
-template <int P>
-struct RowIO<__nv_bfloat16, P> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&r)[P]) {
-    if constexpr (P % 2 == 0) {
+template <typename TP, int P>
+struct RowIO16 {
+  static __device__ __forceinline__ void load(const TP* p, float (&r)[P]) {
+    if constexpr (P % 8 == 0) {
 #pragma unroll
-      for (int i = 0; i < P / 2; ++i) {   // bf16 -> fp32 is a 16-bit shift: one SHL and one AND per pair
-        const uint32_t w = reinterpret_cast<const uint32_t*>(p)[i];
-        r[2 * i] = __uint_as_float(w << 16); r[2 * i + 1] = __uint_as_float(w & 0xffff0000u);
+      for (int i = 0; i < P / 8; ++i) {
+        const uint4 v = reinterpret_cast<const uint4*>(p)[i];
+        Pair16<TP>::unpack(v.x, r[8 * i], r[8 * i + 1]); Pair16<TP>::unpack(v.y, r[8 * i + 2], r[8 * i + 3]);
+        Pair16<TP>::unpack(v.z, r[8 * i + 4], r[8 * i + 5]); Pair16<TP>::unpack(v.w, r[8 * i + 6], r[8 * i + 7]);
       }
+    } else if constexpr (P % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 4; ++i) {
+        const uint2 v = reinterpret_cast<const uint2*>(p)[i];
+        Pair16<TP>::unpack(v.x, r[4 * i], r[4 * i + 1]); Pair16<TP>::unpack(v.y, r[4 * i + 2], r[4 * i + 3]);
+      }
+    } else if constexpr (P % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) Pair16<TP>::unpack(reinterpret_cast<const uint32_t*>(p)[i], r[2 * i], r[2 * i + 1]);
     } else {
 #pragma unroll
-      for (int i = 0; i < P; ++i) r[i] = __bfloat162float(p[i]);
+      for (int i = 0; i < P; ++i) r[i] = static_cast<float>(p[i]);
     }
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&r)[P]) {
-    if constexpr (P % 2 == 0) {
+  static __device__ __forceinline__ void store(TP* p, const float (&r)[P]) {
+    if constexpr (P % 8 == 0) {
 #pragma unroll
-      for (int i = 0; i < P / 2; ++i) reinterpret_cast<__nv_bfloat162*>(p)[i] = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+      for (int i = 0; i < P / 8; ++i)
+        reinterpret_cast<uint4*>(p)[i] = make_uint4(Pair16<TP>::pack(r[8 * i], r[8 * i + 1]), Pair16<TP>::pack(r[8 * i + 2], r[8 * i + 3]),
+                                                    Pair16<TP>::pack(r[8 * i + 4], r[8 * i + 5]), Pair16<TP>::pack(r[8 * i + 6], r[8 * i + 7]));
+    } else if constexpr (P % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 4; ++i)
+        reinterpret_cast<uint2*>(p)[i] = make_uint2(Pair16<TP>::pack(r[4 * i], r[4 * i + 1]), Pair16<TP>::pack(r[4 * i + 2], r[4 * i + 3]));
+    } else if constexpr (P % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) reinterpret_cast<uint32_t*>(p)[i] = Pair16<TP>::pack(r[2 * i], r[2 * i + 1]);
     } else {
 #pragma unroll
-      for (int i = 0; i < P; ++i) p[i] = __float2bfloat16_rn(r[i]);
+      for (int i = 0; i < P; ++i) p[i] = static_cast<TP>(r[i]);
     }
   }
+};
+template <int P>
+struct RowIO<__half, P> : RowIO16<__half, P> {};
+template <int P>
+struct RowIO<__nv_bfloat16, P> : RowIO16<__nv_bfloat16, P> {};
+
+// Rows made of an EVEN number NV of 16-byte vectors (fp32 K = 8, 16; 16-bit K = 16) start at bank groups NV * lane mod 8, which
+// takes only 8 / gcd(NV, 8) distinct values over the 8 lanes of a 128-bit shared-memory wavefront: a gcd(NV, 8)-way bank conflict on
+// every access (K = 16 fp32, 192-byte rows: 4-way; the kernel sat at 0.88 of the HBM roofline on shared-memory bandwidth).  The
+// slab arrives by ONE bulk copy, so rows cannot be padded; instead each lane walks the vectors of every K-element section of its
+// row (mixture logits | locations | log-scales) in an order rotated by rot = (lane / period) % ways: the lanes that share a
+// starting bank group then touch different vectors of the section at every step.  Register slot k holds component
+// (k + VE * rot) mod K of each section -- the same permutation in all three sections, and the likelihood is symmetric in the
+// component index, so value and gradient are those of the unrotated walk up to the order of the K-term sums (gradients are
+// written back through the same permutation).
+constexpr int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
+template <typename TP, int K>
+struct RowRot {
+  static constexpr int P = 3 * K;
+  static constexpr int VE = 16 / static_cast<int>(sizeof(TP));          // elements per 16-byte vector
+  static constexpr bool vec16 = (P * sizeof(TP)) % 16 == 0 && K % VE == 0;
+  static constexpr int NV = vec16 ? P / VE : 1;
+  static constexpr int SV = vec16 ? K / VE : 1;                          // vectors per section
+  static constexpr int ways = gcd_int(NV, 8);
+  static constexpr int period = 8 / ways;
+  static constexpr bool enabled = vec16 && NV % 2 == 0 && (SV & (SV - 1)) == 0 && SV >= ways;
+  static __device__ __forceinline__ int rot(int lane) { return (lane / period) % ways; }
+
+  static __device__ __forceinline__ void load(const TP* p, float (&r)[P], int rot) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+#pragma unroll
+      for (int j = 0; j < SV; ++j) {
+        const uint4 v = reinterpret_cast<const uint4*>(p)[s * SV + ((j + rot) & (SV - 1))];
+        float* d = r + s * K + j * VE;
+        if constexpr (sizeof(TP) == 4) {
+          d[0] = __uint_as_float(v.x); d[1] = __uint_as_float(v.y); d[2] = __uint_as_float(v.z); d[3] = __uint_as_float(v.w);
+        } else {
+          Pair16<TP>::unpack(v.x, d[0], d[1]); Pair16<TP>::unpack(v.y, d[2], d[3]);
+          Pair16<TP>::unpack(v.z, d[4], d[5]); Pair16<TP>::unpack(v.w, d[6], d[7]);
+        }
+      }
+    }
+  }
+  static __device__ __forceinline__ void store(TP* p, const float (&r)[P], int rot) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+#pragma unroll
+      for (int j = 0; j < SV; ++j) {
+        const float* d = r + s * K + j * VE;
+        uint4 v;
+        if constexpr (sizeof(TP) == 4) {
+          v = make_uint4(__float_as_uint(d[0]), __float_as_uint(d[1]), __float_as_uint(d[2]), __float_as_uint(d[3]));
+        } else {
+          v = make_uint4(Pair16<TP>::pack(d[0], d[1]), Pair16<TP>::pack(d[2], d[3]), Pair16<TP>::pack(d[4], d[5]), Pair16<TP>::pack(d[6], d[7]));
+        }
+        reinterpret_cast<uint4*>(p)[s * SV + ((j + rot) & (SV - 1))] = v;
+      }
+    }
+  }
+};
+// Pair16 is only defined for the 16-bit types; fp32 rows never reach its branches
+template <>
+struct Pair16<float> {
+  static __device__ __forceinline__ void unpack(uint32_t, float&, float&) {}
+  static __device__ __forceinline__ uint32_t pack(float, float) { return 0u; }
 };
 
 // Samples per thread: small K means small rows, so a 128-sample tile would be a 1.5 KB slab (K = 1) and the per-CTA
@@ -223,6 +309,8 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
   double* scratch = reinterpret_cast<double*>(smem + kTileBytes + 16);
 
   const int tid = threadIdx.x;
+  constexpr bool kRot = RowRot<TP, K>::enabled && LIK == kLikDmol;   // rotated section walk (bank conflicts, see RowRot)
+  const int rot = kRot ? RowRot<TP, K>::rot(tid & 31) : 0;
   // row-local arithmetic in 32 bits (the host rejects T >= 2^31 and more than 2^31 - 1 tiles); only the flat sample
   // offset of the tile is 64-bit (2.95 G parameter elements at the top of config 5)
   const unsigned tile32 = static_cast<unsigned>(tile_id), cpr = static_cast<unsigned>(A.ctas_per_row);
@@ -278,9 +366,9 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
       bad |= !(yv[j] <= 1.0f && yv[j] >= -1.0f);
       float r[P];
       TP* row = tile + i * P;
-      RowIO<TP, P>::load(row, r);
+      if constexpr (kRot) RowRot<TP, K>::load(row, r, rot); else RowIO<TP, P>::load(row, r);
       const float L = dmol_sample<K, GRAD, UMODE, LIK>(yv[j], r, gs, A.C);
-      if (GRAD) RowIO<TP, P>::store(row, r);
+      if constexpr (kRot) { if (GRAD) RowRot<TP, K>::store(row, r, rot); } else { if (GRAD) RowIO<TP, P>::store(row, r); }
       if (A.lp) A.lp[s0 + i] = L;
       acc += static_cast<double>(L);
     }
@@ -312,13 +400,13 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
         float r[P];
         TP* row = tile + i * P;
         if (!skip) {
-          RowIO<TP, P>::load(row, r);
+          if constexpr (kRot) RowRot<TP, K>::load(row, r, rot); else RowIO<TP, P>::load(row, r);
           L = dmol_sample<K, GRAD, UMODE, LIK>(yv[j], r, g[j], A.C);
         } else {
 #pragma unroll
           for (int q = 0; q < P; ++q) r[q] = 0.f;
         }
-        if (GRAD) RowIO<TP, P>::store(row, r);
+        if constexpr (kRot) { if (GRAD) RowRot<TP, K>::store(row, r, rot); } else { if (GRAD) RowIO<TP, P>::store(row, r); }
         // reference semantics: log_prob * mask (NaN/inf in the padding propagate like `* 0`), vrnn.py:268
         const float Lm = (i < nvalid) ? L : L * 0.0f;
         if (A.lp) A.lp[s0 + i] = (A.flags & kFlagMaskOutput) ? Lm : L;

@@ -163,7 +163,12 @@ __device__ __forceinline__ uint32_t cm_off(int i, int j, int cols) {
   return static_cast<uint32_t>(((i >> 3) * (cols >> 3) + (j >> 3)) * 128 + (i & 7) * 16 + (j & 7) * 2);
 }
 
-#ifndef BLVM_LINEAR_WAIT
+#ifndef BLVM_LINEAR_BACKOFF
+#define BLVM_LINEAR_BACKOFF 0
+#endif
+#if BLVM_LINEAR_BACKOFF
+#define BLVM_LINEAR_WAIT(bar, ph) ptx::mbar_wait_backoff(bar, ph)
+#else
 #define BLVM_LINEAR_WAIT(bar, ph) ptx::mbar_wait(bar, ph)
 #endif
 #ifndef BLVM_LINEAR_MINB
@@ -470,17 +475,38 @@ __global__ void __launch_bounds__(128, LinearSmem<DP>::kOutInG ? BLVM_LINEAR_MIN
   if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
-// dW (P, Din), db (P) = sum over CTAs of the partials, in CTA order (deterministic).  One thread per output element.
+// dW (P, Din), db (P) = sum over CTAs of the partials.  One block per output row p: thread (g, d) adds the partials of CTAs g, g+G, ...
+// for column d (independent coalesced loads), then the G group sums are added in group order -- a fixed order, so the result is
+// deterministic for a given CTA count.  (A single thread per element walking all ~1200 CTAs took 50 us: a chain of dependent L2 loads.)
 template <int DP>
-__global__ void __launch_bounds__(256) linear_dmol_reduce_kernel(const float* __restrict__ part, int64_t ctas, int Din, int P,
-                                                                  float* __restrict__ dW, float* __restrict__ db) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= P * (Din + 1)) return;
-  const int p = i / (Din + 1), d = i - p * (Din + 1);
+__global__ void __launch_bounds__(1024) linear_dmol_reduce_kernel(const float* __restrict__ part, int64_t ctas, int Din, int P,
+                                                                   float* __restrict__ dW, float* __restrict__ db) {
+  constexpr int DL = DP <= 32 ? 32 : 128;   // threads along d
+  constexpr int G = 1024 / DL;              // CTA groups
+  __shared__ float acc[G][DL];
+  const int p = blockIdx.x, d = threadIdx.x % DL, g = threadIdx.x / DL;
   float s = 0.f;
-  for (int64_t c = 0; c < ctas; ++c) s += part[(c * 32 + p) * DP + d];
-  if (d < Din) dW[p * Din + d] = s;
-  else if (db) db[p] = s;
+  if (d <= Din) {
+    const float* src = part + (static_cast<int64_t>(g) * 32 + p) * DP + d;
+    constexpr int64_t kStep = static_cast<int64_t>(G) * 32 * DP;
+    int64_t c = g;
+#pragma unroll 1
+    for (; c + 3 * G < ctas; c += 4 * G, src += 4 * kStep) {
+      const float a0 = src[0], a1 = src[kStep], a2 = src[2 * kStep], a3 = src[3 * kStep];
+      s += a0; s += a1; s += a2; s += a3;
+    }
+    for (; c < ctas; c += G, src += kStep) s += src[0];
+  }
+  acc[g][d] = s;
+  __syncthreads();
+  if (g == 0 && d <= Din) {
+    float t = acc[0][d];
+#pragma unroll
+    for (int j = 1; j < G; ++j) t += acc[j][d];
+    if (d < Din) dW[p * Din + d] = t;
+    else if (db) db[p] = t;
+  }
+  (void)P;
 }
 
 }  // namespace blvm

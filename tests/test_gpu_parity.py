@@ -490,6 +490,50 @@ def test_half_precision_parameters(dtype, K, B, O):
     assert r7.grad.dtype == dtype
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("K", [8, 12, 16, 20])
+def test_wide_rows_and_rotated_section_walk(K, dtype, B, O):
+    """Rows that are a whole number of 16 / 8-byte vectors are lifted with 128 / 64-bit shared-memory accesses, and where a row
+    is an EVEN number of 16-byte vectors (fp32 K = 8 / 16, 16-bit K = 16) each lane walks the three K-element sections in a
+    lane-dependent rotated order (dmol_kernels.cuh: RowRot; removes a 2 / 4-way bank conflict).  The permutation is the same
+    in all sections and the likelihood is symmetric in the component index: values and gradients against the oracle, every
+    gradient lands on its own component, ragged tails and a second tile included."""
+    rng = np.random.default_rng(100 + K)
+    Bn, T, nb = 3, 517, 65536
+    y = (rng.integers(0, nb, (Bn, T)) / (nb - 1) * 2 - 1).astype(np.float32)
+    raw = rng.normal(size=(Bn, T, 3 * K)).astype(np.float32)
+    raw[..., K:2 * K] = y[..., None] + 0.1 * raw[..., K:2 * K]
+    raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+    raw[..., :K] += np.arange(K, dtype=np.float32) * 0.37            # components are distinguishable
+    raw_h = cu(raw).to(dtype)
+    x_sl = torch.tensor([T, 300, 17])
+    r = raw_h.clone().requires_grad_(True)
+    scale = 4096.0 if dtype != torch.float32 else 1.0
+    out = B.fused_elbo(cu(y), B.DMoLParams(r, K, 1, -7.0), x_sl, (), num_bins=nb, want_twise=True)
+    (out.loss * scale).backward()
+    ref = O.fused_elbo_value_and_grad(y, raw_h.float().cpu().numpy(), x_sl.numpy(), [], 1.0, K, nb)
+    assert_sums_close(out.loss.item(), ref["loss"], "loss")
+    g = r.grad.float().cpu().numpy().astype(np.float64) / scale
+    gref = ref["graw"]
+    if dtype == torch.float32:
+        n = float(x_sl.sum())
+        mask = O.sequence_mask(x_sl.numpy(), max_len=T).reshape(-1)
+        assert_grads_close(g, gref, K, mask / n, "d/d raw")
+    else:
+        eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+        tol = eps * np.abs(gref) + 1e-4 * np.abs(gref).max(-1, keepdims=True) + (6e-8 / scale if dtype == torch.float16 else 0)
+        assert (np.abs(g - gref) <= tol).all()
+    # the same rows through the forward-only kernel and the 16-bit rows against the fp32 kernel on the same rounded values
+    lik = B.DiscretizedLogisticMixtureDense(3, 1, K, nb)
+    lp_h = lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(raw_h, K, 1, -7.0))
+    lp_f = lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(raw_h.float(), K, 1, -7.0))
+    assert_values_close(lp_h.cpu().numpy(), lp_f.cpu().numpy().astype(np.float64), "16-bit rows vs fp32 rows", rtol=2e-6)
+    tw = out.log_prob_twise.cpu().numpy() if hasattr(out, "log_prob_twise") else None
+    if tw is not None:
+        m = O.sequence_mask(x_sl.numpy(), max_len=T)
+        assert_values_close(tw[m], lp_h.cpu().numpy()[m], "fused step vs forward-only kernel", rtol=2e-6)
+
+
 def test_fp16_gradients_do_not_underflow_with_loss_scale(B, O):
     """fp16 parameters: d loss/d raw ~ 1/sum(x_sl) ~ 1e-7 is below fp16's subnormal range; with the GradScaler's loss
     scale applied inside the backward launch (device scalar) the scaled gradients are representable."""

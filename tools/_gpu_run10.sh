@@ -1,5 +1,4 @@
 cd $GRAFT_REPO_ROOT
-ncu --set full --clock-control none --import-source on -k regex:linear_dmol_kernel -s 8 -c 1 -o gpurun_out/r2q_linear python tools/test_linear_dmol.py > gpurun_out/r2q_ncu.log 2>&1
-ncu -i gpurun_out/r2q_linear.ncu-rep --page source --csv > gpurun_out/r2q_linear.source.csv 2>/dev/null
-python tools/ncu_summary.py gpurun_out/r2q_linear.ncu-rep > gpurun_out/r2q_linear.summary.json 2>&1
-rm -f gpurun_out/r2q_linear.ncu-rep
+timeout 600 python -m pytest tests/test_gpu_linear_head.py -q 2>&1 | tail -3 > gpurun_out/r2t_linear_tests.log
+echo "== default (DIN=30 specialised)" >> gpurun_out/r2t_linear_perf.log; timeout 180 python tools/test_linear_dmol.py 2>&1 | grep -E "fused head" >> gpurun_out/r2t_linear_perf.log
+echo "== backoff" >> gpurun_out/r2t_linear_perf.log; BLVM_B200_LIB=$PWD/benchmarking-lvms_b200/lib/variants/libblvm_b200_linbo.so timeout 180 python tools/test_linear_dmol.py 2>&1 | grep -E "fused head" >> gpurun_out/r2t_linear_perf.log
