@@ -278,19 +278,30 @@ BLVM_HD F2 rcp_2(F2 a) { return F2{fast_rcp(a.x), fast_rcp(a.y)}; }
 // DRAM 46 %), so the formulas of dl_mid are arranged for the fewest instructions:
 //  * the log-prob is carried in log2 units (lp2 = lp * log2(e)): the MUFU.EX2 arguments p = -ls log2(e) and t = -|m| log2(e)
 //    ARE the two leading terms of lp2, and the mixture's exp / log work in base 2 anyway (dmol_sample converts once);
-//  * selections are arithmetic blends with a 0 / -1 float (one FSET each, packed FMAs afterwards) instead of predicates
+//  * selections are arithmetic blends with a 1 / 0 float (one FSET.BF each, packed FMAs afterwards) instead of predicates
 //    that live across the whole evaluation: with 5-15 pairs in flight the compiler ran out of predicate registers and
 //    spilled them into a bit mask (2-3 LOP3 per predicate);
-//  * signs are folded into constants and into rn = 1/(-(1+E)) because packed operands carry no negate modifier in PTX;
+//  * signs are folded into constants (-u^2 = inv^2 * (-h^2) is what is carried) because packed operands carry no negate
+//    modifier in PTX;
 //  * exp(-ls) is the plain MUFU result: its 2^-22.5 relative error plus the argument rounding (|ls| <= 7: 3e-7) stays
 //    below 4 % of the parity tolerance in m, lp and the gradients (tools/hostsim_accuracy.py; -DBLVM_COMPENSATED_EXP=1
 //    restores the compensated evaluation).
 // Out: lp2 (log2 units); if GRAD, dmu = d lp/d loc and dls = d lp/d raw_log_scale in natural units.
 constexpr float kInvLn2Sixth = kLog2e / 6.0f;
+// max(x, lo) that keeps a NaN x (torch.clamp(min=) propagates NaN; fmaxf would drop it): one FMNMX.NAN
+BLVM_HD float max_keep_nan(float x, float lo) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lo));
+  return r;
+#else
+  return (x < lo) ? lo : x;
+#endif
+}
+
 template <bool GRAD>
 BLVM_HD void dl_mid_pair_tiny(F2 y, F2 mu, F2 raw_ls, const DmolConsts& C, F2& lp2, F2& dmu, F2& dls) {
-  const bool below_x = raw_ls.x < C.log_eps, below_y = raw_ls.y < C.log_eps;
-  const F2 ls = f2(below_x ? C.log_eps : raw_ls.x, below_y ? C.log_eps : raw_ls.y);   // clamp(min): NaN propagates like torch
+  const F2 ls = f2(max_keep_nan(raw_ls.x, C.log_eps), max_keep_nan(raw_ls.y, C.log_eps));   // clamp(min): NaN propagates like torch
   const F2 p = mul2(ls, f2(-kLog2e));                             // log2 of exp(-log_scale)     :203
 #if BLVM_COMPENSATED_EXP == 1
   constexpr float kLog2eLo = 1.925963033500011e-08f;
@@ -301,44 +312,36 @@ BLVM_HD void dl_mid_pair_tiny(F2 y, F2 mu, F2 raw_ls, const DmolConsts& C, F2& l
   const F2 inv = ex2_2(p);
 #endif
   const F2 m = mul2(inv, fma2(mu, f2(-1.f), y));                  // mid_in                     :202,219
-  const F2 u = mul2(inv, f2(C.h));
+  const F2 nu2 = mul2(mul2(inv, inv), f2(-C.h * C.h));            // -u^2, u = h / s (the sign rides on the constant)
   const F2 am = abs2(m);
   const F2 t = mul2(am, f2(-kLog2e));
   const F2 E = ex2_2(t);                                          // exp(-|m|)
-  const F2 p1n = fma2(E, f2(-1.f), f2(-1.f));                     // -(1 + E)
-  const F2 rn = rcp_2(p1n);                                       // -1/(1+E)
-  const F2 l = f2(fast_lg2(-p1n.x), fast_lg2(-p1n.y));            // log2(1+E)   (the negation is an operand modifier)
+  const F2 p1 = add2(E, f2(1.f));                                 // 1 + E
+  const F2 r = rcp_2(p1);                                         // 1/(1+E)
+  const F2 l = lg2_2(p1);                                         // log2(1+E)
   const F2 common2 = fma2(l, f2(-2.f), add2(t, p));               // [m - ls - 2 softplus(m)] log2(e)   :220
   const F2 lp_fb2 = add2(common2, f2(-C.log_half_bins2));         // second arm of :221-223
-  const F2 u2 = mul2(u, u);
-  const F2 Ern = mul2(E, rn);                                     // -E / (1+E)
-  const F2 er2 = mul2(Ern, rn);                                   // E / (1+E)^2
-  const F2 eps = mul2(er2, u2);                                   // E w / (1+E)^2,  w = u^2 + O(u^4)
-  // first arm minus second arm, negated:  -[log(2h) + log(nb/2) + u^2/6 - eps] log2(e)
-  const F2 ndlt2 = fma2(eps, f2(kLog2e), fma2(u2, f2(-kInvLn2Sixth), f2(C.neg_log_ratio2)));
-  const F2 lp_d2 = fma2(ndlt2, f2(-1.f), lp_fb2);                 // log2 cdf_delta, first arm of :221-223
+  const F2 Er = mul2(E, r);                                       // E / (1+E)
+  const F2 er2 = mul2(Er, r);                                     // E / (1+E)^2
+  const F2 neps = mul2(er2, nu2);                                 // -E w / (1+E)^2,  w = u^2 + O(u^4)
+  // first arm minus second arm:  [log(2h) + log(nb/2) + u^2/6 - eps] log2(e)
+  const F2 dlt2 = fma2(neps, f2(kLog2e), fma2(nu2, f2(-kInvLn2Sixth), f2(-C.neg_log_ratio2)));
+  const F2 lp_d2 = add2(dlt2, lp_fb2);                            // log2 cdf_delta, first arm of :221-223
   const float thr2 = C.log_delta_thresh2;
-#if defined(__CUDA_ARCH__)
-  // -[cdf_delta > 1e-5] as one select of a bit pattern per lane (the compiler otherwise selects an integer and converts it)
-  const F2 nsel = f2(__int_as_float(lp_d2.x > thr2 ? 0xBF800000 : 0), __int_as_float(lp_d2.y > thr2 ? 0xBF800000 : 0));
-#else
-  const F2 nsel = f2(lp_d2.x > thr2 ? -1.f : 0.f, lp_d2.y > thr2 ? -1.f : 0.f);   // -[cdf_delta > 1e-5]
-#endif
-  lp2 = fma2(nsel, ndlt2, lp_fb2);
+  // [cdf_delta > 1e-5] as a 1.0 / 0.0 float: one FSET.BF per lane.  (A -1 / 0 blend compiles to FSETP + SEL + I2FP: the compiler
+  // canonicalises any select of -1.0f / 0 into a sign-extended predicate converted to float, and I2FP competes with MUFU.)
+  const F2 sel = f2(lp_d2.x > thr2 ? 1.f : 0.f, lp_d2.y > thr2 ? 1.f : 0.f);
+  lp2 = fma2(sel, dlt2, lp_fb2);
   if (GRAD) {
     // tanh(|m|/2) = (1-E)/(1+E); odd series below 1/4 so that the bin-centre gradient does not cancel
     const F2 hx = mul2(am, f2(0.5f)), hx2 = mul2(hx, hx);
     const F2 th_series = mul2(hx, fma2(hx2, fma2(hx2, f2(2.0f / 15.0f), f2(-1.0f / 3.0f)), f2(1.0f)));
-    const F2 th_exact = fma2(Ern, f2(2.f), f2(1.f));              // 1 - 2E/(1+E) = (1-E)/(1+E)
+    const F2 th_exact = fma2(Er, f2(-2.f), f2(1.f));              // 1 - 2E/(1+E) = (1-E)/(1+E)
     const F2 th = f2(am.x < 0.25f ? th_series.x : th_exact.x, am.y < 0.25f ? th_series.y : th_exact.y);
-    const F2 th_sel = fma2(mul2(nsel, eps), th, th);              // th / (1 + eps) on the first arm, th on the second
-    const F2 c = fma2(mul2(nsel, u2), fma2(er2, f2(-2.0f), f2(1.0f / 3.0f)), f2(-1.0f));   // -(u coth(u) - u cdf_delta)  resp.  -1
-    // clamp(min=eps) blocks the gradient strictly below eps, passes at equality (own compares: the `below` predicates die early)
-#if defined(__CUDA_ARCH__)
-    const F2 gate = f2(__int_as_float(raw_ls.x >= C.log_eps ? 0x3F800000 : 0), __int_as_float(raw_ls.y >= C.log_eps ? 0x3F800000 : 0));
-#else
+    const F2 th_sel = fma2(mul2(sel, neps), th, th);              // th / (1 + eps) on the first arm, th on the second
+    const F2 c = fma2(mul2(sel, nu2), fma2(er2, f2(-2.0f), f2(1.0f / 3.0f)), f2(-1.0f));   // -(u coth(u) - u cdf_delta)  resp.  -1
+    // clamp(min=eps) blocks the gradient strictly below eps, passes at equality
     const F2 gate = f2(raw_ls.x >= C.log_eps ? 1.f : 0.f, raw_ls.y >= C.log_eps ? 1.f : 0.f);
-#endif
     const F2 it = mul2(inv, th_sel);
     dmu = f2(copysignf(it.x, m.x), copysignf(it.y, m.y));         // -inv * d lp/d m
     dls = mul2(fma2(am, th_sel, c), gate);                        // -(m d/dm + u d/du)  resp.  -m d/dm - 1
