@@ -904,6 +904,9 @@ def run_gpu_arm(a):
             "roofline": {"bound": "hbm", "kernel": f"dmol_tile_kernel<K={K},128,grad,{a.dtype}>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": kern_ms * 1e3,
+                         "note": "algorithmic bytes = SURVEY 8d's 4(2+6K) B/sample (fp32; 16-bit parameters: 8+12K); the fused step reduces the "
+                                 "per-sample log-prob to row partials instead of writing it, so the kernel is REQUIRED to move 4 B/sample less "
+                                 "(1.6 % at K=10) -- `traffic` is what it actually moved",
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "sustained_copy_gbs": sustained_copy,
                          "frac_of_sustained_copy": (achieved / sustained_copy) if sustained_copy else None},
@@ -929,8 +932,20 @@ def run_gpu_arm(a):
                     except Exception as err:
                         sweep.append({"K": Ks, "T": Ts, "error": repr(err)})
                     torch.cuda.empty_cache()
-            line["sweep"] = {"what": f"dmol fwd+grad kernel alone, B={a.B}, {a.dtype} parameters, 30 launches between CUDA events, frac = algorithmic GB/s / peak",
+            line["sweep"] = {"what": f"dmol fwd+grad kernel alone, B={a.B}, {a.dtype} parameters, 30 launches between CUDA events, frac = algorithmic GB/s / peak; "
+                                     "as in the fused step the per-sample log-prob is reduced to row partials and not written (the algorithmic figure of "
+                                     "SURVEY 8d, 4(2+6K) B/sample, counts those 4 bytes: 1.6 % at K=10, 12.5 % at K=1)",
                              "points": sweep}
+            # the other instantiated mixture sizes at T = 16000 (stream kernel K <= 5, rotated section walk at K = 8 / 16)
+            other = []
+            for Ks in (2, 3, 4, 5, 8, 12, 16, 20):
+                try:
+                    us, byts = dmol_kernel_us(dev, a.B, 16000, Ks, a.dtype, 30)
+                    other.append({"K": Ks, "T": 16000, "us": us, "GBs": byts / us / 1e3, "frac": byts / us / 1e3 / peak})
+                except Exception as err:
+                    other.append({"K": Ks, "T": 16000, "error": repr(err)})
+                torch.cuda.empty_cache()
+            line["sweep"]["other_K"] = other
         if n_gpus == 1 and not a.no_sweep and a.workload == "config5" and K == 10:
             try:
                 line["fused_head"] = fused_head_record(dev, a.B, T, K, peak)

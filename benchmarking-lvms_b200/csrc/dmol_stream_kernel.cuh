@@ -50,16 +50,39 @@ struct StreamTile {
   bool skip;
 };
 
-template <int TILE>
-__device__ __forceinline__ StreamTile stream_tile(const DmolArgs& A, int64_t tile_id) {
-  StreamTile t;
-  const int64_t b = tile_id / A.chunks;
-  const int64_t t0 = (tile_id - b * A.chunks) * TILE;
-  t.n = static_cast<int>(min(static_cast<int64_t>(TILE), A.T - t0));
-  t.s0 = b * A.T + t0;
+// Position of a tile as (utterance b, chunk c), advanced by the grid stride without a division: the persistent loop used to pay a
+// 64-bit division per thread and tile (~100 instructions, 15 % of a K = 1 tile).  32-bit: the host rejects T >= 2^31 and more than
+// 2^31 - 1 tiles.
+struct TileCursor {
+  unsigned b, c;
+};
+__device__ __forceinline__ TileCursor cursor_at(unsigned tile, unsigned chunks) {
+  TileCursor k;
+  k.b = tile / chunks;
+  k.c = tile - k.b * chunks;
+  return k;
+}
+__device__ __forceinline__ TileCursor cursor_next(TileCursor k, unsigned step_b, unsigned step_c, unsigned chunks) {
+  k.b += step_b;
+  k.c += step_c;
+  if (k.c >= chunks) {
+    k.c -= chunks;
+    ++k.b;
+  }
+  return k;
+}
+__device__ __forceinline__ int row_len(const DmolArgs& A, unsigned b) {
   int64_t len = A.x_sl ? A.x_sl[b] : A.T;
-  len = len < 0 ? 0 : (len > A.T ? A.T : len);
-  t.nvalid = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(t.n), len - t0)));
+  return static_cast<int>(len < 0 ? 0 : (len > A.T ? A.T : len));
+}
+
+template <int TILE>
+__device__ __forceinline__ StreamTile stream_tile(const DmolArgs& A, TileCursor k, int len) {
+  StreamTile t;
+  const int t0 = static_cast<int>(k.c) * TILE;
+  t.n = min(TILE, static_cast<int>(A.T) - t0);
+  t.s0 = static_cast<int64_t>(k.b) * A.T + t0;
+  t.nvalid = max(0, min(t.n, len - t0));
   t.skip = (A.flags & kFlagSkipPadded) && t.nvalid == 0;
   return t;
 }
@@ -84,9 +107,14 @@ __global__ void __launch_bounds__(TPB) dmol_stream_kernel(const DmolArgs A, cons
 
   // producer: arm the stage's barrier and start the two bulk loads of tile `it` (a fully padded tile under
   // kFlagSkipPadded is not read: the barrier still completes its phase so that the parity bookkeeping stays uniform)
+  const unsigned chunks32 = static_cast<unsigned>(A.chunks);
+  const unsigned step_b = static_cast<unsigned>(stride) / chunks32, step_c = static_cast<unsigned>(stride) - step_b * chunks32;
   int st_issue = 0;   // thread 0 only: ring position of the next load
-  auto issue = [&](int64_t it) {
-    const StreamTile t = stream_tile<TILE>(A, first + it * stride);
+  TileCursor pcur = cursor_at(static_cast<unsigned>(first), chunks32);   // thread 0 only: the next tile to load
+  auto issue = [&]() {
+    // the row length only matters to the producer when fully padded tiles are skipped (otherwise every tile is read)
+    const StreamTile t = stream_tile<TILE>(A, pcur, (A.flags & kFlagSkipPadded) ? row_len(A, pcur.b) : static_cast<int>(A.T));
+    pcur = cursor_next(pcur, step_b, step_c, chunks32);
     const int st = st_issue;
     st_issue = (st_issue + 1 == STAGES) ? 0 : st_issue + 1;
     unsigned char* base = smem + L::kStage * st;
@@ -104,22 +132,30 @@ __global__ void __launch_bounds__(TPB) dmol_stream_kernel(const DmolArgs A, cons
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) ptx::mbar_init(full + s, 1);
     ptx::fence_mbar_init();
-    for (int64_t it = 0; it < LOOKAHEAD && it < count; ++it) issue(it);
+    for (int64_t it = 0; it < LOOKAHEAD && it < count; ++it) issue();
   }
   __syncthreads();
 
   int st = 0;
   uint32_t parity = 0;
+  TileCursor cur = cursor_at(static_cast<unsigned>(first), chunks32);
+  int len_next = row_len(A, cur.b);
   for (int64_t it = 0; it < count; ++it) {
-    const int64_t tile_id = first + it * stride;
-    const StreamTile t = stream_tile<TILE>(A, tile_id);
+    // the row length of the NEXT tile is requested now and used one iteration later: its load latency used to sit in front of the
+    // interior / tail decision of every tile
+    const int len = len_next;
+    const TileCursor nxt = cursor_next(cur, step_b, step_c, chunks32);
+    if (it + 1 < count) len_next = row_len(A, nxt.b);
+    const StreamTile t = stream_tile<TILE>(A, cur, len);
+    const int64_t tile_id = static_cast<int64_t>(cur.b) * A.chunks + cur.c;
+    cur = nxt;
     TP* tile = reinterpret_cast<TP*>(smem + L::kStage * st);
     const float* ytile = reinterpret_cast<const float*>(smem + L::kStage * st + L::kSlab);
 
     if (tid == 0 && it + LOOKAHEAD < count) {
       // the target stage was last used by tile it+LOOKAHEAD-STAGES; STAGES-LOOKAHEAD-1 younger stores may still be reading
       if (GRAD) bulk_wait_read_n<STAGES - LOOKAHEAD - 1>();
-      issue(it + LOOKAHEAD);
+      issue();
     }
     ptx::mbar_wait(full + st, parity);
 

@@ -114,6 +114,12 @@ class SumsExchange:
     landed a whole step ago, so this never stalls, and it bounds the skew between ranks, which makes the 4-deep slot ring
     safe.  `consume(lag=0)` (a one-warp kernel) fetches the sums of the latest step, e.g. after the last step of an
     epoch.  All state is on the device: the calls can be captured in a CUDA graph.
+
+    Contract: every rank issues the SAME number of steps with `exchange=ex` (like any collective).  A rank that runs ahead of a peer
+    that has stopped waits in its finalize kernel for that peer's previous-step slot, gives up after ~10 s, sets bit 0 of `self.err`
+    and leaves `global_sums` incomplete; nothing on the host notices by itself, so call `check()` (one sync) wherever the global
+    sums are read on the host, e.g. once per logging interval / at the end of an epoch (bench.py does, after the timed region).
+    With an uneven last batch, run that step without `exchange=` and use `all_reduce_sums` instead.
     """
 
     def __init__(self, group=None, device=None):
