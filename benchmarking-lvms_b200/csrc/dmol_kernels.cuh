@@ -320,19 +320,15 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
   const int t0 = static_cast<int>(c) * TILE;
   const int n = min(TILE, T32 - t0);                    // samples of this tile
   const int64_t s0 = static_cast<int64_t>(b) * A.T + t0;   // first flat sample
-  int64_t len64 = A.x_sl ? A.x_sl[b] : A.T;
-  const int len = static_cast<int>(len64 < 0 ? 0 : (len64 > A.T ? A.T : len64));
-  const int nvalid = max(0, min(n, len - t0));
-
   const TP* gsrc = static_cast<const TP*>(A.raw) + s0 * P;
   TP* gdst = GRAD ? static_cast<TP*>(A.graw) + s0 * P : nullptr;
   const uint32_t bytes = static_cast<uint32_t>(n) * P * sizeof(TP);
-  const bool skip = (A.flags & kFlagSkipPadded) && nvalid == 0;
   const bool bulk_in = ((reinterpret_cast<uintptr_t>(gsrc) | bytes) & 15u) == 0;
   const bool bulk_out = GRAD && ((reinterpret_cast<uintptr_t>(gdst) | bytes) & 15u) == 0;
   const uint64_t pol = ptx::policy_evict_first();
-
-  if (!skip) {
+  // (K > 12 runs at its register cap with spills: there the early request costs more than it hides -- K = 30 bf16 324 -> 344 us)
+  const bool late_load = K > 12 || (A.flags & kFlagSkipPadded) != 0;
+  auto start_load = [&]() {
     if (bulk_in) {
       if (tid == 0) {
         ptx::mbar_init(bar, 1);
@@ -343,9 +339,31 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
     } else {  // unaligned slab (odd T with even K, or an offset view): coalesced element-wise loads
       for (int i = tid; i < n * P; i += TPB) tile[i] = gsrc[i];
     }
+  };
+  // Unless fully padded tiles are to be skipped, the slab is requested BEFORE the row length is read: the x_sl load (a dependent
+  // global access, ~0.4 us) otherwise sits in front of every CTA's bulk copy.
+  // sample j of this thread is tile-local index j*TPB + tid: coalesced y / log-prob accesses, conflict-free smem rows
+  float yv[SPT];
+  auto load_y = [&]() {   // in flight while the slab lands
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const int i = j * TPB + tid;
+      yv[j] = (i < n) ? ptx::ldg_stream(A.y + s0 + i) : 0.f;
+    }
+  };
+  if (!late_load) {
+    start_load();
+    load_y();
+  }
+  int64_t len64 = A.x_sl ? A.x_sl[b] : A.T;
+  const int len = static_cast<int>(len64 < 0 ? 0 : (len64 > A.T ? A.T : len64));
+  const int nvalid = max(0, min(n, len - t0));
+  const bool skip = (A.flags & kFlagSkipPadded) && nvalid == 0;
+  if (late_load) {
+    if (!skip) start_load();
+    load_y();
   }
 
-  // sample j of this thread is tile-local index j*TPB + tid: coalesced y / log-prob accesses, conflict-free smem rows
   float gs = A.gscale;
   if (GRAD && A.gscale_dev) gs *= static_cast<float>(*A.gscale_dev);
   double acc = 0.0;
@@ -354,9 +372,6 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
   // (K > 12 runs at the 128-register cap: a second copy of the sample body costs more in spills than the tests it saves)
   const bool interior = (K <= 12) && !skip && n == TILE && nvalid == TILE && A.gout == nullptr;
   if (interior) {
-    float yv[SPT];
-#pragma unroll
-    for (int j = 0; j < SPT; ++j) yv[j] = ptx::ldg_stream(A.y + s0 + j * TPB + tid);   // in flight while the slab lands
     __syncthreads();  // mbarrier init / plain loads visible to everyone
     if (bulk_in) ptx::mbar_wait(bar, 0);
     bool bad = false;
@@ -374,14 +389,12 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
     }
     if (LIK == kLikDmol && bad && A.err_flag) atomicOr(A.err_flag, 1);
   } else {
-    float yv[SPT], g[SPT];
+    float g[SPT];
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       const int i = j * TPB + tid;
-      yv[j] = 0.f;
       g[j] = 0.f;
       if (i < n) {
-        yv[j] = ptx::ldg_stream(A.y + s0 + i);
         if (LIK == kLikDmol && !(yv[j] <= 1.0f && yv[j] >= -1.0f) && A.err_flag) atomicOr(A.err_flag, 1);
         if (GRAD) {
           g[j] = (i < nvalid) ? gs : 0.f;

@@ -71,10 +71,12 @@ __device__ __forceinline__ TileCursor cursor_next(TileCursor k, unsigned step_b,
   }
   return k;
 }
-__device__ __forceinline__ int row_len(const DmolArgs& A, unsigned b) {
-  int64_t len = A.x_sl ? A.x_sl[b] : A.T;
+// the load and the clamp are separate so that a prefetched length is not touched (= waited for) before it is needed
+__device__ __forceinline__ int64_t row_len_raw(const DmolArgs& A, unsigned b) { return A.x_sl ? A.x_sl[b] : A.T; }
+__device__ __forceinline__ int row_len_clamp(const DmolArgs& A, int64_t len) {
   return static_cast<int>(len < 0 ? 0 : (len > A.T ? A.T : len));
 }
+__device__ __forceinline__ int row_len(const DmolArgs& A, unsigned b) { return row_len_clamp(A, row_len_raw(A, b)); }
 
 template <int TILE>
 __device__ __forceinline__ StreamTile stream_tile(const DmolArgs& A, TileCursor k, int len) {
@@ -139,13 +141,13 @@ __global__ void __launch_bounds__(TPB) dmol_stream_kernel(const DmolArgs A, cons
   int st = 0;
   uint32_t parity = 0;
   TileCursor cur = cursor_at(static_cast<unsigned>(first), chunks32);
-  int len_next = row_len(A, cur.b);
+  int64_t len_next = row_len_raw(A, cur.b);
   for (int64_t it = 0; it < count; ++it) {
     // the row length of the NEXT tile is requested now and used one iteration later: its load latency used to sit in front of the
     // interior / tail decision of every tile
-    const int len = len_next;
+    const int len = row_len_clamp(A, len_next);
     const TileCursor nxt = cursor_next(cur, step_b, step_c, chunks32);
-    if (it + 1 < count) len_next = row_len(A, nxt.b);
+    if (it + 1 < count) len_next = row_len_raw(A, nxt.b);
     const StreamTile t = stream_tile<TILE>(A, cur, len);
     const int64_t tile_id = static_cast<int64_t>(cur.b) * A.chunks + cur.c;
     cur = nxt;

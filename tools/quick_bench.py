@@ -21,7 +21,14 @@ def timeit(fn, iters=20, warm=5):
         b.record()
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) for a, b in evs)
-    return ts[len(ts) // 2], ts[0]
+    # back-to-back launches between ONE event pair (what bench.py reports): no per-launch event / idle-gap overhead
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters, ts[0]
 
 
 def main():
@@ -59,14 +66,14 @@ def main():
         g = -1.0 / float(x_sl.sum())
         med, best = timeit(lambda: ops._dmol_call(y, raw, x_dev, None, g, B, T, K, 1, nb, -7.0, 1, lp, graw, part))
         byt = N * (8 + 6 * K * esz)
-        print(f"K={K:2d} {dtn:8s} dmol fwd+grad: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
+        print(f"K={K:2d} {dtn:8s} dmol fwd+grad: {med * 1e3:8.1f} us loop ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
               f"{byt / med / 1e6:7.0f} GB/s algorithmic")
         med, best = timeit(lambda: ops._dmol_call(y, raw, x_dev, None, 0.0, B, T, K, 1, nb, -7.0, 1, lp, None, part))
         byt = N * (8 + 3 * K * esz)
-        print(f"K={K:2d} {dtn:8s} dmol fwd only: {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
+        print(f"K={K:2d} {dtn:8s} dmol fwd only: {med * 1e3:8.1f} us loop ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
               f"{byt / med / 1e6:7.0f} GB/s algorithmic")
         med, best = timeit(lambda: ops.dmol_sample_mode(raw, K, 1, -7.0))
-        print(f"K={K:2d} {dtn:8s} sample+mode  : {med * 1e3:8.1f} us median ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
+        print(f"K={K:2d} {dtn:8s} sample+mode  : {med * 1e3:8.1f} us loop ({best * 1e3:.1f} best)  {N / med / 1e6:7.2f} Gsamples/s  "
               f"{N * (3 * K * esz + 12) / med / 1e6:7.0f} GB/s if every parameter byte were read")
         del raw, graw
     # single discretized logistic (DiscretizedLogisticDense): packed (B, T, 2)
@@ -79,9 +86,9 @@ def main():
     g2 = torch.empty_like(raw2)
     part = torch.empty(B * int(blvm_b200._lib.lib.blvm_dl_chunks(T)), dtype=torch.float64, device=dev)
     med, best = timeit(lambda: ops._dl_call(y, raw2, x_dev, None, -1e-6, B, T, nb, -7.0, 1, lp, g2, part))
-    print(f"DL fwd+grad: {med * 1e3:8.1f} us median; {B * T * 24 / med / 1e6:7.0f} GB/s algorithmic")
+    print(f"DL fwd+grad: {med * 1e3:8.1f} us loop; {B * T * 24 / med / 1e6:7.0f} GB/s algorithmic")
     med, best = timeit(lambda: ops._dl_call(y, raw2, x_dev, None, 0.0, B, T, nb, -7.0, 1, lp, None, part))
-    print(f"DL fwd only: {med * 1e3:8.1f} us median; {B * T * 16 / med / 1e6:7.0f} GB/s algorithmic")
+    print(f"DL fwd only: {med * 1e3:8.1f} us loop; {B * T * 16 / med / 1e6:7.0f} GB/s algorithmic")
     # KL fused
     S, Z = 64, 64
     Tz = T // S
@@ -97,7 +104,7 @@ def main():
 
     med, best = timeit(kl_step)
     L = B * Tz * Z
-    print(f"KL fused (+finalize, python): {med * 1e3:.1f} us median; {32 * L / med / 1e6:.0f} GB/s algorithmic (L={L})")
+    print(f"KL fused (+finalize, python): {med * 1e3:.1f} us loop; {32 * L / med / 1e6:.0f} GB/s algorithmic (L={L})")
 
 
 if __name__ == "__main__":
