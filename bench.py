@@ -622,6 +622,11 @@ def fused_head_record(dev, B, T, K, peak, iters=20):
         e1.record()
         torch.cuda.synchronize()
         eager_us = e0.elapsed_time(e1) / iters * 1e3
+        # the last eager result keeps its autograd graph (and the leaves' gradient accumulators, bound to the stream they were created
+        # on: here the legacy default stream) alive; a capture that reuses them fails with cudaErrorStreamCaptureImplicit
+        del r
+        x.grad = None
+        lik.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             r = step()
