@@ -49,6 +49,12 @@ struct DmolConsts {
   float log_half_bins2;     // log2(num_bins/2)
   float neg_log_ratio2;     // -log2(num_bins/(num_bins-1)) = -[log(2h) + log(nb/2)] log2(e): first arm minus second arm at u = 0
   float log_delta_thresh2;  // log2(float(1e-5))
+  // linear-domain constants of dl_mid_pair_lin
+  float two_h;          // 2/(num_bins-1): the bin width of the first arm                 log_likelihoods.py:206-210
+  float fb;             // 2/num_bins: exp(-log(num_bins/2)), the factor of the second arm  :222
+  float fd0;            // two_h - fb = 2/(num_bins (num_bins-1)), formed in double
+  float neg_two_h_sixth;  // -two_h/6
+  float neg_h2;         // -h^2
 };
 
 // Host build (tests/hostsim): libm stands in for the MUFU unit.  With -DBLVM_HOSTSIM_MUFU_BITS=n the result is degraded
@@ -288,6 +294,22 @@ BLVM_HD F2 rcp_2(F2 a) { return F2{fast_rcp(a.x), fast_rcp(a.y)}; }
 //    restores the compensated evaluation).
 // Out: lp2 (log2 units); if GRAD, dmu = d lp/d loc and dls = d lp/d raw_log_scale in natural units.
 constexpr float kInvLn2Sixth = kLog2e / 6.0f;
+// single roundings the compiler may not contract into an FMA (results must not depend on which kernel inlines the code)
+BLVM_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+BLVM_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+
 // max(x, lo) that keeps a NaN x (torch.clamp(min=) propagates NaN; fmaxf would drop it): one FMNMX.NAN
 BLVM_HD float max_keep_nan(float x, float lo) {
 #if defined(__CUDA_ARCH__)
@@ -659,6 +681,147 @@ BLVM_HD float dmol_sample(float y, float (&r)[3 * K], float g, const DmolConsts&
     }
   }
   return L;
+}
+
+// ---- linear-domain evaluation (16-bit kernels are bound by the MUFU unit and by issue slots) ------------------------------------------
+// dmol_sample carries log-probabilities: per (sample, component) that costs log2(1+E) for log_pdf_mid and exp2(lp + w - max) for the
+// responsibility, 2 of its 6.4 transcendentals, plus the max chain.  But the likelihood of a component is a PRODUCT of factors the
+// evaluation has anyway:
+//   first arm   cdf_delta            = 2 E sinh(u) / D = [exp(-ls) E/(1+E)^2] * 2h (1 + u^2/6 - eps)      (O(u^4) ~ 1e-8 dropped)
+//   second arm  exp(log_pdf_mid)/(nb/2) = [exp(-ls) E/(1+E)^2] * 2/nb                                         log_likelihoods.py:219-223
+// so  p(y) = sum_k softmax_k lik_k  is formed directly: 4.4 transcendentals per component, no max chain, and the selection
+// `cdf_delta > 1e-5` compares the quantity the reference compares.  What the product cannot do is represent a sample that is more
+// than ~55 scales away from EVERY component (all E underflow; the log-domain value is still finite): dmol_sample_lin then
+// returns false -- also for NaN / inf parameters and for the two edge bins -- and the caller re-reads the row and evaluates it with
+// dmol_sample.  Gradient formulas are those of dl_mid_pair_tiny.
+#ifndef BLVM_LINEAR_DOMAIN
+#define BLVM_LINEAR_DOMAIN 1
+#endif
+constexpr float kLinMinSum = 1e-25f;   // below this the mixture sum has lost components to underflow (FLT_MIN 1.2e-38)
+constexpr float kLinMaxSum = 1e30f;
+
+template <bool GRAD>
+BLVM_HD void dl_mid_pair_lin(F2 y, F2 mu, F2 raw_ls, const DmolConsts& C, F2& lik, F2& dmu, F2& dls) {
+  const F2 ls = f2(max_keep_nan(raw_ls.x, C.log_eps), max_keep_nan(raw_ls.y, C.log_eps));   // clamp(min): NaN propagates like torch
+  const F2 inv = ex2_2(mul2(ls, f2(-kLog2e)));                    // exp(-log_scale)            :203
+  const F2 m = mul2(inv, fma2(mu, f2(-1.f), y));                  // mid_in                     :202,219
+  const F2 nu2 = mul2(mul2(inv, inv), f2(C.neg_h2));              // -u^2, u = h / s
+  const F2 am = abs2(m);
+  const F2 E = ex2_2(mul2(am, f2(-kLog2e)));                      // exp(-|m|)
+  const F2 r = rcp_2(add2(E, f2(1.f)));                           // 1/(1+E)
+  const F2 Er = mul2(E, r);                                       // E / (1+E)
+  const F2 er2 = mul2(Er, r);                                     // E / (1+E)^2
+  const F2 base = mul2(inv, er2);                                 // exp(log_pdf_mid)
+  const F2 neps = mul2(er2, nu2);                                 // -E w / (1+E)^2,  w = u^2 + O(u^4)
+  const F2 fd = fma2(neps, f2(C.two_h), fma2(nu2, f2(C.neg_two_h_sixth), f2(C.fd0)));   // 2h (1 + u^2/6 - eps) - 2/nb
+  const F2 la = mul2(base, add2(fd, f2(C.fb)));                   // cdf_delta, first arm of :221-223
+  const F2 sel = f2(la.x > kDeltaThresh ? 1.f : 0.f, la.y > kDeltaThresh ? 1.f : 0.f);   // one FSET.BF per lane
+  lik = mul2(base, fma2(sel, fd, f2(C.fb)));
+  if (GRAD) {
+    const F2 hx = mul2(am, f2(0.5f)), hx2 = mul2(hx, hx);
+    const F2 th_series = mul2(hx, fma2(hx2, fma2(hx2, f2(2.0f / 15.0f), f2(-1.0f / 3.0f)), f2(1.0f)));
+    const F2 th_exact = fma2(Er, f2(-2.f), f2(1.f));              // (1-E)/(1+E) = tanh(|m|/2)
+    const F2 th = f2(am.x < 0.25f ? th_series.x : th_exact.x, am.y < 0.25f ? th_series.y : th_exact.y);
+    const F2 th_sel = fma2(mul2(sel, neps), th, th);              // th / (1 + eps) on the first arm, th on the second
+    const F2 c = fma2(mul2(sel, nu2), fma2(er2, f2(-2.0f), f2(1.0f / 3.0f)), f2(-1.0f));   // -(u coth(u) - u cdf_delta)  resp.  -1
+    const F2 gate = f2(raw_ls.x >= C.log_eps ? 1.f : 0.f, raw_ls.y >= C.log_eps ? 1.f : 0.f);
+    const F2 it = mul2(inv, th_sel);
+    dmu = f2(copysignf(it.x, m.x), copysignf(it.y, m.y));         // -inv * d lp/d m
+    dls = mul2(fma2(am, th_sel, c), gate);
+  }
+}
+
+// One sample, K >= 2 components, 16-bit-audio mode (kUTiny).  Same in / out convention as dmol_sample; returns false -- with r[]
+// clobbered -- when the sample has to be evaluated in the log domain instead (see above).
+template <int K, bool GRAD>
+BLVM_HD bool dmol_sample_lin(float y, float (&r)[3 * K], float g, const DmolConsts& C, float& L) {
+  static_assert(K >= 2, "one component has no mixture algebra to save");
+  if (dmol_edge(y, C) != kEdgeNone) return false;
+  float m2 = r[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) m2 = fmaxf(m2, r[k]);
+  const float nm2 = -m2 * kLog2e;
+  float n[K];   // softmax numerator times component likelihood
+  F2 s1p = f2(0.f), s2p = f2(0.f);
+  constexpr int KP = (K / 2) * 2;
+#pragma unroll
+  for (int k = 0; k < KP; k += 2) {
+    const F2 ew = ex2_2(fma2(f2(r[k], r[k + 1]), f2(kLog2e), f2(nm2)));   // exp(logit_k - max logit)
+    F2 lik, dmu = f2(0.f), dls = f2(0.f);
+    dl_mid_pair_lin<GRAD>(f2(y), f2(r[K + k], r[K + k + 1]), f2(r[2 * K + k], r[2 * K + k + 1]), C, lik, dmu, dls);
+    const F2 nk = mul2(ew, lik);
+    s1p = fma2(ew, lik, s1p);   // explicitly fused: ptxas contracts a packed mul + add into FFMA2 in some instantiations and not in others
+    s2p = add2(s2p, ew);
+    r[k] = ew.x; r[k + 1] = ew.y;
+    n[k] = nk.x; n[k + 1] = nk.y;
+    if (GRAD) {
+      r[K + k] = dmu.x; r[K + k + 1] = dmu.y;
+      r[2 * K + k] = dls.x; r[2 * K + k + 1] = dls.y;
+    }
+  }
+  float s1 = add_rn(s1p.x, s1p.y), s2 = add_rn(s2p.x, s2p.y);
+  if constexpr (KP < K) {   // leftover component (odd K): the pair function with its lane duplicated
+    constexpr int k = K - 1;
+    const float ew = fast_ex2(fmaf(r[k], kLog2e, nm2));
+    F2 lik, dmu = f2(0.f), dls = f2(0.f);
+    dl_mid_pair_lin<GRAD>(f2(y), f2(r[K + k]), f2(r[2 * K + k]), C, lik, dmu, dls);
+    n[k] = mul_rn(ew, lik.x);   // explicit roundings: every kernel that inlines this must produce the same bits
+    s1 = fmaf(ew, lik.x, s1);
+    s2 = add_rn(s2, ew);
+    r[k] = ew;
+    if (GRAD) {
+      r[K + k] = dmu.x;
+      r[2 * K + k] = dls.x;
+    }
+  }
+  if (!(s1 > kLinMinSum && s1 < kLinMaxSum && s2 < kLinMaxSum)) return false;   // underflow, inf or NaN: log domain
+  L = mul_rn(kLn2, add_rn(fast_lg2(s1), -fast_lg2(s2)));
+  if (GRAD) {
+    const float g1 = mul_rn(g, fast_rcp(s1)), g2 = mul_rn(g, fast_rcp(s2));
+    if constexpr (K % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < K; k += 2) {
+        const F2 gr = mul2(f2(g1), f2(n[k], n[k + 1]));                     // g * responsibility_k
+        const F2 gl = fma2(f2(-g2), f2(r[k], r[k + 1]), gr);                // g * (resp_k - softmax_k)
+        const F2 gm = mul2(f2(r[K + k], r[K + k + 1]), gr);
+        const F2 gs = mul2(f2(r[2 * K + k], r[2 * K + k + 1]), gr);
+        r[k] = gl.x; r[k + 1] = gl.y;
+        r[K + k] = gm.x; r[K + k + 1] = gm.y;
+        r[2 * K + k] = gs.x; r[2 * K + k + 1] = gs.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float gr = mul_rn(g1, n[k]);
+        r[k] = fmaf(-g2, r[k], gr);
+        r[K + k] = mul_rn(r[K + k], gr);
+        r[2 * K + k] = mul_rn(r[2 * K + k], gr);
+      }
+    }
+  }
+  return true;
+}
+
+// The evaluation the kernels call: linear domain where it applies, log domain otherwise.  `reload(r)` re-reads the sample's parameter
+// row (shared memory / tensor memory / the caller's copy) after a failed linear-domain attempt.
+template <int K, bool GRAD, int UMODE, int LIK>
+struct DmolEvalTraits {
+  // K > 12 runs at its register cap: the second copy of the sample body (the log-domain fallback) spills there (K = 16 fp32 239 -> 328 us)
+  static constexpr bool kLin = BLVM_LINEAR_DOMAIN && K >= 2 && K <= 12 && UMODE == kUTiny && LIK == kLikDmol;
+};
+// The evaluation the kernels call.  LIN (chosen by the kernel, see DmolEvalTraits) tries the linear domain first; a sample it
+// cannot represent is re-read through `reload(r)` (shared memory / the caller's copy) and evaluated by dmol_sample.  Measured
+// alternatives for the fallback, all slower on the hot path: a __noinline__ call (calling-convention spills around the call site: bf16
+// K = 10 84.5 -> 90.8 us) and the rolled generic evaluation on a local-memory copy (slow whenever it is taken: K = 2 44 -> 80 us on the
+// bench's synthetic parameters, where 2 % of the samples are far from both components).
+template <int K, bool GRAD, int UMODE, int LIK, bool LIN, typename Reload>
+BLVM_HD float dmol_eval(float y, float (&r)[3 * K], float g, const DmolConsts& C, Reload&& reload) {
+  if constexpr (LIN && DmolEvalTraits<K, GRAD, UMODE, LIK>::kLin) {
+    float L;
+    if (dmol_sample_lin<K, GRAD>(y, r, g, C, L)) return L;
+    reload(r);
+  }
+  return dmol_sample<K, GRAD, UMODE, LIK>(y, r, g, C);
 }
 
 // K == 1 (a single discretized logistic with a dead logit column), 16-bit-audio mode: two SAMPLES of one thread evaluated

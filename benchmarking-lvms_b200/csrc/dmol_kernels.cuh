@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "blvm_math.cuh"
 #include "ptx_sm100.cuh"
 
@@ -106,12 +108,12 @@ struct Pair16;
 template <>
 struct Pair16<__half> {
   static __device__ __forceinline__ void unpack(uint32_t w, float& a, float& b) {
-    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w));
-    a = v.x; b = v.y;
+    asm("{\n.reg .f16 lo, hi;\nmov.b32 {lo, hi}, %2;\ncvt.f32.f16 %0, lo;\ncvt.f32.f16 %1, hi;\n}" : "=f"(a), "=f"(b) : "r"(w));
   }
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
+    uint32_t w;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));   // first source -> upper half
+    return w;
   }
 };
 template <>
@@ -263,9 +265,10 @@ struct DmolSpt {
                           // 79 and K = 10 fwd+grad drops from 156 to 162 us).  The forward-only kernels are left uncapped:
                           // K = 10 fwd 98.7 us capped, 86.3 us (6.07 TB/s) uncapped.
 #endif
-template <int K, bool GRAD = true>
+template <int K, bool GRAD = true, typename TP = float>
 struct DmolMinBlocks {
-  static constexpr int value = K > 20 ? BLVM_MINB_BIGK : (K > 16 ? BLVM_MINB_K20 : (K > 12 ? BLVM_MINB_K16 : ((K > 8 && GRAD) ? BLVM_MINB_MIDK : 0)));   // 0 = no constraint
+  static constexpr int mid = BLVM_MINB_MIDK;
+  static constexpr int value = K > 20 ? BLVM_MINB_BIGK : (K > 16 ? BLVM_MINB_K20 : (K > 12 ? BLVM_MINB_K16 : ((K > 8 && GRAD) ? mid : 0)));   // 0 = no constraint
 };
 
 // Chunks per CTA of the tile kernel.  The partial-sum layout (one fp64 per chunk of 128 * DmolSpt<K> samples, what
@@ -288,6 +291,14 @@ struct DmolGroup {
   // per SM either way) 320 -> 357 us: long serialised load / evaluate / store phases with too few CTAs to overlap them)
   static constexpr int value = (K > 5 && size_t(128) * DmolSpt<K>::value * want * 3 * K * sizeof(TP) <= 32 * 1024) ? want : 1;
 };
+
+// Linear-domain evaluation (blvm_math.cuh: dmol_sample_lin) pays where the kernel is bound by the MUFU unit and by issue slots: 16-bit
+// parameters.  The fp32 kernels are HBM-bound and keep the single log-domain body (64 registers, no second copy of the sample code).
+// fp16, 8 < K <= 12: next to the second (log-domain) copy of the sample body the compiler keeps the whole converted row live -- a bf16
+// element is rematerialised from its packed word by one shift, an fp16 element is not -- and spills 136 bytes at 64 registers (72 at 72):
+// K = 10 93.4 us (no gain over 94.5), K = 12 138 us (117 before).  Those two keep the log-domain body.
+template <typename TP, int K>
+constexpr bool kLinTP = sizeof(TP) == 2 && !(std::is_same<TP, __half>::value && K > 8);
 
 template <int K, int TPB, typename TP>
 constexpr size_t dmol_tile_smem_bytes() {
@@ -382,7 +393,9 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
       float r[P];
       TP* row = tile + i * P;
       if constexpr (kRot) RowRot<TP, K>::load(row, r, rot); else RowIO<TP, P>::load(row, r);
-      const float L = dmol_sample<K, GRAD, UMODE, LIK>(yv[j], r, gs, A.C);
+      const float L = dmol_eval<K, GRAD, UMODE, LIK, kLinTP<TP, K>>(yv[j], r, gs, A.C, [&](float (&rr)[P]) {
+        if constexpr (kRot) RowRot<TP, K>::load(row, rr, rot); else RowIO<TP, P>::load(row, rr);
+      });
       if constexpr (kRot) { if (GRAD) RowRot<TP, K>::store(row, r, rot); } else { if (GRAD) RowIO<TP, P>::store(row, r); }
       if (A.lp) A.lp[s0 + i] = L;
       acc += static_cast<double>(L);
@@ -414,7 +427,9 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
         TP* row = tile + i * P;
         if (!skip) {
           if constexpr (kRot) RowRot<TP, K>::load(row, r, rot); else RowIO<TP, P>::load(row, r);
-          L = dmol_sample<K, GRAD, UMODE, LIK>(yv[j], r, g[j], A.C);
+          L = dmol_eval<K, GRAD, UMODE, LIK, kLinTP<TP, K>>(yv[j], r, g[j], A.C, [&](float (&rr)[P]) {
+            if constexpr (kRot) RowRot<TP, K>::load(row, rr, rot); else RowIO<TP, P>::load(row, rr);
+          });
         } else {
 #pragma unroll
           for (int q = 0; q < P; ++q) r[q] = 0.f;
@@ -458,7 +473,7 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
 }
 
 template <int K, int TPB, bool GRAD, int UMODE, typename TP, int LIK = kLikDmol>
-__global__ void __launch_bounds__(TPB, DmolMinBlocks<K, GRAD>::value) dmol_tile_kernel(const DmolArgs A) {
+__global__ void __launch_bounds__(TPB, DmolMinBlocks<K, GRAD, TP>::value) dmol_tile_kernel(const DmolArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   ptx::pdl_launch_dependents();   // a KL / finalize launch of the same step may fill this grid's tail (they wait for us to finish)
   const bool pending = dmol_tile_body<K, TPB, GRAD, UMODE, TP, LIK>(A, blockIdx.x, smem);

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(TPB) dmol_stream_kernel(const DmolArgs A, cons
           float r[P];
           TP* row = tile + i * P;
           RowIO<TP, P>::load(row, r);
-          const float Lv = dmol_sample<K, GRAD, UMODE, LIK>(yv, r, gs, A.C);
+          const float Lv = dmol_eval<K, GRAD, UMODE, LIK, kLinTP<TP, K>>(yv, r, gs, A.C, [&](float (&rr)[P]) { RowIO<TP, P>::load(row, rr); });
           if (GRAD) RowIO<TP, P>::store(row, r);
           if (A.lp) A.lp[t.s0 + i] = Lv;
           acc += static_cast<double>(Lv);
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(TPB) dmol_stream_kernel(const DmolArgs A, cons
               if (A.gout) g *= ptx::ldg_stream(A.gout + t.s0 + i);
             }
             RowIO<TP, P>::load(row, r);
-            Lv = dmol_sample<K, GRAD, UMODE, LIK>(yv, r, g, A.C);
+            Lv = dmol_eval<K, GRAD, UMODE, LIK, kLinTP<TP, K>>(yv, r, g, A.C, [&](float (&rr)[P]) { RowIO<TP, P>::load(row, rr); });
           } else {
 #pragma unroll
             for (int q = 0; q < P; ++q) r[q] = 0.f;

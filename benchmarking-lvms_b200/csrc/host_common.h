@@ -38,6 +38,12 @@ inline blvm::DmolConsts make_consts(int num_bins, float log_epsilon) {
   C.log_half_bins2 = static_cast<float>(log(num_bins / 2.0) * log2e);
   C.neg_log_ratio2 = static_cast<float>(-log(static_cast<double>(num_bins) / (num_bins - 1)) * log2e);
   C.log_delta_thresh2 = static_cast<float>(log(static_cast<double>(blvm::kDeltaThresh)) * log2e);
+  const double nb = num_bins, two_h = 2.0 / (nb - 1.0);
+  C.two_h = static_cast<float>(two_h);
+  C.fb = static_cast<float>(2.0 / nb);
+  C.fd0 = static_cast<float>(two_h - 2.0 / nb);
+  C.neg_two_h_sixth = static_cast<float>(-two_h / 6.0);
+  C.neg_h2 = static_cast<float>(-1.0 / ((nb - 1.0) * (nb - 1.0)));
   return C;
 }
 

@@ -171,6 +171,10 @@ __device__ __forceinline__ uint32_t cm_off(int i, int j, int cols) {
 #else
 #define BLVM_LINEAR_WAIT(bar, ph) ptx::mbar_wait(bar, ph)
 #endif
+#ifndef BLVM_LINEAR_HEAD_LIN
+#define BLVM_LINEAR_HEAD_LIN 0   // linear-domain sample evaluation in the fused head: 151 -> 143 us when no sample needs the log-domain
+                                 // fallback, 164 us when most do (random weights); off: the head keeps one body
+#endif
 #ifndef BLVM_LINEAR_MINB
 #define BLVM_LINEAR_MINB 8     // CTAs per SM the register allocation is capped for (DP = 32): 8 -> 64 registers.  Measured (B = 256 x
                                // 16000, x_dim 30, bf16, grid = cap x 148): 5 -> 183.6 us (96 registers), 7 -> 169.6, 8 -> 166.9
@@ -341,7 +345,22 @@ __global__ void __launch_bounds__(128, LinearSmem<DP>::kOutInG ? BLVM_LINEAR_MIN
       float rr[P];
 #pragma unroll
       for (int q = 0; q < P; ++q) rr[q] = r[q];
-      L = dmol_sample<K, GRAD, UMODE>(yv, rr, g, A.C);
+      if constexpr (DmolEvalTraits<K, GRAD, UMODE, kLikDmol>::kLin && BLVM_LINEAR_HEAD_LIN) {
+        // linear-domain evaluation; a sample it cannot represent (blvm_math.cuh) is re-read from tensor memory -- a warp-collective
+        // load, so the whole warp re-reads when any lane needs it -- and evaluated in the log domain
+        const bool ok = dmol_sample_lin<K, GRAD>(yv, rr, g, A.C, L);
+        if (__any_sync(0xffffffffu, !ok)) {
+          float r2[32];
+          tc::ld_row32(t_raw + lane_base, r2);
+          if (!ok) {
+#pragma unroll
+            for (int q = 0; q < P; ++q) rr[q] = r2[q];
+            L = dmol_sample<K, GRAD, UMODE>(yv, rr, g, A.C);
+          }
+        }
+      } else {
+        L = dmol_sample<K, GRAD, UMODE>(yv, rr, g, A.C);
+      }
       if (GRAD) {   // rows beyond the tile / the utterance carry g = 0: their gradient rows are exact zeros already
 #pragma unroll
         for (int q = 0; q < P; ++q) r[q] = rr[q];

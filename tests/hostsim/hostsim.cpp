@@ -21,6 +21,12 @@ static DmolConsts make_consts(int num_bins, float log_eps) {
   C.log_half_bins2 = (float)(std::log(num_bins / 2.0) * log2e);
   C.neg_log_ratio2 = (float)(-std::log((double)num_bins / (num_bins - 1)) * log2e);
   C.log_delta_thresh2 = (float)(std::log((double)kDeltaThresh) * log2e);
+  const double nb = num_bins, two_h = 2.0 / (nb - 1.0);
+  C.two_h = (float)two_h;
+  C.fb = (float)(2.0 / nb);
+  C.fd0 = (float)(two_h - 2.0 / nb);
+  C.neg_two_h_sixth = (float)(-two_h / 6.0);
+  C.neg_h2 = (float)(-1.0 / ((nb - 1.0) * (nb - 1.0)));
   return C;
 }
 
@@ -30,8 +36,12 @@ static void run_fixed(const float* y, const float* raw, const float* gout, int64
   for (int64_t n = 0; n < N; ++n) {
     float r[3 * K];
     for (int i = 0; i < 3 * K; ++i) r[i] = raw[n * 3 * K + i];
-    lp[n] = tiny ? dmol_sample<K, true, kUTiny>(y[n], r, gout ? gout[n] : 1.f, C)
-                 : dmol_sample<K, true, kUGeneral>(y[n], r, gout ? gout[n] : 1.f, C);
+    auto reload = [&](float (&rr)[3 * K]) {
+      for (int i = 0; i < 3 * K; ++i) rr[i] = raw[n * 3 * K + i];
+    };
+    // the evaluation the kernels call (linear domain where it applies, log domain otherwise)
+    lp[n] = tiny ? dmol_eval<K, true, kUTiny, kLikDmol, true>(y[n], r, gout ? gout[n] : 1.f, C, reload)
+                 : dmol_eval<K, true, kUGeneral, kLikDmol, true>(y[n], r, gout ? gout[n] : 1.f, C, reload);
     for (int i = 0; i < 3 * K; ++i) graw[n * 3 * K + i] = r[i];
   }
 }

@@ -451,8 +451,8 @@ def test_no_grad_eval_path(B):
 @pytest.mark.parametrize("K", [10, 5, 30])
 def test_half_precision_parameters(dtype, K, B, O):
     """Under AMP the Linear output arrives in bf16/fp16 and the kernels read it as it is (arithmetic stays fp32): values
-    equal the fp32 call on the same rounded parameters bit for bit, gradients come back in the parameter dtype and match
-    the oracle on the rounded parameters to the dtype's resolution."""
+    equal the fp32 call on the same rounded parameters to the parity tolerance, gradients come back in the parameter dtype and
+    match the oracle on the rounded parameters to the dtype's resolution."""
     rng = np.random.default_rng(K)
     Bn, T, nb = 3, 300, 65536
     y = (rng.integers(0, nb, (Bn, T)) / (nb - 1) * 2 - 1).astype(np.float32)
@@ -465,7 +465,10 @@ def test_half_precision_parameters(dtype, K, B, O):
     with torch.autocast("cuda", dtype=dtype):
         lp_h = lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(raw_h, K, 1, -7.0))
     lp_f = lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(raw_h.float(), K, 1, -7.0))
-    assert lp_h.dtype == torch.float32 and torch.equal(lp_h, lp_f)
+    # same rounded parameters: the 16-bit kernels evaluate the mixture in the linear domain (blvm_math.cuh: dmol_sample_lin), the fp32
+    # kernel in the log domain; both are within the tolerance of the fp64 anchor, hence within 2x of it of each other
+    assert lp_h.dtype == torch.float32
+    assert_values_close(lp_h.cpu().numpy(), lp_f.cpu().numpy().astype(np.float64), "16-bit parameters vs fp32 call on the same values", rtol=2e-5)
     # fused op: loss * scale backward (GradScaler-style), gradient dtype == parameter dtype
     scale = 4096.0
     r = raw_h.clone().requires_grad_(True)
