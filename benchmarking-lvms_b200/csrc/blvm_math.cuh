@@ -733,22 +733,35 @@ BLVM_HD void dl_mid_pair_lin(F2 y, F2 mu, F2 raw_ls, const DmolConsts& C, F2& li
 
 // One sample, K >= 2 components, 16-bit-audio mode (kUTiny).  Same in / out convention as dmol_sample; returns false -- with r[]
 // clobbered -- when the sample has to be evaluated in the log domain instead (see above).
-template <int K, bool GRAD>
-BLVM_HD bool dmol_sample_lin(float y, float (&r)[3 * K], float g, const DmolConsts& C, float& L) {
+// `in` hands out the sample's parameters: RowIn reads them from r[] itself (every element is read before its slot is overwritten), the
+// 16-bit tile kernel passes its packed row so that each pair is converted where it is used (dmol_kernels.cuh: PackedRowIn).
+template <int K>
+struct RowIn {
+  const float* r;
+  BLVM_HD float logit(int k) const { return r[k]; }
+  BLVM_HD F2 logit2(int k) const { return f2(r[k], r[k + 1]); }
+  BLVM_HD F2 mu2(int k) const { return f2(r[K + k], r[K + k + 1]); }
+  BLVM_HD F2 ls2(int k) const { return f2(r[2 * K + k], r[2 * K + k + 1]); }
+  BLVM_HD float mu(int k) const { return r[K + k]; }
+  BLVM_HD float ls(int k) const { return r[2 * K + k]; }
+};
+
+template <int K, bool GRAD, typename In>
+BLVM_HD bool dmol_sample_lin_in(float y, const In& in, float (&r)[3 * K], float g, const DmolConsts& C, float& L) {
   static_assert(K >= 2, "one component has no mixture algebra to save");
   if (dmol_edge(y, C) != kEdgeNone) return false;
-  float m2 = r[0];
+  float m2 = in.logit(0);
 #pragma unroll
-  for (int k = 1; k < K; ++k) m2 = fmaxf(m2, r[k]);
+  for (int k = 1; k < K; ++k) m2 = fmaxf(m2, in.logit(k));
   const float nm2 = -m2 * kLog2e;
   float n[K];   // softmax numerator times component likelihood
   F2 s1p = f2(0.f), s2p = f2(0.f);
   constexpr int KP = (K / 2) * 2;
 #pragma unroll
   for (int k = 0; k < KP; k += 2) {
-    const F2 ew = ex2_2(fma2(f2(r[k], r[k + 1]), f2(kLog2e), f2(nm2)));   // exp(logit_k - max logit)
+    const F2 ew = ex2_2(fma2(in.logit2(k), f2(kLog2e), f2(nm2)));   // exp(logit_k - max logit)
     F2 lik, dmu = f2(0.f), dls = f2(0.f);
-    dl_mid_pair_lin<GRAD>(f2(y), f2(r[K + k], r[K + k + 1]), f2(r[2 * K + k], r[2 * K + k + 1]), C, lik, dmu, dls);
+    dl_mid_pair_lin<GRAD>(f2(y), in.mu2(k), in.ls2(k), C, lik, dmu, dls);
     const F2 nk = mul2(ew, lik);
     s1p = fma2(ew, lik, s1p);   // explicitly fused: ptxas contracts a packed mul + add into FFMA2 in some instantiations and not in others
     s2p = add2(s2p, ew);
@@ -762,9 +775,9 @@ BLVM_HD bool dmol_sample_lin(float y, float (&r)[3 * K], float g, const DmolCons
   float s1 = add_rn(s1p.x, s1p.y), s2 = add_rn(s2p.x, s2p.y);
   if constexpr (KP < K) {   // leftover component (odd K): the pair function with its lane duplicated
     constexpr int k = K - 1;
-    const float ew = fast_ex2(fmaf(r[k], kLog2e, nm2));
+    const float ew = fast_ex2(fmaf(in.logit(k), kLog2e, nm2));
     F2 lik, dmu = f2(0.f), dls = f2(0.f);
-    dl_mid_pair_lin<GRAD>(f2(y), f2(r[K + k]), f2(r[2 * K + k]), C, lik, dmu, dls);
+    dl_mid_pair_lin<GRAD>(f2(y), f2(in.mu(k)), f2(in.ls(k)), C, lik, dmu, dls);
     n[k] = mul_rn(ew, lik.x);   // explicit roundings: every kernel that inlines this must produce the same bits
     s1 = fmaf(ew, lik.x, s1);
     s2 = add_rn(s2, ew);
@@ -800,6 +813,11 @@ BLVM_HD bool dmol_sample_lin(float y, float (&r)[3 * K], float g, const DmolCons
     }
   }
   return true;
+}
+
+template <int K, bool GRAD>
+BLVM_HD bool dmol_sample_lin(float y, float (&r)[3 * K], float g, const DmolConsts& C, float& L) {
+  return dmol_sample_lin_in<K, GRAD>(y, RowIn<K>{r}, r, g, C, L);
 }
 
 // The evaluation the kernels call: linear domain where it applies, log domain otherwise.  `reload(r)` re-reads the sample's parameter

@@ -296,9 +296,65 @@ struct DmolGroup {
 // parameters.  The fp32 kernels are HBM-bound and keep the single log-domain body (64 registers, no second copy of the sample code).
 // fp16, 8 < K <= 12: next to the second (log-domain) copy of the sample body the compiler keeps the whole converted row live -- a bf16
 // element is rematerialised from its packed word by one shift, an fp16 element is not -- and spills 136 bytes at 64 registers (72 at 72):
-// K = 10 93.4 us (no gain over 94.5), K = 12 138 us (117 before).  Those two keep the log-domain body.
+// K = 10 93.4 us (no gain over 94.5), K = 12 138 us (117 before).  K = 10 takes the packed-row variant below (88.8 us), K = 12 keeps the
+// log-domain body.
 template <typename TP, int K>
 constexpr bool kLinTP = sizeof(TP) == 2 && !(std::is_same<TP, __half>::value && K > 8);
+
+// fp16, K = 10 (the reference's mixture size): the row stays PACKED in registers (3K/2 words) and every pair is converted where the evaluation uses it.
+// With the row converted up front the compiler keeps all 3K floats live next to the second (log-domain) body -- a bf16 element is
+// rematerialised from its packed word by one shift, an fp16 element is not -- and spills 136 bytes at 64 registers.
+template <typename TP, int K>
+struct PackedRowIn {
+  static_assert(K % 2 == 0, "pairs must not straddle words");
+  const uint32_t* w;
+  __device__ __forceinline__ F2 pair(int e) const {
+    F2 v;
+    Pair16<TP>::unpack(w[e >> 1], v.x, v.y);
+    return v;
+  }
+  __device__ __forceinline__ float one(int e) const {
+    const F2 v = pair(e & ~1);
+    return (e & 1) ? v.y : v.x;
+  }
+  __device__ __forceinline__ float logit(int k) const { return one(k); }
+  __device__ __forceinline__ F2 logit2(int k) const { return pair(k); }
+  __device__ __forceinline__ F2 mu2(int k) const { return pair(K + k); }
+  __device__ __forceinline__ F2 ls2(int k) const { return pair(2 * K + k); }
+  __device__ __forceinline__ float mu(int k) const { return one(K + k); }
+  __device__ __forceinline__ float ls(int k) const { return one(2 * K + k); }
+};
+template <typename TP, int K>
+constexpr bool kLinPackedTP = std::is_same<TP, __half>::value && K > 8 && K <= 10 && K % 2 == 0 && BLVM_LINEAR_DOMAIN;   // K = 12: 114.7 -> 123.5 us (192 bytes of spills)
+
+// value + gradient of the sample whose 16-bit row starts at `row` (4-byte aligned: 3K even), gradient row written back in place
+template <int K, bool GRAD, int UMODE, typename TP>
+__device__ __forceinline__ float dmol_eval_packed_row(float y, TP* row, float g, const DmolConsts& C) {
+  constexpr int P = 3 * K, NW = P / 2;
+  uint32_t w[NW];
+  constexpr int VW = (P * 2) % 16 == 0 ? 4 : ((P * 2) % 8 == 0 ? 2 : 1);   // words per shared-memory access
+#pragma unroll
+  for (int i = 0; i < NW / VW; ++i) {
+    if constexpr (VW == 4) {
+      const uint4 v = reinterpret_cast<const uint4*>(row)[i];
+      w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    } else if constexpr (VW == 2) {
+      const uint2 v = reinterpret_cast<const uint2*>(row)[i];
+      w[2 * i] = v.x; w[2 * i + 1] = v.y;
+    } else {
+      w[i] = reinterpret_cast<const uint32_t*>(row)[i];
+    }
+  }
+  float r[P];
+  float L;
+  if (!dmol_sample_lin_in<K, GRAD>(y, PackedRowIn<TP, K>{w}, r, g, C, L)) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) Pair16<TP>::unpack(w[i], r[2 * i], r[2 * i + 1]);
+    L = dmol_sample<K, GRAD, UMODE, kLikDmol>(y, r, g, C);
+  }
+  if (GRAD) RowIO<TP, P>::store(row, r);
+  return L;
+}
 
 template <int K, int TPB, typename TP>
 constexpr size_t dmol_tile_smem_bytes() {
@@ -390,13 +446,18 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
     for (int j = 0; j < SPT; ++j) {
       const int i = j * TPB + tid;
       bad |= !(yv[j] <= 1.0f && yv[j] >= -1.0f);
-      float r[P];
       TP* row = tile + i * P;
-      if constexpr (kRot) RowRot<TP, K>::load(row, r, rot); else RowIO<TP, P>::load(row, r);
-      const float L = dmol_eval<K, GRAD, UMODE, LIK, kLinTP<TP, K>>(yv[j], r, gs, A.C, [&](float (&rr)[P]) {
-        if constexpr (kRot) RowRot<TP, K>::load(row, rr, rot); else RowIO<TP, P>::load(row, rr);
-      });
-      if constexpr (kRot) { if (GRAD) RowRot<TP, K>::store(row, r, rot); } else { if (GRAD) RowIO<TP, P>::store(row, r); }
+      float L;
+      if constexpr (kLinPackedTP<TP, K> && UMODE == kUTiny && LIK == kLikDmol) {
+        L = dmol_eval_packed_row<K, GRAD, UMODE, TP>(yv[j], row, gs, A.C);
+      } else {
+        float r[P];
+        if constexpr (kRot) RowRot<TP, K>::load(row, r, rot); else RowIO<TP, P>::load(row, r);
+        L = dmol_eval<K, GRAD, UMODE, LIK, kLinTP<TP, K>>(yv[j], r, gs, A.C, [&](float (&rr)[P]) {
+          if constexpr (kRot) RowRot<TP, K>::load(row, rr, rot); else RowIO<TP, P>::load(row, rr);
+        });
+        if constexpr (kRot) { if (GRAD) RowRot<TP, K>::store(row, r, rot); } else { if (GRAD) RowIO<TP, P>::store(row, r); }
+      }
       if (A.lp) A.lp[s0 + i] = L;
       acc += static_cast<double>(L);
     }
@@ -423,18 +484,27 @@ __device__ __forceinline__ bool dmol_tile_body(const DmolArgs& A, const int64_t 
       const int i = j * TPB + tid;
       if (i < n) {
         float L = 0.f;
-        float r[P];
         TP* row = tile + i * P;
-        if (!skip) {
-          if constexpr (kRot) RowRot<TP, K>::load(row, r, rot); else RowIO<TP, P>::load(row, r);
-          L = dmol_eval<K, GRAD, UMODE, LIK, kLinTP<TP, K>>(yv[j], r, g[j], A.C, [&](float (&rr)[P]) {
-            if constexpr (kRot) RowRot<TP, K>::load(row, rr, rot); else RowIO<TP, P>::load(row, rr);
-          });
-        } else {
+        if constexpr (kLinPackedTP<TP, K> && UMODE == kUTiny && LIK == kLikDmol) {
+          if (!skip) {
+            L = dmol_eval_packed_row<K, GRAD, UMODE, TP>(yv[j], row, g[j], A.C);
+          } else if (GRAD) {
 #pragma unroll
-          for (int q = 0; q < P; ++q) r[q] = 0.f;
+            for (int q = 0; q < P / 2; ++q) reinterpret_cast<uint32_t*>(row)[q] = 0u;
+          }
+        } else {
+          float r[P];
+          if (!skip) {
+            if constexpr (kRot) RowRot<TP, K>::load(row, r, rot); else RowIO<TP, P>::load(row, r);
+            L = dmol_eval<K, GRAD, UMODE, LIK, kLinTP<TP, K>>(yv[j], r, g[j], A.C, [&](float (&rr)[P]) {
+              if constexpr (kRot) RowRot<TP, K>::load(row, rr, rot); else RowIO<TP, P>::load(row, rr);
+            });
+          } else {
+#pragma unroll
+            for (int q = 0; q < P; ++q) r[q] = 0.f;
+          }
+          if constexpr (kRot) { if (GRAD) RowRot<TP, K>::store(row, r, rot); } else { if (GRAD) RowIO<TP, P>::store(row, r); }
         }
-        if constexpr (kRot) { if (GRAD) RowRot<TP, K>::store(row, r, rot); } else { if (GRAD) RowIO<TP, P>::store(row, r); }
         // reference semantics: log_prob * mask (NaN/inf in the padding propagate like `* 0`), vrnn.py:268
         const float Lm = (i < nvalid) ? L : L * 0.0f;
         if (A.lp) A.lp[s0 + i] = (A.flags & kFlagMaskOutput) ? Lm : L;
