@@ -537,6 +537,62 @@ def test_wide_rows_and_rotated_section_walk(K, dtype, B, O):
         assert_values_close(tw[m], lp_h.cpu().numpy()[m], "fused step vs forward-only kernel", rtol=2e-6)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("K", [2, 5, 10])
+def test_linear_domain_fallback(K, dtype, B, O):
+    """The 16-bit kernels evaluate the mixture in the linear domain (dmol_sample_lin) and fall back to the log-domain body for
+    samples the product cannot represent: every component tens to thousands of scales away (all exp(-|m|) underflow), NaN /
+    inf parameters, the two edge bins.  Half of the samples here are such cases; values and gradients against the oracle on the
+    rounded parameters, and non-finite rows exactly like the fp32 (log-domain only) kernel."""
+    rng = np.random.default_rng(7 + K)
+    Bn, T, nb = 2, 1100, 65536
+    y = (rng.integers(0, nb, (Bn, T)) / (nb - 1) * 2 - 1).astype(np.float32)
+    y[0, :8] = np.array([-1.0, 1.0, 2 / nb - 1, 1 - 2 / nb, -1.0, 1.0, 0.0, 0.5], np.float32)     # edge bins and their neighbours
+    raw = rng.normal(size=(Bn, T, 3 * K)).astype(np.float32)
+    raw[..., K:2 * K] = y[..., None] + 0.1 * raw[..., K:2 * K]
+    raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+    far = rng.random((Bn, T)) < 0.5                                   # every component far away with a tiny scale
+    shift = rng.choice([0.05, 0.3, 1.5], size=(Bn, T, K)) * rng.choice([-1.0, 1.0], size=(Bn, T, K))
+    raw[..., K:2 * K] = np.where(far[..., None], y[..., None] + shift, raw[..., K:2 * K])
+    raw[..., 2 * K:] = np.where(far[..., None], rng.uniform(-9.0, -5.5, (Bn, T, K)), raw[..., 2 * K:])
+    raw[..., :K] += np.where(far[..., None], rng.normal(0, 20, (Bn, T, K)), 0.0)      # widely spread logits as well
+    raw_h = cu(raw).to(dtype)
+    x_sl = torch.tensor([T, 700])
+    scale = 1024.0
+    r = raw_h.clone().requires_grad_(True)
+    out = B.fused_elbo(cu(y), B.DMoLParams(r, K, 1, -7.0), x_sl, (), num_bins=nb, want_twise=True)
+    (out.loss * scale).backward()
+    ref = O.fused_elbo_value_and_grad(y, raw_h.float().cpu().numpy(), x_sl.numpy(), [], 1.0, K, nb)
+    m = O.sequence_mask(x_sl.numpy(), max_len=T)
+    tw = out.log_prob_twise.cpu().numpy().astype(np.float64)
+    assert_values_close(tw[m], ref["lp_twise"][m], "per-sample log-prob, far-out samples included")
+    assert float(np.abs(ref["lp_twise"][m & far]).max()) > 100.0        # the fallback regime really is exercised
+    assert_sums_close(out.loss.item(), ref["loss"], "loss")
+    g = r.grad.float().cpu().numpy().astype(np.float64) / scale
+    gref = ref["graw"]
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    # absolute floor: d/d logit = g (resp - softmax) cancels to ~1e-7 g when one logit dominates (parity.py uses the same 1e-6 g)
+    tol = eps * np.abs(gref) + 1e-4 * np.abs(gref).max(-1, keepdims=True) + (6e-8 / scale if dtype == torch.float16 else 0) + 1e-6 / float(x_sl.sum())
+    ratio = np.abs(g - gref) / tol
+    w = np.unravel_index(np.argmax(ratio), ratio.shape)
+    assert ratio.max() <= 1.0, (f"worst err/tol {ratio.max():.3g} at {w}: ours {g[w]:.6g} ref {gref[w]:.6g}, far={far[w[0], w[1]]}, y={y[w[0], w[1]]}, "
+                                f"row={raw_h[w[0], w[1]].float().cpu().numpy()}, ref row grad={gref[w[0], w[1]]}, ours={g[w[0], w[1]]}")
+    # non-finite parameters propagate exactly like in the fp32 kernel (log domain only)
+    bad = raw_h.clone()
+    bad[0, 10, 0] = float("nan")            # NaN logit
+    bad[0, 11, K] = float("nan")            # NaN location
+    bad[0, 12, 2 * K] = float("nan")        # NaN log-scale
+    bad[0, 13, 0] = float("inf")            # +inf logit
+    bad[0, 14, 1] = -float("inf")           # -inf logit: that component simply has zero weight
+    lik = B.DiscretizedLogisticMixtureDense(3, 1, K, nb)
+    lp_h = lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(bad, K, 1, -7.0))
+    lp_f = lik.log_prob(cu(y).unsqueeze(-1), B.DMoLParams(bad.float(), K, 1, -7.0))
+    fin_h, fin_f = torch.isfinite(lp_h), torch.isfinite(lp_f)
+    assert torch.equal(fin_h, fin_f) and torch.equal(torch.isnan(lp_h), torch.isnan(lp_f))
+    assert_values_close(lp_h[fin_h].cpu().numpy(), lp_f[fin_f].cpu().numpy().astype(np.float64), "finite rows", rtol=2e-5)
+    assert bool(torch.isfinite(lp_h[0, 14]))
+
+
 def test_fp16_gradients_do_not_underflow_with_loss_scale(B, O):
     """fp16 parameters: d loss/d raw ~ 1/sum(x_sl) ~ 1e-7 is below fp16's subnormal range; with the GradScaler's loss
     scale applied inside the backward launch (device scalar) the scaled gradients are representable."""
