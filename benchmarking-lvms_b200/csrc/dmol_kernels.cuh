@@ -298,8 +298,11 @@ struct DmolGroup {
 // element is rematerialised from its packed word by one shift, an fp16 element is not -- and spills 136 bytes at 64 registers (72 at 72):
 // K = 10 93.4 us (no gain over 94.5), K = 12 138 us (117 before).  K = 10 takes the packed-row variant below (88.8 us), K = 12 keeps the
 // log-domain body.
+#ifndef BLVM_LIN_F32_SMALLK
+#define BLVM_LIN_F32_SMALLK 0   // fp32, K <= 5 (stream kernel): measured, no change (43.4 / 59.5 / 75.3 / 94.0 us for K = 2..5 either way): not issue-bound
+#endif
 template <typename TP, int K>
-constexpr bool kLinTP = sizeof(TP) == 2 && !(std::is_same<TP, __half>::value && K > 8);
+constexpr bool kLinTP = (sizeof(TP) == 2 && !(std::is_same<TP, __half>::value && K > 8)) || (BLVM_LIN_F32_SMALLK && sizeof(TP) == 4 && K <= 5);
 
 // fp16, K = 10 (the reference's mixture size): the row stays PACKED in registers (3K/2 words) and every pair is converted where the evaluation uses it.
 // With the row converted up front the compiler keeps all 3K floats live next to the second (log-domain) body -- a bf16 element is
