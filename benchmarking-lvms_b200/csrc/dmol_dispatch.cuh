@@ -42,12 +42,31 @@ int launch_tile_mode(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
 }
 
 // ---- persistent pipelined variant (dmol_stream_kernel.cuh) ------------------------------------------------------------
+// Ring depth and CTA size.  Defaults: 2 stages / lookahead 1 / 128 threads (round-1 A/B, profiles/r1_ab_stream_kernel.log).  fp32 with
+// K = 3..5 (32 KB stages, 3 CTAs per SM by shared memory at 2 stages): 256 threads and 3 stages -- twice the warps per CTA over two
+// resident CTAs, the store of tile i-1 no longer in front of the load of tile i+1 -- measured K = 5 95.0 -> 88.7 us, K = 4 75.4 -> 71.5,
+// K = 3 60.2 -> 58.3 (T = 64000, K = 5: 378 -> 356 us); 16-bit parameters and K <= 2 are faster with the default (bf16 K = 5 59.7 vs 63.9 us).
+// -DBLVM_STREAM_STAGES / _LOOKAHEAD / _TPB override every instantiation (A/B builds).
+#if defined(BLVM_STREAM_STAGES) || defined(BLVM_STREAM_TPB)
 #ifndef BLVM_STREAM_STAGES
 #define BLVM_STREAM_STAGES 2
+#endif
+#ifndef BLVM_STREAM_LOOKAHEAD
 #define BLVM_STREAM_LOOKAHEAD 1
 #endif
 #ifndef BLVM_STREAM_TPB
 #define BLVM_STREAM_TPB 128
+#endif
+template <int K, typename TP>
+struct StreamCfg {
+  static constexpr int tpb = BLVM_STREAM_TPB, stages = BLVM_STREAM_STAGES, lookahead = BLVM_STREAM_LOOKAHEAD;
+};
+#else
+template <int K, typename TP>
+struct StreamCfg {
+  static constexpr bool wide = sizeof(TP) == 4 && K >= 3;
+  static constexpr int tpb = wide ? 256 : 128, stages = wide ? 3 : 2, lookahead = 1;
+};
 #endif
 #ifndef BLVM_STREAM_MAX_K
 #define BLVM_STREAM_MAX_K 5      // K above this keeps the one-tile-per-CTA kernel (already at the HBM roofline)
@@ -78,8 +97,9 @@ bool stream_eligible(const DmolArgs& A, int K) {
 
 template <int K, bool GRAD, int UMODE, typename TP, int LIK = kLikDmol>
 int launch_stream(const DmolArgs& A, int64_t tiles, cudaStream_t st) {
-  constexpr int TPB = (128 * DmolSpt<K>::value) % BLVM_STREAM_TPB == 0 ? BLVM_STREAM_TPB : 128;
-  constexpr int S = BLVM_STREAM_STAGES, LA = BLVM_STREAM_LOOKAHEAD;
+  using Cfg = StreamCfg<K, TP>;
+  constexpr int TPB = (128 * DmolSpt<K>::value) % Cfg::tpb == 0 ? Cfg::tpb : 128;
+  constexpr int S = Cfg::stages, LA = Cfg::lookahead;
   constexpr size_t smem = StreamLayout<K, TPB, TP>::bytes(S);
   auto kern = dmol_stream_kernel<K, TPB, S, LA, GRAD, UMODE, TP, LIK>;
   static int resident_dev[kMaxDevices] = {};  // CTAs per SM; per instantiation and device, benign race

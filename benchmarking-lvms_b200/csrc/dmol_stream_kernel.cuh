@@ -21,7 +21,7 @@
 //
 // Eligibility (checked on the host): every tile slab 16-byte aligned, i.e. T % 4 == 0, (T * 3K * sizeof(TP)) % 16 == 0 and
 // 16-byte aligned base pointers; other shapes take the tile kernel (which has the element-wise fallback).  Same tiling,
-// same partials layout, bit-identical results to the tile kernel.
+// same partials layout; values and gradients bit-identical to the tile kernel (the fp64 tile sums too when the CTA has 128 threads).
 #pragma once
 #include "dmol_kernels.cuh"
 

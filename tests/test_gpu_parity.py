@@ -908,7 +908,7 @@ def test_gaussian_ll_and_mc_kl(B):
 @pytest.mark.parametrize("Bn,T", [(3, 4096), (7, 20000), (300, 1024), (2, 2052)])
 def test_stream_kernel_bit_identical_to_tile_kernel(K, dtype, Bn, T, B):
     """Small-K shapes with 16-byte aligned slabs run the persistent TMA-ring kernel; it must reproduce the tile kernel
-    bit for bit (values, gradients, fp64 partial sums) — ragged lengths, skipped padding tiles, upstream gradients,
+    bit for bit (values, gradients; the fp64 partial sums to 1e-13, see below) — ragged lengths, skipped padding tiles, upstream gradients,
     forward-only, more tiles than resident CTAs (300 x 1024) and a short tail tile (2052)."""
     from blvm_b200 import ops
     lib = B._lib.lib
@@ -948,7 +948,11 @@ def test_stream_kernel_bit_identical_to_tile_kernel(K, dtype, Bn, T, B):
             continue
         stream_out = res[(1,) + key[1:]]
         for a, b, name in zip(tile_out, stream_out, ("lp", "graw", "partials", "lp (fwd only)", "partials (fwd only)")):
-            assert torch.equal(a, b), f"{name} differs between the tile and the stream kernel, flags={key[1]} gout={key[2]}"
+            if name.startswith("partials"):
+                # fp64 tile sums: the stream kernel runs 256-thread CTAs for fp32 K >= 3 (other warp grouping of the same 512 values)
+                np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-13, atol=1e-9, err_msg=name)
+            else:
+                assert torch.equal(a, b), f"{name} differs between the tile and the stream kernel, flags={key[1]} gout={key[2]}"
         assert torch.equal(tile_out[0], tile_out[3])   # forward-only values equal the fwd+grad values
     # sanity against the oracle on one utterance (the stream path itself is what the golden tests exercise for K <= 5)
     lp = res[(1, 1, False)][0]
