@@ -26,5 +26,5 @@ from .patch import patch_blvm, unpatch_blvm
 from .transforms import Quantize
 from .variational import discount_free_nats, kl_divergence_gaussian, kl_divergence_gaussian_mc
 
-__version__ = "0.2.0"
+__version__ = "0.2.1"
 LIB_PATH = _lib.LIB_PATH

@@ -58,6 +58,7 @@ SIGNATURES = {
     "blvm_kl_elbo_fwd_grad": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
     "blvm_kl_reduce_fwd_grad": (_i32, [_p, _p, _i64, _i64, _i64, _f64, _f32, _p, _p, _p, _i32, _p]),
     "blvm_kl_elbo_levels_fwd_grad": (_i32, [ctypes.POINTER(KLLevelStruct), _i32, _i64, _f32, _i32, _p]),
+    "blvm_kl_elbo_levels_fwd_grad_scaled": (_i32, [ctypes.POINTER(KLLevelStruct), _i32, _i64, _f32, _p, _i32, _p]),
     "blvm_elbo_finalize": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64, _f64, _f64, _p, _p, _p, _p]),
     "blvm_elbo_finalize_publish": (_i32, [_p, _i64, ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_i64), _i32, _p, _i64,
                                           _f64, _f64, _p, _p, _p, ctypes.POINTER(_p), _i32, _i32, _p, _p, _p, _p]),

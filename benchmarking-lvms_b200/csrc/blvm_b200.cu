@@ -398,8 +398,8 @@ int blvm_kl_reduce_fwd_grad(const float* kl, const int64_t* lens, int64_t B, int
 
 // Validate the level descriptors and lay out the concatenated tile ranges (shared by the level-array entry point and the
 // single-launch step).
-static int build_kl_multi(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, KlMultiArgs& M, bool& any_grad,
-                          int64_t& total) {
+static int build_kl_multi(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, const double* gscale_dev, KlMultiArgs& M,
+                          bool& any_grad, int64_t& total) {
   if (n_levels < 1 || n_levels > kMaxLevels) return fail(BLVM_ERR_INVALID_ARGUMENT, "n_levels=%d out of [1, %d]", n_levels, kMaxLevels);
   if (!levels_host || B < 0) return fail(BLVM_ERR_INVALID_ARGUMENT, "null levels / negative B");
   M.n_levels = n_levels;
@@ -410,7 +410,7 @@ static int build_kl_multi(const blvm_kl_level_t* levels_host, int n_levels, int6
     if (L.Tz < 0 || L.Z < 1) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: bad shape Tz=%lld Z=%lld", l, (long long)L.Tz, (long long)L.Z);
     if (!L.part_kl || !L.part_klfn) return fail(BLVM_ERR_INVALID_ARGUMENT, "level %d: null partials", l);
     KlArgs& A = M.level[l];
-    A.lens = L.lens; A.gscale = gscale; A.fn_enabled = (L.free_nats != 0.0) ? 1 : 0;
+    A.lens = L.lens; A.gscale = gscale; A.gscale_dev = gscale_dev; A.fn_enabled = (L.free_nats != 0.0) ? 1 : 0;
     A.min_kl = static_cast<float>(L.free_nats / static_cast<double>(L.Z));
     A.part_kl = L.part_kl; A.part_klfn = L.part_klfn; A.B = B; A.row_elems = L.Tz * L.Z; A.Z = L.Z;
     A.chunks = blvm_kl_chunks(A.row_elems);
@@ -442,10 +442,15 @@ static int build_kl_multi(const blvm_kl_level_t* levels_host, int n_levels, int6
 
 int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, int flags,
                                  blvm_stream_t stream) {
+  return blvm_kl_elbo_levels_fwd_grad_scaled(levels_host, n_levels, B, gscale, nullptr, flags, stream);
+}
+
+int blvm_kl_elbo_levels_fwd_grad_scaled(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, const double* gscale_dev,
+                                        int flags, blvm_stream_t stream) {
   KlMultiArgs M{};
   bool any_grad = false;
   int64_t total = 0;
-  if (int rc = build_kl_multi(levels_host, n_levels, B, gscale, M, any_grad, total)) return rc;
+  if (int rc = build_kl_multi(levels_host, n_levels, B, gscale, gscale_dev, M, any_grad, total)) return rc;
   if (total == 0) return BLVM_OK;
   const bool pdl = (flags & BLVM_FLAG_OVERLAP_PREV) != 0 && pdl_enabled();
   const unsigned g = static_cast<unsigned>(total);
@@ -587,7 +592,9 @@ int blvm_elbo_step(const blvm_elbo_step_t* desc, blvm_stream_t stream) {
       part += 2 * S.B * kl_chunks[l];
     }
     // the launch just before is this step's likelihood kernel, which produces none of the KL inputs: overlap its tail
-    const int rc = blvm_kl_elbo_levels_fwd_grad(lv, L, S.B, kl_grad ? static_cast<float>(S.beta / dn) : 0.f, has_lik ? BLVM_FLAG_OVERLAP_PREV : 0, stream);
+    // the loss scale (fp16 AMP) is applied to the KL gradients here as it is to the likelihood's: no rescale pass in the backward
+    const int rc = blvm_kl_elbo_levels_fwd_grad_scaled(lv, L, S.B, kl_grad ? static_cast<float>(S.beta / dn) : 0.f, S.loss_scale,
+                                                       has_lik ? BLVM_FLAG_OVERLAP_PREV : 0, stream);
     if (rc) return rc;
   }
 

@@ -19,6 +19,7 @@ struct KlArgs {
   const int64_t* lens;   // (B) valid latent steps per row, nullptr = all
   const float* gout;     // per-element upstream gradient, nullptr = 1
   float gscale;          // scalar multiplier of every gradient (e.g. beta / sum(x_sl))
+  const double* gscale_dev;  // optional device scalar multiplied into gscale (the GradScaler's loss scale under fp16 AMP), nullptr = 1
   float min_kl;          // free_nats / Z
   int fn_enabled;        // 0 = discount_free_nats is the identity (free_nats None/0, variational.py:107-108)
   float* kl;             // per-element raw KL out (nullable)
@@ -45,7 +46,7 @@ static_assert(kKlChunk % (kKlTPB * kKlVec) == 0, "a CTA covers its chunk with wh
 // sum is good to ~1e-7 relative — and are widened to fp64 once per thread for the block reduction (fp32->fp64
 // conversions run on the 16-lane XU pipe; per element they were 2 of ~6 XU operations).
 template <bool GRAD>
-__device__ __forceinline__ void kl_element(const KlArgs& A, int64_t idx, bool valid, float mq, float sq, float mp, float sp,
+__device__ __forceinline__ void kl_element(const KlArgs& A, float gs, int64_t idx, bool valid, float mq, float sq, float mp, float sp,
                                            float& kl, float& gmq, float& gsq, float& gmp, float& gsp, float& s_kl,
                                            float& s_fn) {
   const KlTerms t = kl_gaussian_terms(mq, sq, mp, sp);
@@ -54,7 +55,7 @@ __device__ __forceinline__ void kl_element(const KlArgs& A, int64_t idx, bool va
   s_kl += valid ? kl : kl * 0.0f;                                      // `kld * mask` semantics (vrnn.py:272)
   s_fn += valid ? klfn : klfn * 0.0f;
   if (GRAD) {
-    float g = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
+    float g = valid ? gs * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
     if (A.gout) g *= A.gout[idx];
     kl_gaussian_grads(t, sq, g, gmq, gsq, gmp, gsp);
   }
@@ -78,6 +79,8 @@ __device__ __forceinline__ void kl_tile_body(const KlArgs& A, const int64_t tile
   const int64_t nvalid_row = len * A.Z;
   const int64_t base = b * A.row_elems;
   float s_kl = 0.f, s_fn = 0.f;
+  float gs = A.gscale;
+  if (A.gscale_dev) gs *= static_cast<float>(*A.gscale_dev);
 
   if (A.kl_in) {                                         // materialised KL: mask, free nats, sums, d/d kl
 #pragma unroll
@@ -90,7 +93,7 @@ __device__ __forceinline__ void kl_tile_body(const KlArgs& A, const int64_t tile
         const float klfn = (A.fn_enabled && kl < A.min_kl) ? A.min_kl : kl;
         s_kl += valid ? kl : kl * 0.0f;
         s_fn += valid ? klfn : klfn * 0.0f;
-        if (A.gkl) A.gkl[i] = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
+        if (A.gkl) A.gkl[i] = valid ? gs * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
       }
     }
   } else if (A.z) {                                      // Monte-Carlo KL at the sample z (signed terms; not a hot path)
@@ -107,7 +110,7 @@ __device__ __forceinline__ void kl_tile_body(const KlArgs& A, const int64_t tile
         s_fn += valid ? klfn : klfn * 0.0f;
         if (A.kl) A.kl[i] = kl;
         if (GRAD) {
-          float g = valid ? A.gscale * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
+          float g = valid ? gs * free_nats_gate(kl, A.min_kl, A.fn_enabled != 0) : 0.f;
           if (A.gout) g *= A.gout[i];
           float gz;
           kl_mc_grads(t, g, A.g_mu_q[i], A.g_sd_q[i], A.g_mu_p[i], A.g_sd_p[i], gz);
@@ -126,10 +129,10 @@ __device__ __forceinline__ void kl_tile_body(const KlArgs& A, const int64_t tile
         const float4 mp = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.mu_p + i));
         const float4 sp = ptx::ldg_stream4(reinterpret_cast<const float4*>(A.sd_p + i));
         float4 kl, gmq, gsq, gmp, gsp;
-        kl_element<GRAD>(A, i + 0, e + 0 < nvalid_row, mq.x, sq.x, mp.x, sp.x, kl.x, gmq.x, gsq.x, gmp.x, gsp.x, s_kl, s_fn);
-        kl_element<GRAD>(A, i + 1, e + 1 < nvalid_row, mq.y, sq.y, mp.y, sp.y, kl.y, gmq.y, gsq.y, gmp.y, gsp.y, s_kl, s_fn);
-        kl_element<GRAD>(A, i + 2, e + 2 < nvalid_row, mq.z, sq.z, mp.z, sp.z, kl.z, gmq.z, gsq.z, gmp.z, gsp.z, s_kl, s_fn);
-        kl_element<GRAD>(A, i + 3, e + 3 < nvalid_row, mq.w, sq.w, mp.w, sp.w, kl.w, gmq.w, gsq.w, gmp.w, gsp.w, s_kl, s_fn);
+        kl_element<GRAD>(A, gs, i + 0, e + 0 < nvalid_row, mq.x, sq.x, mp.x, sp.x, kl.x, gmq.x, gsq.x, gmp.x, gsp.x, s_kl, s_fn);
+        kl_element<GRAD>(A, gs, i + 1, e + 1 < nvalid_row, mq.y, sq.y, mp.y, sp.y, kl.y, gmq.y, gsq.y, gmp.y, gsp.y, s_kl, s_fn);
+        kl_element<GRAD>(A, gs, i + 2, e + 2 < nvalid_row, mq.z, sq.z, mp.z, sp.z, kl.z, gmq.z, gsq.z, gmp.z, gsp.z, s_kl, s_fn);
+        kl_element<GRAD>(A, gs, i + 3, e + 3 < nvalid_row, mq.w, sq.w, mp.w, sp.w, kl.w, gmq.w, gsq.w, gmp.w, gsp.w, s_kl, s_fn);
         if (A.kl) ptx::stg_stream4(reinterpret_cast<float4*>(A.kl + i), kl);
         if (GRAD) {
           ptx::stg_stream4(reinterpret_cast<float4*>(A.g_mu_q + i), gmq);
@@ -146,7 +149,7 @@ __device__ __forceinline__ void kl_tile_body(const KlArgs& A, const int64_t tile
       if (e < A.row_elems) {
         const int64_t i = base + e;
         float kl, gmq, gsq, gmp, gsp;
-        kl_element<GRAD>(A, i, e < nvalid_row, A.mu_q[i], A.sd_q[i], A.mu_p[i], A.sd_p[i], kl, gmq, gsq, gmp, gsp, s_kl, s_fn);
+        kl_element<GRAD>(A, gs, i, e < nvalid_row, A.mu_q[i], A.sd_q[i], A.mu_p[i], A.sd_p[i], kl, gmq, gsq, gmp, gsp, s_kl, s_fn);
         if (A.kl) A.kl[i] = kl;
         if (GRAD) {
           A.g_mu_q[i] = gmq;

@@ -547,13 +547,12 @@ class _FusedELBO(torch.autograd.Function):
                 check(rc, "blvm_scale_inplace_multi")
             _count()
 
-        if ctx.prescale is not None and grads[0] is not None:
-            # the likelihood gradient already carries the loss scale S: multiply by grad_output / S, which is exactly 1 for
-            # scaler.scale(loss).backward() (the launch then exits at once); everything else gets the plain grad_output
-            rescale([grads[0]], g / ctx.prescale)
-            rest = [b for b in grads[1:] if b is not None]
-            if rest and not is_unit:
-                rescale(rest, g)
+        if ctx.prescale is not None:
+            # every gradient of the step (likelihood and KL levels) already carries the loss scale S: multiply by grad_output / S, which
+            # is exactly 1 for scaler.scale(loss).backward() -- the one launch then exits at once
+            bufs = [b for b in grads if b is not None]
+            if bufs:
+                rescale(bufs, g / ctx.prescale)
         else:
             bufs = [b for b in grads if b is not None]
             if bufs and not is_unit:
@@ -668,7 +667,9 @@ class _FusedLinearELBO(torch.autograd.Function):
                     kl_ptrs.append(pk)
                     klfn_ptrs.append(pf)
                     kl_chunks.append(c)
-                check(lib.blvm_kl_elbo_levels_fwd_grad(multi, L, B, spec.beta / spec.denom, 0, stream), "blvm_kl_elbo_levels_fwd_grad")
+                check(lib.blvm_kl_elbo_levels_fwd_grad_scaled(multi, L, B, spec.beta / spec.denom,
+                                                              spec.loss_scale.data_ptr() if spec.loss_scale is not None else None, 0, stream),
+                      "blvm_kl_elbo_levels_fwd_grad_scaled")
                 _count()
             PtrArr, I64Arr = ctypes.c_void_p * max(L, 1), ctypes.c_int64 * max(L, 1)
             check(lib.blvm_elbo_finalize(logp_ptr, chunks, PtrArr(*kl_ptrs), PtrArr(*klfn_ptrs), I64Arr(*kl_chunks), L, x_sl_dev.data_ptr(), B,
@@ -706,11 +707,9 @@ class _FusedLinearELBO(torch.autograd.Function):
 
         head = [b for b in grads[:3] if b is not None]
         rest = [b for b in grads[3:] if b is not None]
-        if ctx.prescale is not None:     # the head's gradients already carry the loss scale S: multiply by grad_output / S (== 1 for scaler.scale(loss))
-            if head:
-                rescale(head, g / ctx.prescale)
-            if rest and not is_unit:
-                rescale(rest, g)
+        if ctx.prescale is not None:     # all gradients already carry the loss scale S: multiply by grad_output / S (== 1 for scaler.scale(loss))
+            if head or rest:
+                rescale(head + rest, g / ctx.prescale)
         elif (head or rest) and not is_unit:
             rescale(head + rest, g)
         ctx.grads = None

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BLVM_B200_VERSION 200 /* 0.2.0 */
+#define BLVM_B200_VERSION 201 /* 0.2.1 */
 
 enum {
   BLVM_OK = 0,
@@ -189,6 +189,11 @@ typedef struct blvm_kl_level {
 } blvm_kl_level_t;
 int blvm_kl_elbo_levels_fwd_grad(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale, int flags,
                                  blvm_stream_t stream);
+/* The same with `gscale_dev`, a nullable fp64 DEVICE scalar multiplied into gscale by the kernel (the GradScaler's loss scale of
+ * experiments/experiment_vrnn_audio.py:222-226 under fp16 AMP: the KL gradients then carry it like the likelihood's do and the
+ * backward needs no rescale pass over them). */
+int blvm_kl_elbo_levels_fwd_grad_scaled(const blvm_kl_level_t* levels_host, int n_levels, int64_t B, float gscale,
+                                        const double* gscale_dev, int flags, blvm_stream_t stream);
 
 /*
  * Partials -> per-utterance log p(x|z), KL, free-nats KL, ELBO -> loss and bits-per-dim.
@@ -238,7 +243,8 @@ int64_t blvm_exchange_buffer_bytes(void);
  * wavenet.py:128-146).
  *   likelihood  BLVM_LIK_*; with BLVM_LIK_NONE the step is KL-only (log p = 0)
  *   graw        nullable: NULL = forward only (no gradient is written anywhere: the levels' g_* must be NULL too)
- *   loss_scale  nullable fp64 device scalar multiplied into the likelihood gradient (fp16 parameters under a GradScaler)
+ *   loss_scale  nullable fp64 device scalar multiplied into EVERY gradient the step writes, likelihood and KL (fp16 parameters
+ *               under a GradScaler: the scaled gradients are representable and the backward only multiplies by grad_output / scale)
  *   levels      n_levels descriptors; their part_kl / part_klfn members are IGNORED (placed in the workspace)
  *   workspace   blvm_elbo_step_workspace_doubles(desc) fp64 values: [scalars 8 | rows (4 + n_levels) x B | partial sums];
  *               scalars and rows are the outputs documented at blvm_elbo_finalize

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/blvm_b200.h but not exported by {blvm_b200.LIB_PATH}"
     assert set(names) == set(blvm_b200._lib.SIGNATURES), "ctypes signatures and header out of sync"
-    assert blvm_b200._lib.lib.blvm_version() == 200
+    assert blvm_b200._lib.lib.blvm_version() == 201
     # host-only entry points are callable without a GPU
     assert blvm_b200._lib.lib.blvm_dmol_chunks(16000, 10, 1) == 125
     assert blvm_b200._lib.lib.blvm_dmol_chunks(16000, 1, 1) == 16      # 8 samples per thread at K = 1

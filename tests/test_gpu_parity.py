@@ -1079,9 +1079,9 @@ def test_sample_mode_tile_kernel_matches_direct_kernel(K, dtype, B):
 
 def test_fp16_single_pass_with_known_grad_scaler(B):
     """`--use_amp True` (fp16 autocast + GradScaler): with the scaler known, the fp16 likelihood gradient is written in the
-    forward pass pre-multiplied by the scaler's device-side scale, and `scaler.scale(loss).backward()` only launches the
-    early-exit rescale; results are bit-identical to the deferred two-pass path, also for a second, different upstream
-    factor, and the KL gradients still receive the plain upstream gradient."""
+    forward pass pre-multiplied by the scaler's device-side scale -- and so are the KL gradients (the KL kernel reads the same
+    device scalar) -- so `scaler.scale(loss).backward()` launches ONE rescale that exits at once; results are bit-identical to
+    the deferred two-pass path (power-of-two scales), also for a second, different upstream factor."""
     from blvm_b200 import amp, ops
     g = load_golden("elbo_srnn_a")
     K, nb = int(g["K"]), int(g["num_bins"])
@@ -1102,7 +1102,7 @@ def test_fp16_single_pass_with_known_grad_scaler(B):
     assert amp.active_grad_scaler(torch.device("cuda", torch.cuda.current_device())) is None   # nothing registered: explicit only
     fa, ba, graw_a, gkl_a, loss_a = run(True)
     fb, bb, graw_b, gkl_b, loss_b = run(False)
-    assert (fa, fb) == (3, 3) and ba == 2 and bb == 2     # a: 2 rescale launches (1 early exit); b: KL rescale + gradient kernel
+    assert (fa, fb) == (3, 3) and ba == 1 and bb == 2     # a: one early-exit rescale of all gradients; b: KL rescale + gradient kernel
     assert loss_a == loss_b
     assert graw_a.dtype == torch.float16 and torch.equal(graw_a, graw_b)
     assert all(torch.equal(x, y) for x, y in zip(gkl_a, gkl_b))
