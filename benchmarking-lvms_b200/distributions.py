@@ -198,7 +198,7 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
     (mixture logit, mean, log-scale); data assumed rescaled to `num_bins` discrete values in [-1, 1]."""
 
     def __init__(self, x_dim: int, y_dim: int, num_mix: int = 10, num_bins: int = 256, log_epsilon: float = -7.0,
-                 fuse_linear: bool = False):
+                 fuse_linear: bool = False, lazy_samples: bool = False):
         super().__init__()
         self.x_dim = x_dim
         self.y_dim = y_dim
@@ -210,6 +210,11 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
         # opt-in (not a reference argument): under AMP, hand `fused_elbo` the Linear's input instead of its output so that the
         # whole head runs as one tensor-core kernel (see LinearDMoLParams); everything else behaves as before
         self.fuse_linear = fuse_linear
+        # opt-in (patch_blvm(lazy_samples=True)): sample() / mode() on CUDA parameters return promises (variational.LazyResult) that run
+        # the fused sample + mode kernel the first time either of them is read -- the reference models call both on every training step
+        # (vrnn.py:332-333) and store the results in outputs a training loop never looks at.  The random draw then happens at the first
+        # read, and a lazily read mode() is detached (nothing in the reference differentiates it).
+        self.lazy_samples = lazy_samples
         self.reset_parameters()
 
     @staticmethod
@@ -263,12 +268,29 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
                 return fn(params)
         return LazyResult((*x.shape[:-1], self.y_dim), dtype, x.device, thunk)
 
+    def _lazy_sample_mode(self, params: "DMoLParams", which: int):
+        """lazy_samples=True: a promise of sample() (which = 0) / mode() (1) on packed CUDA parameters; both come from ONE launch of the
+        fused kernel, issued when the first of them is read (cached on the parameter container like the eager call)."""
+        from .variational import LazyResult, _LAZY_DEVICE_TYPES
+        raw = params.raw
+        if raw.device.type not in _LAZY_DEVICE_TYPES:
+            return self._fused_sample_mode(params)[which]      # raises for CPU tensors: no fallback
+        dtype = torch.float32 if (which == 0 or raw.dtype == torch.float32) else raw.dtype
+
+        def thunk():
+            with torch.no_grad():
+                out = self._fused_sample_mode(params)[which]
+                return out if out.dtype == dtype else out.to(dtype)
+        return LazyResult((*raw.shape[:-1], self.y_dim), dtype, raw.device, thunk)
+
     @torch.no_grad()
     def sample(self, params):
         """A sample of the mixture, clamped to [-1, 1] (distributions.py:359-361, variational.py:309-349): the fused
         sample + mode kernel.  CUDA only, like every kernel of this package (CPU tensors raise; no torch fallback)."""
         if isinstance(params, LinearDMoLParams) and not params.materialized:
             return self._deferred(params, 0)
+        if self.lazy_samples:
+            return self._lazy_sample_mode(self._as_packed(params), 0)
         return self._fused_sample_mode(self._as_packed(params))[0]
 
     def mode(self, params):
@@ -277,6 +299,8 @@ class DiscretizedLogisticMixtureDense(ConditionalDistribution):
         if isinstance(params, LinearDMoLParams) and not params.materialized:
             return self._deferred(params, 1)               # (read lazily, it is detached: nothing in the reference differentiates it)
         params = self._as_packed(params)
+        if self.lazy_samples:
+            return self._lazy_sample_mode(params, 1)
         _, mode, index = self._fused_sample_mode(params)
         if torch.is_grad_enabled() and params.raw.requires_grad:
             return ops.mode_with_grad(params.raw, mode, index, params.K, params.D)

@@ -26,13 +26,18 @@ def _rebind_method(cls, name, replacement):
     setattr(cls, name, replacement)
 
 
-def patch_blvm(fuse_linear: bool = False):
+def patch_blvm(fuse_linear: bool = False, lazy_samples: bool = False):
     """Import `blvm` (must be on sys.path) and rebind the hot-path functions, classes and model reducers to blvm_b200.
     Returns the list of `module.attr` names that were rebound.
 
     fuse_linear=True: every DiscretizedLogisticMixtureDense constructed from now on also fuses its `nn.Linear` into the
     likelihood kernel when it runs under AMP (fp16 / bf16 activations, num_mix = 10, even x_dim <= 79): Linear, DMoL value +
-    gradient and the Linear's backward as one tcgen05 tensor-core kernel (csrc/linear_dmol_kernel.cuh)."""
+    gradient and the Linear's backward as one tcgen05 tensor-core kernel (csrc/linear_dmol_kernel.cuh).
+
+    lazy_samples=True: `likelihood.sample(params)` / `.mode(params)` of those modules return promises that launch the fused sample + mode
+    kernel only when somebody reads them (the models call both on every training step, vrnn.py:332-333, and a training loop never looks):
+    a patched training step is then 3 launches of ours -- likelihood, KL, finalize -- and draws nothing (so it can be captured in a CUDA
+    graph).  The random draw happens at the first read; a lazily read mode is detached."""
     import importlib
 
     import blvm.modules.distributions as ref_dist
@@ -50,10 +55,13 @@ def patch_blvm(fuse_linear: bool = False):
     # (vrnn.py:81,91), which are outside this path; blvm_b200.gaussian_ll / kl_divergence_gaussian_mc exist for callers
     # that want the kernels (e.g. bottom-up STCN).
     dmol_cls = distributions.DiscretizedLogisticMixtureDense
-    if fuse_linear:
+    if fuse_linear or lazy_samples:
         class DiscretizedLogisticMixtureDense(distributions.DiscretizedLogisticMixtureDense):   # same name: repr / checkpoints unchanged
             def __init__(self, *args, **kwargs):
-                kwargs.setdefault("fuse_linear", True)
+                if fuse_linear:
+                    kwargs.setdefault("fuse_linear", True)
+                if lazy_samples:
+                    kwargs.setdefault("lazy_samples", True)
                 super().__init__(*args, **kwargs)
         dmol_cls = DiscretizedLogisticMixtureDense
     _rebind_everywhere(ref_dist.DiscretizedLogisticMixtureDense, dmol_cls)

@@ -332,6 +332,44 @@ def test_patched_step_has_one_fused_kl_launch_and_one_metric_sync(name, ref):
     assert len(ours(syncs_ref)) >= 5
 
 
+def test_lazy_samples_make_the_patched_step_three_launches(ref):
+    """patch_blvm(lazy_samples=True): sample() / mode() of the patched likelihood return promises, so a VRNN training step is three
+    launches of ours (likelihood, KL, finalize); the fused sample + mode kernel runs once, when a reconstruction is first read, and
+    the mode it returns is the eager one."""
+    import blvm_b200 as B
+    M = ref
+    name = "vrnn"
+    x, x_sl, kwargs = inputs(name)
+    state = copy.deepcopy(build(M, name).state_dict())
+    try:
+        B.patch_blvm(lazy_samples=True)
+        model = build(M, name).cuda()
+        model.load_state_dict(state)
+        assert model.vrnn.likelihood.lazy_samples
+        torch.manual_seed(5)
+        B.reset_launch_count()
+        loss, metrics, out = model(x.cuda(), x_sl, **kwargs)
+        loss.backward()
+        assert B.launch_count() == 3, B.launch_count()
+        lazy = [v for v in vars(out).values() if isinstance(v, B.variational.LazyResult)]
+        assert len(lazy) >= 2 and all(v._blvm_value is None for v in lazy)
+        first = lazy[0] + 0                                   # reading one launches the fused kernel for both
+        assert B.launch_count() == 4 and torch.isfinite(first).all() and float(first.abs().max()) <= 1.0
+        second = lazy[1] + 0
+        assert B.launch_count() == 4 and second.shape == first.shape
+    finally:
+        B.unpatch_blvm()
+    # the lazily read mode equals the eager one (same kernel, same parameters)
+    lik_lazy = B.DiscretizedLogisticMixtureDense(30, 1, 10, 65536, lazy_samples=True).cuda()
+    lik = B.DiscretizedLogisticMixtureDense(30, 1, 10, 65536).cuda()
+    lik.load_state_dict(lik_lazy.state_dict())
+    h = torch.randn(3, 50, 30, device="cuda")
+    with torch.no_grad():
+        m_lazy, m = lik_lazy.mode(lik_lazy(h)), lik.mode(lik(h))
+    assert isinstance(m_lazy, B.variational.LazyResult) and torch.equal(m_lazy + 0, m)
+    assert tuple(lik_lazy.sample(lik_lazy(h)).shape) == (3, 50, 1)
+
+
 def test_wavenet_nansum_keeps_gradient_of_finite_rows(ref):
     """WaveNet.compute_loss reduces with nansum (wavenet.py:143-145): an utterance whose log-prob is NaN drops out of the
     loss and gets a zero upstream gradient, the finite utterances train on.  The real reference method is the checker."""
