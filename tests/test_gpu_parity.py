@@ -1,6 +1,7 @@
 """GPU parity: the CUDA path (through the Python boundary -> ctypes -> C ABI -> sm_100a kernels) against the golden
 vectors generated from the reference and against the numpy oracle.  Run on the B200 box: pytest -m gpu."""
 import math
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -591,6 +592,67 @@ def test_linear_domain_fallback(K, dtype, B, O):
     assert torch.equal(fin_h, fin_f) and torch.equal(torch.isnan(lp_h), torch.isnan(lp_f))
     assert_values_close(lp_h[fin_h].cpu().numpy(), lp_f[fin_f].cpu().numpy().astype(np.float64), "finite rows", rtol=2e-5)
     assert bool(torch.isfinite(lp_h[0, 14]))
+
+
+def _random_cases():
+    rng = np.random.default_rng(int(os.environ.get("BLVM_TEST_SEED", "20260")))   # another seed = another set of shapes
+    cases = []
+    for K in (1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 30):
+        for dt in ("float32", "bfloat16", "float16"):
+            Bn = int(rng.integers(1, 5))
+            T = int(rng.choice([int(rng.integers(1, 200)), int(rng.integers(200, 2600)), 4 * int(rng.integers(50, 700))]))
+            cases.append((K, dt, Bn, T, int(rng.integers(0, 2 ** 31))))
+    return cases
+
+
+@pytest.mark.parametrize("K,dt,Bn,T,seed", _random_cases())
+def test_random_shapes_against_oracle(K, dt, Bn, T, seed, B, O):
+    """Every instantiated mixture size x parameter dtype at a random (batch, length) with ragged lengths, one KL level of a random
+    stride: the whole fused step (loss, row sums, per-sample log-prob, every gradient) against the oracle on the rounded parameters.
+    Covers the kernel variants no dedicated test pins to a shape: tile / stream kernel by alignment, tails shorter than a tile,
+    rotated and packed row walks, linear-domain evaluation with its fallback, 64/128-bit row accesses."""
+    dtype = getattr(torch, dt)
+    rng = np.random.default_rng(seed)
+    nb = 65536
+    y = (rng.integers(0, nb, (Bn, T)) / (nb - 1) * 2 - 1).astype(np.float32)
+    raw = rng.normal(size=(Bn, T, 3 * K)).astype(np.float32)
+    raw[..., K:2 * K] = y[..., None] + rng.choice([0.02, 0.1, 0.5], size=(Bn, T, 1)) * raw[..., K:2 * K]
+    raw[..., 2 * K:] = raw[..., 2 * K:] * 2 - 4
+    raw_h = cu(raw).to(dtype)
+    x_sl = torch.from_numpy(rng.integers(1, T + 1, Bn))
+    x_sl[int(rng.integers(0, Bn))] = T
+    S = int(rng.choice([1, 3, 16, 64]))
+    Tz, Z = -(-T // S), int(rng.choice([1, 3, 8]))
+    klin = [rng.normal(size=(Bn, Tz, Z)).astype(np.float32), (rng.random((Bn, Tz, Z)) + 0.1).astype(np.float32),
+            rng.normal(size=(Bn, Tz, Z)).astype(np.float32), (rng.random((Bn, Tz, Z)) + 0.1).astype(np.float32)]
+    kl_t = [cu(t).requires_grad_(True) for t in klin]
+    r = raw_h.clone().requires_grad_(True)
+    scale = 1.0 if dtype == torch.float32 else 1024.0
+    out = B.fused_elbo(cu(y), B.DMoLParams(r, K, 1, -7.0), x_sl, [B.KLLevel(*kl_t, stride=S)], 0.7, 0.5, num_bins=nb, want_twise=True)
+    (out.loss * scale).backward()
+    B.check_input_range()
+    ref = O.fused_elbo_value_and_grad(y, raw_h.float().cpu().numpy(), x_sl.numpy(),
+                                      [dict(mu_q=klin[0], sd_q=klin[1], mu_p=klin[2], sd_p=klin[3], stride=S, free_nats=0.5)], 0.7, K, nb)
+    m = O.sequence_mask(x_sl.numpy(), max_len=T)
+    assert_sums_close(out.loss.item(), ref["loss"], "loss")
+    assert_sums_close(out.log_prob.cpu().numpy(), ref["logp"], "row log-prob")
+    assert_sums_close(out.kl.cpu().numpy(), ref["kl"], "row KL", rtol=2e-6)
+    tw = out.log_prob_twise.cpu().numpy().astype(np.float64)
+    assert_values_close(tw[m], ref["lp_twise"][m], "per-sample log-prob")
+    assert (tw[~m] == 0).all()
+    g = r.grad.float().cpu().numpy().astype(np.float64) / scale
+    gref = ref["graw"]
+    n = float(x_sl.sum())
+    if dtype == torch.float32:
+        assert_grads_close(g, gref, K, m.reshape(-1) / n, "d/d raw")
+    else:
+        eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+        tol = eps * np.abs(gref) + 1e-4 * np.abs(gref).max(-1, keepdims=True) + (6e-8 / scale if dtype == torch.float16 else 0) + 1e-6 / n
+        ratio = np.abs(g - gref) / tol
+        assert ratio.max() <= 1.0, f"worst err/tol {ratio.max():.3g} at {np.unravel_index(np.argmax(ratio), ratio.shape)}"
+    assert (g[~m] == 0).all()
+    for t, gr_ref, nm in zip(kl_t, ref["gkl"][0], ("mu_q", "sd_q", "mu_p", "sd_p")):
+        np.testing.assert_allclose(t.grad.cpu().numpy() / scale, gr_ref, rtol=2e-5, atol=1e-7 * np.abs(gr_ref).max() + 1e-12, err_msg=nm)
 
 
 def test_fp16_gradients_do_not_underflow_with_loss_scale(B, O):
