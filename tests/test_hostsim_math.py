@@ -273,3 +273,40 @@ def test_kl_mc_closed_forms(sim):
     h = 1e-6
     fd = (O.kl_divergence_gaussian_mc(q, sq, p, sp, z64 + h) - O.kl_divergence_gaussian_mc(q, sq, p, sp, z64 - h)) / (2 * h) * gout
     np.testing.assert_allclose(outs[5], fd, rtol=2e-4, atol=1e-5 * np.abs(fd).max())
+
+
+def test_linear_domain_agrees_with_log_domain_and_falls_back():
+    """The 16-bit kernels evaluate the mixture in the linear domain (blvm_math.cuh: dmol_sample_lin) with a per-sample fallback to
+    the log-domain body.  Host builds with and without it: on ordinary samples the two agree to a few ulp but are NOT the same
+    computation (the linear path is really taken); on samples far from every component, on edge bins and on non-finite parameters
+    the results are bit-identical (the fallback IS the log-domain body)."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    sims = {}
+    for tag, flag in (("lin", "-DBLVM_LINEAR_DOMAIN=1"), ("log", "-DBLVM_LINEAR_DOMAIN=0")):
+        lib = LIB.replace(".so", f"_{tag}.so")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", flag, "-I",
+                        os.path.join(ROOT, "benchmarking-lvms_b200", "csrc"), "-o", lib, SRC], check=True)
+        sims[tag] = ctypes.CDLL(lib)
+    g = load_golden("dmol_K10_nb65536")
+    lp_lin, gr_lin = run_dmol(sims["lin"], g)
+    lp_log, gr_log = run_dmol(sims["log"], g)
+    assert_values_close(lp_lin, lp_log.astype(np.float64), "linear vs log domain", rtol=2e-6)
+    assert (lp_lin != lp_log).mean() > 0.05, "the linear-domain path does not seem to be compiled in"
+    assert_values_close(lp_lin, g["lp64"], "linear domain vs the reference in fp64")
+    assert_grads_close(gr_lin, g["graw64"], 10, np.abs(g["gout"]), "linear-domain grads")
+    # far-out / edge / non-finite samples: the fallback
+    rng = np.random.default_rng(3)
+    K, nb, N = 10, 65536, 4000
+    y = (rng.integers(0, nb, N) / (nb - 1) * 2 - 1).astype(np.float32)
+    y[:4] = np.array([-1.0, 1.0, -1.0, 1.0], np.float32)
+    raw = rng.normal(size=(N, 3 * K)).astype(np.float32)
+    raw[:, K:2 * K] = y[:, None] + rng.choice([-1.0, 1.0], size=(N, K)) * rng.uniform(0.2, 1.5, (N, K))   # >= 0.2 away ...
+    raw[:, 2 * K:] = rng.uniform(-9.0, -5.7, (N, K))                                                       # ... at scales <= 3.3e-3
+    raw[10, 0] = np.nan
+    raw[11, 2 * K] = np.inf
+    gout = rng.normal(size=N).astype(np.float32)
+    fake = dict(K=K, D=1, num_bins=nb, y=y.reshape(N, 1), raw=raw, gout=gout)
+    a_lp, a_gr = run_dmol(sims["lin"], fake)
+    b_lp, b_gr = run_dmol(sims["log"], fake)
+    assert np.array_equal(a_lp, b_lp, equal_nan=True) and np.array_equal(a_gr, b_gr, equal_nan=True)
+    assert np.isfinite(a_lp[20:]).all() and float(np.abs(a_lp[20:]).min()) > 50.0       # the log-domain values are finite and huge
