@@ -20,7 +20,8 @@ static_assert(BLVM_DMOL_TILE == 128, "tile constant mirrors the kernel template 
 static_assert(BLVM_KL_TILE == kKlChunk, "tile constant mirrors the KL kernel");
 static_assert(BLVM_MAX_KL_LEVELS == kMaxLevels, "level cap");
 static_assert(BLVM_MAX_SCALE_BUFFERS == kMaxScaleBuffers, "scale buffer cap");
-static_assert(BLVM_FLAG_MASK_OUTPUT == kFlagMaskOutput && BLVM_FLAG_SKIP_PADDED == kFlagSkipPadded, "flags");
+static_assert(static_cast<int>(BLVM_FLAG_MASK_OUTPUT) == static_cast<int>(kFlagMaskOutput) &&
+                  static_cast<int>(BLVM_FLAG_SKIP_PADDED) == static_cast<int>(kFlagSkipPadded), "flags");
 using blvm_host::kMaxDevices;
 using blvm_host::current_device;
 
@@ -554,7 +555,6 @@ int blvm_elbo_step(const blvm_elbo_step_t* desc, blvm_stream_t stream) {
   const int64_t logp_chunks = step_logp_chunks(S);
   double* logp_part = has_lik ? part : nullptr;
   part += S.B * logp_chunks;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   if (has_lik) {
     const int kflags = S.flags & (BLVM_FLAG_MASK_OUTPUT | BLVM_FLAG_SKIP_PADDED);
