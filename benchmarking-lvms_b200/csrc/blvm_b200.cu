@@ -617,7 +617,6 @@ int blvm_elbo_step(const blvm_elbo_step_t* desc, blvm_stream_t stream) {
     const int P = S.likelihood == BLVM_LIK_DL ? 2 : S.K * (2 * S.D + 1);
     return blvm_row_gate_inplace(S.graw, S.raw_dtype, S.B, S.T * P, rows /* row 0 = log p per utterance */, stream);
   }
-  (void)st;
   return BLVM_OK;
 }
 
