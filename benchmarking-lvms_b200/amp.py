@@ -11,6 +11,7 @@ for `scaler.scale(loss).backward()` (one early-exit launch).
 A scaler becomes known either explicitly (`fused_elbo(..., grad_scaler=scaler)` / `register_grad_scaler(scaler)`) or, after
 `patch_blvm()`, automatically: GradScaler construction is observed and the single enabled instance is used.
 """
+import warnings
 import weakref
 
 import torch
@@ -25,6 +26,9 @@ def register_grad_scaler(scaler):
     """Make `scaler` (torch.amp.GradScaler / torch.cuda.amp.GradScaler) known to the fused op."""
     _scalers.add(scaler)
     return scaler
+
+
+_warned_ambiguous = False
 
 
 def active_grad_scaler(device: torch.device):
@@ -43,6 +47,12 @@ def active_grad_scaler(device: torch.device):
         if scale is None or scale.device != device:
             continue
         if found is not None:
+            global _warned_ambiguous
+            if not _warned_ambiguous:
+                _warned_ambiguous = True
+                warnings.warn("blvm_b200: more than one enabled GradScaler is alive on this device, so the loss scale of the step is "
+                              "ambiguous: fp16 gradients fall back to the deferred (two-pass) path and the fused likelihood head is not "
+                              "taken.  Pass fused_elbo(..., grad_scaler=scaler) or drop the stale scaler objects.", RuntimeWarning, stacklevel=3)
             return None
         found = s
     return found

@@ -370,6 +370,50 @@ def test_lazy_samples_make_the_patched_step_three_launches(ref):
     assert tuple(lik_lazy.sample(lik_lazy(h)).shape) == (3, 50, 1)
 
 
+@pytest.mark.parametrize("name", ["srnn", "cwvae", "stcn", "stcn_bottom_up", "wavenet", "lstm"])
+def test_lazy_samples_and_fused_head_leave_every_model_step_unchanged(name, ref, monkeypatch):
+    """patch_blvm(fuse_linear=True, lazy_samples=True) against plain patch_blvm() on the other six models: the fp16-AMP training step
+    runs, the loss and the weight gradients are those of the plain patched step (to the fused head's tolerance where it engages), and
+    the reconstructions the model returns are promises nobody had to evaluate."""
+    import blvm_b200 as B
+    from blvm_b200 import ops
+    M = ref
+    x, x_sl, kwargs = inputs(name)
+    state = copy.deepcopy(build(M, name).state_dict())
+    res = {}
+    calls = {"head": 0}
+    real = ops.fused_linear_elbo_apply
+    monkeypatch.setattr(ops, "fused_linear_elbo_apply", lambda *a, **k: (calls.__setitem__("head", calls["head"] + 1), real(*a, **k))[1])
+    for tag, opts in (("plain", {}), ("lazy", dict(fuse_linear=True, lazy_samples=True))):
+        try:
+            B.patch_blvm(**opts)
+            model = build(M, name).cuda()
+            model.load_state_dict(state)
+            B.reset_launch_count()
+            loss, grads, values, outputs, scaler = train_step(model, x, x_sl, kwargs, True, torch.cuda.amp.GradScaler)
+            res[tag] = (float(loss), grads, B.launch_count(), outputs)
+        finally:
+            B.unpatch_blvm()
+        del scaler, model      # a second live GradScaler would make the next run's loss scale ambiguous (amp.active_grad_scaler)
+        import gc
+        gc.collect()
+    (l0, g0, n0, _), (l1, g1, n1, out1) = res["plain"], res["lazy"]
+    assert abs(l1 - l0) <= 2e-3 * abs(l0), (l0, l1)
+    assert set(g0) == set(g1)
+    worst = 0.0
+    for k, g in g0.items():
+        scale = float(g.abs().max())
+        if scale > 0 and torch.isfinite(g).all():
+            worst = max(worst, float((g1[k] - g).abs().max()) / scale)
+    assert worst < 5e-2, worst
+    lazies = [v for v in vars(out1).values() if isinstance(v, B.variational.LazyResult)] if hasattr(out1, "__dict__") else []
+    print(f"\n[{name}] plain patched: loss {l0:.9f}, {n0} launches; lazy + fused head: loss {l1:.9f}, {n1} launches, {len(lazies)} promises, "
+          f"head calls {calls['head']}, worst grad diff {worst:.2e}")
+    assert n1 <= n0
+    assert all(v._blvm_value is None for v in lazies)
+    assert calls["head"] == (1 if name in ("srnn", "cwvae", "stcn", "stcn_bottom_up") else 0)   # WaveNet: nansum + per-sample output; LSTM: log_prob
+
+
 def test_wavenet_nansum_keeps_gradient_of_finite_rows(ref):
     """WaveNet.compute_loss reduces with nansum (wavenet.py:143-145): an utterance whose log-prob is NaN drops out of the
     loss and gets a zero upstream gradient, the finite utterances train on.  The real reference method is the checker."""
